@@ -1,0 +1,200 @@
+/*
+ * truss_b200.h -- C ABI of the B200-native batched direct-stiffness truss solver.
+ *
+ * The reference (slientruss3d v2.0.3) has no FFI/plugin interface: its boundary for
+ * this path is the Python method Truss.Solve() (slientruss3d/truss.py:329-364) and
+ * its two batched callers, GA.GetFitness (slientruss3d/ga.py:132-149) and the
+ * generator's solve site (slientruss3d/generate.py:354-357).  This header is the
+ * C-level boundary a reference-side binding (ctypes) attaches to;
+ * each entry point names the reference lines it replaces.
+ *
+ * Conventions
+ *   - all floating point is IEEE binary64; all indices are int32 unless noted
+ *   - dim d in {2,3}; nJ joints, M members, N = d*nJ DOFs (index j*d + axis, as in
+ *     truss.py:303-304), n free DOFs, s = N - n supported DOFs
+ *   - support codes are the reference's SupportType ints (type.py:30-35):
+ *     NO=0 PIN=1 ROLLER_X=2 ROLLER_Y=3 ROLLER_Z=4
+ *   - every function returns 0 on success, <0 for an argument error, >0 for a CUDA
+ *     error (cudaError_t value); nothing throws across the ABI; tb_strerror() names codes
+ *   - numerical status is PER SYSTEM in info[b]:
+ *        0  solved
+ *        k>0  leading minor k of the reduced stiffness matrix is not positive definite
+ *             (LAPACK potrf convention; the reference would raise numpy LinAlgError or
+ *             return garbage for a singular K, truss.py:343)
+ *        -1  fails the counting rule of truss.py:158-164 (reference: TrussNotStableError)
+ *        -2  a member has zero length (reference: ZeroDivisionError, truss.py:58)
+ *        -3  invalid support code for this dim (device-side check; type.py:48-74)
+ *        -4  a member or gene index is out of range (device-side check)
+ *     outputs of a system with info != 0 are zero-filled (fitness: +inf), never NaN
+ *   - "device" entry points take device pointers, enqueue on the given stream and do not
+ *     synchronise; "_host" entry points take host pointers and perform the H2D copies,
+ *     the solve, and the D2H copies themselves (they synchronise before returning)
+ *   - the caller owns every in/out buffer; a plan owns only its maps and workspace
+ */
+#ifndef TRUSS_B200_H
+#define TRUSS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TB_VERSION 100
+
+/* error codes (negative = argument errors) */
+#define TB_OK 0
+#define TB_ERR_NULL (-1)       /* required pointer is NULL */
+#define TB_ERR_DIM (-2)        /* dim not in {2,3} (utils.py:70-74 CheckDim) */
+#define TB_ERR_SIZE (-3)       /* negative / inconsistent sizes */
+#define TB_ERR_INDEX (-4)      /* connectivity refers to a joint that does not exist */
+#define TB_ERR_SUPPORT (-5)    /* invalid support code for this dim (type.py:48-74) */
+#define TB_ERR_TOO_LARGE (-6)  /* system too large for the selected path / workspace */
+#define TB_ERR_NO_DEVICE (-7)  /* no CUDA device: there is NO CPU fallback */
+#define TB_ERR_ALLOC (-8)
+
+/* per-system status codes in info[] */
+#define TB_INFO_OK 0
+#define TB_INFO_NOT_STABLE (-1)
+#define TB_INFO_ZERO_LENGTH (-2)
+#define TB_INFO_BAD_SUPPORT (-3)
+#define TB_INFO_BAD_INDEX (-4)
+
+typedef struct tb_plan tb_plan; /* opaque */
+
+/* Topology shared by every system of a uniform batch (one Truss, many genes / load cases /
+ * geometries).  Host pointers; copied by tb_plan_create. */
+typedef struct {
+  int32_t dim;            /* Truss(dim), truss.py:110-112 */
+  int32_t n_joint;        /* Truss.nJoint */
+  int32_t n_member;       /* Truss.nMember */
+  const int32_t* conn;    /* [M,2] (jointID0, jointID1), truss.py:184-187 */
+  const uint8_t* support; /* [nJ] SupportType codes, truss.py:174-175 */
+} tb_topology;
+
+typedef struct {
+  int32_t dim, n_joint, n_member;
+  int32_t n_dof;       /* N */
+  int32_t n_free;      /* n */
+  int32_t n_support;   /* s */
+  int32_t n_resist;    /* Truss.nResistance, truss.py:154-156 */
+  int32_t stable;      /* Truss.isStable, truss.py:158-164 */
+  int32_t path;        /* 0 = fused shared-memory kernel, 1 = blocked global-memory pipeline */
+  int32_t n_pad;       /* padded order used by the blocked pipeline (multiple of the tile) */
+  int64_t nnz_lower;   /* structural non-zeros of the lower triangle of K_ff */
+  int64_t n_contrib;   /* entries of the scatter map (member contributions to the lower triangle) */
+  int64_t half_bandwidth; /* max (row - col) over structural non-zeros of K_ff */
+} tb_plan_info;
+
+/* Build the integer maps of truss.py:319-326 (free/supported DOF order = ascending DOF index)
+ * and the deterministic scatter map replacing the "+=" block loop of truss.py:307-316.
+ * The maps are built on the host and mirrored on the device.  Without a CUDA device the
+ * plan is host-only: maps can be queried, every solve returns TB_ERR_NO_DEVICE. */
+int tb_plan_create(const tb_topology* topo, tb_plan** plan_out);
+void tb_plan_destroy(tb_plan* plan);
+int tb_plan_query(const tb_plan* plan, tb_plan_info* info_out);
+/* Override the automatic path choice (0 fused shared-memory kernel, 1 blocked pipeline);
+ * used by the parity tests to push small trusses through the blocked pipeline too. */
+int tb_plan_set_path(tb_plan* plan, int32_t path);
+
+/* Host copies of the DOF maps, for bit-exact checks against
+ * np.nonzero(GetDisplacementUnknownMask()) (truss.py:319-326):
+ *   free_idx[n]  DOF index of free DOF r;  dof2free[N]  inverse map, -1 at supported DOFs;
+ *   sup_idx[s]   DOF index of supported DOF r.  Any pointer may be NULL. */
+int tb_plan_get_maps(const tb_plan* plan, int32_t* free_idx, int32_t* dof2free, int32_t* sup_idx);
+
+/* Host copy of the scatter map (CSR over the structural non-zeros of the lower triangle of
+ * K_ff, row-major order): entry e covers K_ff[row[e], col[e]] and sums contributions
+ * contrib_ptr[e] .. contrib_ptr[e+1]-1 in ascending member order (the order of the
+ * reference's loop, truss.py:310); contribution c is member contrib_member[c], local
+ * stiffness entry (contrib_local[c] / 2d, contrib_local[c] % 2d) of truss.py:65-86.
+ * Any pointer may be NULL; sizes are tb_plan_info.nnz_lower / n_contrib. */
+int tb_plan_get_scatter(const tb_plan* plan, int32_t* row, int32_t* col, int64_t* contrib_ptr,
+                        int32_t* contrib_member, int32_t* contrib_local);
+
+/* One uniform batch: B systems sharing the plan's topology.  A stride is the distance in
+ * ELEMENTS between consecutive systems; stride 0 shares the array across the batch. */
+typedef struct {
+  int32_t batch;
+  const double* joint_xyz;   /* [B][nJ][d]  joint positions, truss.py:174-175 */
+  int64_t joint_stride;
+  const double* member_aed;  /* [B][M][3]   (a, e, density) per member, type.py:5-9; or NULL with gene */
+  int64_t member_stride;
+  const int32_t* gene;       /* [B][M]      indices into type_table (ga.py:132-137); or NULL */
+  int64_t gene_stride;
+  const double* type_table;  /* [T][3]      (a, e, density) per member type */
+  int32_t n_type;
+  const double* force;       /* [B][N]      dense load vector, truss.py:303-304 */
+  int64_t force_stride;
+} tb_batch_in;
+
+/* Outputs (dense; the reference's sparse dicts are the |x| >= 1e-10 entries, truss.py:344-361).
+ * Any pointer may be NULL to skip that output.  Rows are contiguous per system. */
+typedef struct {
+  double* u;       /* [B][N]  displacements, 0 at supported DOFs        (truss.py:342-345) */
+  double* ext;     /* [B][N]  loads with reactions at supported DOFs    (truss.py:347-351) */
+  double* axial;   /* [B][M]  member axial force, tension positive      (truss.py:353-361) */
+  double* weight;  /* [B]     sum a*L*density                           (truss.py:166-168) */
+  int32_t* info;   /* [B]     per-system status                                           */
+} tb_batch_out;
+
+/* GA fitness outputs (ga.py:139-149): fitness = weight + penalties; flags[b][0] = stress
+ * allowed, flags[b][1] = displacement allowed (truss.py:429-462 with isGetSumViolation). */
+typedef struct {
+  double* fitness;   /* [B]    */
+  uint8_t* flags;    /* [B][2] */
+  int32_t* info;     /* [B]    */
+} tb_fit_out;
+
+/* Truss.Solve() for B systems (truss.py:329-364). */
+int tb_solve(tb_plan* plan, const tb_batch_in* in, const tb_batch_out* out, void* cuda_stream);
+int tb_solve_host(tb_plan* plan, const tb_batch_in* in, const tb_batch_out* out);
+
+/* GA.GetFitness for B genes (ga.py:139-149); `full` may be NULL or receive the full results. */
+int tb_fitness(tb_plan* plan, const tb_batch_in* in, double allow_stress, double allow_displace,
+               const tb_fit_out* fit, const tb_batch_out* full, void* cuda_stream);
+int tb_fitness_host(tb_plan* plan, const tb_batch_in* in, double allow_stress, double allow_displace,
+                    const tb_fit_out* fit, const tb_batch_out* full);
+
+/* Ragged batch: B independent trusses with their own topology (the generator's solve site,
+ * generate.py:354-357).  Arrays are packed back to back; system b owns joints
+ * joint_off[b]..joint_off[b+1]-1 and members member_off[b]..member_off[b+1]-1; conn holds
+ * LOCAL joint ids.  Outputs are packed the same way (u/ext: d*joint_off, axial: member_off). */
+typedef struct {
+  int32_t dim;
+  int32_t batch;
+  const int64_t* joint_off;   /* [B+1] */
+  const int64_t* member_off;  /* [B+1] */
+  const double* joint_xyz;    /* [sum nJ][d] */
+  const uint8_t* support;     /* [sum nJ]    */
+  const int32_t* conn;        /* [sum M][2]  */
+  const double* member_aed;   /* [sum M][3]  */
+  const double* force;        /* [d * sum nJ] */
+  int32_t max_joint;          /* max nJ over the batch (sizes the shared-memory kernel) */
+  int32_t max_member;         /* max M over the batch */
+} tb_ragged_in;
+
+int tb_solve_ragged(const tb_ragged_in* in, const tb_batch_out* out, void* cuda_stream);
+int tb_solve_ragged_host(const tb_ragged_in* in, const tb_batch_out* out);
+
+/* Page-locked host buffers for callers of the *_host entry points (full-speed H2D/D2H). */
+int tb_pinned_alloc(void** ptr, size_t bytes);
+int tb_pinned_free(void* ptr);
+
+/* Largest system (free DOFs are bounded by d*nJ) the fused shared-memory kernel accepts. */
+int tb_small_path_limits(int32_t* max_dof, int32_t* max_member);
+
+/* FP64 pipe microbenchmarks used as roofline denominators (MEASURED_PEAKS.json has no FP64
+ * entry): which = 0 DFMA (vector), 1 DMMA m8n8k4 (tensor).  Returns TFLOP/s in *tflops. */
+int tb_fp64_peak(int32_t which, int32_t iters, double* tflops, float* ms);
+
+/* Kernel launches issued by this library since load (bench.py's gpu_launches). */
+int64_t tb_launch_count(void);
+const char* tb_strerror(int code);
+int tb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRUSS_B200_H */

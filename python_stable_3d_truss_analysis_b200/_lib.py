@@ -1,0 +1,367 @@
+"""ctypes binding of ``csrc/libtruss_b200.so`` (the C ABI declared in ``include/truss_b200.h``).
+
+The product has no CPU fallback: if the library has not been built, importing the solver
+raises; if it is loaded on a machine without a CUDA device, every solve raises
+``NoCudaDeviceError`` (``TB_ERR_NO_DEVICE``).  Build with ``python __graft_entry__.py`` or
+``python -m python_stable_3d_truss_analysis_b200._lib``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
+LIB_PATH = os.path.join(CSRC, "libtruss_b200.so")
+SOURCES = ["tb_plan.cu", "tb_small.cu", "tb_large.cu", "tb_api.cu", "tb_peak.cu"]
+
+TB_ERR_NO_DEVICE = -7
+TB_ERR_TOO_LARGE = -6
+
+
+class TrussLibError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"truss_b200 error {code}: {msg}")
+        self.code = code
+
+
+class NoCudaDeviceError(TrussLibError):
+    pass
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    srcs = [os.path.join(CSRC, s) for s in SOURCES]
+    deps = srcs + [os.path.join(CSRC, "tb_common.cuh"), os.path.join(INCLUDE, "truss_b200.h")]
+    if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
+        return LIB_PATH
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+           "-Xcompiler", "-fPIC", "-shared", "-I", INCLUDE, "-o", LIB_PATH] + srcs
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    if verbose:
+        print(res.stderr)
+    return LIB_PATH
+
+
+# --------------------------------------------------------------------------- ctypes mirrors
+class TbTopology(C.Structure):
+    _fields_ = [("dim", C.c_int32), ("n_joint", C.c_int32), ("n_member", C.c_int32),
+                ("conn", C.c_void_p), ("support", C.c_void_p)]
+
+
+class TbPlanInfo(C.Structure):
+    _fields_ = [("dim", C.c_int32), ("n_joint", C.c_int32), ("n_member", C.c_int32), ("n_dof", C.c_int32),
+                ("n_free", C.c_int32), ("n_support", C.c_int32), ("n_resist", C.c_int32), ("stable", C.c_int32),
+                ("path", C.c_int32), ("n_pad", C.c_int32), ("nnz_lower", C.c_int64), ("n_contrib", C.c_int64),
+                ("half_bandwidth", C.c_int64)]
+
+
+class TbBatchIn(C.Structure):
+    _fields_ = [("batch", C.c_int32), ("joint_xyz", C.c_void_p), ("joint_stride", C.c_int64),
+                ("member_aed", C.c_void_p), ("member_stride", C.c_int64), ("gene", C.c_void_p),
+                ("gene_stride", C.c_int64), ("type_table", C.c_void_p), ("n_type", C.c_int32),
+                ("force", C.c_void_p), ("force_stride", C.c_int64)]
+
+
+class TbBatchOut(C.Structure):
+    _fields_ = [("u", C.c_void_p), ("ext", C.c_void_p), ("axial", C.c_void_p), ("weight", C.c_void_p),
+                ("info", C.c_void_p)]
+
+
+class TbFitOut(C.Structure):
+    _fields_ = [("fitness", C.c_void_p), ("flags", C.c_void_p), ("info", C.c_void_p)]
+
+
+class TbRaggedIn(C.Structure):
+    _fields_ = [("dim", C.c_int32), ("batch", C.c_int32), ("joint_off", C.c_void_p), ("member_off", C.c_void_p),
+                ("joint_xyz", C.c_void_p), ("support", C.c_void_p), ("conn", C.c_void_p), ("member_aed", C.c_void_p),
+                ("force", C.c_void_p), ("max_joint", C.c_int32), ("max_member", C.c_int32)]
+
+
+EXPORTS = ["tb_plan_create", "tb_plan_destroy", "tb_plan_query", "tb_plan_set_path", "tb_plan_get_maps",
+           "tb_plan_get_scatter", "tb_solve", "tb_solve_host", "tb_fitness", "tb_fitness_host", "tb_solve_ragged",
+           "tb_solve_ragged_host", "tb_pinned_alloc", "tb_pinned_free", "tb_small_path_limits", "tb_fp64_peak",
+           "tb_launch_count", "tb_strerror", "tb_version"]
+
+_lib = None
+
+
+def lib():
+    """Load the shared library (once).  Raises if it has not been built -- no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: the CUDA library has not been built and there is no CPU fallback. "
+            "Run `python __graft_entry__.py` (needs nvcc).")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+    L.tb_plan_create.argtypes = [C.POINTER(TbTopology), C.POINTER(vp)]
+    L.tb_plan_destroy.argtypes = [vp]
+    L.tb_plan_destroy.restype = None
+    L.tb_plan_query.argtypes = [vp, C.POINTER(TbPlanInfo)]
+    L.tb_plan_set_path.argtypes = [vp, i32]
+    L.tb_plan_get_maps.argtypes = [vp, vp, vp, vp]
+    L.tb_plan_get_scatter.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.tb_solve.argtypes = [vp, C.POINTER(TbBatchIn), C.POINTER(TbBatchOut), vp]
+    L.tb_solve_host.argtypes = [vp, C.POINTER(TbBatchIn), C.POINTER(TbBatchOut)]
+    L.tb_fitness.argtypes = [vp, C.POINTER(TbBatchIn), dbl, dbl, C.POINTER(TbFitOut), C.POINTER(TbBatchOut), vp]
+    L.tb_fitness_host.argtypes = [vp, C.POINTER(TbBatchIn), dbl, dbl, C.POINTER(TbFitOut), C.POINTER(TbBatchOut)]
+    L.tb_solve_ragged.argtypes = [C.POINTER(TbRaggedIn), C.POINTER(TbBatchOut), vp]
+    L.tb_solve_ragged_host.argtypes = [C.POINTER(TbRaggedIn), C.POINTER(TbBatchOut)]
+    L.tb_pinned_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
+    L.tb_pinned_free.argtypes = [vp]
+    L.tb_small_path_limits.argtypes = [C.POINTER(i32), C.POINTER(i32)]
+    L.tb_fp64_peak.argtypes = [i32, i32, C.POINTER(dbl), C.POINTER(C.c_float)]
+    L.tb_launch_count.restype = i64
+    L.tb_strerror.argtypes = [C.c_int]
+    L.tb_strerror.restype = C.c_char_p
+    _lib = L
+    return L
+
+
+def check(rc: int):
+    if rc == 0:
+        return
+    msg = lib().tb_strerror(rc).decode()
+    if rc == TB_ERR_NO_DEVICE:
+        raise NoCudaDeviceError(rc, msg)
+    raise TrussLibError(rc, msg)
+
+
+def _ptr(a):
+    """Address of a numpy array / torch tensor / None."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    return a.data_ptr()  # torch tensor
+
+
+def _np(a, dtype, shape=None):
+    a = np.ascontiguousarray(a, dtype=dtype)
+    if shape is not None:
+        a = a.reshape(shape)
+    return a
+
+
+def pinned_empty(shape, dtype=np.float64):
+    """numpy array backed by page-locked memory from the library (freed with the array)."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    p = C.c_void_p()
+    check(lib().tb_pinned_alloc(C.byref(p), max(n, 1)))
+    buf = (C.c_char * max(n, 1)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    class _Owner:
+        def __init__(self, addr):
+            self.addr = addr
+
+        def __del__(self):
+            try:
+                lib().tb_pinned_free(self.addr)
+            except Exception:
+                pass
+
+    _PINNED_OWNERS[p.value] = _Owner(p.value)
+    return arr
+
+
+_PINNED_OWNERS = {}
+
+
+def fp64_peak(which: int, iters: int = 4096):
+    t, ms = C.c_double(), C.c_float()
+    check(lib().tb_fp64_peak(which, iters, C.byref(t), C.byref(ms)))
+    return t.value, ms.value
+
+
+def launch_count() -> int:
+    return int(lib().tb_launch_count())
+
+
+# --------------------------------------------------------------------------- Plan
+class Plan:
+    """One topology (dim, connectivity, supports) -> integer maps + device mirrors."""
+
+    def __init__(self, dim, conn, support):
+        L = lib()
+        self.conn = _np(conn, np.int32).reshape(-1, 2)
+        self.support = _np(support, np.uint8).reshape(-1)
+        topo = TbTopology(int(dim), int(self.support.shape[0]), int(self.conn.shape[0]),
+                          self.conn.ctypes.data, self.support.ctypes.data)
+        h = C.c_void_p()
+        check(L.tb_plan_create(C.byref(topo), C.byref(h)))
+        self._h = h
+        info = TbPlanInfo()
+        check(L.tb_plan_query(self._h, C.byref(info)))
+        self.info = info
+        self.dim, self.nJ, self.M = info.dim, info.n_joint, info.n_member
+        self.N, self.n, self.s = info.n_dof, info.n_free, info.n_support
+        self.stable = bool(info.stable)
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            try:
+                lib().tb_plan_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    @property
+    def path(self):
+        info = TbPlanInfo()
+        check(lib().tb_plan_query(self._h, C.byref(info)))
+        return info.path
+
+    def set_path(self, path: int):
+        check(lib().tb_plan_set_path(self._h, int(path)))
+
+    def maps(self):
+        free_idx = np.empty(self.n, np.int32)
+        dof2free = np.empty(self.N, np.int32)
+        sup_idx = np.empty(self.s, np.int32)
+        check(lib().tb_plan_get_maps(self._h, free_idx.ctypes.data, dof2free.ctypes.data, sup_idx.ctypes.data))
+        return free_idx, dof2free, sup_idx
+
+    def scatter(self):
+        nnz, nc = self.info.nnz_lower, self.info.n_contrib
+        row, col = np.empty(nnz, np.int32), np.empty(nnz, np.int32)
+        ptr = np.empty(nnz + 1, np.int64)
+        mem, loc = np.empty(nc, np.int32), np.empty(nc, np.int32)
+        check(lib().tb_plan_get_scatter(self._h, row.ctypes.data, col.ctypes.data, ptr.ctypes.data,
+                                        mem.ctypes.data, loc.ctypes.data))
+        return row, col, ptr, mem, loc
+
+    # ------------------------------------------------------------------ batch packing
+    def _batch_in(self, B, xyz, aed, gene, type_table, force, keep):
+        """Build tb_batch_in from arrays whose leading dim is B or is absent (shared, stride 0)."""
+        def rows(a, row, dtype):
+            a = _np(a, dtype) if isinstance(a, (np.ndarray, list, tuple)) else a
+            total = int(np.prod(a.shape))
+            if total == row:
+                return a, 0
+            if total == row * B:
+                return a, row
+            raise ValueError(f"array of {total} elements is neither [{row}] nor [{B},{row}]")
+        bi = TbBatchIn()
+        bi.batch = B
+        x, sx = rows(xyz, self.nJ * self.dim, np.float64)
+        f, sf = rows(force, self.N, np.float64)
+        keep += [x, f]
+        bi.joint_xyz, bi.joint_stride, bi.force, bi.force_stride = _ptr(x), sx, _ptr(f), sf
+        if aed is not None:
+            m, sm = rows(aed, self.M * 3, np.float64)
+            keep.append(m)
+            bi.member_aed, bi.member_stride = _ptr(m), sm
+        else:
+            g, sg = rows(gene, self.M, np.int32)
+            t = _np(type_table, np.float64).reshape(-1, 3) if isinstance(type_table, (np.ndarray, list)) else type_table
+            keep += [g, t]
+            bi.gene, bi.gene_stride, bi.type_table, bi.n_type = _ptr(g), sg, _ptr(t), int(t.shape[0])
+        return bi
+
+    def solve_host(self, B, xyz, force, aed=None, gene=None, type_table=None, want=("u", "ext", "axial", "weight"),
+                   out=None):
+        """Truss.Solve() for B systems, host (numpy) buffers; H2D/D2H happen inside the library."""
+        keep = []
+        bi = self._batch_in(B, xyz, aed, gene, type_table, force, keep)
+        out = {} if out is None else out
+        shp = {"u": (B, self.N), "ext": (B, self.N), "axial": (B, self.M), "weight": (B,)}
+        for k in want:
+            if k not in out:
+                out[k] = np.empty(shp[k], np.float64)
+        if "info" not in out:
+            out["info"] = np.empty(B, np.int32)
+        bo = TbBatchOut(_ptr(out.get("u")), _ptr(out.get("ext")), _ptr(out.get("axial")), _ptr(out.get("weight")),
+                        _ptr(out["info"]))
+        check(lib().tb_solve_host(self._h, C.byref(bi), C.byref(bo)))
+        return out
+
+    def fitness_host(self, B, xyz, force, gene, type_table, allow_stress, allow_displace, aed=None, full=False,
+                     out=None):
+        keep = []
+        bi = self._batch_in(B, xyz, aed, gene, type_table, force, keep)
+        out = {} if out is None else out
+        out.setdefault("fitness", np.empty(B, np.float64))
+        out.setdefault("flags", np.empty((B, 2), np.uint8))
+        out.setdefault("info", np.empty(B, np.int32))
+        fo = TbFitOut(_ptr(out["fitness"]), _ptr(out["flags"]), _ptr(out["info"]))
+        bo = None
+        if full:
+            for k, s in (("u", (B, self.N)), ("ext", (B, self.N)), ("axial", (B, self.M)), ("weight", (B,))):
+                out.setdefault(k, np.empty(s, np.float64))
+            bo = C.byref(TbBatchOut(_ptr(out["u"]), _ptr(out["ext"]), _ptr(out["axial"]), _ptr(out["weight"]), None))
+        check(lib().tb_fitness_host(self._h, C.byref(bi), float(allow_stress), float(allow_displace), C.byref(fo), bo))
+        return out
+
+    def solve_device(self, B, xyz, force, aed=None, gene=None, type_table=None, out=None, stream=None):
+        """Device pointers (torch CUDA tensors); enqueues on ``stream`` (a torch stream or None = current)."""
+        import torch
+
+        keep = []
+        bi = self._batch_in(B, xyz, aed, gene, type_table, force, keep)
+        st = torch.cuda.current_stream() if stream is None else stream
+        bo = TbBatchOut(_ptr(out.get("u")), _ptr(out.get("ext")), _ptr(out.get("axial")), _ptr(out.get("weight")),
+                        _ptr(out.get("info")))
+        check(lib().tb_solve(self._h, C.byref(bi), C.byref(bo), C.c_void_p(st.cuda_stream)))
+        return out
+
+    def fitness_device(self, B, xyz, force, gene, type_table, allow_stress, allow_displace, out, aed=None, stream=None):
+        import torch
+
+        keep = []
+        bi = self._batch_in(B, xyz, aed, gene, type_table, force, keep)
+        st = torch.cuda.current_stream() if stream is None else stream
+        fo = TbFitOut(_ptr(out.get("fitness")), _ptr(out.get("flags")), _ptr(out.get("info")))
+        bo = None
+        if out.get("u") is not None or out.get("axial") is not None or out.get("ext") is not None:
+            bo = C.byref(TbBatchOut(_ptr(out.get("u")), _ptr(out.get("ext")), _ptr(out.get("axial")),
+                                    _ptr(out.get("weight")), None))
+        check(lib().tb_fitness(self._h, C.byref(bi), float(allow_stress), float(allow_displace), C.byref(fo), bo,
+                               C.c_void_p(st.cuda_stream)))
+        return out
+
+
+# --------------------------------------------------------------------------- ragged batches
+def small_path_limits():
+    a, b = C.c_int32(), C.c_int32()
+    lib().tb_small_path_limits(C.byref(a), C.byref(b))
+    return a.value, b.value
+
+
+def solve_ragged_host(dim, joint_off, member_off, xyz, support, conn, aed, force, want=("u", "ext", "axial", "weight")):
+    """B independent trusses with their own topology (generate.py:354-357), packed back to back."""
+    joint_off = _np(joint_off, np.int64)
+    member_off = _np(member_off, np.int64)
+    B = joint_off.shape[0] - 1
+    xyz, force = _np(xyz, np.float64), _np(force, np.float64)
+    support, conn, aed = _np(support, np.uint8), _np(conn, np.int32), _np(aed, np.float64)
+    SJ, SM = int(joint_off[-1]), int(member_off[-1])
+    ri = TbRaggedIn(int(dim), int(B), joint_off.ctypes.data, member_off.ctypes.data, xyz.ctypes.data,
+                    support.ctypes.data, conn.ctypes.data, aed.ctypes.data, force.ctypes.data,
+                    int(np.diff(joint_off).max()) if B else 0, int(np.diff(member_off).max()) if B else 0)
+    out = {"info": np.empty(B, np.int32)}
+    shp = {"u": SJ * dim, "ext": SJ * dim, "axial": SM, "weight": B}
+    for k in want:
+        out[k] = np.empty(shp[k], np.float64)
+    bo = TbBatchOut(_ptr(out.get("u")), _ptr(out.get("ext")), _ptr(out.get("axial")), _ptr(out.get("weight")),
+                    _ptr(out["info"]))
+    check(lib().tb_solve_ragged_host(C.byref(ri), C.byref(bo)))
+    return out
+
+
+if __name__ == "__main__":
+    print(build(force=True, verbose=True))

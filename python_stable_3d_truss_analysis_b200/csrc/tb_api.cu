@@ -1,0 +1,422 @@
+// C-ABI entry points (include/truss_b200.h).  Device variants enqueue on the caller's stream;
+// *_host variants stage host buffers through a grow-only device arena owned by the plan (or a
+// process-wide one for ragged batches), run the same device path, and copy the results back.
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+
+#include "tb_common.cuh"
+
+namespace {
+
+size_t ws_cap_bytes() {
+  static size_t cap = [] {
+    const char* s = getenv("TB_WORKSPACE_MAX_GB");
+    double gb = s ? atof(s) : 64.0;
+    if (gb < 0.25) gb = 0.25;
+    return (size_t)(gb * (1ull << 30));
+  }();
+  return cap;
+}
+
+int have_device() {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+    (void)cudaGetLastError();
+    return 0;
+  }
+  return 1;
+}
+
+int check_batch_in(const tb_plan* p, const tb_batch_in* in) {
+  if (!p || !in) return TB_ERR_NULL;
+  if (p->device < 0) return TB_ERR_NO_DEVICE;
+  if (in->batch < 0) return TB_ERR_SIZE;
+  if (in->batch == 0) return TB_OK;
+  if (!in->joint_xyz || !in->force) return TB_ERR_NULL;
+  if (!in->member_aed && !(in->gene && in->type_table && in->n_type > 0)) return TB_ERR_NULL;
+  return TB_OK;
+}
+
+int run_plan(tb_plan* p, const tb_batch_in* in, const tb_batch_out* out, const tb_fit_out* fit, double allow_s,
+             double allow_d, cudaStream_t st) {
+  const int fitness_mode = fit ? 1 : 0;
+  static const tb_batch_out none = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  if (!out) out = &none;
+  if (p->path == 0) {
+    SmallArgs a;
+    memset(&a, 0, sizeof(a));
+    a.batch = in->batch;
+    a.nJ = p->nJ;
+    a.M = p->M;
+    a.xyz = in->joint_xyz;
+    a.xyz_stride = in->joint_stride;
+    a.support = p->d_support;
+    a.support_stride = 0;
+    a.conn = p->d_conn;
+    a.conn_stride = 0;
+    a.aed = in->member_aed;
+    a.aed_stride = in->member_stride;
+    a.gene = in->member_aed ? nullptr : in->gene;
+    a.gene_stride = in->gene_stride;
+    a.type_table = in->type_table;
+    a.n_type = in->n_type;
+    a.force = in->force;
+    a.force_stride = in->force_stride;
+    a.u = out->u;
+    a.ext = out->ext;
+    a.axial = out->axial;
+    a.weight = out->weight;
+    a.info = fit && fit->info ? fit->info : out->info;
+    a.fitness = fit ? fit->fitness : nullptr;
+    a.flags = fit ? fit->flags : nullptr;
+    a.allow_stress = allow_s;
+    a.allow_displace = allow_d;
+    a.fitness_mode = fitness_mode;
+    a.max_n = p->n;
+    int rc = tb_launch_small(a, p->dim, st);
+    if (rc) return rc;
+    if (fit && fit->info && out->info) {
+      TB_CUDA(cudaMemcpyAsync(out->info, fit->info, sizeof(int32_t) * in->batch, cudaMemcpyDeviceToDevice, st));
+    }
+    return TB_OK;
+  }
+
+  // blocked path: process the batch in chunks that fit the workspace cap
+  const size_t per_sys = tb_large_workspace_bytes(1, p->dim, p->M, p->n_pad);
+  int chunk = (int)std::min<size_t>((size_t)in->batch, std::max<size_t>(1, ws_cap_bytes() / per_sys));
+  const size_t need = tb_large_workspace_bytes(chunk, p->dim, p->M, p->n_pad);
+  if (p->ws_bytes < need) {
+    if (p->ws) {
+      TB_CUDA(cudaStreamSynchronize(st));
+      TB_CUDA(cudaFree(p->ws));
+      p->ws = nullptr;
+      p->ws_bytes = 0;
+    }
+    TB_CUDA(cudaMalloc(&p->ws, need));
+    p->ws_bytes = need;
+  }
+  for (int b0 = 0; b0 < in->batch; b0 += chunk) {
+    const int nb = std::min(chunk, in->batch - b0);
+    LargeArgs a;
+    memset(&a, 0, sizeof(a));
+    a.batch = nb;
+    a.dim = p->dim;
+    a.nJ = p->nJ;
+    a.M = p->M;
+    a.N = p->N;
+    a.n = p->n;
+    a.n_pad = p->n_pad;
+    a.nt = p->nt;
+    a.s = p->s;
+    a.xyz = in->joint_xyz + (int64_t)b0 * in->joint_stride;
+    a.xyz_stride = in->joint_stride;
+    a.aed = in->member_aed ? in->member_aed + (int64_t)b0 * in->member_stride : nullptr;
+    a.aed_stride = in->member_stride;
+    a.gene = in->member_aed ? nullptr : in->gene + (int64_t)b0 * in->gene_stride;
+    a.gene_stride = in->gene_stride;
+    a.type_table = in->type_table;
+    a.n_type = in->n_type;
+    a.force = in->force + (int64_t)b0 * in->force_stride;
+    a.force_stride = in->force_stride;
+    a.conn = p->d_conn;
+    a.free_idx = p->d_free_idx;
+    a.dof2free = p->d_dof2free;
+    a.sup_idx = p->d_sup_idx;
+    a.ent_row = p->d_ent_row;
+    a.ent_col = p->d_ent_col;
+    a.ent_ptr = p->d_ent_ptr;
+    a.ctr_member = p->d_ctr_member;
+    a.ctr_local = p->d_ctr_local;
+    a.tile_ent_ptr = p->d_tile_ent_ptr;
+    a.tile_ent = p->d_tile_ent;
+    a.inc_ptr = p->d_inc_ptr;
+    a.inc_mem = p->d_inc_mem;
+    tb_large_carve(a, p->ws);
+    a.u = out->u ? out->u + (int64_t)b0 * p->N : nullptr;
+    a.ext = out->ext ? out->ext + (int64_t)b0 * p->N : nullptr;
+    a.axial = out->axial ? out->axial + (int64_t)b0 * p->M : nullptr;
+    a.weight = out->weight ? out->weight + b0 : nullptr;
+    int32_t* info = fit && fit->info ? fit->info : out->info;
+    a.info = info ? info + b0 : nullptr;
+    a.fitness = fit && fit->fitness ? fit->fitness + b0 : nullptr;
+    a.flags = fit && fit->flags ? fit->flags + 2 * (int64_t)b0 : nullptr;
+    a.allow_stress = allow_s;
+    a.allow_displace = allow_d;
+    a.fitness_mode = fitness_mode;
+    a.plan_stable = p->stable;
+    int rc = tb_launch_large(a, p->num_sm, st);
+    if (rc) return rc;
+  }
+  if (fit && fit->info && out->info) {
+    TB_CUDA(cudaMemcpyAsync(out->info, fit->info, sizeof(int32_t) * in->batch, cudaMemcpyDeviceToDevice, st));
+  }
+  return TB_OK;
+}
+
+// ---- bump allocator over a grow-only device arena -------------------------------------------
+struct Arena {
+  void** base;
+  size_t* cap;
+  size_t used = 0;
+  Arena(void** b, size_t* c) : base(b), cap(c) {}
+  static size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
+};
+
+int arena_reserve(void** base, size_t* cap, size_t need) {
+  if (*cap >= need) return 0;
+  if (*base) {
+    TB_CUDA(cudaDeviceSynchronize());
+    TB_CUDA(cudaFree(*base));
+    *base = nullptr;
+    *cap = 0;
+  }
+  need += need / 8;
+  TB_CUDA(cudaMalloc(base, need));
+  *cap = need;
+  return 0;
+}
+
+template <typename Tp>
+Tp* take(char*& cur, size_t count) {
+  Tp* p = (Tp*)cur;
+  cur += Arena::al(count * sizeof(Tp));
+  return p;
+}
+
+cudaStream_t host_stream() {
+  static cudaStream_t st = [] {
+    cudaStream_t s = nullptr;
+    cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+    return s;
+  }();
+  return st;
+}
+
+int stride_ok(int64_t stride, int64_t row) { return stride == 0 || stride == row; }
+
+int run_plan_host(tb_plan* p, const tb_batch_in* in, const tb_batch_out* out, const tb_fit_out* fit, double allow_s,
+                  double allow_d) {
+  int rc = check_batch_in(p, in);
+  if (rc) return rc;
+  const int B = in->batch;
+  if (B == 0) return TB_OK;
+  const int64_t rowJ = (int64_t)p->nJ * p->dim, rowM3 = (int64_t)p->M * 3, rowM = p->M, rowN = p->N;
+  if (!stride_ok(in->joint_stride, rowJ) || !stride_ok(in->force_stride, rowN)) return TB_ERR_SIZE;
+  if (in->member_aed && !stride_ok(in->member_stride, rowM3)) return TB_ERR_SIZE;
+  if (!in->member_aed && !stride_ok(in->gene_stride, rowM)) return TB_ERR_SIZE;
+  auto cnt = [&](int64_t stride, int64_t row) { return (size_t)(stride == 0 ? row : row * B); };
+  const size_t nxyz = cnt(in->joint_stride, rowJ), nf = cnt(in->force_stride, rowN);
+  const size_t naed = in->member_aed ? cnt(in->member_stride, rowM3) : 0;
+  const size_t ngene = in->member_aed ? 0 : cnt(in->gene_stride, rowM);
+  const size_t ntab = in->member_aed ? 0 : (size_t)in->n_type * 3;
+  static const tb_batch_out none = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  if (!out) out = &none;
+
+  size_t need = 0;
+  auto add = [&](size_t bytes) { need += Arena::al(bytes); };
+  add(nxyz * 8); add(nf * 8); add(naed * 8); add(ngene * 4); add(ntab * 8);
+  add(out->u ? (size_t)B * rowN * 8 : 0); add(out->ext ? (size_t)B * rowN * 8 : 0);
+  add(out->axial ? (size_t)B * rowM * 8 : 0); add(out->weight ? (size_t)B * 8 : 0);
+  add((size_t)B * 4); add(fit ? (size_t)B * 8 : 0); add(fit ? (size_t)B * 2 : 0);
+  rc = arena_reserve(&p->stage_dev, &p->stage_dev_bytes, need + 4096);
+  if (rc) return rc;
+
+  cudaStream_t st = host_stream();
+  char* cur = (char*)p->stage_dev;
+  tb_batch_in din = *in;
+  double* dxyz = take<double>(cur, nxyz);
+  double* df = take<double>(cur, nf);
+  double* daed = take<double>(cur, naed);
+  int32_t* dgene = take<int32_t>(cur, ngene);
+  double* dtab = take<double>(cur, ntab);
+  TB_CUDA(cudaMemcpyAsync(dxyz, in->joint_xyz, nxyz * 8, cudaMemcpyHostToDevice, st));
+  TB_CUDA(cudaMemcpyAsync(df, in->force, nf * 8, cudaMemcpyHostToDevice, st));
+  din.joint_xyz = dxyz;
+  din.force = df;
+  if (in->member_aed) {
+    TB_CUDA(cudaMemcpyAsync(daed, in->member_aed, naed * 8, cudaMemcpyHostToDevice, st));
+    din.member_aed = daed;
+    din.gene = nullptr;
+  } else {
+    TB_CUDA(cudaMemcpyAsync(dgene, in->gene, ngene * 4, cudaMemcpyHostToDevice, st));
+    TB_CUDA(cudaMemcpyAsync(dtab, in->type_table, ntab * 8, cudaMemcpyHostToDevice, st));
+    din.gene = dgene;
+    din.type_table = dtab;
+  }
+  tb_batch_out dout;
+  dout.u = out->u ? take<double>(cur, (size_t)B * rowN) : nullptr;
+  dout.ext = out->ext ? take<double>(cur, (size_t)B * rowN) : nullptr;
+  dout.axial = out->axial ? take<double>(cur, (size_t)B * rowM) : nullptr;
+  dout.weight = out->weight ? take<double>(cur, (size_t)B) : nullptr;
+  dout.info = take<int32_t>(cur, (size_t)B);
+  tb_fit_out dfit = {nullptr, nullptr, nullptr};
+  if (fit) {
+    dfit.fitness = take<double>(cur, (size_t)B);
+    dfit.flags = take<uint8_t>(cur, (size_t)B * 2);
+    dfit.info = dout.info;
+    dout.info = nullptr;
+  }
+  rc = run_plan(p, &din, &dout, fit ? &dfit : nullptr, allow_s, allow_d, st);
+  if (rc) return rc;
+  int32_t* dinfo = fit ? dfit.info : dout.info;
+  if (out->u) TB_CUDA(cudaMemcpyAsync(out->u, dout.u, (size_t)B * rowN * 8, cudaMemcpyDeviceToHost, st));
+  if (out->ext) TB_CUDA(cudaMemcpyAsync(out->ext, dout.ext, (size_t)B * rowN * 8, cudaMemcpyDeviceToHost, st));
+  if (out->axial) TB_CUDA(cudaMemcpyAsync(out->axial, dout.axial, (size_t)B * rowM * 8, cudaMemcpyDeviceToHost, st));
+  if (out->weight) TB_CUDA(cudaMemcpyAsync(out->weight, dout.weight, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
+  if (out->info) TB_CUDA(cudaMemcpyAsync(out->info, dinfo, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+  if (fit) {
+    if (fit->fitness) TB_CUDA(cudaMemcpyAsync(fit->fitness, dfit.fitness, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
+    if (fit->flags) TB_CUDA(cudaMemcpyAsync(fit->flags, dfit.flags, (size_t)B * 2, cudaMemcpyDeviceToHost, st));
+    if (fit->info) TB_CUDA(cudaMemcpyAsync(fit->info, dinfo, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+  }
+  TB_CUDA(cudaStreamSynchronize(st));
+  return TB_OK;
+}
+
+int check_ragged(const tb_ragged_in* in) {
+  if (!in) return TB_ERR_NULL;
+  if (in->dim != 2 && in->dim != 3) return TB_ERR_DIM;
+  if (in->batch < 0 || in->max_joint < 0 || in->max_member < 0) return TB_ERR_SIZE;
+  if (in->batch == 0) return TB_OK;
+  if (!in->joint_off || !in->member_off || !in->joint_xyz || !in->support || !in->conn || !in->member_aed || !in->force)
+    return TB_ERR_NULL;
+  if (in->max_joint * in->dim > TB_SMALL_MAX_DOF || in->max_member > TB_SMALL_MAX_MEMBER ||
+      in->max_joint > TB_SMALL_MAX_JOINT)
+    return TB_ERR_TOO_LARGE;
+  return TB_OK;
+}
+
+int run_ragged(const tb_ragged_in* in, const tb_batch_out* out, cudaStream_t st) {
+  SmallArgs a;
+  memset(&a, 0, sizeof(a));
+  a.batch = in->batch;
+  a.nJ = in->max_joint;
+  a.M = in->max_member;
+  a.joint_off = in->joint_off;
+  a.member_off = in->member_off;
+  a.xyz = in->joint_xyz;
+  a.support = in->support;
+  a.conn = in->conn;
+  a.aed = in->member_aed;
+  a.force = in->force;
+  a.u = out->u;
+  a.ext = out->ext;
+  a.axial = out->axial;
+  a.weight = out->weight;
+  a.info = out->info;
+  a.max_n = in->max_joint * in->dim;
+  return tb_launch_small(a, in->dim, st);
+}
+
+void* g_rag_dev = nullptr;
+size_t g_rag_dev_bytes = 0;
+std::mutex g_rag_mu;
+
+}  // namespace
+
+extern "C" int tb_solve(tb_plan* plan, const tb_batch_in* in, const tb_batch_out* out, void* cuda_stream) {
+  int rc = check_batch_in(plan, in);
+  if (rc) return rc;
+  if (in->batch == 0) return TB_OK;
+  return run_plan(plan, in, out, nullptr, 0.0, 0.0, (cudaStream_t)cuda_stream);
+}
+
+extern "C" int tb_solve_host(tb_plan* plan, const tb_batch_in* in, const tb_batch_out* out) {
+  return run_plan_host(plan, in, out, nullptr, 0.0, 0.0);
+}
+
+extern "C" int tb_fitness(tb_plan* plan, const tb_batch_in* in, double allow_stress, double allow_displace,
+                          const tb_fit_out* fit, const tb_batch_out* full, void* cuda_stream) {
+  int rc = check_batch_in(plan, in);
+  if (rc) return rc;
+  if (!fit) return TB_ERR_NULL;
+  if (in->batch == 0) return TB_OK;
+  return run_plan(plan, in, full, fit, allow_stress, allow_displace, (cudaStream_t)cuda_stream);
+}
+
+extern "C" int tb_fitness_host(tb_plan* plan, const tb_batch_in* in, double allow_stress, double allow_displace,
+                               const tb_fit_out* fit, const tb_batch_out* full) {
+  if (!fit) return TB_ERR_NULL;
+  return run_plan_host(plan, in, full, fit, allow_stress, allow_displace);
+}
+
+extern "C" int tb_solve_ragged(const tb_ragged_in* in, const tb_batch_out* out, void* cuda_stream) {
+  int rc = check_ragged(in);
+  if (rc) return rc;
+  if (!out) return TB_ERR_NULL;
+  if (!have_device()) return TB_ERR_NO_DEVICE;
+  if (in->batch == 0) return TB_OK;
+  return run_ragged(in, out, (cudaStream_t)cuda_stream);
+}
+
+extern "C" int tb_solve_ragged_host(const tb_ragged_in* in, const tb_batch_out* out) {
+  int rc = check_ragged(in);
+  if (rc) return rc;
+  if (!out) return TB_ERR_NULL;
+  if (!have_device()) return TB_ERR_NO_DEVICE;
+  const int B = in->batch, d = in->dim;
+  if (B == 0) return TB_OK;
+  // host-side validation of the offsets (they are host pointers here)
+  if (in->joint_off[0] != 0 || in->member_off[0] != 0) return TB_ERR_SIZE;
+  for (int b = 0; b < B; ++b) {
+    const int64_t nj = in->joint_off[b + 1] - in->joint_off[b], nm = in->member_off[b + 1] - in->member_off[b];
+    if (nj < 0 || nm < 0) return TB_ERR_SIZE;
+    if (nj > in->max_joint || nm > in->max_member) return TB_ERR_TOO_LARGE;
+  }
+  const size_t SJ = (size_t)in->joint_off[B], SM = (size_t)in->member_off[B];
+  std::lock_guard<std::mutex> lock(g_rag_mu);
+  size_t need = 0;
+  auto add = [&](size_t bytes) { need += Arena::al(bytes); };
+  add((B + 1) * 8); add((B + 1) * 8); add(SJ * d * 8); add(SJ); add(SM * 8); add(SM * 24); add(SJ * d * 8);
+  add(out->u ? SJ * d * 8 : 0); add(out->ext ? SJ * d * 8 : 0); add(out->axial ? SM * 8 : 0);
+  add(out->weight ? (size_t)B * 8 : 0); add((size_t)B * 4);
+  rc = arena_reserve(&g_rag_dev, &g_rag_dev_bytes, need + 4096);
+  if (rc) return rc;
+  cudaStream_t st = host_stream();
+  char* cur = (char*)g_rag_dev;
+  tb_ragged_in din = *in;
+  int64_t* djo = take<int64_t>(cur, B + 1);
+  int64_t* dmo = take<int64_t>(cur, B + 1);
+  double* dxyz = take<double>(cur, SJ * d);
+  uint8_t* dsup = take<uint8_t>(cur, SJ);
+  int32_t* dconn = take<int32_t>(cur, SM * 2);
+  double* daed = take<double>(cur, SM * 3);
+  double* df = take<double>(cur, SJ * d);
+  TB_CUDA(cudaMemcpyAsync(djo, in->joint_off, (B + 1) * 8, cudaMemcpyHostToDevice, st));
+  TB_CUDA(cudaMemcpyAsync(dmo, in->member_off, (B + 1) * 8, cudaMemcpyHostToDevice, st));
+  TB_CUDA(cudaMemcpyAsync(dxyz, in->joint_xyz, SJ * d * 8, cudaMemcpyHostToDevice, st));
+  TB_CUDA(cudaMemcpyAsync(dsup, in->support, SJ, cudaMemcpyHostToDevice, st));
+  TB_CUDA(cudaMemcpyAsync(dconn, in->conn, SM * 8, cudaMemcpyHostToDevice, st));
+  TB_CUDA(cudaMemcpyAsync(daed, in->member_aed, SM * 24, cudaMemcpyHostToDevice, st));
+  TB_CUDA(cudaMemcpyAsync(df, in->force, SJ * d * 8, cudaMemcpyHostToDevice, st));
+  din.joint_off = djo; din.member_off = dmo; din.joint_xyz = dxyz; din.support = dsup;
+  din.conn = dconn; din.member_aed = daed; din.force = df;
+  tb_batch_out dout;
+  dout.u = out->u ? take<double>(cur, SJ * d) : nullptr;
+  dout.ext = out->ext ? take<double>(cur, SJ * d) : nullptr;
+  dout.axial = out->axial ? take<double>(cur, SM) : nullptr;
+  dout.weight = out->weight ? take<double>(cur, (size_t)B) : nullptr;
+  dout.info = take<int32_t>(cur, (size_t)B);
+  rc = run_ragged(&din, &dout, st);
+  if (rc) return rc;
+  if (out->u) TB_CUDA(cudaMemcpyAsync(out->u, dout.u, SJ * d * 8, cudaMemcpyDeviceToHost, st));
+  if (out->ext) TB_CUDA(cudaMemcpyAsync(out->ext, dout.ext, SJ * d * 8, cudaMemcpyDeviceToHost, st));
+  if (out->axial) TB_CUDA(cudaMemcpyAsync(out->axial, dout.axial, SM * 8, cudaMemcpyDeviceToHost, st));
+  if (out->weight) TB_CUDA(cudaMemcpyAsync(out->weight, dout.weight, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
+  if (out->info) TB_CUDA(cudaMemcpyAsync(out->info, dout.info, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+  TB_CUDA(cudaStreamSynchronize(st));
+  return TB_OK;
+}
+
+// pinned host buffers for callers that want full-speed H2D/D2H through the *_host entry points
+extern "C" int tb_pinned_alloc(void** ptr, size_t bytes) {
+  if (!ptr) return TB_ERR_NULL;
+  if (!have_device()) return TB_ERR_NO_DEVICE;
+  TB_CUDA(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault));
+  return TB_OK;
+}
+extern "C" int tb_pinned_free(void* ptr) {
+  if (ptr) TB_CUDA(cudaFreeHost(ptr));
+  return TB_OK;
+}

@@ -1,0 +1,154 @@
+// Shared declarations for the truss_b200 CUDA library (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <vector>
+
+#include "truss_b200.h"
+
+// SupportType codes, slientruss3d/type.py:30-35
+enum : int { SUP_NO = 0, SUP_PIN = 1, SUP_ROLLER_X = 2, SUP_ROLLER_Y = 3, SUP_ROLLER_Z = 4 };
+
+// utils.py:79-84 IsZero / IsZeroVector default eps
+#define TB_ZERO_EPS 1e-10
+
+// tile geometry of the blocked (global-memory) path
+constexpr int TB_TILE = 64;                     // tile order
+constexpr int TB_TILE_ELEMS = TB_TILE * TB_TILE;  // doubles per tile
+
+// limits of the fused shared-memory path
+constexpr int TB_SMALL_MAX_DOF = 160;     // max d*nJ (bounds the free-DOF count)
+constexpr int TB_SMALL_MAX_MEMBER = 1024;
+constexpr int TB_SMALL_MAX_JOINT = 80;
+
+extern std::atomic<int64_t> g_tb_launches;
+inline void tb_count_launch(int n = 1) { g_tb_launches.fetch_add(n, std::memory_order_relaxed); }
+
+#define TB_CUDA(expr)                         \
+  do {                                        \
+    cudaError_t _e = (expr);                  \
+    if (_e != cudaSuccess) return (int)_e;    \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// Plan: host-built integer maps for one topology (truss.py:307-326), mirrored on the device.
+// ---------------------------------------------------------------------------------------------
+struct tb_plan {
+  int dim = 0, nJ = 0, M = 0, N = 0, n = 0, s = 0;
+  int n_resist = 0, stable = 0, path = 0, n_pad = 0, nt = 0;
+  int64_t half_bw = 0;
+  int device = 0;
+  int num_sm = 0;
+
+  // host copies
+  std::vector<int32_t> conn;       // [M,2]
+  std::vector<uint8_t> support;    // [nJ]
+  std::vector<int32_t> free_idx;   // [n]
+  std::vector<int32_t> dof2free;   // [N]
+  std::vector<int32_t> sup_idx;    // [s]
+  // scatter map over the lower triangle of K_ff (row-major order of entries)
+  std::vector<int32_t> ent_row, ent_col;   // [nnz]
+  std::vector<int64_t> ent_ptr;            // [nnz+1]
+  std::vector<int32_t> ctr_member;         // [n_contrib]
+  std::vector<int32_t> ctr_local;          // [n_contrib] a*2d+b
+  std::vector<int64_t> tile_ent_ptr;       // [ntiles+1] entries grouped per 64x64 tile (blocked path)
+  std::vector<int32_t> tile_ent;           // [nnz] entry ids sorted by tile
+  // joint -> incident (member, end) lists, ascending member (recovery of reactions)
+  std::vector<int32_t> inc_ptr;            // [nJ+1]
+  std::vector<int32_t> inc_mem;            // [2M]  member*2 + end
+
+  // device mirrors
+  int32_t* d_conn = nullptr;
+  uint8_t* d_support = nullptr;
+  int32_t* d_free_idx = nullptr;
+  int32_t* d_dof2free = nullptr;
+  int32_t* d_sup_idx = nullptr;
+  int32_t* d_ent_row = nullptr;
+  int32_t* d_ent_col = nullptr;
+  int64_t* d_ent_ptr = nullptr;
+  int32_t* d_ctr_member = nullptr;
+  int32_t* d_ctr_local = nullptr;
+  int64_t* d_tile_ent_ptr = nullptr;
+  int32_t* d_tile_ent = nullptr;
+  int32_t* d_inc_ptr = nullptr;
+  int32_t* d_inc_mem = nullptr;
+
+  // grow-only device workspace of the blocked path
+  void* ws = nullptr;
+  size_t ws_bytes = 0;
+  // grow-only staging for the *_host entry points
+  void* stage_dev = nullptr;
+  size_t stage_dev_bytes = 0;
+  void* stage_pinned = nullptr;
+  size_t stage_pinned_bytes = 0;
+};
+
+// ---------------------------------------------------------------------------------------------
+// Kernel argument blocks
+// ---------------------------------------------------------------------------------------------
+struct SmallArgs {
+  int batch, nJ, M;                     // uniform sizes, or the maxima of a ragged batch
+  const int64_t* joint_off;             // ragged when non-null
+  const int64_t* member_off;
+  const double* xyz;      int64_t xyz_stride;
+  const uint8_t* support; int64_t support_stride;
+  const int32_t* conn;    int64_t conn_stride;
+  const double* aed;      int64_t aed_stride;
+  const int32_t* gene;    int64_t gene_stride;
+  const double* type_table; int n_type;
+  const double* force;    int64_t force_stride;
+  double* u; double* ext; double* axial; double* weight; int32_t* info;
+  double* fitness; uint8_t* flags;
+  double allow_stress, allow_displace;
+  int fitness_mode;
+  int max_n;                            // bound on the free-DOF count (sizes shared memory)
+};
+
+struct LargeArgs {
+  int batch, dim, nJ, M, N, n, n_pad, nt, s;
+  const double* xyz;      int64_t xyz_stride;
+  const double* aed;      int64_t aed_stride;
+  const int32_t* gene;    int64_t gene_stride;
+  const double* type_table; int n_type;
+  const double* force;    int64_t force_stride;
+  // plan maps (device)
+  const int32_t* conn; const int32_t* free_idx; const int32_t* dof2free; const int32_t* sup_idx;
+  const int32_t* ent_row; const int32_t* ent_col; const int64_t* ent_ptr;
+  const int32_t* ctr_member; const int32_t* ctr_local;
+  const int64_t* tile_ent_ptr; const int32_t* tile_ent;
+  const int32_t* inc_ptr; const int32_t* inc_mem;
+  // workspace
+  double* mk;      // [B][M]      EA/L
+  double* mc;      // [B][M][d]   direction cosines
+  double* mw;      // [B][M]      a*L*density
+  double* L;       // [B][ntiles][4096] packed lower tiles, fragment-major
+  double* y;       // [B][n_pad]  rhs -> forward solution -> free displacements
+  int32_t* status; // [B] 0 ok / k>0 pivot / <0 input problem
+  // outputs
+  double* u; double* ext; double* axial; double* weight; int32_t* info;
+  double* fitness; uint8_t* flags;
+  double allow_stress, allow_displace;
+  int fitness_mode;
+  int plan_stable;
+};
+
+// launchers (return cudaError_t as int)
+int tb_launch_small(const SmallArgs& a, int dim, cudaStream_t st);
+int tb_small_smem_bytes(int dim, int nJ, int M, int max_n, int* threads);
+int tb_launch_large(const LargeArgs& a, int num_sm, cudaStream_t st);
+size_t tb_large_workspace_bytes(int batch, int dim, int M, int n_pad);
+void tb_large_carve(LargeArgs& a, void* ws);
+
+// fragment-major offset of element (r, c) inside one 64x64 tile:
+//   [k-half 2][row-block 8][k-slab 8][lane 32], lane = (r%8)*4 + c%4
+// so that one DMMA m8n8k4 operand fragment (8 rows x 4 k) is 32 consecutive doubles and a
+// 64-row x 32-k half tile is one contiguous 16 KB chunk (a single bulk copy).
+__host__ __device__ __forceinline__ int tb_tile_off(int r, int c) {
+  return ((((c >> 5) << 3) + (r >> 3)) << 8) + (((c >> 2) & 7) << 5) + ((r & 7) << 2) + (c & 3);
+}
+__host__ __device__ __forceinline__ int64_t tb_tile_index(int ti, int tj) {  // ti >= tj
+  return (int64_t)ti * (ti + 1) / 2 + tj;
+}

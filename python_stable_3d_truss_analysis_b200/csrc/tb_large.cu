@@ -1,0 +1,650 @@
+// Blocked global-memory path for systems that do not fit the fused shared-memory kernel
+// (bar-942: n = 696; cube 12^3: n = 6084).  Four kernels per batch:
+//
+//   k_geom      member length / EA/L / cosines / weight terms      Member.length,k,cosines  truss.py:19,56-63
+//   k_assemble  K_ff tiles through the plan's scatter map          Truss.GetKMatrix + mask  truss.py:307-316,343
+//   k_chol      tiled left-looking Cholesky, DMMA updates,         np.linalg.solve          truss.py:343
+//               fused forward substitution, back substitution
+//   k_recover   displacements, axial forces, reactions, weight,    truss.py:344-361,166-168; ga.py:139-149
+//               optional GA fitness
+//
+// Storage: only the lower triangle, as 64x64 tiles, tile (i,j) at index i(i+1)/2+j.  Inside a tile
+// elements are kept "fragment-major" (tb_tile_off): the 8x4 operand fragment of one FP64
+// mma.m8n8k4 is 32 consecutive doubles, so a warp's operand load is one conflict-free 256 B
+// shared-memory read, and a 64-row x 32-k half tile is one contiguous 16 KB chunk in HBM.
+#include <math.h>
+
+#include "tb_common.cuh"
+
+namespace {
+
+constexpr int T = TB_TILE;          // 64
+constexpr int HALF = T * 32;        // doubles in a 64 x 32 half tile (16 KB)
+constexpr int CH_THREADS = 256;
+
+// ------------------------------------------------------------------------------------------
+// k_geom
+// ------------------------------------------------------------------------------------------
+template <int DIM>
+__global__ void k_geom(const LargeArgs a) {
+  const int64_t total = (int64_t)a.batch * a.M;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(idx / a.M), m = (int)(idx - (int64_t)b * a.M);
+    const double* xyz = a.xyz + b * a.xyz_stride;
+    double ar, e, rho;
+    bool ok = true;
+    if (a.gene) {
+      const int g = a.gene[b * a.gene_stride + m];
+      if ((unsigned)g < (unsigned)a.n_type) {
+        ar = a.type_table[3 * g];
+        e = a.type_table[3 * g + 1];
+        rho = a.type_table[3 * g + 2];
+      } else {
+        ok = false;
+        ar = e = rho = 0.0;
+      }
+    } else {
+      const double* t = a.aed + b * a.aed_stride + 3 * (int64_t)m;
+      ar = t[0];
+      e = t[1];
+      rho = t[2];
+    }
+    const int j0 = a.conn[2 * m], j1 = a.conn[2 * m + 1];
+    double dx[DIM], c[DIM];
+#pragma unroll
+    for (int i = 0; i < DIM; ++i) dx[i] = __dsub_rn(xyz[j1 * DIM + i], xyz[j0 * DIM + i]);
+    double l2 = __dmul_rn(dx[0], dx[0]);
+#pragma unroll
+    for (int i = 1; i < DIM; ++i) l2 = __dadd_rn(l2, __dmul_rn(dx[i], dx[i]));
+    const double len = __dsqrt_rn(l2);
+    double k = 0.0;
+#pragma unroll
+    for (int i = 0; i < DIM; ++i) c[i] = 0.0;
+    if (!ok) {
+      atomicMin(&a.status[b], TB_INFO_BAD_INDEX);
+    } else if (!(len > 0.0)) {
+      atomicMin(&a.status[b], TB_INFO_ZERO_LENGTH);
+    } else {
+      k = __ddiv_rn(__dmul_rn(e, ar), len);
+#pragma unroll
+      for (int i = 0; i < DIM; ++i) c[i] = __ddiv_rn(dx[i], len);
+    }
+    a.mk[idx] = k;
+#pragma unroll
+    for (int i = 0; i < DIM; ++i) a.mc[idx * DIM + i] = c[i];
+    a.mw[idx] = __dmul_rn(__dmul_rn(ar, len), rho);
+  }
+}
+
+__global__ void k_init_status(int32_t* status, int batch, int value) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < batch; i += gridDim.x * blockDim.x) status[i] = value;
+}
+
+// ------------------------------------------------------------------------------------------
+// k_assemble: one CTA builds one 64x64 tile of one system in shared memory (zero fill, then one
+// thread per structural non-zero sums its member contributions in ascending member order) and
+// streams it out as one contiguous 32 KB block.  Also gathers the reduced load vector.
+// ------------------------------------------------------------------------------------------
+template <int DIM>
+__global__ void __launch_bounds__(256) k_assemble(const LargeArgs a) {
+  __shared__ __align__(16) double sT[TB_TILE_ELEMS];
+  const int tid = threadIdx.x;
+  const int64_t ntiles = (int64_t)a.nt * (a.nt + 1) / 2;
+  const int64_t work = ntiles * a.batch;
+  for (int64_t w = blockIdx.x; w < work; w += gridDim.x) {
+    const int b = (int)(w / ntiles);
+    const int64_t t = w - (int64_t)b * ntiles;
+    // decode t -> (ti, tj)
+    int ti = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+    while ((int64_t)(ti + 1) * (ti + 2) / 2 <= t) ++ti;
+    while ((int64_t)ti * (ti + 1) / 2 > t) --ti;
+    const int tj = (int)(t - (int64_t)ti * (ti + 1) / 2);
+
+    for (int i = tid; i < TB_TILE_ELEMS; i += 256) sT[i] = 0.0;
+    __syncthreads();
+    const double* mk = a.mk + (int64_t)b * a.M;
+    const double* mc = a.mc + (int64_t)b * a.M * DIM;
+    const int64_t e0 = a.tile_ent_ptr[t], e1 = a.tile_ent_ptr[t + 1];
+    for (int64_t q = e0 + tid; q < e1; q += 256) {
+      const int e = a.tile_ent[q];
+      const int r = a.ent_row[e], c = a.ent_col[e];
+      double v = 0.0;
+      for (int64_t p = a.ent_ptr[e]; p < a.ent_ptr[e + 1]; ++p) {
+        const int m = a.ctr_member[p], loc = a.ctr_local[p];
+        const int la = loc / (2 * DIM), lb = loc - la * (2 * DIM);
+        const int A = la / DIM, i = la - A * DIM, B = lb / DIM, j = lb - B * DIM;
+        double pr = __dmul_rn(mc[m * DIM + i], mc[m * DIM + j]);   // truss.py:69,80
+        if (A != B) pr = -pr;
+        v = __dadd_rn(v, __dmul_rn(mk[m], pr));                    // truss.py:70,314
+      }
+      sT[tb_tile_off(r - ti * T, c - tj * T)] = v;
+    }
+    if (ti == tj) {  // identity on the padded part of the diagonal
+      for (int r = tid; r < T; r += 256)
+        if (ti * T + r >= a.n) sT[tb_tile_off(r, r)] = 1.0;
+    }
+    __syncthreads();
+    double2* dst = reinterpret_cast<double2*>(a.L + ((int64_t)b * ntiles + t) * TB_TILE_ELEMS);
+    const double2* src = reinterpret_cast<const double2*>(sT);
+    for (int i = tid; i < TB_TILE_ELEMS / 2; i += 256) dst[i] = src[i];
+    // reduced load vector (rows of this tile row, written once by the diagonal tile's CTA)
+    if (ti == tj) {
+      const double* f = a.force + b * a.force_stride;
+      for (int r = tid; r < T; r += 256) {
+        const int fr = ti * T + r;
+        a.y[(int64_t)b * a.n_pad + fr] = fr < a.n ? f[a.free_idx[fr]] : 0.0;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_chol
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// shared-memory carve of k_chol (bytes)
+constexpr int STAGE_DOUBLES = 2 * HALF + 32;          // A half tile, B half tile, 32 y values
+constexpr int SM_STAGE = 2 * STAGE_DOUBLES;           // two stages
+constexpr int SCR_LD = 67;                             // potrf scratch: 66 rows, column-major
+constexpr int SM_W = TB_TILE_ELEMS;                    // W = inv(L_jj), fragment-major
+constexpr int SM_MISC = 4 * T + 8;                     // rhs acc [64], u block [64], rinv [64], diag [64]
+constexpr int CHOL_SMEM_BYTES = (SM_STAGE + SM_W + SM_MISC) * 8;
+static_assert(SCR_LD * T <= SM_STAGE, "potrf scratch must fit in the stage buffers");
+static_assert(TB_TILE_ELEMS <= SM_STAGE, "C staging tile must fit in the stage buffers");
+
+struct Frag {
+  double c[2][4][2];  // [m-block][n-block][2]
+};
+
+// acc += A(ti, 0..nk-1) * B(tj, 0..nk-1)^T, streamed as 64x32 half tiles through a two-stage
+// cp.async pipeline.  When with_y, also accumulates rows of A times the forward solution y.
+__device__ __forceinline__ void gemm_stream(const double* __restrict__ Lsys, const double* __restrict__ ysys, int ti,
+                                            int tj, int nk, bool with_y, double* sStage, Frag& acc, double (&accy)[2],
+                                            int tid) {
+  const int lane = tid & 31, warp = tid >> 5, wm = warp >> 1, wn = warp & 1;
+  const bool same = (ti == tj);
+  const int S = 2 * nk;
+  auto issue = [&](int s) {
+    const int kt = s >> 1, h = s & 1;
+    double* buf = sStage + (s & 1) * STAGE_DOUBLES;
+    const double* ga = Lsys + tb_tile_index(ti, kt) * TB_TILE_ELEMS + h * HALF;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) cp_async16(buf + (tid + q * 256) * 2, ga + (tid + q * 256) * 2);
+    if (!same) {
+      const double* gb = Lsys + tb_tile_index(tj, kt) * TB_TILE_ELEMS + h * HALF;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) cp_async16(buf + HALF + (tid + q * 256) * 2, gb + (tid + q * 256) * 2);
+    }
+    if (with_y && tid < 16) cp_async16(buf + 2 * HALF + tid * 2, ysys + kt * T + h * 32 + tid * 2);
+    cp_async_commit();
+  };
+  if (S > 0) issue(0);
+  for (int s = 0; s < S; ++s) {
+    if (s + 1 < S) {
+      issue(s + 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const double* bufA = sStage + (s & 1) * STAGE_DOUBLES;
+    const double* bufB = same ? bufA : bufA + HALF;
+    const double* bufY = bufA + 2 * HALF;
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {
+      double af[2], bf[4];
+#pragma unroll
+      for (int mb = 0; mb < 2; ++mb) af[mb] = bufA[(((2 * wm + mb) << 3) + ks) * 32 + lane];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) bf[q] = bufB[(((4 * wn + q) << 3) + ks) * 32 + lane];
+#pragma unroll
+      for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) dmma(acc.c[mb][q][0], acc.c[mb][q][1], af[mb], bf[q]);
+      if (with_y && wn == 0) {
+        const double yv = bufY[ks * 4 + (lane & 3)];
+        accy[0] = fma(af[0], yv, accy[0]);
+        accy[1] = fma(af[1], yv, accy[1]);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+__device__ __forceinline__ int zrow(int r) { return r == 0 ? 64 : r - 1; }
+
+__global__ void __launch_bounds__(CH_THREADS, 2) k_chol(const LargeArgs a) {
+  extern __shared__ __align__(16) double sm[];
+  double* sStage = sm;                 // stage buffers | potrf scratch | C staging tile
+  double* sScr = sm;                   // alias
+  double* sC = sm;                     // alias
+  double* sW = sm + SM_STAGE;
+  double* sRhs = sW + SM_W;            // [64] L(j,:) y accumulations
+  double* sUb = sRhs + T;              // [64] one block of u during back substitution
+  double* sRinv = sUb + T;             // [64]
+  double* sDiag = sRinv + T;           // [64] L_kk of the block being factorised
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wm = warp >> 1, wn = warp & 1;
+  const int nt = a.nt;
+  const int64_t ntiles = (int64_t)nt * (nt + 1) / 2;
+
+  for (int b = blockIdx.x; b < a.batch; b += gridDim.x) {
+    double* Lsys = a.L + (int64_t)b * ntiles * TB_TILE_ELEMS;
+    double* ysys = a.y + (int64_t)b * a.n_pad;
+    if (a.status[b] != 0) continue;  // input problem flagged by k_geom (uniform per CTA)
+    int fail = 0;
+
+    for (int j = 0; j < nt && !fail; ++j) {
+      // ================= diagonal tile: C = A(j,j) - sum_k L(j,k) L(j,k)^T =================
+      Frag acc;
+#pragma unroll
+      for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc.c[mb][q][0] = acc.c[mb][q][1] = 0.0;
+      double accy[2] = {0.0, 0.0};
+      gemm_stream(Lsys, ysys, j, j, j, true, sStage, acc, accy, tid);
+      if (wn == 0) {  // rows of L(j,0:j) times y(0:j): reduce over the quad
+#pragma unroll
+        for (int mb = 0; mb < 2; ++mb) {
+          double v = accy[mb];
+          v += __shfl_xor_sync(0xffffffffu, v, 1);
+          v += __shfl_xor_sync(0xffffffffu, v, 2);
+          if ((lane & 3) == 0) sRhs[(2 * wm + mb) * 8 + (lane >> 2)] = v;
+        }
+      }
+      // scratch rows: L row i -> row i (cols 0..i); Z row r -> row zrow(r) (cols r..63); rhs -> row 65
+      {
+        const double* At = Lsys + tb_tile_index(j, j) * TB_TILE_ELEMS;
+#pragma unroll
+        for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int r = (2 * wm + mb) * 8 + (lane >> 2);
+            const int c = (4 * wn + q) * 8 + 2 * (lane & 3);
+            const double2 av = *reinterpret_cast<const double2*>(At + tb_tile_off(r, c));
+            if (c <= r) sScr[r + c * SCR_LD] = av.x - acc.c[mb][q][0];
+            if (c + 1 <= r) sScr[r + (c + 1) * SCR_LD] = av.y - acc.c[mb][q][1];
+          }
+      }
+      __syncthreads();  // sRhs + lower part of C are in place
+      if (tid < T) {
+        const int r = tid;
+        for (int c = r; c < T; ++c) sScr[zrow(r) + c * SCR_LD] = (c == r) ? 1.0 : 0.0;
+        sScr[65 + r * SCR_LD] = ysys[j * T + r] - sRhs[r];
+      }
+      __syncthreads();
+
+      // ---- potrf of the 64x64 block with L^{-1} (as extra rows: Z = L^{-T}) and the rhs riding along
+      {
+        const bool isL = tid < T, isZ = (tid >= T && tid < 2 * T), isR = (tid == 2 * T);
+        const int zr = tid - T;
+        const int myrow = isL ? tid : (isZ ? zrow(zr) : 65);
+        const int p0 = isZ ? zr : 0;  // first column with data in my row
+        for (int k = 0; k < T; ++k) {
+          const bool act = isL ? (tid >= k) : (isZ ? (zr <= k) : isR);
+          const double* rowk = sScr + k;
+          const double* rowi = sScr + (act ? myrow : k);
+          double d0 = rowk[k * SCR_LD], d1 = 0.0;
+          double s0 = rowi[k * SCR_LD], s1 = 0.0;
+          int p = 0;
+          for (; p + 1 < k; p += 2) {
+            const double b0 = rowk[p * SCR_LD], b1 = rowk[(p + 1) * SCR_LD];
+            const double a0 = (p >= p0) ? rowi[p * SCR_LD] : 0.0;
+            const double a1 = (p + 1 >= p0) ? rowi[(p + 1) * SCR_LD] : 0.0;
+            d0 = fma(-b0, b0, d0);
+            d1 = fma(-b1, b1, d1);
+            s0 = fma(-a0, b0, s0);
+            s1 = fma(-a1, b1, s1);
+          }
+          if (p < k) {
+            const double b0 = rowk[p * SCR_LD];
+            const double a0 = (p >= p0) ? rowi[p * SCR_LD] : 0.0;
+            d0 = fma(-b0, b0, d0);
+            s0 = fma(-a0, b0, s0);
+          }
+          const double d = d0 + d1, s = s0 + s1;
+          if (!(d > 0.0)) {
+            fail = j * T + k + 1;
+            break;
+          }
+          const double lkk = sqrt(d);
+          const double rinv = 1.0 / lkk;
+          // the diagonal goes to sDiag: S[k][k] may still be read as the pivot seed by slower warps
+          if (isL && tid == k) sDiag[k] = lkk;
+          else if (act) sScr[myrow + k * SCR_LD] = s * rinv;
+          __syncthreads();
+        }
+      }
+      if (fail) break;  // uniform
+
+      // ---- publish: L(j,j) -> HBM, W = L(j,j)^{-1} -> shared (both fragment-major), y_j -> HBM
+      {
+        double* Lt = Lsys + tb_tile_index(j, j) * TB_TILE_ELEMS;
+#pragma unroll 4
+        for (int q = 0; q < 16; ++q) {
+          const int idx = tid + q * 256;
+          const int l = idx & 31, slot = idx >> 5;
+          const int ks = slot & 7, rb = (slot >> 3) & 7, h = slot >> 6;
+          const int r = rb * 8 + (l >> 2), c = h * 32 + ks * 4 + (l & 3);
+          Lt[idx] = (c < r) ? sScr[r + c * SCR_LD] : (c == r ? sDiag[r] : 0.0);
+          // W[r][c] = Z[c][r] for r >= c
+          sW[idx] = (r >= c) ? sScr[zrow(c) + r * SCR_LD] : 0.0;
+        }
+        if (tid < T) ysys[j * T + tid] = sScr[65 + tid * SCR_LD];
+      }
+      __syncthreads();
+
+      // ================= panel tiles below the diagonal =================
+      for (int i = j + 1; i < nt; ++i) {
+#pragma unroll
+        for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) acc.c[mb][q][0] = acc.c[mb][q][1] = 0.0;
+        gemm_stream(Lsys, ysys, i, j, j, false, sStage, acc, accy, tid);
+        double* Xt = Lsys + tb_tile_index(i, j) * TB_TILE_ELEMS;
+        // C = A(i,j) - acc  -> shared (fragment-major, as the A operand of the triangular solve)
+#pragma unroll
+        for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int r = (2 * wm + mb) * 8 + (lane >> 2);
+            const int c = (4 * wn + q) * 8 + 2 * (lane & 3);
+            const int off = tb_tile_off(r, c);
+            const double2 av = *reinterpret_cast<const double2*>(Xt + off);
+            *reinterpret_cast<double2*>(sC + off) = make_double2(av.x - acc.c[mb][q][0], av.y - acc.c[mb][q][1]);
+          }
+        __syncthreads();
+        // X = C * W^T  (W lower triangular: k-slabs above the n-block's diagonal are zero)
+#pragma unroll
+        for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) acc.c[mb][q][0] = acc.c[mb][q][1] = 0.0;
+        const int ks_end = 2 * (4 * wn + 3) + 2;  // slabs 0 .. 2*nb_max+1
+        for (int kS = 0; kS < ks_end; ++kS) {
+          const int hoff = (kS >> 3) * HALF, ks = kS & 7;
+          double af[2], bf[4];
+#pragma unroll
+          for (int mb = 0; mb < 2; ++mb) af[mb] = sC[hoff + (((2 * wm + mb) << 3) + ks) * 32 + lane];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) bf[q] = sW[hoff + (((4 * wn + q) << 3) + ks) * 32 + lane];
+#pragma unroll
+          for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) dmma(acc.c[mb][q][0], acc.c[mb][q][1], af[mb], bf[q]);
+        }
+#pragma unroll
+        for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int r = (2 * wm + mb) * 8 + (lane >> 2);
+            const int c = (4 * wn + q) * 8 + 2 * (lane & 3);
+            *reinterpret_cast<double2*>(Xt + tb_tile_off(r, c)) = make_double2(acc.c[mb][q][0], acc.c[mb][q][1]);
+          }
+        __syncthreads();  // sC is about to be overwritten by the next stream; X visible to the CTA
+      }
+    }
+
+    if (fail) {
+      if (tid == 0) a.status[b] = fail;
+      __syncthreads();
+      continue;
+    }
+
+    // ================= back substitution  L^T u = y  (u overwrites y) =================
+    for (int j = nt - 1; j >= 0; --j) {
+      // acc_c = sum_{i>j} sum_r L(i,j)[r][c] u_i[r]; thread (warp w, lane l) owns columns
+      // c = h*32 + w*4 + (l&3) and rows r = rb*8 + (l>>2) of every tile (coalesced tile reads)
+      double a0 = 0.0, a1 = 0.0;
+      for (int i = j + 1; i < nt; ++i) {
+        __syncthreads();
+        if (tid < T) sUb[tid] = ysys[i * T + tid];
+        __syncthreads();
+        const double* Lt = Lsys + tb_tile_index(i, j) * TB_TILE_ELEMS;
+#pragma unroll
+        for (int rb = 0; rb < 8; ++rb) {
+          const double uv = sUb[rb * 8 + (lane >> 2)];
+          a0 = fma(Lt[tid + rb * 256], uv, a0);
+          a1 = fma(Lt[tid + (rb + 8) * 256], uv, a1);
+        }
+      }
+#pragma unroll
+      for (int o = 4; o < 32; o <<= 1) {
+        a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+        a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+      }
+      __syncthreads();
+      if (lane < 4) {
+        sRhs[warp * 4 + lane] = a0;
+        sRhs[32 + warp * 4 + lane] = a1;
+      }
+      // diagonal block into the scratch (column-major, lower part)
+      {
+        const double* Lt = Lsys + tb_tile_index(j, j) * TB_TILE_ELEMS;
+#pragma unroll 4
+        for (int q = 0; q < 16; ++q) {
+          const int idx = tid + q * 256;
+          const int l = idx & 31, slot = idx >> 5;
+          const int ks = slot & 7, rb = (slot >> 3) & 7, h = slot >> 6;
+          const int r = rb * 8 + (l >> 2), c = h * 32 + ks * 4 + (l & 3);
+          if (c <= r) sScr[r + c * SCR_LD] = Lt[idx];
+        }
+      }
+      __syncthreads();
+      if (tid < T) sRinv[tid] = 1.0 / sScr[tid + tid * SCR_LD];
+      double rp = (tid < T) ? ysys[j * T + tid] - sRhs[tid] : 0.0;
+      __syncthreads();
+      for (int k = T - 1; k >= 0; --k) {
+        if (tid == k) sUb[k] = rp * sRinv[k];
+        __syncthreads();
+        if (tid < k) rp = fma(-sScr[k + tid * SCR_LD], sUb[k], rp);
+      }
+      if (tid < T) ysys[j * T + tid] = sUb[tid];
+      __syncthreads();
+    }
+    if (tid == 0) a.status[b] = 0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_recover: one CTA per system
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double block_sum256(double v, double* sRed, int tid) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((tid & 31) == 0) sRed[tid >> 5] = v;
+  __syncthreads();
+  double t = 0.0;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) t += sRed[w];
+  return t;
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(256) k_recover(const LargeArgs a) {
+  __shared__ double sRed[8];
+  const int tid = threadIdx.x;
+  for (int b = blockIdx.x; b < a.batch; b += gridDim.x) {
+    int status = a.status[b];
+    if (status == 0 && !a.plan_stable) status = TB_INFO_NOT_STABLE;
+    double* u_out = a.u ? a.u + (int64_t)b * a.N : nullptr;
+    double* ext_out = a.ext ? a.ext + (int64_t)b * a.N : nullptr;
+    double* ax_out = a.axial ? a.axial + (int64_t)b * a.M : nullptr;
+    if (status != 0) {
+      for (int i = tid; i < a.N; i += 256) {
+        if (u_out) u_out[i] = 0.0;
+        if (ext_out) ext_out[i] = 0.0;
+      }
+      for (int m = tid; m < a.M; m += 256)
+        if (ax_out) ax_out[m] = 0.0;
+      if (tid == 0) {
+        if (a.weight) a.weight[b] = 0.0;
+        if (a.info) a.info[b] = status;
+        if (a.fitness_mode) {
+          if (a.fitness) a.fitness[b] = INFINITY;
+          if (a.flags) { a.flags[2 * b] = 0; a.flags[2 * b + 1] = 0; }
+        }
+      }
+      continue;
+    }
+    const double* uf = a.y + (int64_t)b * a.n_pad;
+    const double* mk = a.mk + (int64_t)b * a.M;
+    const double* mc = a.mc + (int64_t)b * a.M * DIM;
+    const double* mw = a.mw + (int64_t)b * a.M;
+    double* axw = a.mw + (int64_t)b * a.M;  // reuse the weight terms' slot for axial after reading them
+    double w = 0.0, vs = 0.0, vd = 0.0;
+    for (int i = tid; i < a.N; i += 256) {
+      const int fr = a.dof2free[i];
+      if (u_out) u_out[i] = fr >= 0 ? uf[fr] : 0.0;
+    }
+    for (int m = tid; m < a.M; m += 256) {
+      const int j0 = a.conn[2 * m], j1 = a.conn[2 * m + 1];
+      double t = 0.0;
+#pragma unroll
+      for (int i = 0; i < DIM; ++i) {
+        const int f1 = a.dof2free[j1 * DIM + i], f0 = a.dof2free[j0 * DIM + i];
+        const double u1 = f1 >= 0 ? uf[f1] : 0.0, u0 = f0 >= 0 ? uf[f0] : 0.0;
+        t = fma(mc[m * DIM + i], u1 - u0, t);
+      }
+      const double nm = mk[m] * t;
+      w += mw[m];
+      axw[m] = nm;
+      if (ax_out) ax_out[m] = nm;
+      if (a.fitness_mode) {
+        const double f = fabs(nm);
+        if (!(f < TB_ZERO_EPS)) {
+          double ar;
+          if (a.gene) ar = a.type_table[3 * a.gene[b * a.gene_stride + m]];
+          else ar = a.aed[b * a.aed_stride + 3 * (int64_t)m];
+          const double sg = f / ar;
+          if (sg > a.allow_stress) vs += sg - a.allow_stress;
+        }
+      }
+    }
+    __syncthreads();  // axial forces of this system are visible to the CTA
+    if (ext_out) {
+      const double* f = a.force + b * a.force_stride;
+      for (int dof = tid; dof < a.N; dof += 256) {
+        double e;
+        if (a.dof2free[dof] >= 0) {
+          e = f[dof];
+        } else {
+          const int J = dof / DIM, ax = dof - J * DIM;
+          e = 0.0;
+          for (int p = a.inc_ptr[J]; p < a.inc_ptr[J + 1]; ++p) {
+            const int me = a.inc_mem[p], m = me >> 1;
+            const double g = (me & 1) ? mc[m * DIM + ax] : -mc[m * DIM + ax];
+            e = fma(g, axw[m], e);
+          }
+        }
+        ext_out[dof] = e;
+      }
+    }
+    if (a.fitness_mode) {
+      for (int j = tid; j < a.nJ; j += 256) {
+        bool any = false;
+        double l2 = 0.0;
+#pragma unroll
+        for (int i = 0; i < DIM; ++i) {
+          const int fr = a.dof2free[j * DIM + i];
+          const double v = fr >= 0 ? uf[fr] : 0.0;
+          any |= !(fabs(v) < TB_ZERO_EPS);
+          l2 += v * v;
+        }
+        if (any) {
+          const double l = sqrt(l2);
+          if (l > a.allow_displace) vd += l - a.allow_displace;
+        }
+      }
+    }
+    w = block_sum256(w, sRed, tid);
+    if (a.fitness_mode) {
+      vs = block_sum256(vs, sRed, tid);
+      vd = block_sum256(vd, sRed, tid);
+    }
+    if (tid == 0) {
+      if (a.weight) a.weight[b] = w;
+      if (a.info) a.info[b] = 0;
+      if (a.fitness_mode) {
+        const bool ok_s = fabs(vs) < TB_ZERO_EPS, ok_d = fabs(vd) < TB_ZERO_EPS;
+        double fit = w;
+        if (!ok_s) fit += vs / a.allow_stress * 1e5;
+        if (!ok_d) fit += vd / a.allow_displace * 1e5;
+        if (a.fitness) a.fitness[b] = fit;
+        if (a.flags) { a.flags[2 * b] = ok_s; a.flags[2 * b + 1] = ok_d; }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace
+
+size_t tb_large_workspace_bytes(int batch, int dim, int M, int n_pad) {
+  const int nt = n_pad / TB_TILE;
+  const size_t ntiles = (size_t)nt * (nt + 1) / 2;
+  size_t doubles = (size_t)batch * ((size_t)M * (2 + dim) + ntiles * TB_TILE_ELEMS + (size_t)n_pad);
+  return doubles * 8 + (size_t)batch * 4 + 1024;
+}
+
+void tb_large_carve(LargeArgs& a, void* ws) {
+  const size_t ntiles = (size_t)a.nt * (a.nt + 1) / 2;
+  double* p = (double*)ws;
+  a.L = p;  p += (size_t)a.batch * ntiles * TB_TILE_ELEMS;   // first: 32 KB-aligned tiles
+  a.y = p;  p += (size_t)a.batch * a.n_pad;
+  a.mk = p; p += (size_t)a.batch * a.M;
+  a.mc = p; p += (size_t)a.batch * a.M * a.dim;
+  a.mw = p; p += (size_t)a.batch * a.M;
+  a.status = (int32_t*)p;
+}
+
+int tb_launch_large(const LargeArgs& a, int num_sm, cudaStream_t st) {
+  if (a.batch <= 0) return 0;
+  if (num_sm <= 0) num_sm = 148;
+  k_init_status<<<(a.batch + 255) / 256, 256, 0, st>>>(a.status, a.batch, 0);
+  {
+    const int64_t total = (int64_t)a.batch * a.M;
+    int grid = (int)((total + 255) / 256 < (int64_t)num_sm * 8 ? (total + 255) / 256 : (int64_t)num_sm * 8);
+    if (grid < 1) grid = 1;
+    if (a.dim == 3) k_geom<3><<<grid, 256, 0, st>>>(a);
+    else k_geom<2><<<grid, 256, 0, st>>>(a);
+  }
+  {
+    const int64_t work = (int64_t)a.nt * (a.nt + 1) / 2 * a.batch;
+    int grid = (int)(work < (int64_t)num_sm * 16 ? work : (int64_t)num_sm * 16);
+    if (a.dim == 3) k_assemble<3><<<grid, 256, 0, st>>>(a);
+    else k_assemble<2><<<grid, 256, 0, st>>>(a);
+  }
+  {
+    cudaError_t e = cudaFuncSetAttribute(k_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, CHOL_SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_chol, CH_THREADS, CHOL_SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    if (per_sm < 1) per_sm = 1;
+    int grid = num_sm * per_sm;
+    if (grid > a.batch) grid = a.batch;
+    k_chol<<<grid, CH_THREADS, CHOL_SMEM_BYTES, st>>>(a);
+  }
+  {
+    int grid = a.batch < num_sm * 8 ? a.batch : num_sm * 8;
+    if (a.dim == 3) k_recover<3><<<grid, 256, 0, st>>>(a);
+    else k_recover<2><<<grid, 256, 0, st>>>(a);
+  }
+  tb_count_launch(5);
+  return (int)cudaGetLastError();
+}

@@ -1,0 +1,289 @@
+// Plan construction: the integer maps of the reference's assembly/reduction, built once per
+// topology on the host and mirrored on the device.
+//   DOF maps      <- Truss.GetDisplacementUnknownMask / SupportType.GetResistanceMask
+//                    (slientruss3d/truss.py:319-326, type.py:48-74) + boolean-mask ordering (truss.py:343,348)
+//   scatter map   <- the four d x d block "+=" of Truss.GetKMatrix (truss.py:307-316), as a
+//                    CSR of per-entry contribution lists in ascending member order (no atomics)
+//   stability     <- Truss.isStable / nResistance (truss.py:154-164, type.py:37-46)
+#include <algorithm>
+#include <cstring>
+#include <new>
+#include <numeric>
+
+#include "tb_common.cuh"
+
+std::atomic<int64_t> g_tb_launches{0};
+
+namespace {
+
+template <typename T>
+int upload(T** dptr, const std::vector<T>& h) {
+  *dptr = nullptr;
+  size_t bytes = std::max<size_t>(h.size(), 1) * sizeof(T);
+  cudaError_t e = cudaMalloc((void**)dptr, bytes);
+  if (e != cudaSuccess) return (int)e;
+  if (!h.empty()) {
+    e = cudaMemcpy(*dptr, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return (int)e;
+  }
+  return 0;
+}
+
+struct Contrib {
+  int32_t row, col, member, local;
+};
+
+}  // namespace
+
+extern "C" int tb_plan_create(const tb_topology* topo, tb_plan** plan_out) {
+  if (!topo || !plan_out) return TB_ERR_NULL;
+  *plan_out = nullptr;
+  const int d = topo->dim;
+  if (d != 2 && d != 3) return TB_ERR_DIM;
+  if (topo->n_joint < 0 || topo->n_member < 0) return TB_ERR_SIZE;
+  if ((topo->n_member > 0 && !topo->conn) || (topo->n_joint > 0 && !topo->support)) return TB_ERR_NULL;
+  if ((int64_t)topo->n_joint * d > (int64_t)1 << 24) return TB_ERR_TOO_LARGE;
+
+  // The maps are host work; without a CUDA device the plan is host-only (maps can still be
+  // queried) and every solve entry point returns TB_ERR_NO_DEVICE -- there is no CPU fallback.
+  int ndev = 0;
+  const bool has_dev = (cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0);
+  if (!has_dev) (void)cudaGetLastError();
+
+  tb_plan* p = new (std::nothrow) tb_plan();
+  if (!p) return TB_ERR_ALLOC;
+  p->dim = d;
+  p->nJ = topo->n_joint;
+  p->M = topo->n_member;
+  p->N = d * p->nJ;
+  p->device = -1;
+  if (has_dev) {
+    cudaGetDevice(&p->device);
+    cudaDeviceGetAttribute(&p->num_sm, cudaDevAttrMultiProcessorCount, p->device);
+  }
+  p->conn.assign(topo->conn, topo->conn + 2 * (size_t)p->M);
+  p->support.assign(topo->support, topo->support + p->nJ);
+
+  for (int m = 0; m < p->M; ++m)
+    for (int e = 0; e < 2; ++e) {
+      int j = p->conn[2 * m + e];
+      if (j < 0 || j >= p->nJ) {
+        delete p;
+        return TB_ERR_INDEX;
+      }
+    }
+
+  // ---- DOF maps: free DOFs in ascending DOF order (boolean-mask indexing, truss.py:343)
+  p->dof2free.assign(p->N, -1);
+  p->n_resist = 0;
+  for (int j = 0; j < p->nJ; ++j) {
+    int s = p->support[j];
+    if (s > SUP_ROLLER_Z || (d == 2 && s == SUP_ROLLER_Z)) {  // type.py:62,74
+      delete p;
+      return TB_ERR_SUPPORT;
+    }
+    for (int ax = 0; ax < d; ++ax) {
+      bool resist = (s == SUP_PIN) || (s == SUP_ROLLER_X + ax);
+      int dof = j * d + ax;
+      if (resist) {
+        p->sup_idx.push_back(dof);
+        p->n_resist++;
+      } else {
+        p->dof2free[dof] = (int)p->free_idx.size();
+        p->free_idx.push_back(dof);
+      }
+    }
+  }
+  p->n = (int)p->free_idx.size();
+  p->s = (int)p->sup_idx.size();
+  // truss.py:158-164
+  if (d == 2)
+    p->stable = (p->M + p->n_resist >= p->nJ * d);
+  else
+    p->stable = (p->n_resist >= 6) && (p->M + p->n_resist >= p->nJ * d);
+
+  // ---- scatter map over the lower triangle of K_ff
+  std::vector<Contrib> cs;
+  cs.reserve((size_t)p->M * 4 * d * d);
+  for (int m = 0; m < p->M; ++m) {
+    // block order of truss.py:312-314: (A,B) = (0,0),(0,1),(1,0),(1,1)
+    for (int A = 0; A < 2; ++A)
+      for (int B = 0; B < 2; ++B)
+        for (int i = 0; i < d; ++i)
+          for (int j = 0; j < d; ++j) {
+            int r = p->dof2free[p->conn[2 * m + A] * d + i];
+            int c = p->dof2free[p->conn[2 * m + B] * d + j];
+            if (r < 0 || c < 0 || r < c) continue;
+            cs.push_back({r, c, m, (A * d + i) * 2 * d + (B * d + j)});
+          }
+  }
+  std::stable_sort(cs.begin(), cs.end(), [](const Contrib& a, const Contrib& b) {
+    return a.row != b.row ? a.row < b.row : a.col < b.col;
+  });
+  p->half_bw = 0;
+  for (size_t i = 0; i < cs.size(); ++i) {
+    if (i == 0 || cs[i].row != cs[i - 1].row || cs[i].col != cs[i - 1].col) {
+      p->ent_row.push_back(cs[i].row);
+      p->ent_col.push_back(cs[i].col);
+      p->ent_ptr.push_back((int64_t)i);
+      p->half_bw = std::max<int64_t>(p->half_bw, cs[i].row - cs[i].col);
+    }
+    p->ctr_member.push_back(cs[i].member);
+    p->ctr_local.push_back(cs[i].local);
+  }
+  p->ent_ptr.push_back((int64_t)cs.size());
+
+  // ---- path + tile grouping of entries for the blocked path
+  p->path = (p->N <= TB_SMALL_MAX_DOF && p->M <= TB_SMALL_MAX_MEMBER && p->nJ <= TB_SMALL_MAX_JOINT) ? 0 : 1;
+  p->n_pad = std::max(TB_TILE, (p->n + TB_TILE - 1) / TB_TILE * TB_TILE);
+  p->nt = p->n_pad / TB_TILE;
+  {
+    const int64_t ntiles = (int64_t)p->nt * (p->nt + 1) / 2;
+    const size_t nnz = p->ent_row.size();
+    std::vector<int64_t> cnt(ntiles + 1, 0);
+    for (size_t e = 0; e < nnz; ++e) cnt[tb_tile_index(p->ent_row[e] / TB_TILE, p->ent_col[e] / TB_TILE) + 1]++;
+    for (int64_t t = 0; t < ntiles; ++t) cnt[t + 1] += cnt[t];
+    p->tile_ent_ptr = cnt;
+    p->tile_ent.assign(nnz, 0);
+    std::vector<int64_t> pos(cnt.begin(), cnt.end() - 1);
+    for (size_t e = 0; e < nnz; ++e)
+      p->tile_ent[pos[tb_tile_index(p->ent_row[e] / TB_TILE, p->ent_col[e] / TB_TILE)]++] = (int32_t)e;
+  }
+
+  // ---- joint incidence lists (ascending member, then end)
+  p->inc_ptr.assign(p->nJ + 1, 0);
+  for (int m = 0; m < p->M; ++m)
+    for (int e = 0; e < 2; ++e) p->inc_ptr[p->conn[2 * m + e] + 1]++;
+  for (int j = 0; j < p->nJ; ++j) p->inc_ptr[j + 1] += p->inc_ptr[j];
+  p->inc_mem.assign(2 * (size_t)p->M, 0);
+  {
+    std::vector<int32_t> pos(p->inc_ptr.begin(), p->inc_ptr.end() - 1);
+    for (int m = 0; m < p->M; ++m)
+      for (int e = 0; e < 2; ++e) p->inc_mem[pos[p->conn[2 * m + e]]++] = m * 2 + e;
+  }
+
+  if (!has_dev) {
+    *plan_out = p;
+    return TB_OK;
+  }
+  int rc = 0;
+  if (!rc) rc = upload(&p->d_conn, p->conn);
+  if (!rc) rc = upload(&p->d_support, p->support);
+  if (!rc) rc = upload(&p->d_free_idx, p->free_idx);
+  if (!rc) rc = upload(&p->d_dof2free, p->dof2free);
+  if (!rc) rc = upload(&p->d_sup_idx, p->sup_idx);
+  if (!rc) rc = upload(&p->d_ent_row, p->ent_row);
+  if (!rc) rc = upload(&p->d_ent_col, p->ent_col);
+  if (!rc) rc = upload(&p->d_ent_ptr, p->ent_ptr);
+  if (!rc) rc = upload(&p->d_ctr_member, p->ctr_member);
+  if (!rc) rc = upload(&p->d_ctr_local, p->ctr_local);
+  if (!rc) rc = upload(&p->d_tile_ent_ptr, p->tile_ent_ptr);
+  if (!rc) rc = upload(&p->d_tile_ent, p->tile_ent);
+  if (!rc) rc = upload(&p->d_inc_ptr, p->inc_ptr);
+  if (!rc) rc = upload(&p->d_inc_mem, p->inc_mem);
+  if (rc) {
+    tb_plan_destroy(p);
+    return rc;
+  }
+  *plan_out = p;
+  return TB_OK;
+}
+
+extern "C" void tb_plan_destroy(tb_plan* p) {
+  if (!p) return;
+  if (p->device < 0) {
+    delete p;
+    return;
+  }
+  cudaFree(p->d_conn);
+  cudaFree(p->d_support);
+  cudaFree(p->d_free_idx);
+  cudaFree(p->d_dof2free);
+  cudaFree(p->d_sup_idx);
+  cudaFree(p->d_ent_row);
+  cudaFree(p->d_ent_col);
+  cudaFree(p->d_ent_ptr);
+  cudaFree(p->d_ctr_member);
+  cudaFree(p->d_ctr_local);
+  cudaFree(p->d_tile_ent_ptr);
+  cudaFree(p->d_tile_ent);
+  cudaFree(p->d_inc_ptr);
+  cudaFree(p->d_inc_mem);
+  cudaFree(p->ws);
+  cudaFree(p->stage_dev);
+  if (p->stage_pinned) cudaFreeHost(p->stage_pinned);
+  delete p;
+}
+
+extern "C" int tb_plan_query(const tb_plan* p, tb_plan_info* o) {
+  if (!p || !o) return TB_ERR_NULL;
+  o->dim = p->dim;
+  o->n_joint = p->nJ;
+  o->n_member = p->M;
+  o->n_dof = p->N;
+  o->n_free = p->n;
+  o->n_support = p->s;
+  o->n_resist = p->n_resist;
+  o->stable = p->stable;
+  o->path = p->path;
+  o->n_pad = p->n_pad;
+  o->nnz_lower = (int64_t)p->ent_row.size();
+  o->n_contrib = (int64_t)p->ctr_member.size();
+  o->half_bandwidth = p->half_bw;
+  return TB_OK;
+}
+
+extern "C" int tb_plan_set_path(tb_plan* p, int32_t path) {
+  if (!p) return TB_ERR_NULL;
+  if (path != 0 && path != 1) return TB_ERR_SIZE;
+  if (path == 0 && !(p->N <= TB_SMALL_MAX_DOF && p->M <= TB_SMALL_MAX_MEMBER && p->nJ <= TB_SMALL_MAX_JOINT))
+    return TB_ERR_TOO_LARGE;
+  p->path = path;
+  return TB_OK;
+}
+
+extern "C" int tb_plan_get_maps(const tb_plan* p, int32_t* free_idx, int32_t* dof2free, int32_t* sup_idx) {
+  if (!p) return TB_ERR_NULL;
+  if (free_idx && p->n) memcpy(free_idx, p->free_idx.data(), sizeof(int32_t) * p->n);
+  if (dof2free && p->N) memcpy(dof2free, p->dof2free.data(), sizeof(int32_t) * p->N);
+  if (sup_idx && p->s) memcpy(sup_idx, p->sup_idx.data(), sizeof(int32_t) * p->s);
+  return TB_OK;
+}
+
+extern "C" int tb_plan_get_scatter(const tb_plan* p, int32_t* row, int32_t* col, int64_t* contrib_ptr,
+                                   int32_t* contrib_member, int32_t* contrib_local) {
+  if (!p) return TB_ERR_NULL;
+  size_t nnz = p->ent_row.size(), nc = p->ctr_member.size();
+  if (row && nnz) memcpy(row, p->ent_row.data(), sizeof(int32_t) * nnz);
+  if (col && nnz) memcpy(col, p->ent_col.data(), sizeof(int32_t) * nnz);
+  if (contrib_ptr) memcpy(contrib_ptr, p->ent_ptr.data(), sizeof(int64_t) * (nnz + 1));
+  if (contrib_member && nc) memcpy(contrib_member, p->ctr_member.data(), sizeof(int32_t) * nc);
+  if (contrib_local && nc) memcpy(contrib_local, p->ctr_local.data(), sizeof(int32_t) * nc);
+  return TB_OK;
+}
+
+extern "C" int tb_small_path_limits(int32_t* max_dof, int32_t* max_member) {
+  if (max_dof) *max_dof = TB_SMALL_MAX_DOF;
+  if (max_member) *max_member = TB_SMALL_MAX_MEMBER;
+  return TB_OK;
+}
+
+extern "C" int64_t tb_launch_count(void) { return g_tb_launches.load(); }
+extern "C" int tb_version(void) { return TB_VERSION; }
+
+extern "C" const char* tb_strerror(int code) {
+  switch (code) {
+    case TB_OK: return "ok";
+    case TB_ERR_NULL: return "required pointer is NULL";
+    case TB_ERR_DIM: return "dimension of truss must be 2 or 3";
+    case TB_ERR_SIZE: return "negative or inconsistent size";
+    case TB_ERR_INDEX: return "member refers to a joint that does not exist";
+    case TB_ERR_SUPPORT: return "invalid support type for this dimension";
+    case TB_ERR_TOO_LARGE: return "system too large for the selected path";
+    case TB_ERR_NO_DEVICE: return "no CUDA device (this library has no CPU fallback)";
+    case TB_ERR_ALLOC: return "allocation failed";
+    default: break;
+  }
+  if (code > 0) return cudaGetErrorString((cudaError_t)code);
+  return "unknown error";
+}

@@ -1,0 +1,134 @@
+"""CPU-side checks of the C-ABI library and the host logic (no compute calls: there is no GPU here).
+
+ * the library loads and exports every function include/truss_b200.h declares
+ * the plan's DOF maps are bit-exact against the oracle's boolean-mask order (truss.py:319-326,343)
+ * the plan's scatter map, replayed in numpy, rebuilds the oracle's reduced K bit for bit (truss.py:307-316)
+ * argument errors map to the documented codes; solving without a device fails loudly
+"""
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import truss_oracle as orc
+from python_stable_3d_truss_analysis_b200 import _lib
+from tests import helpers as H
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def all_cases():
+    cases = [(n, d, data) for n, d, data, _ in H.shipped_cases()]
+    cases += [(f"random{i}", c["dim"], c["data"]) for i, c in enumerate(H.load_json("live_random.json"))]
+    cases += [(n, d, data) for n, d, data, _ in H.cube7_shipped()[:3]]
+    return cases
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "truss_b200.h")).read()
+    declared = set(re.findall(r"\b(tb_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    L = _lib.lib()
+    missing = [s for s in sorted(declared) if not hasattr(L, s)]
+    assert not missing, f"library does not export {missing}"
+    assert set(_lib.EXPORTS) == declared
+    assert L.tb_version() == 100
+
+
+@pytest.mark.parametrize("name,dim,data", all_cases(), ids=lambda v: v if isinstance(v, str) else None)
+def test_plan_dof_maps_bit_exact(name, dim, data):
+    joints, support, conn, aed, force = orc.arrays_from_json(data, dim)
+    plan = _lib.Plan(dim, conn, support)
+    free_idx, dof2free, sup_idx = plan.maps()
+    want = orc.dof_maps(dim, support)
+    assert np.array_equal(free_idx, want[0]) and free_idx.dtype == np.int32
+    assert np.array_equal(dof2free, want[1])
+    assert np.array_equal(sup_idx, want[2])
+    assert plan.stable == orc.is_stable(dim, support, conn.shape[0])
+    assert plan.info.n_resist == sum(orc.resistance_number(int(s), dim) for s in support)
+
+
+@pytest.mark.parametrize("name,dim,data", all_cases(), ids=lambda v: v if isinstance(v, str) else None)
+def test_scatter_map_rebuilds_reference_K(name, dim, data):
+    joints, support, conn, aed, force = orc.arrays_from_json(data, dim)
+    plan = _lib.Plan(dim, conn, support)
+    row, col, ptr, mem, loc = plan.scatter()
+    # entries are unique, lower-triangular, row-major sorted
+    assert np.all(row >= col)
+    order = np.lexsort((col, row))
+    assert np.array_equal(order, np.arange(len(row)))
+    # contributions of one entry come in ascending member order
+    for e in range(len(row)):
+        seg = mem[ptr[e]:ptr[e + 1]]
+        assert np.all(np.diff(seg) >= 0)
+    # replay: k * (+-(c_i c_j)) summed in list order == reference K[mask][:, mask]
+    d = dim
+    K = np.zeros((plan.n, plan.n))
+    for e in range(len(row)):
+        v = 0.0
+        for p in range(ptr[e], ptr[e + 1]):
+            m = mem[p]
+            la, lb = divmod(int(loc[p]), 2 * d)
+            A, i = divmod(la, d)
+            B, j = divmod(lb, d)
+            L = orc.member_length(joints[conn[m, 0]], joints[conn[m, 1]])
+            c = orc.member_cosines(joints[conn[m, 0]], joints[conn[m, 1]], L)
+            pr = c[i] ** 2. if i == j else c[i] * c[j]
+            if A != B:
+                pr = -pr
+            v = v + orc.member_k(aed[m, 0], aed[m, 1], L) * pr
+        K[row[e], col[e]] = v
+    mask = orc.free_mask(dim, support)
+    Kref = orc.assemble_K(dim, joints, conn, aed)[np.ix_(mask, mask)]
+    assert np.array_equal(np.tril(Kref), K), "scatter map does not rebuild the reference matrix bit for bit"
+    assert plan.info.half_bandwidth == (np.abs(row - col).max() if len(row) else 0)
+
+
+def test_argument_errors():
+    conn = np.array([[0, 1]], np.int32)
+    sup = np.array([1, 0], np.uint8)
+    with pytest.raises(_lib.TrussLibError) as e:
+        _lib.Plan(4, conn, sup)
+    assert e.value.code == -2
+    with pytest.raises(_lib.TrussLibError) as e:
+        _lib.Plan(3, np.array([[0, 2]], np.int32), sup)
+    assert e.value.code == -4
+    with pytest.raises(_lib.TrussLibError) as e:
+        _lib.Plan(2, conn, np.array([4, 0], np.uint8))      # ROLLER_Z does not exist in 2D (type.py:66-74)
+    assert e.value.code == -5
+    with pytest.raises(_lib.TrussLibError) as e:
+        _lib.Plan(3, conn, np.array([7, 0], np.uint8))
+    assert e.value.code == -5
+    assert _lib.lib().tb_strerror(-7).decode().startswith("no CUDA device")
+
+
+def _has_cuda():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+@pytest.mark.skipif(_has_cuda(), reason="only meaningful on a machine without a GPU")
+def test_no_cpu_fallback():
+    from python_stable_3d_truss_analysis_b200.truss import Truss
+    data = json.load(open(f"{H.GOLDEN}/ref_data/bar-6_input_0.json"))
+    t = Truss(3).LoadFromJSON(data=data)
+    with pytest.raises(_lib.NoCudaDeviceError):
+        t.Solve()
+    assert not t.isSolved
+
+
+def test_path_selection_and_padding():
+    for name, dim, data, _ in H.shipped_cases():
+        _, support, conn, _, _ = orc.arrays_from_json(data, dim)
+        plan = _lib.Plan(dim, conn, support)
+        big = name.startswith("bar-942")
+        assert plan.path == (1 if big else 0)
+        assert plan.info.n_pad % 64 == 0 and plan.info.n_pad >= plan.n
+        if not big:
+            plan.set_path(1)
+            assert plan.path == 1
