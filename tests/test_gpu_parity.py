@@ -1,0 +1,270 @@
+"""Parity of the CUDA path (through the C ABI) against the reference's golden files, the
+live-reference vectors and the oracle.  Tolerance: 1e-9 norm-wise per field (north_star);
+index maps are checked bit-exact in tests/test_abi_cpu.py."""
+import json
+
+import numpy as np
+import pytest
+
+from oracle import truss_oracle as orc
+from python_stable_3d_truss_analysis_b200 import _lib
+from python_stable_3d_truss_analysis_b200.batch import (FitnessBatch, SolveBatch, SolveLoadCases, SolveMemberTypes,
+                                                          type_table)
+from python_stable_3d_truss_analysis_b200.truss import Truss
+from python_stable_3d_truss_analysis_b200.type import MemberType, SupportType
+from python_stable_3d_truss_analysis_b200.utils import TrussNotStableError
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def dense(t):
+    return {"u": t._dense["u"], "ext": t._dense["ext"], "axial": t._dense["axial"], "weight": t.weight}
+
+
+@pytest.mark.parametrize("path", [0, 1], ids=["fused", "blocked"])
+@pytest.mark.parametrize("name,dim,data,gold", H.shipped_cases(), ids=lambda v: v if isinstance(v, str) else None)
+def test_solve_vs_shipped_goldens(name, dim, data, gold, path):
+    t = Truss(dim).LoadFromJSON(data=data)
+    plan = t._get_plan()
+    if path == 0 and plan.path == 1:
+        pytest.skip("too large for the fused kernel")
+    plan.set_path(path)
+    t.Solve()
+    H.assert_close(dense(t), gold, what=f"{name} path{path}")
+    for k in H.FIELDS:
+        assert H.key_sets_match(t._dense[k], gold[k]), (name, k)
+    # sparse dict views follow the 1e-10 filter
+    for j, v in t.GetDisplacements().items():
+        assert not (np.abs(v) < 1e-10).all()
+    ser = t.Serialize()
+    assert set(ser) >= {"displace", "external", "internal", "weight"}
+
+
+@pytest.mark.parametrize("name,dim,data,gold", H.cube7_shipped(), ids=lambda v: v if isinstance(v, str) else None)
+def test_solve_vs_shipped_cube7(name, dim, data, gold):
+    t = Truss(dim).LoadFromJSON(data=data)
+    t.Solve()
+    H.assert_close(dense(t), gold, what=name)
+
+
+@pytest.mark.parametrize("path", [0, 1], ids=["fused", "blocked"])
+def test_solve_vs_live_random(path):
+    for i, case in enumerate(H.load_json("live_random.json")):
+        dim = case["dim"]
+        t = Truss(dim).LoadFromJSON(data=case["data"])
+        t._get_plan().set_path(path)
+        t.Solve()
+        want = {k: np.array(v) if k != "weight" else v for k, v in case["result"].items()}
+        H.assert_close(dense(t), want, what=f"random[{i}] path{path}")
+
+
+def test_ragged_batch_vs_live_cube7_aug():
+    live = H.load_json("live_cube7_aug.json")
+    trusses = [Truss(3).LoadFromJSON(data=g) for g in live]
+    assert len({(t.nJoint, t.nMember) for t in trusses}) > 1          # genuinely ragged
+    info = SolveBatch(trusses)
+    assert not info.any()
+    for i, (t, g) in enumerate(zip(trusses, live)):
+        H.assert_close(dense(t), H.dense_from_output(g, 3), what=f"cube7_aug[{i}]")
+
+
+def test_uniform_batch_equals_single_solves_bitwise():
+    name, dim, data, gold = [c for c in H.shipped_cases() if c[0] == "bar-72_input_0"][0]
+    trusses = [Truss(dim).LoadFromJSON(data=data) for _ in range(5)]
+    for k, t in enumerate(trusses):
+        t.SetJointPosition(16 + (k % 4), tuple(v + 0.5 * k for v in t.GetJointPosition(16 + (k % 4))))
+    SolveBatch(trusses)
+    for t in trusses:
+        s = Truss(dim).LoadFromJSON(data=t.Serialize())
+        s.Solve()
+        for k in H.FIELDS:
+            assert np.array_equal(s._dense[k], t._dense[k]), k
+
+
+def test_ga_fitness_vs_live_reference():
+    g = H.load_json("live_ga_bar72.json")
+    types = [MemberType(*row) for row in g["type_table"]]
+    blocks = [(c, v, g["allow_stress"], g["allow_displace"]) for c, v in g["cases"].items()]
+    blocks.append((g["tight"]["case"], g["tight"], g["tight"]["allow_stress"], g["tight"]["allow_displace"]))
+    n_pen = 0
+    for case, v, a_s, a_d in blocks:
+        t = Truss(3).LoadFromJSON(f"{H.GOLDEN}/ref_data/{case}.json")
+        for path in (0, 1):
+            t._get_plan().set_path(path)
+            out = FitnessBatch(t, v["genes"], types, a_s, a_d)
+            assert not out["info"].any()
+            fit = np.array(v["fitness"])
+            assert np.all(np.abs(out["fitness"] - fit) <= 1e-9 * np.abs(fit)), (case, path)
+            assert out["flags"][:, 0].astype(bool).tolist() == v["stress_ok"]
+            assert out["flags"][:, 1].astype(bool).tolist() == v["displace_ok"]
+        n_pen += sum(1 for a, b in zip(v["stress_ok"], v["displace_ok"]) if not (a and b))
+    assert n_pen > 0
+
+
+def test_ga_class_uses_batched_fitness():
+    import random
+    from python_stable_3d_truss_analysis_b200.ga import GA
+    g = H.load_json("live_ga_bar72.json")
+    types = [MemberType(*row) for row in g["type_table"]]
+    t = Truss(3).LoadFromJSON(f"{H.GOLDEN}/ref_data/bar-72_input_0.json")
+    ga = GA(t, types, g["allow_stress"], g["allow_displace"], nIteration=3, nPop=64, nElite=16)
+    v = g["cases"]["bar-72_input_0"]
+    batch = ga.GetFitnessBatch(v["genes"][:8])
+    for (f, s, d), fr, sr, dr in zip(batch, v["fitness"], v["stress_ok"], v["displace_ok"]):
+        assert abs(f - fr) <= 1e-9 * abs(fr) and (s, d) == (sr, dr)
+    single = ga.GetFitness(v["genes"][3])
+    assert abs(single[0] - v["fitness"][3]) <= 1e-9 * abs(v["fitness"][3]) and t.isSolved
+    random.seed(5)
+    gene, info, pop, hist = ga.Evolve(isPrintMessage=False)
+    assert len(pop) == 64 and len(hist) == 3 and hist == sorted(hist, reverse=True)
+
+
+def test_load_cases_bar942_vs_live():
+    z = np.load(f"{H.GOLDEN}/live_loadcases_bar942.npz")
+    t = Truss(3).LoadFromJSON(f"{H.GOLDEN}/ref_data/bar-942_input_0.json")
+    out = SolveLoadCases(t, z["F"])
+    for b in range(z["F"].shape[0]):
+        for k in H.FIELDS:
+            err = orc.normwise_err(out[k][b], z[k][b])
+            assert err <= H.TOL, (b, k, err)
+
+
+def test_member_type_batch_vs_oracle_bar942():
+    rng = np.random.default_rng(3)
+    data = json.load(open(f"{H.GOLDEN}/ref_data/bar-942_input_0.json"))
+    joints, support, conn, aed, force = orc.arrays_from_json(data, 3)
+    types = [MemberType(a, 1e4, 0.1) for a in (0.5, 1.0, 2.0, 4.0)]
+    genes = rng.integers(0, 4, size=(3, conn.shape[0]))
+    t = Truss(3).LoadFromJSON(data=data)
+    out = SolveMemberTypes(t, genes, types)
+    tab = type_table(types)
+    for b in range(3):
+        want = orc.solve_closed_form(3, joints, support, conn, tab[genes[b]], force)
+        for k in H.FIELDS:
+            assert orc.normwise_err(out[k][b], want[k]) <= H.TOL, (b, k)
+        assert abs(out["weight"][b] - want["weight"]) <= 1e-9 * want["weight"]
+
+
+def test_error_reporting_per_system():
+    mt = MemberType(1, 1e7, 1)
+    # counting rule (truss.py:158-164)
+    u = Truss(3)
+    for p, s in [((0, 0, 0), SupportType.PIN), ((1, 0, 0), SupportType.NO)]:
+        u.AddNewJoint(p, s)
+    u.AddNewMember(0, 1, mt)
+    with pytest.raises(TrussNotStableError):
+        u.Solve()
+    # passes the counting rule but is a mechanism: a free joint hanging from one bar
+    m = Truss(2)
+    for p, s in [((0, 0), SupportType.PIN), ((4, 0), SupportType.PIN), ((2, 3), SupportType.NO), ((6, 3), SupportType.NO)]:
+        m.AddNewJoint(p, s)
+    for a, b in [(0, 2), (1, 2), (2, 3), (0, 1)]:
+        m.AddNewMember(a, b, mt)
+    m.AddExternalForce(3, (0, -1))
+    assert m.isStable
+    with pytest.raises(np.linalg.LinAlgError):
+        m.Solve()
+    assert not m.isSolved
+    # zero-length member
+    z = Truss(2)
+    for p, s in [((0, 0), SupportType.PIN), ((4, 0), SupportType.PIN), ((2, 3), SupportType.NO), ((2, 3), SupportType.NO)]:
+        z.AddNewJoint(p, s)
+    for a, b in [(0, 2), (1, 2), (2, 3), (0, 3), (1, 3)]:
+        z.AddNewMember(a, b, mt)
+    with pytest.raises(ZeroDivisionError):
+        z.Solve()
+    # a batch reports per system and zero-fills the failures
+    good = Truss(3).LoadFromJSON(f"{H.GOLDEN}/ref_data/bar-6_input_0.json")
+    bad = Truss(3).LoadFromJSON(f"{H.GOLDEN}/ref_data/bar-6_input_0.json")
+    bad.SetSupportType(0, SupportType.NO); bad.SetSupportType(1, SupportType.NO); bad.SetSupportType(3, SupportType.NO)
+    info = SolveBatch([good, bad, good.Copy()], raise_on_error=False)
+    assert info.tolist()[0] == 0 and info[1] != 0 and info[2] == 0
+    assert good.isSolved and not bad.isSolved
+
+
+def test_edge_cases():
+    mt = MemberType(1, 1e7, 1)
+    # every DOF supported: n = 0, reactions are zero, loads on supports are overwritten (truss.py:343,349)
+    t = Truss(3)
+    for p in [(0, 0, 0), (1, 0, 0), (0, 1, 0)]:
+        t.AddNewJoint(p, SupportType.PIN)
+    for a, b in [(0, 1), (1, 2), (0, 2)]:
+        t.AddNewMember(a, b, mt)
+    t.AddExternalForce(1, (5, 5, 5))
+    t.Solve()
+    assert t.GetDisplacements() == {} and t.GetExternalForces() == {} and t.GetInternalForces() == {}
+    # no load at all: everything is zero
+    name, dim, data, gold = H.shipped_cases()[0]
+    data = dict(data); data["force"] = []
+    t = Truss(dim).LoadFromJSON(data=data)
+    t.Solve()
+    assert not np.any(t._dense["u"]) and not np.any(t._dense["axial"])
+
+
+def test_full_size_properties_bar942_x1024():
+    """BASELINE configs[1] at full size: linearity in the load and bitwise determinism."""
+    t = Truss(3).LoadFromJSON(f"{H.GOLDEN}/ref_data/bar-942_input_0.json")
+    rng = np.random.default_rng(0)
+    N = t.nJoint * 3
+    base = rng.uniform(-10, 10, size=(4, N))
+    coef = rng.uniform(-2, 2, size=(1024, 4))
+    F = coef @ base
+    out = SolveLoadCases(t, F)
+    again = SolveLoadCases(t, F)
+    for k in H.FIELDS:
+        assert np.array_equal(out[k], again[k]), k                       # deterministic
+    basis = SolveLoadCases(t, base)
+    mask = t.GetDisplacementUnknownMask()
+    for k in ("u", "axial"):
+        want = coef @ basis[k]
+        assert orc.normwise_err(out[k], want) <= 1e-9, k
+    # equilibrium: reactions + applied loads on free DOFs sum to zero in every direction
+    applied = np.where(mask, F, 0.0)
+    react = np.where(~mask, out["ext"], 0.0)
+    tot = (applied + react).reshape(1024, -1, 3).sum(axis=1)
+    assert np.abs(tot).max() <= 1e-7 * np.abs(applied).sum(axis=1).max()
+
+
+def test_ga_population_8192_properties():
+    """BASELINE configs[2] at full size: batch == its own slices, and a sample against the oracle."""
+    import random
+    random.seed(0)
+    types = [MemberType(i, random.uniform(1e7, 3e7), random.uniform(0.1, 1.0)) for i in range(1, 21)]
+    genes = np.array([random.choices(range(20), k=72) for _ in range(8192)], dtype=np.int32)
+    t = Truss(3).LoadFromJSON(f"{H.GOLDEN}/ref_data/bar-72_input_0.json")
+    out = FitnessBatch(t, genes, types, 30000.0, 10.0)
+    part = FitnessBatch(t, genes[4096:4160], types, 30000.0, 10.0)
+    assert np.array_equal(out["fitness"][4096:4160], part["fitness"])
+    data = json.load(open(f"{H.GOLDEN}/ref_data/bar-72_input_0.json"))
+    joints, support, conn, _, force = orc.arrays_from_json(data, 3)
+    tab = type_table(types)
+    for b in (0, 777, 8191):
+        f, s, d = orc.fitness(3, joints, support, conn, genes[b], tab, force, 30000.0, 10.0)
+        assert abs(out["fitness"][b] - f) <= 1e-9 * abs(f) and tuple(out["flags"][b]) == (s, d)
+
+
+def test_device_pointer_entry_point_matches_host_entry_point():
+    import torch
+    name, dim, data, gold = [c for c in H.shipped_cases() if c[0] == "bar-120_input_0"][0]
+    t = Truss(dim).LoadFromJSON(data=data)
+    xyz, support, conn, aed, force = t._pack()
+    plan = t._get_plan()
+    B = 7
+    host = plan.solve_host(B, xyz, force, aed=aed)
+    dev = torch.device("cuda:0")
+    td = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+    out = {"u": torch.empty(B, plan.N, dtype=torch.float64, device=dev), "ext": torch.empty(B, plan.N, dtype=torch.float64, device=dev),
+           "axial": torch.empty(B, plan.M, dtype=torch.float64, device=dev), "weight": torch.empty(B, dtype=torch.float64, device=dev),
+           "info": torch.empty(B, dtype=torch.int32, device=dev)}
+    plan.solve_device(B, td(xyz), td(force), aed=td(aed), out=out)
+    torch.cuda.synchronize()
+    for k in ("u", "ext", "axial", "weight"):
+        assert np.array_equal(out[k].cpu().numpy(), host[k]), k
+    H.assert_close({k: host[k][0] for k in H.FIELDS} | {"weight": host["weight"][0]}, gold, what=name)
+
+
+def test_fp64_peaks_are_measurable():
+    for which in (0, 1):
+        tf, ms = _lib.fp64_peak(which, 1024)
+        assert tf > 1.0 and ms > 0

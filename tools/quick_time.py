@@ -1,0 +1,60 @@
+"""Quick device-resident timings of the main configs (development aid, not the bench)."""
+import json, os, sys, time
+import numpy as np
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from python_stable_3d_truss_analysis_b200 import _lib
+from python_stable_3d_truss_analysis_b200.truss import Truss
+from python_stable_3d_truss_analysis_b200.batch import type_table
+from python_stable_3d_truss_analysis_b200.type import MemberType
+
+dev = torch.device("cuda:0")
+td = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+def timeit(fn, n=5, warm=2):
+    for _ in range(warm): fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(n):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return min(ts), sorted(ts)[len(ts)//2]
+
+for which, name in ((0, "DFMA"), (1, "DMMA m8n8k4"), (2, "DMMA m16n8k8")):
+    tf, ms = _lib.fp64_peak(which, 8192)
+    print(f"FP64 peak {name}: {tf:.2f} TFLOP/s ({ms:.3f} ms)")
+
+G = os.path.join(ROOT, "tests", "golden", "ref_data")
+# config 2: bar-942 x B load cases (independent K per system)
+t = Truss(3).LoadFromJSON(os.path.join(G, "bar-942_input_0.json"))
+xyz, sup, conn, aed, force = t._pack()
+plan = t._get_plan()
+for B in (148, 1024):
+    rng = np.random.default_rng(0)
+    F = td(rng.uniform(-10, 10, size=(B, plan.N)))
+    out = {k: torch.empty(B, plan.N if k in ("u", "ext") else plan.M, dtype=torch.float64, device=dev) for k in ("u", "ext", "axial")}
+    out["weight"] = torch.empty(B, dtype=torch.float64, device=dev); out["info"] = torch.empty(B, dtype=torch.int32, device=dev)
+    dx, da = td(xyz), td(aed)
+    best, med = timeit(lambda: plan.solve_device(B, dx, F, aed=da, out=out))
+    fl = B * (696**3 / 3 + 2 * 696**2)
+    print(f"bar-942 x{B}: best {best:.3f} ms  median {med:.3f} ms  -> {B/best*1e3:.0f} trusses/s, {fl/best/1e9:.2f} TFLOP/s potrf-equivalent; info any={bool(out['info'].any())}")
+
+# config 3: bar-72 x 8192 genes fitness
+import random
+random.seed(0)
+types = [MemberType(i, random.uniform(1e7, 3e7), random.uniform(0.1, 1.0)) for i in range(1, 21)]
+genes = np.array([random.choices(range(20), k=72) for _ in range(8192)], dtype=np.int32)
+t = Truss(3).LoadFromJSON(os.path.join(G, "bar-72_input_0.json"))
+xyz, sup, conn, aed, force = t._pack()
+plan = t._get_plan()
+B = 8192
+o = {"fitness": torch.empty(B, dtype=torch.float64, device=dev), "flags": torch.empty(B, 2, dtype=torch.uint8, device=dev), "info": torch.empty(B, dtype=torch.int32, device=dev)}
+dx, df, dg, dt = td(xyz), td(force), td(genes), td(type_table(types))
+best, med = timeit(lambda: plan.fitness_device(B, dx, df, dg, dt, 30000.0, 10.0, o), n=10)
+print(f"bar-72 GA x{B}: best {best:.3f} ms median {med:.3f} ms -> {B/best*1e3:.0f} fitness/s")
+for path in (1,):
+    plan.set_path(path)
+    best, med = timeit(lambda: plan.fitness_device(B, dx, df, dg, dt, 30000.0, 10.0, o), n=5)
+    print(f"bar-72 GA x{B} (blocked path): best {best:.3f} ms -> {B/best*1e3:.0f} fitness/s")
