@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: FP64 trusses solved / second through the batched Truss.Solve.
+
+    python bench.py --gpus N --steps K --warmup W            # the CUDA path (one rank per GPU under torchrun for N > 1)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host cores (oracle port)
+
+Workload (BASELINE.json configs[1]): the bar-942 truss (tests/golden/ref_data/bar-942_input_0.json) under a batch of
+1024 synthetic load cases per GPU (SURVEY.md section 8d recipe: the fixture's loaded joints, components ~ U(-10,10),
+default_rng(0)).  Every load case is solved as an independent Truss.Solve(): member geometry, assembly of K_ff, dense
+blocked Cholesky, forward/back substitution, recovery of axial forces and reactions -- nothing is shared or skipped
+between the systems of a batch (the factor-once / 1024-right-hand-sides shortcut is NOT what is timed here).
+
+One JSON line on stdout (rank 0).  `value` = systems of all ranks / device time (inputs resident in HBM);
+`e2e` = same metric through the C ABI's host entry point (tb_solve_host) with pinned host buffers, H2D + D2H inside the
+timed region; `roofline` = the dominant kernel (k_chol) against the FP64 tensor (DMMA) peak measured in this run;
+`cpu_baseline` = the oracle port of the reference (numpy, per-member Python loops + LAPACK) on this box's cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FIXTURE = os.path.join(ROOT, "tests", "golden", "ref_data", "bar-942_input_0.json")
+BATCH_PER_GPU = 1024
+METRIC = "FP64 trusses solved/sec (batched Truss.Solve)"
+UNIT = "trusses/s"
+WORKLOAD = "bar-942 (n=696 free DOF, 942 members) x 1024 independent load-case solves per GPU, FP64"
+
+
+def load_cases(n_case: int, seed: int = 0):
+    """keep the fixture's loaded joints, components ~ U(-10,10)."""
+    data = json.load(open(FIXTURE))
+    loaded = sorted(j for j, v in data["force"] if any(abs(float(x)) >= 1e-10 for x in v))
+    rng = np.random.default_rng(seed)
+    nj = len(data["joint"])
+    F = np.zeros((n_case, nj, 3))
+    F[:, loaded, :] = rng.uniform(-10.0, 10.0, size=(n_case, len(loaded), 3))
+    return data, F.reshape(n_case, nj * 3)
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def _cpu_worker(args):
+    os.environ["OPENBLAS_NUM_THREADS"] = "1"
+    from oracle import truss_oracle as orc
+    dim, arrs, Fs = args
+    joints, support, conn, aed = arrs
+    out = 0.0
+    for f in Fs:
+        r = orc.solve(dim, joints, support, conn, aed, f)
+        out += float(r["u"][0])
+    return out
+
+
+def cpu_port_throughput(n_solve_per_core: int = 6):
+    """Oracle port (reference algorithm: per-member Python loops + LAPACK dgesv) on all host cores."""
+    import multiprocessing as mp
+    from oracle import truss_oracle as orc
+
+    data, F = load_cases(64)
+    joints, support, conn, aed, _ = orc.arrays_from_json(data, 3)
+    cores = len(os.sched_getaffinity(0))
+    # serial figure first (what one Truss.Solve() loop gives a user today)
+    t0 = time.perf_counter()
+    orc.solve(3, joints, support, conn, aed, F[0])
+    warm = time.perf_counter() - t0
+    n_serial = max(3, min(12, int(3.0 / max(warm, 1e-3))))
+    t0 = time.perf_counter()
+    for i in range(n_serial):
+        orc.solve(3, joints, support, conn, aed, F[i % 64])
+    serial = n_serial / (time.perf_counter() - t0)
+    # all cores: one process per core, OPENBLAS_NUM_THREADS=1
+    per = n_solve_per_core
+    jobs = [(3, (joints, support, conn, aed), [F[(c * per + i) % 64] for i in range(per)]) for c in range(cores)]
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        pool.map(_cpu_worker, [(3, (joints, support, conn, aed), [F[0]])] * cores)   # warm the workers
+        t0 = time.perf_counter()
+        pool.map(_cpu_worker, jobs)
+        dt = time.perf_counter() - t0
+    return {"value": cores * per / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{cores * per} of the 1024 bar-942 load cases, {cores} processes x {per} solves, "
+                      f"OPENBLAS_NUM_THREADS=1 (oracle/truss_oracle.py: solve)",
+            "serial_value": serial, "serial_sample": f"{n_serial} solves on one core, OpenBLAS default threads"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals = []
+    for _ in range(max(1, args.warmup)):
+        cpu_port_throughput(2)
+    base = None
+    for _ in range(max(1, args.steps)):
+        base = cpu_port_throughput(6)
+        vals.append(base["value"])
+    v = float(np.mean(vals))
+    base["value"] = v
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * BATCH_PER_GPU * args.gpus / v, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH_PER_GPU,
+                       "note": "reference algorithm (oracle port) on the host cores; each step is a bounded sample"},
+            "cpu_baseline": base,
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu), "-f", self.path],
+                                         stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        try:
+            rows = [r.split(",") for r in open(self.path).read().strip().splitlines() if r.strip()]
+            sm = [float(r[1]) for r in rows]
+            pw = [float(r[3]) for r in rows]
+            busy = [s for s, p in zip(sm, pw) if p >= 0.5 * max(pw)] or sm
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            reasons = sorted({n for r in rows for n, v in zip(names, r[5:9]) if v.strip().lower().startswith("active")})
+            out = {"sm_mhz": float(np.median(busy)), "sm_max_mhz": float(rows[0][2]), "reasons": reasons,
+                   "samples": len(rows), "power_w_max": max(pw)}
+        except Exception as exc:  # keep the bench line even if nvidia-smi misbehaves
+            out["error"] = str(exc)
+        finally:
+            try:
+                os.unlink(self.path)
+            except OSError:
+                pass
+        return out
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    from python_stable_3d_truss_analysis_b200 import _lib
+    from python_stable_3d_truss_analysis_b200.truss import Truss
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    B = BATCH_PER_GPU
+    data, F_all = load_cases(B * world)
+    F = F_all[rank * B:(rank + 1) * B]                      # contiguous block partition
+    truss = Truss(3).LoadFromJSON(data=data)
+    xyz, support, conn, aed, _ = truss._pack()
+    plan = truss._get_plan(support, conn)
+    N, M, n = plan.N, plan.M, plan.n
+
+    td = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+    d_xyz, d_aed, d_F = td(xyz), td(aed), td(F)
+    out = {"u": torch.empty(B, N, dtype=torch.float64, device=dev), "ext": torch.empty(B, N, dtype=torch.float64, device=dev),
+           "axial": torch.empty(B, M, dtype=torch.float64, device=dev), "weight": torch.empty(B, dtype=torch.float64, device=dev),
+           "info": torch.empty(B, dtype=torch.int32, device=dev)}
+    gathered = None
+    if world > 1:   # results go back to rank 0 over NCCL (north_star: gather only)
+        packed = torch.empty(B, 2 * N + M, dtype=torch.float64, device=dev)
+        gathered = [torch.empty_like(packed) for _ in range(world)] if rank == 0 else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
+    stream = torch.cuda.current_stream()
+
+    def step():
+        plan.solve_device(B, d_xyz, d_F, aed=d_aed, out=out, stream=stream)
+        if world > 1:
+            torch.cat([out["u"], out["ext"], out["axial"]], dim=1, out=packed)
+            dist.gather(packed, gathered, dst=0)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
+    assert not bool(out["info"].any().item()), "a system failed to factorise"
+
+    # ---- parity gate on the timed batch (oracle = checker only): 2 sampled systems, 1e-9 norm-wise
+    if rank == 0:
+        from oracle import truss_oracle as orc
+        joints, sup_o, conn_o, aed_o, _ = orc.arrays_from_json(data, 3)
+        for b in (0, B - 1):
+            want = orc.solve_closed_form(3, joints, sup_o, conn_o, aed_o, F[b])
+            for k in ("u", "ext", "axial"):
+                err = orc.normwise_err(out[k][b].cpu().numpy(), want[k])
+                assert err <= 1e-9, f"parity gate failed: system {b} field {k} err {err:.3e}"
+
+    # ---- timed region: K steps, each timed on the device; L2 flushed between steps (outside the events)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    _lib.profile_enable(True)
+    _lib.profile_read()
+    launches0 = _lib.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    wall0 = time.perf_counter()
+    for e0, e1 in ev:
+        flush.zero_()
+        e0.record(stream)
+        step()
+        e1.record(stream)
+    barrier()
+    wall = time.perf_counter() - wall0
+    launches = _lib.launch_count() - launches0
+    prof = _lib.profile_read()
+    _lib.profile_enable(False)
+    dev_ms = sum(e0.elapsed_time(e1) for e0, e1 in ev)
+    t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms = float(t.item())
+    ms_per_step = dev_ms / args.steps
+    value = B * world / (ms_per_step * 1e-3)
+
+    # ---- end to end through the C ABI host entry point: pinned host buffers, H2D + D2H inside the timed region
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()  # noqa: E731
+    h_xyz, h_aed, h_F = pin(xyz), pin(aed), pin(F)
+    h_out = {"u": pin(np.empty((B, N))), "ext": pin(np.empty((B, N))), "axial": pin(np.empty((B, M))),
+             "weight": pin(np.empty(B)), "info": torch.empty(B, dtype=torch.int32).pin_memory().numpy()}
+    for _ in range(2):
+        plan.solve_host(B, h_xyz, h_F, aed=h_aed, out=h_out)
+    barrier()
+    e2e_steps = max(3, min(args.steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        plan.solve_host(B, h_xyz, h_F, aed=h_aed, out=h_out)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = B * world * e2e_steps / float(t.item())
+    assert np.array_equal(h_out["u"], out["u"].cpu().numpy()), "host and device entry points disagree"
+    h2d = int(h_xyz.nbytes + h_aed.nbytes + h_F.nbytes)
+    d2h = int(sum(v.nbytes for v in h_out.values()))
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (k_chol) against the FP64 tensor peak measured on this GPU
+    peak_dmma, _ = _lib.fp64_peak(1, 8192)
+    peak_dfma, _ = _lib.fp64_peak(0, 8192)
+    chol_ms, chol_n = prof["chol"]
+    flops_per_system = n ** 3 / 3.0 + n ** 2 / 2.0 + n / 6.0 + 2.0 * n * n        # potrf + two triangular solves
+    achieved = B * flops_per_system / (chol_ms / max(chol_n, 1) * 1e-3) / 1e12
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("k_chol_dram_bytes_per_launch")
+    kernels = {k: {"ms_per_step": v[0] / args.steps, "launches": v[1]} for k, v in prof.items() if v[1]}
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    ntiles = (plan.info.n_pad // 64) * (plan.info.n_pad // 64 + 1) // 2
+    asm_bytes = B * (ntiles * 32768 + M * (2 + 3) * 8 + plan.info.n_pad * 8)
+    asm_ms = prof["assemble"][0] / max(prof["assemble"][1], 1)
+    if prof["assemble"][1]:
+        asm_gbs = asm_bytes / (asm_ms * 1e-3) / 1e9
+        roof_asm = {"kernel": "k_assemble", "bound": "hbm", "achieved": asm_gbs, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": asm_gbs / hbm_peak, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650"}
+    else:
+        roof_asm = {"kernel": "(none)", "note": "assembly is fused into k_chol: K_ff tiles are built in shared memory from "
+                    "the scatter map and never exist in HBM; run with TB_UNFUSED_ASSEMBLY=1 for the standalone kernel"}
+
+    cpu = cpu_port_throughput(6)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "batch_per_gpu": B, "n_free": n, "n_member": M, "mode": "independent K per system",
+                   "l2": "per-step working set (2.2 GB of factor tiles) >> 126 MB L2, plus an explicit 256 MB flush between steps",
+                   "multi_gpu": "contiguous block partition of the batch, NCCL gather of u/ext/axial to rank 0 inside the step"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "api": "tb_solve_host (C ABI) with pinned host buffers", "steps": e2e_steps},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"kernel": "k_chol (tiled left-looking Cholesky + forward/back substitution)", "bound": "tensor",
+                     "achieved": achieved, "peak": peak_dmma, "unit": "TFLOP/s", "frac": achieved / peak_dmma,
+                     "traffic": traffic, "flops_per_system": flops_per_system,
+                     "peak_source": "FP64 DMMA m8n8k4 microbenchmark (tb_fp64_peak) measured in this run; "
+                                    "MEASURED_PEAKS.json has no FP64 entry", "peak_dfma": peak_dfma,
+                     "share_of_step": chol_ms / dev_ms},
+        "roofline_assemble": roof_asm,
+        "kernels": kernels,
+        "cpu_baseline": cpu,
+        "wall_s_timed_region": wall,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

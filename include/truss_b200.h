@@ -189,6 +189,13 @@ int tb_small_path_limits(int32_t* max_dof, int32_t* max_member);
  * entry): which = 0 DFMA (vector), 1 DMMA m8n8k4 (tensor).  Returns TFLOP/s in *tflops. */
 int tb_fp64_peak(int32_t which, int32_t iters, double* tflops, float* ms);
 
+/* Optional per-kernel CUDA-event timing on the launching stream (bench.py's roofline line).
+ * tb_profile_read adds the milliseconds / launch counts recorded since the last read into
+ * ms[8] / count[8]; slots: 0 member geometry, 1 assembly, 2 blocked Cholesky+solve, 3 recovery,
+ * 4 fused shared-memory kernel. */
+int tb_profile_enable(int32_t on);
+int tb_profile_read(float* ms, int64_t* count);
+
 /* Kernel launches issued by this library since load (bench.py's gpu_launches). */
 int64_t tb_launch_count(void);
 const char* tb_strerror(int code);

@@ -89,7 +89,7 @@ class TbRaggedIn(C.Structure):
 
 EXPORTS = ["tb_plan_create", "tb_plan_destroy", "tb_plan_query", "tb_plan_set_path", "tb_plan_get_maps",
            "tb_plan_get_scatter", "tb_solve", "tb_solve_host", "tb_fitness", "tb_fitness_host", "tb_solve_ragged",
-           "tb_solve_ragged_host", "tb_pinned_alloc", "tb_pinned_free", "tb_small_path_limits", "tb_fp64_peak",
+           "tb_solve_ragged_host", "tb_pinned_alloc", "tb_pinned_free", "tb_small_path_limits", "tb_fp64_peak", "tb_profile_enable", "tb_profile_read",
            "tb_launch_count", "tb_strerror", "tb_version"]
 
 _lib = None
@@ -123,6 +123,8 @@ def lib():
     L.tb_pinned_free.argtypes = [vp]
     L.tb_small_path_limits.argtypes = [C.POINTER(i32), C.POINTER(i32)]
     L.tb_fp64_peak.argtypes = [i32, i32, C.POINTER(dbl), C.POINTER(C.c_float)]
+    L.tb_profile_enable.argtypes = [i32]
+    L.tb_profile_read.argtypes = [vp, vp]
     L.tb_launch_count.restype = i64
     L.tb_strerror.argtypes = [C.c_int]
     L.tb_strerror.restype = C.c_char_p
@@ -185,6 +187,21 @@ def fp64_peak(which: int, iters: int = 4096):
     t, ms = C.c_double(), C.c_float()
     check(lib().tb_fp64_peak(which, iters, C.byref(t), C.byref(ms)))
     return t.value, ms.value
+
+
+PROFILE_SLOTS = ("geom", "assemble", "chol", "recover", "small")
+
+
+def profile_enable(on: bool):
+    check(lib().tb_profile_enable(1 if on else 0))
+
+
+def profile_read():
+    """{slot: (total_ms, launches)} recorded since the last read."""
+    ms = np.zeros(8, np.float32)
+    cnt = np.zeros(8, np.int64)
+    check(lib().tb_profile_read(ms.ctypes.data, cnt.ctypes.data))
+    return {name: (float(ms[i]), int(cnt[i])) for i, name in enumerate(PROFILE_SLOTS)}
 
 
 def launch_count() -> int:

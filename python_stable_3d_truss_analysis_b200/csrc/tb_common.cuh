@@ -27,6 +27,12 @@ constexpr int TB_SMALL_MAX_JOINT = 80;
 extern std::atomic<int64_t> g_tb_launches;
 inline void tb_count_launch(int n = 1) { g_tb_launches.fetch_add(n, std::memory_order_relaxed); }
 
+// optional per-kernel CUDA-event timing (bench.py's roofline line); slots:
+enum : int { TB_PROF_GEOM = 0, TB_PROF_ASSEMBLE = 1, TB_PROF_CHOL = 2, TB_PROF_RECOVER = 3, TB_PROF_SMALL = 4, TB_PROF_SLOTS = 8 };
+bool tb_prof_on();
+void tb_prof_begin(int slot, cudaStream_t st);
+void tb_prof_end(int slot, cudaStream_t st);
+
 #define TB_CUDA(expr)                         \
   do {                                        \
     cudaError_t _e = (expr);                  \

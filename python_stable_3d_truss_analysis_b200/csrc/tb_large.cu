@@ -13,6 +13,7 @@
 // mma.m8n8k4 is 32 consecutive doubles, so a warp's operand load is one conflict-free 256 B
 // shared-memory read, and a 64-row x 32-k half tile is one contiguous 16 KB chunk in HBM.
 #include <math.h>
+#include <stdlib.h>
 
 #include "tb_common.cuh"
 
@@ -156,15 +157,24 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// shared-memory carve of k_chol (bytes)
+// shared-memory carve of k_chol (doubles)
 constexpr int STAGE_DOUBLES = 2 * HALF + 32;          // A half tile, B half tile, 32 y values
-constexpr int SM_STAGE = 2 * STAGE_DOUBLES;           // two stages
-constexpr int SCR_LD = 67;                             // potrf scratch: 66 rows, column-major
-constexpr int SM_W = TB_TILE_ELEMS;                    // W = inv(L_jj), fragment-major
-constexpr int SM_MISC = 4 * T + 8;                     // rhs acc [64], u block [64], rinv [64], diag [64]
-constexpr int CHOL_SMEM_BYTES = (SM_STAGE + SM_W + SM_MISC) * 8;
-static_assert(SCR_LD * T <= SM_STAGE, "potrf scratch must fit in the stage buffers");
+constexpr int SM_STAGE = 2 * STAGE_DOUBLES;           // two stages (aliased: C staging tile, small scratches)
+constexpr int SCR_LD = 67;                             // back-substitution scratch: column-major 64 x 64
+constexpr int SM_LJJ = TB_TILE_ELEMS;                  // L(j,j), fragment-major
+constexpr int SM_WD = 4 * 256;                         // the four 16x16 inverse diagonal blocks of L(j,j)
+constexpr int SM_MISC = 4 * T + 48;                    // rhs acc, u block, y block, rhs vector, diag16, flag
+constexpr int CHOL_SMEM_BYTES = (SM_STAGE + SM_LJJ + SM_WD + SM_MISC) * 8;
+constexpr int BASE_LD = 33;                            // 16x16 base-case scratch: 32 rows (L | Z), column-major
+static_assert(SCR_LD * T <= SM_STAGE, "back-substitution scratch must fit in the stage buffers");
 static_assert(TB_TILE_ELEMS <= SM_STAGE, "C staging tile must fit in the stage buffers");
+
+// offset of the 32-double operand fragment (8-row block `blk`, k-slab kS in 0..15) inside a tile
+__device__ __forceinline__ int frag_off(int blk, int kS) { return ((((kS >> 3) << 3) + blk) << 8) + ((kS & 7) << 5); }
+// offset of this lane's accumulator pair (row 8*mb + lane/4, cols 8*nb + 2*(lane%4) + {0,1})
+__device__ __forceinline__ int cfrag_off(int mb, int nb, int lane) {
+  return frag_off(mb, 2 * nb + ((lane & 3) >> 1)) + ((lane >> 2) << 2) + ((lane & 1) << 1);
+}
 
 struct Frag {
   double c[2][4][2];  // [m-block][n-block][2]
@@ -225,18 +235,48 @@ __device__ __forceinline__ void gemm_stream(const double* __restrict__ Lsys, con
   }
 }
 
-__device__ __forceinline__ int zrow(int r) { return r == 0 ? 64 : r - 1; }
 
+// K_ff entry e of the plan's scatter map: sum of k * (+-(c_i c_j)) over its members, ascending
+// member order (truss.py:65-86 values, truss.py:310 order).
+__device__ __forceinline__ double entry_value(const LargeArgs& a, const double* __restrict__ mk,
+                                              const double* __restrict__ mc, int e) {
+  const int d = a.dim, d2 = 2 * d;
+  double v = 0.0;
+  for (int64_t p = a.ent_ptr[e]; p < a.ent_ptr[e + 1]; ++p) {
+    const int m = a.ctr_member[p], loc = a.ctr_local[p];
+    const int la = loc / d2, lb = loc - la * d2;
+    const int A = la >= d, i = la - A * d, B = lb >= d, j = lb - B * d;
+    double pr = __dmul_rn(mc[m * d + i], mc[m * d + j]);
+    if (A != B) pr = -pr;
+    v = __dadd_rn(v, __dmul_rn(mk[m], pr));
+  }
+  return v;
+}
+
+// FUSED: K_ff tiles are assembled straight into shared memory from the scatter map when the
+// factorisation first touches them (K never exists in HBM); otherwise they are read from the
+// tile storage k_assemble filled.
+//
+// Per block column j:  (1) diagonal tile: C = A(j,j) - sum_k L(j,k) L(j,k)^T by DMMA, then factor it
+// in shared memory, left-looking over four 16-column sub-panels (DMMA updates; the 16x16 diagonal
+// blocks and their inverses by one warp); (2) every tile below: C = A(i,j) - sum_k L(i,k) L(j,k)^T,
+// then X L(j,j)^T = C solved per 8-row block entirely inside one warp using the 16x16 inverses.
+template <bool FUSED>
 __global__ void __launch_bounds__(CH_THREADS, 2) k_chol(const LargeArgs a) {
   extern __shared__ __align__(16) double sm[];
-  double* sStage = sm;                 // stage buffers | potrf scratch | C staging tile
-  double* sScr = sm;                   // alias
-  double* sC = sm;                     // alias
-  double* sW = sm + SM_STAGE;
-  double* sRhs = sW + SM_W;            // [64] L(j,:) y accumulations
+  double* sStage = sm;                 // stage buffers | C staging tile | small scratches
+  double* sScr = sm;                   // alias (back substitution)
+  double* sC = sm;                     // alias (panel tiles)
+  double* sBase = sm;                  // alias (16x16 base case)
+  double* sLjj = sm + SM_STAGE;
+  double* sWd = sLjj + SM_LJJ;
+  double* sRhs = sWd + SM_WD;          // [64] L(j,:) y accumulations
   double* sUb = sRhs + T;              // [64] one block of u during back substitution
-  double* sRinv = sUb + T;             // [64]
-  double* sDiag = sRinv + T;           // [64] L_kk of the block being factorised
+  double* sY = sUb + T;                // [64] y_j
+  double* sRv = sY + T;                // [64] rhs of the block
+  double* sDiag16 = sRv + T;           // [16]
+  double* sT16 = sDiag16 + 16;         // [16]
+  int* sFlag = (int*)(sT16 + 16);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wm = warp >> 1, wn = warp & 1;
   const int nt = a.nt;
@@ -245,8 +285,12 @@ __global__ void __launch_bounds__(CH_THREADS, 2) k_chol(const LargeArgs a) {
   for (int b = blockIdx.x; b < a.batch; b += gridDim.x) {
     double* Lsys = a.L + (int64_t)b * ntiles * TB_TILE_ELEMS;
     double* ysys = a.y + (int64_t)b * a.n_pad;
+    const double* mk = a.mk + (int64_t)b * a.M;
+    const double* mc = a.mc + (int64_t)b * a.M * a.dim;
+    const double* fsys = a.force + b * a.force_stride;
     if (a.status[b] != 0) continue;  // input problem flagged by k_geom (uniform per CTA)
     int fail = 0;
+    if (tid == 0) *sFlag = 0;
 
     for (int j = 0; j < nt && !fail; ++j) {
       // ================= diagonal tile: C = A(j,j) - sum_k L(j,k) L(j,k)^T =================
@@ -266,72 +310,128 @@ __global__ void __launch_bounds__(CH_THREADS, 2) k_chol(const LargeArgs a) {
           if ((lane & 3) == 0) sRhs[(2 * wm + mb) * 8 + (lane >> 2)] = v;
         }
       }
-      // scratch rows: L row i -> row i (cols 0..i); Z row r -> row zrow(r) (cols r..63); rhs -> row 65
       {
         const double* At = Lsys + tb_tile_index(j, j) * TB_TILE_ELEMS;
 #pragma unroll
         for (int mb = 0; mb < 2; ++mb)
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const int r = (2 * wm + mb) * 8 + (lane >> 2);
-            const int c = (4 * wn + q) * 8 + 2 * (lane & 3);
-            const double2 av = *reinterpret_cast<const double2*>(At + tb_tile_off(r, c));
-            if (c <= r) sScr[r + c * SCR_LD] = av.x - acc.c[mb][q][0];
-            if (c + 1 <= r) sScr[r + (c + 1) * SCR_LD] = av.y - acc.c[mb][q][1];
+            const int off = cfrag_off(2 * wm + mb, 4 * wn + q, lane);
+            double2 av = make_double2(0.0, 0.0);
+            if (!FUSED) av = *reinterpret_cast<const double2*>(At + off);
+            *reinterpret_cast<double2*>(sLjj + off) = make_double2(av.x - acc.c[mb][q][0], av.y - acc.c[mb][q][1]);
           }
-      }
-      __syncthreads();  // sRhs + lower part of C are in place
-      if (tid < T) {
-        const int r = tid;
-        for (int c = r; c < T; ++c) sScr[zrow(r) + c * SCR_LD] = (c == r) ? 1.0 : 0.0;
-        sScr[65 + r * SCR_LD] = ysys[j * T + r] - sRhs[r];
       }
       __syncthreads();
+      if (tid < T) {
+        const int r = tid, row = j * T + r;
+        if (FUSED) {
+          sRv[r] = (row < a.n ? fsys[a.free_idx[row]] : 0.0) - sRhs[r];
+          if (row >= a.n) sLjj[tb_tile_off(r, r)] += 1.0;  // identity on the padded diagonal
+        } else {
+          sRv[r] = ysys[row] - sRhs[r];
+        }
+      }
+      if (FUSED) {  // scatter-map entries of tile (j,j): one thread per structural non-zero
+        const int64_t t = tb_tile_index(j, j);
+        for (int64_t q = a.tile_ent_ptr[t] + tid; q < a.tile_ent_ptr[t + 1]; q += CH_THREADS) {
+          const int e = a.tile_ent[q];
+          sLjj[tb_tile_off(a.ent_row[e] - j * T, a.ent_col[e] - j * T)] += entry_value(a, mk, mc, e);
+        }
+      }
 
-      // ---- potrf of the 64x64 block with L^{-1} (as extra rows: Z = L^{-T}) and the rhs riding along
-      {
-        const bool isL = tid < T, isZ = (tid >= T && tid < 2 * T), isR = (tid == 2 * T);
-        const int zr = tid - T;
-        const int myrow = isL ? tid : (isZ ? zrow(zr) : 65);
-        const int p0 = isZ ? zr : 0;  // first column with data in my row
-        for (int k = 0; k < T; ++k) {
-          const bool act = isL ? (tid >= k) : (isZ ? (zr <= k) : isR);
-          const double* rowk = sScr + k;
-          const double* rowi = sScr + (act ? myrow : k);
-          double d0 = rowk[k * SCR_LD], d1 = 0.0;
-          double s0 = rowi[k * SCR_LD], s1 = 0.0;
-          int p = 0;
-          for (; p + 1 < k; p += 2) {
-            const double b0 = rowk[p * SCR_LD], b1 = rowk[(p + 1) * SCR_LD];
-            const double a0 = (p >= p0) ? rowi[p * SCR_LD] : 0.0;
-            const double a1 = (p + 1 >= p0) ? rowi[(p + 1) * SCR_LD] : 0.0;
-            d0 = fma(-b0, b0, d0);
-            d1 = fma(-b1, b1, d1);
-            s0 = fma(-a0, b0, s0);
-            s1 = fma(-a1, b1, s1);
+      // ---- factor the tile in place: four 16-column sub-panels, left-looking
+      for (int sb = 0; sb < 4; ++sb) {
+        __syncthreads();
+        if (sb > 0 && warp >= 2 * sb) {  // P(mb, sub-panel) -= L(mb, 0:16sb) L(sub-panel rows, 0:16sb)^T
+          double c2[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+          for (int kS = 0; kS < 4 * sb; ++kS) {
+            const double av = sLjj[frag_off(warp, kS) + lane];
+#pragma unroll
+            for (int nbp = 0; nbp < 2; ++nbp) dmma(c2[nbp][0], c2[nbp][1], av, sLjj[frag_off(2 * sb + nbp, kS) + lane]);
           }
-          if (p < k) {
-            const double b0 = rowk[p * SCR_LD];
-            const double a0 = (p >= p0) ? rowi[p * SCR_LD] : 0.0;
-            d0 = fma(-b0, b0, d0);
-            s0 = fma(-a0, b0, s0);
+#pragma unroll
+          for (int nbp = 0; nbp < 2; ++nbp) {
+            double2* pv = reinterpret_cast<double2*>(sLjj + cfrag_off(warp, 2 * sb + nbp, lane));
+            double2 v = *pv;
+            v.x -= c2[nbp][0];
+            v.y -= c2[nbp][1];
+            *pv = v;
           }
-          const double d = d0 + d1, s = s0 + s1;
-          if (!(d > 0.0)) {
-            fail = j * T + k + 1;
-            break;
+        }
+        __syncthreads();
+        if (warp == 0) {
+          // 16x16 diagonal block: lanes 0-15 own the rows of L, lanes 16-31 the rows of Z = L^{-T}
+          const int base = 16 * sb;
+          {
+            const int r = lane & 15;
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+              double v;
+              if (lane < 16) v = (c <= r) ? sLjj[tb_tile_off(base + r, base + c)] : 0.0;
+              else v = (c == r) ? 1.0 : 0.0;
+              sBase[lane + c * BASE_LD] = v;
+            }
           }
-          const double lkk = sqrt(d);
-          const double rinv = 1.0 / lkk;
-          // the diagonal goes to sDiag: S[k][k] may still be read as the pivot seed by slower warps
-          if (isL && tid == k) sDiag[k] = lkk;
-          else if (act) sScr[myrow + k * SCR_LD] = s * rinv;
-          __syncthreads();
+          __syncwarp();
+          int bad = 0;
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            const bool act = lane < 16 ? (lane >= k) : (lane - 16 <= k);
+            double d0 = sBase[k + k * BASE_LD], d1 = 0.0, s0 = sBase[lane + k * BASE_LD], s1 = 0.0;
+#pragma unroll
+            for (int p = 0; p < k; ++p) {
+              const double bk = sBase[k + p * BASE_LD], ai = sBase[lane + p * BASE_LD];
+              if (p & 1) { d1 = fma(-bk, bk, d1); s1 = fma(-ai, bk, s1); }
+              else       { d0 = fma(-bk, bk, d0); s0 = fma(-ai, bk, s0); }
+            }
+            const double d = d0 + d1, sv = s0 + s1;
+            if (!(d > 0.0) && !bad) bad = j * T + base + k + 1;
+            const double rinv = rsqrt(bad ? 1.0 : d);
+            if (lane == k) sDiag16[k] = d * rinv;          // the seed S[k][k] stays untouched (read by all lanes)
+            else if (act) sBase[lane + k * BASE_LD] = sv * rinv;
+            __syncwarp();
+          }
+          if (bad) {
+            if (lane == 0) *sFlag = bad;
+          } else {
+            if (lane < 16) {  // L back into the tile (upper part of the block zeroed)
+              const int r = lane;
+#pragma unroll
+              for (int c = 0; c < 16; ++c)
+                sLjj[tb_tile_off(base + r, base + c)] = (c < r) ? sBase[r + c * BASE_LD] : (c == r ? sDiag16[r] : 0.0);
+            }
+            // W = L^{-1} of the block as a DMMA B operand: W[c'][kk] = Z[kk][c'] (kk <= c'), else 0
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const int idx = lane + 32 * q;
+              const int l = idx & 31, slot = idx >> 5;           // slot = nbp*4 + ks
+              const int cp = (slot >> 2) * 8 + (l >> 2), kk = (slot & 3) * 4 + (l & 3);
+              sWd[sb * 256 + idx] = (kk <= cp) ? sBase[(16 + kk) + cp * BASE_LD] : 0.0;
+            }
+          }
+        }
+        __syncthreads();
+        fail = *sFlag;
+        if (fail) break;  // uniform
+        if (warp >= 2 * sb + 2) {  // rows below the block: X = P W^T, in place
+          double a4[4];
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) a4[ks] = sLjj[frag_off(warp, 4 * sb + ks) + lane];
+          __syncwarp();
+#pragma unroll
+          for (int nbp = 0; nbp < 2; ++nbp) {
+            double x0 = 0.0, x1 = 0.0;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) dmma(x0, x1, a4[ks], sWd[sb * 256 + (nbp * 4 + ks) * 32 + lane]);
+            *reinterpret_cast<double2*>(sLjj + cfrag_off(warp, 2 * sb + nbp, lane)) = make_double2(x0, x1);
+          }
         }
       }
       if (fail) break;  // uniform
+      __syncthreads();
 
-      // ---- publish: L(j,j) -> HBM, W = L(j,j)^{-1} -> shared (both fragment-major), y_j -> HBM
+      // ---- publish L(j,j) (strictly-upper part zeroed) and solve L(j,j) y_j = rhs with the 16x16 inverses
       {
         double* Lt = Lsys + tb_tile_index(j, j) * TB_TILE_ELEMS;
 #pragma unroll 4
@@ -340,11 +440,27 @@ __global__ void __launch_bounds__(CH_THREADS, 2) k_chol(const LargeArgs a) {
           const int l = idx & 31, slot = idx >> 5;
           const int ks = slot & 7, rb = (slot >> 3) & 7, h = slot >> 6;
           const int r = rb * 8 + (l >> 2), c = h * 32 + ks * 4 + (l & 3);
-          Lt[idx] = (c < r) ? sScr[r + c * SCR_LD] : (c == r ? sDiag[r] : 0.0);
-          // W[r][c] = Z[c][r] for r >= c
-          sW[idx] = (r >= c) ? sScr[zrow(c) + r * SCR_LD] : 0.0;
+          Lt[idx] = (c <= r) ? sLjj[idx] : 0.0;
         }
-        if (tid < T) ysys[j * T + tid] = sScr[65 + tid * SCR_LD];
+      }
+      if (warp == 0) {
+        const int c = lane & 15, hh = lane >> 4;
+        for (int sb = 0; sb < 4; ++sb) {
+          double t = 0.0;
+          for (int kk = hh; kk < 16 * sb; kk += 2) t = fma(sLjj[tb_tile_off(16 * sb + c, kk)], sY[kk], t);
+          t += __shfl_xor_sync(0xffffffffu, t, 16);
+          if (lane < 16) sT16[c] = sRv[16 * sb + c] - t;
+          __syncwarp();
+          double yv = 0.0;
+          for (int cc = hh; cc <= c; cc += 2)
+            yv = fma(sWd[sb * 256 + (((c >> 3) * 4 + (cc >> 2)) << 5) + ((c & 7) << 2) + (cc & 3)], sT16[cc], yv);
+          yv += __shfl_xor_sync(0xffffffffu, yv, 16);
+          if (lane < 16) {
+            sY[16 * sb + c] = yv;
+            ysys[j * T + 16 * sb + c] = yv;
+          }
+          __syncwarp();
+        }
       }
       __syncthreads();
 
@@ -356,44 +472,68 @@ __global__ void __launch_bounds__(CH_THREADS, 2) k_chol(const LargeArgs a) {
           for (int q = 0; q < 4; ++q) acc.c[mb][q][0] = acc.c[mb][q][1] = 0.0;
         gemm_stream(Lsys, ysys, i, j, j, false, sStage, acc, accy, tid);
         double* Xt = Lsys + tb_tile_index(i, j) * TB_TILE_ELEMS;
-        // C = A(i,j) - acc  -> shared (fragment-major, as the A operand of the triangular solve)
+        // C = A(i,j) - acc  -> shared (fragment-major)
 #pragma unroll
         for (int mb = 0; mb < 2; ++mb)
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const int r = (2 * wm + mb) * 8 + (lane >> 2);
-            const int c = (4 * wn + q) * 8 + 2 * (lane & 3);
-            const int off = tb_tile_off(r, c);
-            const double2 av = *reinterpret_cast<const double2*>(Xt + off);
+            const int off = cfrag_off(2 * wm + mb, 4 * wn + q, lane);
+            double2 av = make_double2(0.0, 0.0);
+            if (!FUSED) av = *reinterpret_cast<const double2*>(Xt + off);
             *reinterpret_cast<double2*>(sC + off) = make_double2(av.x - acc.c[mb][q][0], av.y - acc.c[mb][q][1]);
           }
-        __syncthreads();
-        // X = C * W^T  (W lower triangular: k-slabs above the n-block's diagonal are zero)
-#pragma unroll
-        for (int mb = 0; mb < 2; ++mb)
-#pragma unroll
-          for (int q = 0; q < 4; ++q) acc.c[mb][q][0] = acc.c[mb][q][1] = 0.0;
-        const int ks_end = 2 * (4 * wn + 3) + 2;  // slabs 0 .. 2*nb_max+1
-        for (int kS = 0; kS < ks_end; ++kS) {
-          const int hoff = (kS >> 3) * HALF, ks = kS & 7;
-          double af[2], bf[4];
-#pragma unroll
-          for (int mb = 0; mb < 2; ++mb) af[mb] = sC[hoff + (((2 * wm + mb) << 3) + ks) * 32 + lane];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) bf[q] = sW[hoff + (((4 * wn + q) << 3) + ks) * 32 + lane];
-#pragma unroll
-          for (int mb = 0; mb < 2; ++mb)
-#pragma unroll
-            for (int q = 0; q < 4; ++q) dmma(acc.c[mb][q][0], acc.c[mb][q][1], af[mb], bf[q]);
-        }
-#pragma unroll
-        for (int mb = 0; mb < 2; ++mb)
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int r = (2 * wm + mb) * 8 + (lane >> 2);
-            const int c = (4 * wn + q) * 8 + 2 * (lane & 3);
-            *reinterpret_cast<double2*>(Xt + tb_tile_off(r, c)) = make_double2(acc.c[mb][q][0], acc.c[mb][q][1]);
+        if (FUSED) {
+          const int64_t t = tb_tile_index(i, j);
+          const int64_t e0 = a.tile_ent_ptr[t], e1 = a.tile_ent_ptr[t + 1];
+          if (e1 > e0) {  // uniform
+            __syncthreads();
+            for (int64_t q = e0 + tid; q < e1; q += CH_THREADS) {
+              const int e = a.tile_ent[q];
+              sC[tb_tile_off(a.ent_row[e] - i * T, a.ent_col[e] - j * T)] += entry_value(a, mk, mc, e);
+            }
           }
+        }
+        __syncthreads();
+        // X L(j,j)^T = C, row block `warp` (8 rows) handled entirely by this warp:
+        //   X[:,sb] = (C[:,sb] - X[:,0:sb] L(sb rows, 0:16sb)^T) W_sb^T      for sb = 0..3
+#pragma unroll 1
+        for (int sb = 0; sb < 4; ++sb) {
+          double c2[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+          for (int kS = 0; kS < 4 * sb; ++kS) {
+            const double av = sC[frag_off(warp, kS) + lane];
+#pragma unroll
+            for (int nbp = 0; nbp < 2; ++nbp) dmma(c2[nbp][0], c2[nbp][1], av, sLjj[frag_off(2 * sb + nbp, kS) + lane]);
+          }
+#pragma unroll
+          for (int nbp = 0; nbp < 2; ++nbp) {
+            double2* pv = reinterpret_cast<double2*>(sC + cfrag_off(warp, 2 * sb + nbp, lane));
+            double2 v = *pv;
+            v.x -= c2[nbp][0];
+            v.y -= c2[nbp][1];
+            *pv = v;
+          }
+          __syncwarp();
+          double a4[4];
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) a4[ks] = sC[frag_off(warp, 4 * sb + ks) + lane];
+          __syncwarp();
+#pragma unroll
+          for (int nbp = 0; nbp < 2; ++nbp) {
+            double x0 = 0.0, x1 = 0.0;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) dmma(x0, x1, a4[ks], sWd[sb * 256 + (nbp * 4 + ks) * 32 + lane]);
+            *reinterpret_cast<double2*>(sC + cfrag_off(warp, 2 * sb + nbp, lane)) = make_double2(x0, x1);
+          }
+          __syncwarp();
+        }
+        // this warp's 8 rows of X -> HBM: two contiguous 2 KB runs of the fragment-major tile
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int o = ((h * 8 + warp) << 8);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<double2*>(Xt + o + (lane + 32 * q) * 2) = *reinterpret_cast<const double2*>(sC + o + (lane + 32 * q) * 2);
+        }
         __syncthreads();  // sC is about to be overwritten by the next stream; X visible to the CTA
       }
     }
@@ -409,16 +549,15 @@ __global__ void __launch_bounds__(CH_THREADS, 2) k_chol(const LargeArgs a) {
       // acc_c = sum_{i>j} sum_r L(i,j)[r][c] u_i[r]; thread (warp w, lane l) owns columns
       // c = h*32 + w*4 + (l&3) and rows r = rb*8 + (l>>2) of every tile (coalesced tile reads)
       double a0 = 0.0, a1 = 0.0;
+#pragma unroll 2
       for (int i = j + 1; i < nt; ++i) {
-        __syncthreads();
-        if (tid < T) sUb[tid] = ysys[i * T + tid];
-        __syncthreads();
         const double* Lt = Lsys + tb_tile_index(i, j) * TB_TILE_ELEMS;
+        const double* ui = ysys + i * T + (lane >> 2);
 #pragma unroll
         for (int rb = 0; rb < 8; ++rb) {
-          const double uv = sUb[rb * 8 + (lane >> 2)];
-          a0 = fma(Lt[tid + rb * 256], uv, a0);
-          a1 = fma(Lt[tid + (rb + 8) * 256], uv, a1);
+          const double uv = __ldcg(ui + rb * 8);
+          a0 = fma(__ldcg(Lt + tid + rb * 256), uv, a0);
+          a1 = fma(__ldcg(Lt + tid + (rb + 8) * 256), uv, a1);
         }
       }
 #pragma unroll
@@ -426,7 +565,6 @@ __global__ void __launch_bounds__(CH_THREADS, 2) k_chol(const LargeArgs a) {
         a0 += __shfl_xor_sync(0xffffffffu, a0, o);
         a1 += __shfl_xor_sync(0xffffffffu, a1, o);
       }
-      __syncthreads();
       if (lane < 4) {
         sRhs[warp * 4 + lane] = a0;
         sRhs[32 + warp * 4 + lane] = a1;
@@ -440,19 +578,20 @@ __global__ void __launch_bounds__(CH_THREADS, 2) k_chol(const LargeArgs a) {
           const int l = idx & 31, slot = idx >> 5;
           const int ks = slot & 7, rb = (slot >> 3) & 7, h = slot >> 6;
           const int r = rb * 8 + (l >> 2), c = h * 32 + ks * 4 + (l & 3);
-          if (c <= r) sScr[r + c * SCR_LD] = Lt[idx];
+          if (c <= r) sScr[r + c * SCR_LD] = __ldcg(Lt + idx);
         }
       }
       __syncthreads();
-      if (tid < T) sRinv[tid] = 1.0 / sScr[tid + tid * SCR_LD];
-      double rp = (tid < T) ? ysys[j * T + tid] - sRhs[tid] : 0.0;
-      __syncthreads();
-      for (int k = T - 1; k >= 0; --k) {
-        if (tid == k) sUb[k] = rp * sRinv[k];
-        __syncthreads();
-        if (tid < k) rp = fma(-sScr[k + tid * SCR_LD], sUb[k], rp);
+      if (tid < T) {  // two warps walk the 64 columns; the rest wait at the barrier below
+        const double rinv = 1.0 / sScr[tid + tid * SCR_LD];
+        double rp = __ldcg(ysys + j * T + tid) - sRhs[tid];
+        for (int k = T - 1; k >= 0; --k) {
+          if (tid == k) sUb[k] = rp * rinv;
+          asm volatile("bar.sync 2, 64;" ::: "memory");
+          if (tid < k) rp = fma(-sScr[k + tid * SCR_LD], sUb[k], rp);
+        }
+        ysys[j * T + tid] = sUb[tid];
       }
-      if (tid < T) ysys[j * T + tid] = sUb[tid];
       __syncthreads();
     }
     if (tid == 0) a.status[b] = 0;
@@ -615,36 +754,47 @@ void tb_large_carve(LargeArgs& a, void* ws) {
 int tb_launch_large(const LargeArgs& a, int num_sm, cudaStream_t st) {
   if (a.batch <= 0) return 0;
   if (num_sm <= 0) num_sm = 148;
+  // TB_UNFUSED_ASSEMBLY=1 keeps the separate HBM-bound assembly kernel (A/B measurements)
+  static const bool fused = [] { const char* s = getenv("TB_UNFUSED_ASSEMBLY"); return !(s && s[0] == '1'); }();
   k_init_status<<<(a.batch + 255) / 256, 256, 0, st>>>(a.status, a.batch, 0);
   {
     const int64_t total = (int64_t)a.batch * a.M;
     int grid = (int)((total + 255) / 256 < (int64_t)num_sm * 8 ? (total + 255) / 256 : (int64_t)num_sm * 8);
     if (grid < 1) grid = 1;
+    tb_prof_begin(TB_PROF_GEOM, st);
     if (a.dim == 3) k_geom<3><<<grid, 256, 0, st>>>(a);
     else k_geom<2><<<grid, 256, 0, st>>>(a);
+    tb_prof_end(TB_PROF_GEOM, st);
   }
-  {
+  if (!fused) {
     const int64_t work = (int64_t)a.nt * (a.nt + 1) / 2 * a.batch;
     int grid = (int)(work < (int64_t)num_sm * 16 ? work : (int64_t)num_sm * 16);
+    tb_prof_begin(TB_PROF_ASSEMBLE, st);
     if (a.dim == 3) k_assemble<3><<<grid, 256, 0, st>>>(a);
     else k_assemble<2><<<grid, 256, 0, st>>>(a);
+    tb_prof_end(TB_PROF_ASSEMBLE, st);
   }
   {
-    cudaError_t e = cudaFuncSetAttribute(k_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, CHOL_SMEM_BYTES);
+    auto kern = fused ? k_chol<true> : k_chol<false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CHOL_SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_chol, CH_THREADS, CHOL_SMEM_BYTES);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, CH_THREADS, CHOL_SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     if (per_sm < 1) per_sm = 1;
     int grid = num_sm * per_sm;
     if (grid > a.batch) grid = a.batch;
-    k_chol<<<grid, CH_THREADS, CHOL_SMEM_BYTES, st>>>(a);
+    tb_prof_begin(TB_PROF_CHOL, st);
+    kern<<<grid, CH_THREADS, CHOL_SMEM_BYTES, st>>>(a);
+    tb_prof_end(TB_PROF_CHOL, st);
   }
   {
     int grid = a.batch < num_sm * 8 ? a.batch : num_sm * 8;
+    tb_prof_begin(TB_PROF_RECOVER, st);
     if (a.dim == 3) k_recover<3><<<grid, 256, 0, st>>>(a);
     else k_recover<2><<<grid, 256, 0, st>>>(a);
+    tb_prof_end(TB_PROF_RECOVER, st);
   }
-  tb_count_launch(5);
+  tb_count_launch(fused ? 4 : 5);
   return (int)cudaGetLastError();
 }

@@ -14,6 +14,49 @@
 
 std::atomic<int64_t> g_tb_launches{0};
 
+// ---- optional per-kernel event timing ---------------------------------------------------------
+namespace {
+struct ProfRec { int slot; cudaEvent_t e0, e1; };
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof_recs;
+cudaEvent_t g_prof_open[TB_PROF_SLOTS];
+}  // namespace
+bool tb_prof_on() { return g_prof_on; }
+void tb_prof_begin(int slot, cudaStream_t st) {
+  if (!g_prof_on) return;
+  cudaEventCreate(&g_prof_open[slot]);
+  cudaEventRecord(g_prof_open[slot], st);
+}
+void tb_prof_end(int slot, cudaStream_t st) {
+  if (!g_prof_on) return;
+  ProfRec r;
+  r.slot = slot;
+  r.e0 = g_prof_open[slot];
+  cudaEventCreate(&r.e1);
+  cudaEventRecord(r.e1, st);
+  g_prof_recs.push_back(r);
+}
+extern "C" int tb_profile_enable(int32_t on) {
+  g_prof_on = on != 0;
+  return TB_OK;
+}
+// Adds the elapsed milliseconds / launch counts recorded since the last read to ms[slot] / count[slot]
+// (arrays of 8) and clears the records.  Synchronises on the recorded events.
+extern "C" int tb_profile_read(float* ms, int64_t* count) {
+  for (auto& r : g_prof_recs) {
+    float t = 0.f;
+    cudaError_t e = cudaEventSynchronize(r.e1);
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&t, r.e0, r.e1);
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+    if (e != cudaSuccess) { g_prof_recs.clear(); return (int)e; }
+    if (ms) ms[r.slot] += t;
+    if (count) count[r.slot] += 1;
+  }
+  g_prof_recs.clear();
+  return TB_OK;
+}
+
 namespace {
 
 template <typename T>

@@ -409,7 +409,9 @@ int tb_launch_small(const SmallArgs& a, int dim, cudaStream_t st) {
   if (per_sm < 1) per_sm = 1;
   long long grid = (long long)sms * per_sm;   // persistent: a multiple of the SM count
   if (grid > a.batch) grid = a.batch;
+  tb_prof_begin(TB_PROF_SMALL, st);
   kern<<<(unsigned)grid, threads, smem, st>>>(a);
+  tb_prof_end(TB_PROF_SMALL, st);
   tb_count_launch();
   return (int)cudaGetLastError();
 }
