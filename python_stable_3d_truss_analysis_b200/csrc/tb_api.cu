@@ -83,9 +83,9 @@ int run_plan(tb_plan* p, const tb_batch_in* in, const tb_batch_out* out, const t
   }
 
   // blocked path: process the batch in chunks that fit the workspace cap
-  const size_t per_sys = tb_large_workspace_bytes(1, p->dim, p->M, p->n_pad);
+  const size_t per_sys = tb_large_workspace_bytes(1, p->dim, p->M, p->n_pad, (int64_t)p->ent_row.size());
   int chunk = (int)std::min<size_t>((size_t)in->batch, std::max<size_t>(1, ws_cap_bytes() / per_sys));
-  const size_t need = tb_large_workspace_bytes(chunk, p->dim, p->M, p->n_pad);
+  const size_t need = tb_large_workspace_bytes(chunk, p->dim, p->M, p->n_pad, (int64_t)p->ent_row.size());
   if (p->ws_bytes < need) {
     if (p->ws) {
       TB_CUDA(cudaStreamSynchronize(st));
@@ -130,6 +130,8 @@ int run_plan(tb_plan* p, const tb_batch_in* in, const tb_batch_out* out, const t
     a.ctr_local = p->d_ctr_local;
     a.tile_ent_ptr = p->d_tile_ent_ptr;
     a.tile_ent = p->d_tile_ent;
+    a.tile_pos = p->d_tile_pos;
+    a.nnz = (int64_t)p->ent_row.size();
     a.inc_ptr = p->d_inc_ptr;
     a.inc_mem = p->d_inc_mem;
     tb_large_carve(a, p->ws);

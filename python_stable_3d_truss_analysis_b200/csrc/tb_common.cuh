@@ -62,6 +62,7 @@ struct tb_plan {
   std::vector<int32_t> ctr_local;          // [n_contrib] a*2d+b
   std::vector<int64_t> tile_ent_ptr;       // [ntiles+1] entries grouped per 64x64 tile (blocked path)
   std::vector<int32_t> tile_ent;           // [nnz] entry ids sorted by tile
+  std::vector<int32_t> tile_pos;           // [nnz] fragment-major offset inside the tile, same order
   // joint -> incident (member, end) lists, ascending member (recovery of reactions)
   std::vector<int32_t> inc_ptr;            // [nJ+1]
   std::vector<int32_t> inc_mem;            // [2M]  member*2 + end
@@ -79,6 +80,7 @@ struct tb_plan {
   int32_t* d_ctr_local = nullptr;
   int64_t* d_tile_ent_ptr = nullptr;
   int32_t* d_tile_ent = nullptr;
+  int32_t* d_tile_pos = nullptr;
   int32_t* d_inc_ptr = nullptr;
   int32_t* d_inc_mem = nullptr;
 
@@ -124,12 +126,14 @@ struct LargeArgs {
   const int32_t* conn; const int32_t* free_idx; const int32_t* dof2free; const int32_t* sup_idx;
   const int32_t* ent_row; const int32_t* ent_col; const int64_t* ent_ptr;
   const int32_t* ctr_member; const int32_t* ctr_local;
-  const int64_t* tile_ent_ptr; const int32_t* tile_ent;
+  const int64_t* tile_ent_ptr; const int32_t* tile_ent; const int32_t* tile_pos;
+  int64_t nnz;
   const int32_t* inc_ptr; const int32_t* inc_mem;
   // workspace
   double* mk;      // [B][M]      EA/L
   double* mc;      // [B][M][d]   direction cosines
   double* mw;      // [B][M]      a*L*density
+  double* kv;      // [B][nnz]    K_ff non-zeros, grouped by tile (tile_ent order)
   double* L;       // [B][ntiles][4096] packed lower tiles, fragment-major
   double* y;       // [B][n_pad]  rhs -> forward solution -> free displacements
   int32_t* status; // [B] 0 ok / k>0 pivot / <0 input problem
@@ -145,7 +149,7 @@ struct LargeArgs {
 int tb_launch_small(const SmallArgs& a, int dim, cudaStream_t st);
 int tb_small_smem_bytes(int dim, int nJ, int M, int max_n, int* threads);
 int tb_launch_large(const LargeArgs& a, int num_sm, cudaStream_t st);
-size_t tb_large_workspace_bytes(int batch, int dim, int M, int n_pad);
+size_t tb_large_workspace_bytes(int batch, int dim, int M, int n_pad, int64_t nnz);
 void tb_large_carve(LargeArgs& a, void* ws);
 
 // fragment-major offset of element (r, c) inside one 64x64 tile:

@@ -78,6 +78,30 @@ __global__ void k_geom(const LargeArgs a) {
   }
 }
 
+// K_ff non-zeros of every system, one thread per (system, structural non-zero), written in the
+// plan's tile-grouped order so the factorisation scatters a tile's entries with coalesced reads.
+__global__ void k_kval(const LargeArgs a) {
+  const int64_t total = (int64_t)a.batch * a.nnz;
+  const int d = a.dim, d2 = 2 * d;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = idx / a.nnz, q = idx - b * a.nnz;
+    const double* mk = a.mk + b * a.M;
+    const double* mc = a.mc + b * a.M * d;
+    const int e = a.tile_ent[q];
+    double v = 0.0;
+    for (int64_t p = a.ent_ptr[e]; p < a.ent_ptr[e + 1]; ++p) {   // ascending member order (truss.py:310)
+      const int m = a.ctr_member[p], loc = a.ctr_local[p];
+      const int la = loc / d2, lb = loc - la * d2;
+      const int A = la >= d, i = la - A * d, B = lb >= d, j = lb - B * d;
+      double pr = __dmul_rn(mc[m * d + i], mc[m * d + j]);         // truss.py:69,80
+      if (A != B) pr = -pr;
+      v = __dadd_rn(v, __dmul_rn(mk[m], pr));                      // truss.py:70,314
+    }
+    a.kv[idx] = v;
+  }
+}
+
 __global__ void k_init_status(int32_t* status, int batch, int value) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < batch; i += gridDim.x * blockDim.x) status[i] = value;
 }
@@ -158,15 +182,16 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // shared-memory carve of k_chol (doubles)
-constexpr int STAGE_DOUBLES = 2 * HALF + 32;          // A half tile, B half tile, 32 y values
-constexpr int SM_STAGE = 2 * STAGE_DOUBLES;           // two stages (aliased: C staging tile, small scratches)
+constexpr int KCH = 16;                                // k-depth of one pipeline stage
+constexpr int CHUNK = T * KCH;                         // doubles in a 64-row x 16-k chunk (8 KB)
+constexpr int STAGE_DOUBLES = 2 * CHUNK + KCH;         // A chunk, B chunk, 16 y values
+constexpr int SM_STAGE = 2 * STAGE_DOUBLES;            // two stages (aliased: C staging tile, scratch)
 constexpr int SCR_LD = 67;                             // back-substitution scratch: column-major 64 x 64
 constexpr int SM_LJJ = TB_TILE_ELEMS;                  // L(j,j), fragment-major
 constexpr int SM_WD = 4 * 256;                         // the four 16x16 inverse diagonal blocks of L(j,j)
 constexpr int SM_MISC = 4 * T + 48;                    // rhs acc, u block, y block, rhs vector, diag16, flag
 constexpr int CHOL_SMEM_BYTES = (SM_STAGE + SM_LJJ + SM_WD + SM_MISC) * 8;
-constexpr int BASE_LD = 33;                            // 16x16 base-case scratch: 32 rows (L | Z), column-major
-static_assert(SCR_LD * T <= SM_STAGE, "back-substitution scratch must fit in the stage buffers");
+static_assert(SCR_LD * T <= SM_STAGE + SM_LJJ, "back-substitution scratch must fit in stage buffers + L(j,j)");
 static_assert(TB_TILE_ELEMS <= SM_STAGE, "C staging tile must fit in the stage buffers");
 
 // offset of the 32-double operand fragment (8-row block `blk`, k-slab kS in 0..15) inside a tile
@@ -180,26 +205,29 @@ struct Frag {
   double c[2][4][2];  // [m-block][n-block][2]
 };
 
-// acc += A(ti, 0..nk-1) * B(tj, 0..nk-1)^T, streamed as 64x32 half tiles through a two-stage
+// acc += A(ti, 0..nk-1) * B(tj, 0..nk-1)^T, streamed as 64-row x 16-k chunks through a two-stage
 // cp.async pipeline.  When with_y, also accumulates rows of A times the forward solution y.
 __device__ __forceinline__ void gemm_stream(const double* __restrict__ Lsys, const double* __restrict__ ysys, int ti,
                                             int tj, int nk, bool with_y, double* sStage, Frag& acc, double (&accy)[2],
                                             int tid) {
   const int lane = tid & 31, warp = tid >> 5, wm = warp >> 1, wn = warp & 1;
   const bool same = (ti == tj);
-  const int S = 2 * nk;
+  const int S = 4 * nk;
+  // this thread's two 16-byte pieces of a chunk: piece e2 covers doubles 2*e2, 2*e2+1 of [rb 8][slab 4][lane 32]
   auto issue = [&](int s) {
-    const int kt = s >> 1, h = s & 1;
+    const int kt = s >> 2, qd = s & 3;
     double* buf = sStage + (s & 1) * STAGE_DOUBLES;
-    const double* ga = Lsys + tb_tile_index(ti, kt) * TB_TILE_ELEMS + h * HALF;
+    const int64_t tbase = ((qd >> 1) << 11) + ((qd & 1) << 7);   // k-half offset + slab offset inside the tile
+    const double* ga = Lsys + tb_tile_index(ti, kt) * TB_TILE_ELEMS + tbase;
+    const double* gb = Lsys + tb_tile_index(tj, kt) * TB_TILE_ELEMS + tbase;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) cp_async16(buf + (tid + q * 256) * 2, ga + (tid + q * 256) * 2);
-    if (!same) {
-      const double* gb = Lsys + tb_tile_index(tj, kt) * TB_TILE_ELEMS + h * HALF;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) cp_async16(buf + HALF + (tid + q * 256) * 2, gb + (tid + q * 256) * 2);
+    for (int q = 0; q < 2; ++q) {
+      const int e = (tid + q * 256) * 2;
+      const int src = ((e >> 7) << 8) + (e & 127);               // row block stride is 8 slabs in the tile
+      cp_async16(buf + e, ga + src);
+      if (!same) cp_async16(buf + CHUNK + e, gb + src);
     }
-    if (with_y && tid < 16) cp_async16(buf + 2 * HALF + tid * 2, ysys + kt * T + h * 32 + tid * 2);
+    if (with_y && tid < KCH / 2) cp_async16(buf + 2 * CHUNK + tid * 2, ysys + kt * T + qd * KCH + tid * 2);
     cp_async_commit();
   };
   if (S > 0) issue(0);
@@ -212,19 +240,21 @@ __device__ __forceinline__ void gemm_stream(const double* __restrict__ Lsys, con
     }
     __syncthreads();
     const double* bufA = sStage + (s & 1) * STAGE_DOUBLES;
-    const double* bufB = same ? bufA : bufA + HALF;
-    const double* bufY = bufA + 2 * HALF;
+    const double* bufB = same ? bufA : bufA + CHUNK;
+    const double* bufY = bufA + 2 * CHUNK;
 #pragma unroll
-    for (int ks = 0; ks < 8; ++ks) {
+    for (int ks = 0; ks < 4; ++ks) {
       double af[2], bf[4];
 #pragma unroll
-      for (int mb = 0; mb < 2; ++mb) af[mb] = bufA[(((2 * wm + mb) << 3) + ks) * 32 + lane];
+      for (int mb = 0; mb < 2; ++mb) af[mb] = bufA[(((2 * wm + mb) << 2) + ks) * 32 + lane];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) bf[q] = bufB[(((4 * wn + q) << 3) + ks) * 32 + lane];
+      for (int q = 0; q < 4; ++q) bf[q] = bufB[(((4 * wn + q) << 2) + ks) * 32 + lane];
 #pragma unroll
       for (int mb = 0; mb < 2; ++mb)
 #pragma unroll
-        for (int q = 0; q < 4; ++q) dmma(acc.c[mb][q][0], acc.c[mb][q][1], af[mb], bf[q]);
+        for (int q = 0; q < 4; ++q)
+          if (!same || 4 * wn + q <= 2 * wm + mb)   // diagonal tile: only blocks on/below the diagonal (warp-uniform)
+            dmma(acc.c[mb][q][0], acc.c[mb][q][1], af[mb], bf[q]);
       if (with_y && wn == 0) {
         const double yv = bufY[ks * 4 + (lane & 3)];
         accy[0] = fma(af[0], yv, accy[0]);
@@ -233,24 +263,6 @@ __device__ __forceinline__ void gemm_stream(const double* __restrict__ Lsys, con
     }
     __syncthreads();
   }
-}
-
-
-// K_ff entry e of the plan's scatter map: sum of k * (+-(c_i c_j)) over its members, ascending
-// member order (truss.py:65-86 values, truss.py:310 order).
-__device__ __forceinline__ double entry_value(const LargeArgs& a, const double* __restrict__ mk,
-                                              const double* __restrict__ mc, int e) {
-  const int d = a.dim, d2 = 2 * d;
-  double v = 0.0;
-  for (int64_t p = a.ent_ptr[e]; p < a.ent_ptr[e + 1]; ++p) {
-    const int m = a.ctr_member[p], loc = a.ctr_local[p];
-    const int la = loc / d2, lb = loc - la * d2;
-    const int A = la >= d, i = la - A * d, B = lb >= d, j = lb - B * d;
-    double pr = __dmul_rn(mc[m * d + i], mc[m * d + j]);
-    if (A != B) pr = -pr;
-    v = __dadd_rn(v, __dmul_rn(mk[m], pr));
-  }
-  return v;
 }
 
 // FUSED: K_ff tiles are assembled straight into shared memory from the scatter map when the
@@ -262,12 +274,11 @@ __device__ __forceinline__ double entry_value(const LargeArgs& a, const double* 
 // blocks and their inverses by one warp); (2) every tile below: C = A(i,j) - sum_k L(i,k) L(j,k)^T,
 // then X L(j,j)^T = C solved per 8-row block entirely inside one warp using the 16x16 inverses.
 template <bool FUSED>
-__global__ void __launch_bounds__(CH_THREADS, 2) k_chol(const LargeArgs a) {
+__global__ void __launch_bounds__(CH_THREADS, 3) k_chol(const LargeArgs a) {
   extern __shared__ __align__(16) double sm[];
   double* sStage = sm;                 // stage buffers | C staging tile | small scratches
   double* sScr = sm;                   // alias (back substitution)
   double* sC = sm;                     // alias (panel tiles)
-  double* sBase = sm;                  // alias (16x16 base case)
   double* sLjj = sm + SM_STAGE;
   double* sWd = sLjj + SM_LJJ;
   double* sRhs = sWd + SM_WD;          // [64] L(j,:) y accumulations
@@ -285,8 +296,7 @@ __global__ void __launch_bounds__(CH_THREADS, 2) k_chol(const LargeArgs a) {
   for (int b = blockIdx.x; b < a.batch; b += gridDim.x) {
     double* Lsys = a.L + (int64_t)b * ntiles * TB_TILE_ELEMS;
     double* ysys = a.y + (int64_t)b * a.n_pad;
-    const double* mk = a.mk + (int64_t)b * a.M;
-    const double* mc = a.mc + (int64_t)b * a.M * a.dim;
+    const double* kvs = a.kv + (int64_t)b * a.nnz;
     const double* fsys = a.force + b * a.force_stride;
     if (a.status[b] != 0) continue;  // input problem flagged by k_geom (uniform per CTA)
     int fail = 0;
@@ -334,10 +344,8 @@ __global__ void __launch_bounds__(CH_THREADS, 2) k_chol(const LargeArgs a) {
       }
       if (FUSED) {  // scatter-map entries of tile (j,j): one thread per structural non-zero
         const int64_t t = tb_tile_index(j, j);
-        for (int64_t q = a.tile_ent_ptr[t] + tid; q < a.tile_ent_ptr[t + 1]; q += CH_THREADS) {
-          const int e = a.tile_ent[q];
-          sLjj[tb_tile_off(a.ent_row[e] - j * T, a.ent_col[e] - j * T)] += entry_value(a, mk, mc, e);
-        }
+        for (int64_t q = a.tile_ent_ptr[t] + tid; q < a.tile_ent_ptr[t + 1]; q += CH_THREADS)
+          sLjj[a.tile_pos[q]] += kvs[q];
       }
 
       // ---- factor the tile in place: four 16-column sub-panels, left-looking
@@ -361,54 +369,35 @@ __global__ void __launch_bounds__(CH_THREADS, 2) k_chol(const LargeArgs a) {
         }
         __syncthreads();
         if (warp == 0) {
-          // 16x16 diagonal block: lanes 0-15 own the rows of L, lanes 16-31 the rows of Z = L^{-T}
-          const int base = 16 * sb;
-          {
-            const int r = lane & 15;
+          // 16x16 diagonal block, right-looking, entirely in registers: lanes 0-15 hold the rows of
+          // the block, lanes 16-31 the rows of Z = L^{-T} (identity to start with); the pivot and the
+          // column being eliminated travel by shuffle.  Critical path per column: rsqrt + mul + fma.
+          const int base = 16 * sb, r = lane & 15;
+          double row[16];
 #pragma unroll
-            for (int c = 0; c < 16; ++c) {
-              double v;
-              if (lane < 16) v = (c <= r) ? sLjj[tb_tile_off(base + r, base + c)] : 0.0;
-              else v = (c == r) ? 1.0 : 0.0;
-              sBase[lane + c * BASE_LD] = v;
-            }
+          for (int c = 0; c < 16; ++c) {
+            if (lane < 16) row[c] = (c <= r) ? sLjj[tb_tile_off(base + r, base + c)] : 0.0;
+            else row[c] = (c == r) ? 1.0 : 0.0;
           }
-          __syncwarp();
           int bad = 0;
 #pragma unroll
           for (int k = 0; k < 16; ++k) {
-            const bool act = lane < 16 ? (lane >= k) : (lane - 16 <= k);
-            double d0 = sBase[k + k * BASE_LD], d1 = 0.0, s0 = sBase[lane + k * BASE_LD], s1 = 0.0;
+            const double d = __shfl_sync(0xffffffffu, row[k], k);
+            if (!(d > 0.0) && !bad) bad = j * T + base + k + 1;   // same value in every lane
+            const double lk = row[k] * rsqrt(bad ? 1.0 : d);       // lane k: d * rsqrt(d) = sqrt(d)
+            row[k] = lk;
 #pragma unroll
-            for (int p = 0; p < k; ++p) {
-              const double bk = sBase[k + p * BASE_LD], ai = sBase[lane + p * BASE_LD];
-              if (p & 1) { d1 = fma(-bk, bk, d1); s1 = fma(-ai, bk, s1); }
-              else       { d0 = fma(-bk, bk, d0); s0 = fma(-ai, bk, s0); }
-            }
-            const double d = d0 + d1, sv = s0 + s1;
-            if (!(d > 0.0) && !bad) bad = j * T + base + k + 1;
-            const double rinv = rsqrt(bad ? 1.0 : d);
-            if (lane == k) sDiag16[k] = d * rinv;          // the seed S[k][k] stays untouched (read by all lanes)
-            else if (act) sBase[lane + k * BASE_LD] = sv * rinv;
-            __syncwarp();
+            for (int c = k + 1; c < 16; ++c) row[c] = fma(-lk, __shfl_sync(0xffffffffu, lk, c), row[c]);
           }
           if (bad) {
             if (lane == 0) *sFlag = bad;
-          } else {
-            if (lane < 16) {  // L back into the tile (upper part of the block zeroed)
-              const int r = lane;
+          } else if (lane < 16) {  // L back into the tile (upper part of the block zeroed)
 #pragma unroll
-              for (int c = 0; c < 16; ++c)
-                sLjj[tb_tile_off(base + r, base + c)] = (c < r) ? sBase[r + c * BASE_LD] : (c == r ? sDiag16[r] : 0.0);
-            }
-            // W = L^{-1} of the block as a DMMA B operand: W[c'][kk] = Z[kk][c'] (kk <= c'), else 0
+            for (int c = 0; c < 16; ++c) sLjj[tb_tile_off(base + r, base + c)] = (c <= r) ? row[c] : 0.0;
+          } else {  // W = L^{-1} as a DMMA B operand: W[c'][kk] = Z[kk][c'] for kk <= c' (this lane: kk = r)
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const int idx = lane + 32 * q;
-              const int l = idx & 31, slot = idx >> 5;           // slot = nbp*4 + ks
-              const int cp = (slot >> 2) * 8 + (l >> 2), kk = (slot & 3) * 4 + (l & 3);
-              sWd[sb * 256 + idx] = (kk <= cp) ? sBase[(16 + kk) + cp * BASE_LD] : 0.0;
-            }
+            for (int cp = 0; cp < 16; ++cp)
+              sWd[sb * 256 + ((((cp >> 3) << 2) + (r >> 2)) << 5) + ((cp & 7) << 2) + (r & 3)] = (cp >= r) ? row[cp] : 0.0;
           }
         }
         __syncthreads();
@@ -487,10 +476,7 @@ __global__ void __launch_bounds__(CH_THREADS, 2) k_chol(const LargeArgs a) {
           const int64_t e0 = a.tile_ent_ptr[t], e1 = a.tile_ent_ptr[t + 1];
           if (e1 > e0) {  // uniform
             __syncthreads();
-            for (int64_t q = e0 + tid; q < e1; q += CH_THREADS) {
-              const int e = a.tile_ent[q];
-              sC[tb_tile_off(a.ent_row[e] - i * T, a.ent_col[e] - j * T)] += entry_value(a, mk, mc, e);
-            }
+            for (int64_t q = e0 + tid; q < e1; q += CH_THREADS) sC[a.tile_pos[q]] += kvs[q];
           }
         }
         __syncthreads();
@@ -733,10 +719,10 @@ __global__ void __launch_bounds__(256) k_recover(const LargeArgs a) {
 
 }  // namespace
 
-size_t tb_large_workspace_bytes(int batch, int dim, int M, int n_pad) {
+size_t tb_large_workspace_bytes(int batch, int dim, int M, int n_pad, int64_t nnz) {
   const int nt = n_pad / TB_TILE;
   const size_t ntiles = (size_t)nt * (nt + 1) / 2;
-  size_t doubles = (size_t)batch * ((size_t)M * (2 + dim) + ntiles * TB_TILE_ELEMS + (size_t)n_pad);
+  size_t doubles = (size_t)batch * ((size_t)M * (2 + dim) + ntiles * TB_TILE_ELEMS + (size_t)n_pad + (size_t)nnz);
   return doubles * 8 + (size_t)batch * 4 + 1024;
 }
 
@@ -748,6 +734,7 @@ void tb_large_carve(LargeArgs& a, void* ws) {
   a.mk = p; p += (size_t)a.batch * a.M;
   a.mc = p; p += (size_t)a.batch * a.M * a.dim;
   a.mw = p; p += (size_t)a.batch * a.M;
+  a.kv = p; p += (size_t)a.batch * a.nnz;
   a.status = (int32_t*)p;
 }
 
@@ -766,7 +753,14 @@ int tb_launch_large(const LargeArgs& a, int num_sm, cudaStream_t st) {
     else k_geom<2><<<grid, 256, 0, st>>>(a);
     tb_prof_end(TB_PROF_GEOM, st);
   }
-  if (!fused) {
+  if (fused) {
+    const int64_t total = (int64_t)a.batch * a.nnz;
+    int grid = (int)((total + 255) / 256 < (int64_t)num_sm * 16 ? (total + 255) / 256 : (int64_t)num_sm * 16);
+    if (grid < 1) grid = 1;
+    tb_prof_begin(TB_PROF_ASSEMBLE, st);
+    k_kval<<<grid, 256, 0, st>>>(a);
+    tb_prof_end(TB_PROF_ASSEMBLE, st);
+  } else {
     const int64_t work = (int64_t)a.nt * (a.nt + 1) / 2 * a.batch;
     int grid = (int)(work < (int64_t)num_sm * 16 ? work : (int64_t)num_sm * 16);
     tb_prof_begin(TB_PROF_ASSEMBLE, st);
@@ -795,6 +789,6 @@ int tb_launch_large(const LargeArgs& a, int num_sm, cudaStream_t st) {
     else k_recover<2><<<grid, 256, 0, st>>>(a);
     tb_prof_end(TB_PROF_RECOVER, st);
   }
-  tb_count_launch(fused ? 4 : 5);
+  tb_count_launch(5);
   return (int)cudaGetLastError();
 }

@@ -191,6 +191,11 @@ extern "C" int tb_plan_create(const tb_topology* topo, tb_plan** plan_out) {
     std::vector<int64_t> pos(cnt.begin(), cnt.end() - 1);
     for (size_t e = 0; e < nnz; ++e)
       p->tile_ent[pos[tb_tile_index(p->ent_row[e] / TB_TILE, p->ent_col[e] / TB_TILE)]++] = (int32_t)e;
+    p->tile_pos.assign(nnz, 0);
+    for (size_t q = 0; q < nnz; ++q) {
+      const int e = p->tile_ent[q];
+      p->tile_pos[q] = tb_tile_off(p->ent_row[e] % TB_TILE, p->ent_col[e] % TB_TILE);
+    }
   }
 
   // ---- joint incidence lists (ascending member, then end)
@@ -222,6 +227,7 @@ extern "C" int tb_plan_create(const tb_topology* topo, tb_plan** plan_out) {
   if (!rc) rc = upload(&p->d_ctr_local, p->ctr_local);
   if (!rc) rc = upload(&p->d_tile_ent_ptr, p->tile_ent_ptr);
   if (!rc) rc = upload(&p->d_tile_ent, p->tile_ent);
+  if (!rc) rc = upload(&p->d_tile_pos, p->tile_pos);
   if (!rc) rc = upload(&p->d_inc_ptr, p->inc_ptr);
   if (!rc) rc = upload(&p->d_inc_mem, p->inc_mem);
   if (rc) {
@@ -250,6 +256,7 @@ extern "C" void tb_plan_destroy(tb_plan* p) {
   cudaFree(p->d_ctr_local);
   cudaFree(p->d_tile_ent_ptr);
   cudaFree(p->d_tile_ent);
+  cudaFree(p->d_tile_pos);
   cudaFree(p->d_inc_ptr);
   cudaFree(p->d_inc_mem);
   cudaFree(p->ws);
