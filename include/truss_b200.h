@@ -85,6 +85,11 @@ typedef struct {
   int64_t nnz_lower;   /* structural non-zeros of the lower triangle of K_ff */
   int64_t n_contrib;   /* entries of the scatter map (member contributions to the lower triangle) */
   int64_t half_bandwidth; /* max (row - col) over structural non-zeros of K_ff */
+  /* blocked pipeline: block-level symbolic factorisation over 64x64 tiles of the lower triangle */
+  int64_t n_tiles;          /* nt(nt+1)/2 */
+  int64_t n_tiles_nonzero;  /* tiles of L that are structurally non-zero (the only ones touched) */
+  int64_t n_tile_products;  /* tile x tile^T updates the factorisation performs */
+  double chol_flops;        /* flops of that block-sparse factorisation + the two triangular solves */
 } tb_plan_info;
 
 /* Build the integer maps of truss.py:319-326 (free/supported DOF order = ascending DOF index)

@@ -62,7 +62,8 @@ class TbPlanInfo(C.Structure):
     _fields_ = [("dim", C.c_int32), ("n_joint", C.c_int32), ("n_member", C.c_int32), ("n_dof", C.c_int32),
                 ("n_free", C.c_int32), ("n_support", C.c_int32), ("n_resist", C.c_int32), ("stable", C.c_int32),
                 ("path", C.c_int32), ("n_pad", C.c_int32), ("nnz_lower", C.c_int64), ("n_contrib", C.c_int64),
-                ("half_bandwidth", C.c_int64)]
+                ("half_bandwidth", C.c_int64), ("n_tiles", C.c_int64), ("n_tiles_nonzero", C.c_int64),
+                ("n_tile_products", C.c_int64), ("chol_flops", C.c_double)]
 
 
 class TbBatchIn(C.Structure):

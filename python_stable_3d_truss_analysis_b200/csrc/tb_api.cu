@@ -132,6 +132,9 @@ int run_plan(tb_plan* p, const tb_batch_in* in, const tb_batch_out* out, const t
     a.tile_ent = p->d_tile_ent;
     a.tile_pos = p->d_tile_pos;
     a.nnz = (int64_t)p->ent_row.size();
+    a.tile_nz = p->d_tile_nz;
+    a.prod_ptr = p->d_prod_ptr;
+    a.prod_k = p->d_prod_k;
     a.inc_ptr = p->d_inc_ptr;
     a.inc_mem = p->d_inc_mem;
     tb_large_carve(a, p->ws);

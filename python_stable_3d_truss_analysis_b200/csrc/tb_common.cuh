@@ -63,6 +63,13 @@ struct tb_plan {
   std::vector<int64_t> tile_ent_ptr;       // [ntiles+1] entries grouped per 64x64 tile (blocked path)
   std::vector<int32_t> tile_ent;           // [nnz] entry ids sorted by tile
   std::vector<int32_t> tile_pos;           // [nnz] fragment-major offset inside the tile, same order
+  // block-level symbolic factorisation: which 64x64 tiles of L are structurally non-zero, and for
+  // each such tile (i,j) the list of k < j with L(i,k) and L(j,k) both non-zero
+  std::vector<uint8_t> tile_nz;            // [ntiles]
+  std::vector<int32_t> prod_ptr;           // [ntiles+1]
+  std::vector<int32_t> prod_k;             // [n_prod]
+  int64_t n_tiles_nz = 0;
+  double chol_flops = 0.0;                 // flops of the block-sparse factorisation + two triangular solves
   // joint -> incident (member, end) lists, ascending member (recovery of reactions)
   std::vector<int32_t> inc_ptr;            // [nJ+1]
   std::vector<int32_t> inc_mem;            // [2M]  member*2 + end
@@ -81,6 +88,9 @@ struct tb_plan {
   int64_t* d_tile_ent_ptr = nullptr;
   int32_t* d_tile_ent = nullptr;
   int32_t* d_tile_pos = nullptr;
+  uint8_t* d_tile_nz = nullptr;
+  int32_t* d_prod_ptr = nullptr;
+  int32_t* d_prod_k = nullptr;
   int32_t* d_inc_ptr = nullptr;
   int32_t* d_inc_mem = nullptr;
 
@@ -128,6 +138,7 @@ struct LargeArgs {
   const int32_t* ctr_member; const int32_t* ctr_local;
   const int64_t* tile_ent_ptr; const int32_t* tile_ent; const int32_t* tile_pos;
   int64_t nnz;
+  const uint8_t* tile_nz; const int32_t* prod_ptr; const int32_t* prod_k;
   const int32_t* inc_ptr; const int32_t* inc_mem;
   // workspace
   double* mk;      // [B][M]      EA/L

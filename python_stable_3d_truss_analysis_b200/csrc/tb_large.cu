@@ -205,17 +205,19 @@ struct Frag {
   double c[2][4][2];  // [m-block][n-block][2]
 };
 
-// acc += A(ti, 0..nk-1) * B(tj, 0..nk-1)^T, streamed as 64-row x 16-k chunks through a two-stage
+// acc += sum over the nk block columns k in klist of L(ti,k) * L(tj,k)^T, streamed as 64-row x 16-k chunks through a two-stage
 // cp.async pipeline.  When with_y, also accumulates rows of A times the forward solution y.
 __device__ __forceinline__ void gemm_stream(const double* __restrict__ Lsys, const double* __restrict__ ysys, int ti,
-                                            int tj, int nk, bool with_y, double* sStage, Frag& acc, double (&accy)[2],
-                                            int tid) {
+                                            int tj, const int32_t* __restrict__ klist, int nk, bool with_y,
+                                            double* sStage, Frag& acc, double (&accy)[2], int tid) {
   const int lane = tid & 31, warp = tid >> 5, wm = warp >> 1, wn = warp & 1;
   const bool same = (ti == tj);
   const int S = 4 * nk;
   // this thread's two 16-byte pieces of a chunk: piece e2 covers doubles 2*e2, 2*e2+1 of [rb 8][slab 4][lane 32]
+  int kt = 0;
   auto issue = [&](int s) {
-    const int kt = s >> 2, qd = s & 3;
+    const int qd = s & 3;
+    if (qd == 0) kt = __ldg(klist + (s >> 2));   // stages are issued in order: one list read per block column
     double* buf = sStage + (s & 1) * STAGE_DOUBLES;
     const int64_t tbase = ((qd >> 1) << 11) + ((qd & 1) << 7);   // k-half offset + slab offset inside the tile
     const double* ga = Lsys + tb_tile_index(ti, kt) * TB_TILE_ELEMS + tbase;
@@ -310,7 +312,11 @@ __global__ void __launch_bounds__(CH_THREADS, 3) k_chol(const LargeArgs a) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) acc.c[mb][q][0] = acc.c[mb][q][1] = 0.0;
       double accy[2] = {0.0, 0.0};
-      gemm_stream(Lsys, ysys, j, j, j, true, sStage, acc, accy, tid);
+      {
+        const int64_t t = tb_tile_index(j, j);
+        gemm_stream(Lsys, ysys, j, j, a.prod_k + a.prod_ptr[t], a.prod_ptr[t + 1] - a.prod_ptr[t], true, sStage, acc,
+                    accy, tid);
+      }
       if (wn == 0) {  // rows of L(j,0:j) times y(0:j): reduce over the quad
 #pragma unroll
         for (int mb = 0; mb < 2; ++mb) {
@@ -455,11 +461,14 @@ __global__ void __launch_bounds__(CH_THREADS, 3) k_chol(const LargeArgs a) {
 
       // ================= panel tiles below the diagonal =================
       for (int i = j + 1; i < nt; ++i) {
+        const int64_t tij = tb_tile_index(i, j);
+        if (!a.tile_nz[tij]) continue;  // structurally zero tile of L: never touched (uniform)
 #pragma unroll
         for (int mb = 0; mb < 2; ++mb)
 #pragma unroll
           for (int q = 0; q < 4; ++q) acc.c[mb][q][0] = acc.c[mb][q][1] = 0.0;
-        gemm_stream(Lsys, ysys, i, j, j, false, sStage, acc, accy, tid);
+        gemm_stream(Lsys, ysys, i, j, a.prod_k + a.prod_ptr[tij], a.prod_ptr[tij + 1] - a.prod_ptr[tij], false, sStage,
+                    acc, accy, tid);
         double* Xt = Lsys + tb_tile_index(i, j) * TB_TILE_ELEMS;
         // C = A(i,j) - acc  -> shared (fragment-major)
 #pragma unroll
@@ -537,6 +546,7 @@ __global__ void __launch_bounds__(CH_THREADS, 3) k_chol(const LargeArgs a) {
       double a0 = 0.0, a1 = 0.0;
 #pragma unroll 2
       for (int i = j + 1; i < nt; ++i) {
+        if (!a.tile_nz[tb_tile_index(i, j)]) continue;
         const double* Lt = Lsys + tb_tile_index(i, j) * TB_TILE_ELEMS;
         const double* ui = ysys + i * T + (lane >> 2);
 #pragma unroll

@@ -6,6 +6,7 @@
 //                    CSR of per-entry contribution lists in ascending member order (no atomics)
 //   stability     <- Truss.isStable / nResistance (truss.py:154-164, type.py:37-46)
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <numeric>
@@ -198,6 +199,49 @@ extern "C" int tb_plan_create(const tb_topology* topo, tb_plan** plan_out) {
     }
   }
 
+  // ---- block-level symbolic Cholesky: a tile of L is structurally non-zero if K_ff has entries in
+  // it or an earlier block column couples its block row and block column.  TB_DENSE_TILES=1 treats
+  // every tile as non-zero (dense reference mode for roofline measurements).
+  {
+    const int nt = p->nt;
+    const int64_t ntiles = (int64_t)nt * (nt + 1) / 2;
+    const char* env = getenv("TB_DENSE_TILES");
+    const bool dense = env && env[0] == '1';
+    p->tile_nz.assign(ntiles, 0);
+    p->prod_ptr.assign(ntiles + 1, 0);
+    std::vector<std::vector<int32_t>> lists(ntiles);
+    for (int j = 0; j < nt; ++j)
+      for (int i = j; i < nt; ++i) {
+        const int64_t t = tb_tile_index(i, j);
+        bool nz = dense || i == j || p->tile_ent_ptr[t + 1] > p->tile_ent_ptr[t];
+        for (int k = 0; k < j; ++k)
+          if (p->tile_nz[tb_tile_index(i, k)] && p->tile_nz[tb_tile_index(j, k)]) {
+            lists[t].push_back(k);
+            nz = true;
+          }
+        p->tile_nz[t] = nz ? 1 : 0;
+      }
+    p->n_tiles_nz = 0;
+    double fl = 0.0;
+    const double T3 = (double)TB_TILE * TB_TILE * TB_TILE;
+    for (int64_t t = 0; t < ntiles; ++t) {
+      p->prod_ptr[t + 1] = p->prod_ptr[t] + (p->tile_nz[t] ? (int32_t)lists[t].size() : 0);
+      if (p->tile_nz[t]) {
+        p->n_tiles_nz++;
+        p->prod_k.insert(p->prod_k.end(), lists[t].begin(), lists[t].end());
+      }
+    }
+    for (int j = 0; j < nt; ++j)
+      for (int i = j; i < nt; ++i) {
+        const int64_t t = tb_tile_index(i, j);
+        if (!p->tile_nz[t]) continue;
+        const double np = (double)lists[t].size();
+        if (i == j) fl += np * T3 + T3 / 3.0 + 2.0 * TB_TILE * TB_TILE;          // syrk-like update + potrf + two trsv
+        else fl += np * 2.0 * T3 + T3 + 4.0 * TB_TILE * TB_TILE;                 // gemm update + trsm + two gemv
+      }
+    p->chol_flops = fl;
+  }
+
   // ---- joint incidence lists (ascending member, then end)
   p->inc_ptr.assign(p->nJ + 1, 0);
   for (int m = 0; m < p->M; ++m)
@@ -228,6 +272,9 @@ extern "C" int tb_plan_create(const tb_topology* topo, tb_plan** plan_out) {
   if (!rc) rc = upload(&p->d_tile_ent_ptr, p->tile_ent_ptr);
   if (!rc) rc = upload(&p->d_tile_ent, p->tile_ent);
   if (!rc) rc = upload(&p->d_tile_pos, p->tile_pos);
+  if (!rc) rc = upload(&p->d_tile_nz, p->tile_nz);
+  if (!rc) rc = upload(&p->d_prod_ptr, p->prod_ptr);
+  if (!rc) rc = upload(&p->d_prod_k, p->prod_k);
   if (!rc) rc = upload(&p->d_inc_ptr, p->inc_ptr);
   if (!rc) rc = upload(&p->d_inc_mem, p->inc_mem);
   if (rc) {
@@ -257,6 +304,9 @@ extern "C" void tb_plan_destroy(tb_plan* p) {
   cudaFree(p->d_tile_ent_ptr);
   cudaFree(p->d_tile_ent);
   cudaFree(p->d_tile_pos);
+  cudaFree(p->d_tile_nz);
+  cudaFree(p->d_prod_ptr);
+  cudaFree(p->d_prod_k);
   cudaFree(p->d_inc_ptr);
   cudaFree(p->d_inc_mem);
   cudaFree(p->ws);
@@ -280,6 +330,10 @@ extern "C" int tb_plan_query(const tb_plan* p, tb_plan_info* o) {
   o->nnz_lower = (int64_t)p->ent_row.size();
   o->n_contrib = (int64_t)p->ctr_member.size();
   o->half_bandwidth = p->half_bw;
+  o->n_tiles = (int64_t)p->nt * (p->nt + 1) / 2;
+  o->n_tiles_nonzero = p->n_tiles_nz;
+  o->n_tile_products = (int64_t)p->prod_k.size();
+  o->chol_flops = p->chol_flops;
   return TB_OK;
 }
 
