@@ -132,6 +132,8 @@ int run_plan(tb_plan* p, const tb_batch_in* in, const tb_batch_out* out, const t
     a.tile_ent = p->d_tile_ent;
     a.tile_pos = p->d_tile_pos;
     a.nnz = (int64_t)p->ent_row.size();
+    a.q_ptr = p->d_q_ptr;
+    a.q_pack = p->d_q_pack;
     a.tile_nz = p->d_tile_nz;
     a.prod_ptr = p->d_prod_ptr;
     a.prod_k = p->d_prod_k;

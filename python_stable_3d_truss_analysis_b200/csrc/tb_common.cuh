@@ -63,6 +63,8 @@ struct tb_plan {
   std::vector<int64_t> tile_ent_ptr;       // [ntiles+1] entries grouped per 64x64 tile (blocked path)
   std::vector<int32_t> tile_ent;           // [nnz] entry ids sorted by tile
   std::vector<int32_t> tile_pos;           // [nnz] fragment-major offset inside the tile, same order
+  std::vector<int32_t> q_ptr;              // [nnz+1] contribution ranges in tile_ent order
+  std::vector<int32_t> q_pack;             // [n_contrib] member<<4 | negate<<3 | index of (i<=j) cosine product
   // block-level symbolic factorisation: which 64x64 tiles of L are structurally non-zero, and for
   // each such tile (i,j) the list of k < j with L(i,k) and L(j,k) both non-zero
   std::vector<uint8_t> tile_nz;            // [ntiles]
@@ -88,6 +90,8 @@ struct tb_plan {
   int64_t* d_tile_ent_ptr = nullptr;
   int32_t* d_tile_ent = nullptr;
   int32_t* d_tile_pos = nullptr;
+  int32_t* d_q_ptr = nullptr;
+  int32_t* d_q_pack = nullptr;
   uint8_t* d_tile_nz = nullptr;
   int32_t* d_prod_ptr = nullptr;
   int32_t* d_prod_k = nullptr;
@@ -139,12 +143,15 @@ struct LargeArgs {
   const int64_t* tile_ent_ptr; const int32_t* tile_ent; const int32_t* tile_pos;
   int64_t nnz;
   const uint8_t* tile_nz; const int32_t* prod_ptr; const int32_t* prod_k;
+  const int32_t* q_ptr; const int32_t* q_pack;
   const int32_t* inc_ptr; const int32_t* inc_mem;
   // workspace
   double* mk;      // [B][M]      EA/L
   double* mc;      // [B][M][d]   direction cosines
   double* mw;      // [B][M]      a*L*density
+  double* mkc;     // [B][M][d(d+1)/2]  k * (c_i c_j), i <= j  (the distinct entries of truss.py:65-86)
   double* kv;      // [B][nnz]    K_ff non-zeros, grouped by tile (tile_ent order)
+  double* wd;      // [B][nt][1024] inverses of the 16x16 diagonal blocks of every L(j,j) (DMMA B-operand layout)
   double* L;       // [B][ntiles][4096] packed lower tiles, fragment-major
   double* y;       // [B][n_pad]  rhs -> forward solution -> free displacements
   int32_t* status; // [B] 0 ok / k>0 pivot / <0 input problem

@@ -17,6 +17,23 @@
 
 #include "tb_common.cuh"
 
+#ifdef TB_PHASE_TIMING
+__device__ unsigned long long g_phase_cycles[16];
+#define PH_DECL long long _ph_t = clock64(); unsigned long long _ph_acc[16] = {0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0};
+#define PH(i) { long long _n = clock64(); _ph_acc[i] += (unsigned long long)(_n - _ph_t); _ph_t = _n; }
+#define PH_FLUSH if (threadIdx.x == 0) { for (int _i = 0; _i < 16; ++_i) atomicAdd(&g_phase_cycles[_i], _ph_acc[_i]); }
+extern "C" int tb_phase_read(unsigned long long* out) {
+  cudaMemcpyFromSymbol(out, g_phase_cycles, sizeof(unsigned long long) * 16);
+  unsigned long long z[16] = {0};
+  cudaMemcpyToSymbol(g_phase_cycles, z, sizeof(z));
+  return 0;
+}
+#else
+#define PH_DECL
+#define PH(i) {}
+#define PH_FLUSH
+#endif
+
 namespace {
 
 constexpr int T = TB_TILE;          // 64
@@ -75,30 +92,35 @@ __global__ void k_geom(const LargeArgs a) {
 #pragma unroll
     for (int i = 0; i < DIM; ++i) a.mc[idx * DIM + i] = c[i];
     a.mw[idx] = __dmul_rn(__dmul_rn(ar, len), rho);
+    {   // k * (c_i c_j) for i <= j: product first, then the scale, exactly as truss.py:69-70 / 80-81
+      constexpr int NV = DIM * (DIM + 1) / 2;
+      double* o = a.mkc + idx * NV;
+      int t = 0;
+#pragma unroll
+      for (int i = 0; i < DIM; ++i)
+#pragma unroll
+        for (int j = i; j < DIM; ++j) o[t++] = __dmul_rn(k, __dmul_rn(c[i], c[j]));
+    }
   }
 }
 
-// K_ff non-zeros of every system, one thread per (system, structural non-zero), written in the
-// plan's tile-grouped order so the factorisation scatters a tile's entries with coalesced reads.
-__global__ void k_kval(const LargeArgs a) {
-  const int64_t total = (int64_t)a.batch * a.nnz;
-  const int d = a.dim, d2 = 2 * d;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t b = idx / a.nnz, q = idx - b * a.nnz;
-    const double* mk = a.mk + b * a.M;
-    const double* mc = a.mc + b * a.M * d;
-    const int e = a.tile_ent[q];
-    double v = 0.0;
-    for (int64_t p = a.ent_ptr[e]; p < a.ent_ptr[e + 1]; ++p) {   // ascending member order (truss.py:310)
-      const int m = a.ctr_member[p], loc = a.ctr_local[p];
-      const int la = loc / d2, lb = loc - la * d2;
-      const int A = la >= d, i = la - A * d, B = lb >= d, j = lb - B * d;
-      double pr = __dmul_rn(mc[m * d + i], mc[m * d + j]);         // truss.py:69,80
-      if (A != B) pr = -pr;
-      v = __dadd_rn(v, __dmul_rn(mk[m], pr));                      // truss.py:70,314
+// K_ff non-zeros of one system per CTA (the member products it gathers stay in L1), one thread per
+// structural non-zero, summed in ascending member order (truss.py:310) and written in the plan's
+// tile-grouped order so the factorisation scatters a tile's entries with coalesced reads.
+__global__ void __launch_bounds__(256) k_kval(const LargeArgs a) {
+  const int nv = a.dim * (a.dim + 1) / 2;
+  for (int b = blockIdx.x; b < a.batch; b += gridDim.x) {
+    const double* mkc = a.mkc + (int64_t)b * a.M * nv;
+    double* kv = a.kv + (int64_t)b * a.nnz;
+    for (int q = threadIdx.x; q < a.nnz; q += 256) {
+      double v = 0.0;
+      for (int p = a.q_ptr[q]; p < a.q_ptr[q + 1]; ++p) {
+        const int pk = a.q_pack[p];
+        const double t = mkc[(pk >> 4) * nv + (pk & 7)];
+        v = __dadd_rn(v, (pk & 8) ? -t : t);                       // truss.py:71-76 signs, :314 accumulation
+      }
+      kv[q] = v;
     }
-    a.kv[idx] = v;
   }
 }
 
@@ -189,7 +211,7 @@ constexpr int SM_STAGE = 2 * STAGE_DOUBLES;            // two stages (aliased: C
 constexpr int SCR_LD = 67;                             // back-substitution scratch: column-major 64 x 64
 constexpr int SM_LJJ = TB_TILE_ELEMS;                  // L(j,j), fragment-major
 constexpr int SM_WD = 4 * 256;                         // the four 16x16 inverse diagonal blocks of L(j,j)
-constexpr int SM_MISC = 4 * T + 48;                    // rhs acc, u block, y block, rhs vector, diag16, flag
+constexpr int SM_MISC = 4 * T + 64;                    // rhs acc, u block, y block, rhs vector, diag16, flag
 constexpr int CHOL_SMEM_BYTES = (SM_STAGE + SM_LJJ + SM_WD + SM_MISC) * 8;
 static_assert(SCR_LD * T <= SM_STAGE + SM_LJJ, "back-substitution scratch must fit in stage buffers + L(j,j)");
 static_assert(TB_TILE_ELEMS <= SM_STAGE, "C staging tile must fit in the stage buffers");
@@ -288,8 +310,8 @@ __global__ void __launch_bounds__(CH_THREADS, 3) k_chol(const LargeArgs a) {
   double* sY = sUb + T;                // [64] y_j
   double* sRv = sY + T;                // [64] rhs of the block
   double* sDiag16 = sRv + T;           // [16]
-  double* sT16 = sDiag16 + 16;         // [16]
-  int* sFlag = (int*)(sT16 + 16);
+  double* sT16 = sDiag16 + 16;         // [32]
+  int* sFlag = (int*)(sT16 + 32);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wm = warp >> 1, wn = warp & 1;
   const int nt = a.nt;
@@ -299,10 +321,13 @@ __global__ void __launch_bounds__(CH_THREADS, 3) k_chol(const LargeArgs a) {
     double* Lsys = a.L + (int64_t)b * ntiles * TB_TILE_ELEMS;
     double* ysys = a.y + (int64_t)b * a.n_pad;
     const double* kvs = a.kv + (int64_t)b * a.nnz;
+    double* wds = a.wd + (int64_t)b * nt * 1024;
+    int64_t resident = -1;   // tile of L currently held in sC (fragment-major), if any
     const double* fsys = a.force + b * a.force_stride;
     if (a.status[b] != 0) continue;  // input problem flagged by k_geom (uniform per CTA)
     int fail = 0;
     if (tid == 0) *sFlag = 0;
+    PH_DECL
 
     for (int j = 0; j < nt && !fail; ++j) {
       // ================= diagonal tile: C = A(j,j) - sum_k L(j,k) L(j,k)^T =================
@@ -314,9 +339,35 @@ __global__ void __launch_bounds__(CH_THREADS, 3) k_chol(const LargeArgs a) {
       double accy[2] = {0.0, 0.0};
       {
         const int64_t t = tb_tile_index(j, j);
-        gemm_stream(Lsys, ysys, j, j, a.prod_k + a.prod_ptr[t], a.prod_ptr[t + 1] - a.prod_ptr[t], true, sStage, acc,
-                    accy, tid);
+        const int np = a.prod_ptr[t + 1] - a.prod_ptr[t];
+        const int32_t* kl = a.prod_k + a.prod_ptr[t];
+        if (np == 1 && resident == tb_tile_index(j, __ldg(kl))) {
+          // block-tridiagonal case: the only tile this update needs is the one the previous block
+          // column just left in shared memory -- no trip through HBM/L2
+#pragma unroll 4
+          for (int kS = 0; kS < 16; ++kS) {
+            double af[2], bf[4];
+#pragma unroll
+            for (int mb = 0; mb < 2; ++mb) af[mb] = sC[frag_off(2 * wm + mb, kS) + lane];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) bf[q] = sC[frag_off(4 * wn + q, kS) + lane];
+#pragma unroll
+            for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                if (4 * wn + q <= 2 * wm + mb) dmma(acc.c[mb][q][0], acc.c[mb][q][1], af[mb], bf[q]);
+            if (wn == 0) {
+              const double yv = sY[kS * 4 + (lane & 3)];   // y of the previous block column
+              accy[0] = fma(af[0], yv, accy[0]);
+              accy[1] = fma(af[1], yv, accy[1]);
+            }
+          }
+        } else {
+          gemm_stream(Lsys, ysys, j, j, kl, np, true, sStage, acc, accy, tid);
+          resident = -1;
+        }
       }
+      PH(0)
       if (wn == 0) {  // rows of L(j,0:j) times y(0:j): reduce over the quad
 #pragma unroll
         for (int mb = 0; mb < 2; ++mb) {
@@ -357,6 +408,7 @@ __global__ void __launch_bounds__(CH_THREADS, 3) k_chol(const LargeArgs a) {
       // ---- factor the tile in place: four 16-column sub-panels, left-looking
       for (int sb = 0; sb < 4; ++sb) {
         __syncthreads();
+        PH(1)
         if (sb > 0 && warp >= 2 * sb) {  // P(mb, sub-panel) -= L(mb, 0:16sb) L(sub-panel rows, 0:16sb)^T
           double c2[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
           for (int kS = 0; kS < 4 * sb; ++kS) {
@@ -374,32 +426,53 @@ __global__ void __launch_bounds__(CH_THREADS, 3) k_chol(const LargeArgs a) {
           }
         }
         __syncthreads();
+        PH(2)
         if (warp == 0) {
-          // 16x16 diagonal block, right-looking, entirely in registers: lanes 0-15 hold the rows of
-          // the block, lanes 16-31 the rows of Z = L^{-T} (identity to start with); the pivot and the
-          // column being eliminated travel by shuffle.  Critical path per column: rsqrt + mul + fma.
+          // 16x16 diagonal block, right-looking, in registers: lanes 0-15 hold the rows of the block,
+          // lanes 16-31 the rows of Z = L^{-T} (identity to start with).  The pivot chain is kept
+          // short: the lane that owns row k+1 forms its next pivot from its own registers
+          // (d' = a - l*l), one shuffle broadcasts it and the rsqrt for column k+1 is issued before
+          // the trailing update of column k.  The eliminated column reaches the other lanes through
+          // a double-buffered 16-entry shared array (broadcast reads), not shuffles.
+          // (A rolled variant with shifting registers and a shared-memory variant were measured
+          // 2-3x slower: tools/scratch/base.cu.)
           const int base = 16 * sb, r = lane & 15;
+          const int rowpart = (((base + r) >> 3) << 8) + (((base + r) & 7) << 2);
+          const int colpart = ((sb >> 1) << 11) + (((4 * sb) & 7) << 5);
           double row[16];
 #pragma unroll
           for (int c = 0; c < 16; ++c) {
-            if (lane < 16) row[c] = (c <= r) ? sLjj[tb_tile_off(base + r, base + c)] : 0.0;
-            else row[c] = (c == r) ? 1.0 : 0.0;
+            const double v = sLjj[rowpart + colpart + ((c >> 2) << 5) + (c & 3)];
+            row[c] = lane < 16 ? (c <= r ? v : 0.0) : (c == r ? 1.0 : 0.0);
           }
+          PH(11)
           int bad = 0;
+          double d = __shfl_sync(0xffffffffu, row[0], 0);
+          if (!(d > 0.0)) bad = j * T + base + 1;
+          double rinv = rsqrt(bad ? 1.0 : d);
 #pragma unroll
           for (int k = 0; k < 16; ++k) {
-            const double d = __shfl_sync(0xffffffffu, row[k], k);
-            if (!(d > 0.0) && !bad) bad = j * T + base + k + 1;   // same value in every lane
-            const double lk = row[k] * rsqrt(bad ? 1.0 : d);       // lane k: d * rsqrt(d) = sqrt(d)
+            const double lk = row[k] * rinv;                       // lane k: d * rsqrt(d) = sqrt(d)
             row[k] = lk;
+            double rinv_next = 0.0;
+            if (k < 15) {
+              const double dn = __shfl_sync(0xffffffffu, fma(-lk, lk, row[k + 1]), k + 1);
+              if (!(dn > 0.0) && !bad) bad = j * T + base + k + 2;  // same value in every lane
+              rinv_next = rsqrt(bad ? 1.0 : dn);
+            }
+            double* col = sT16 + ((k & 1) << 4);
+            if (lane < 16) col[lane] = lk;
+            __syncwarp();
 #pragma unroll
-            for (int c = k + 1; c < 16; ++c) row[c] = fma(-lk, __shfl_sync(0xffffffffu, lk, c), row[c]);
+            for (int c = k + 1; c < 16; ++c) row[c] = fma(-lk, col[c], row[c]);
+            rinv = rinv_next;
           }
+          PH(12)
           if (bad) {
             if (lane == 0) *sFlag = bad;
           } else if (lane < 16) {  // L back into the tile (upper part of the block zeroed)
 #pragma unroll
-            for (int c = 0; c < 16; ++c) sLjj[tb_tile_off(base + r, base + c)] = (c <= r) ? row[c] : 0.0;
+            for (int c = 0; c < 16; ++c) sLjj[rowpart + colpart + ((c >> 2) << 5) + (c & 3)] = (c <= r) ? row[c] : 0.0;
           } else {  // W = L^{-1} as a DMMA B operand: W[c'][kk] = Z[kk][c'] for kk <= c' (this lane: kk = r)
 #pragma unroll
             for (int cp = 0; cp < 16; ++cp)
@@ -407,6 +480,7 @@ __global__ void __launch_bounds__(CH_THREADS, 3) k_chol(const LargeArgs a) {
           }
         }
         __syncthreads();
+        PH(3)
         fail = *sFlag;
         if (fail) break;  // uniform
         if (warp >= 2 * sb + 2) {  // rows below the block: X = P W^T, in place
@@ -425,6 +499,7 @@ __global__ void __launch_bounds__(CH_THREADS, 3) k_chol(const LargeArgs a) {
       }
       if (fail) break;  // uniform
       __syncthreads();
+      PH(4)
 
       // ---- publish L(j,j) (strictly-upper part zeroed) and solve L(j,j) y_j = rhs with the 16x16 inverses
       {
@@ -437,6 +512,8 @@ __global__ void __launch_bounds__(CH_THREADS, 3) k_chol(const LargeArgs a) {
           const int r = rb * 8 + (l >> 2), c = h * 32 + ks * 4 + (l & 3);
           Lt[idx] = (c <= r) ? sLjj[idx] : 0.0;
         }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) wds[j * 1024 + tid + q * 256] = sWd[tid + q * 256];
       }
       if (warp == 0) {
         const int c = lane & 15, hh = lane >> 4;
@@ -458,9 +535,10 @@ __global__ void __launch_bounds__(CH_THREADS, 3) k_chol(const LargeArgs a) {
         }
       }
       __syncthreads();
+      PH(5)
 
       // ================= panel tiles below the diagonal =================
-      for (int i = j + 1; i < nt; ++i) {
+      for (int i = nt - 1; i > j; --i) {   // descending: the tile the next diagonal update needs first is left in sC
         const int64_t tij = tb_tile_index(i, j);
         if (!a.tile_nz[tij]) continue;  // structurally zero tile of L: never touched (uniform)
 #pragma unroll
@@ -469,6 +547,7 @@ __global__ void __launch_bounds__(CH_THREADS, 3) k_chol(const LargeArgs a) {
           for (int q = 0; q < 4; ++q) acc.c[mb][q][0] = acc.c[mb][q][1] = 0.0;
         gemm_stream(Lsys, ysys, i, j, a.prod_k + a.prod_ptr[tij], a.prod_ptr[tij + 1] - a.prod_ptr[tij], false, sStage,
                     acc, accy, tid);
+        PH(6)
         double* Xt = Lsys + tb_tile_index(i, j) * TB_TILE_ELEMS;
         // C = A(i,j) - acc  -> shared (fragment-major)
 #pragma unroll
@@ -489,6 +568,7 @@ __global__ void __launch_bounds__(CH_THREADS, 3) k_chol(const LargeArgs a) {
           }
         }
         __syncthreads();
+        PH(7)
         // X L(j,j)^T = C, row block `warp` (8 rows) handled entirely by this warp:
         //   X[:,sb] = (C[:,sb] - X[:,0:sb] L(sb rows, 0:16sb)^T) W_sb^T      for sb = 0..3
 #pragma unroll 1
@@ -530,6 +610,8 @@ __global__ void __launch_bounds__(CH_THREADS, 3) k_chol(const LargeArgs a) {
             *reinterpret_cast<double2*>(Xt + o + (lane + 32 * q) * 2) = *reinterpret_cast<const double2*>(sC + o + (lane + 32 * q) * 2);
         }
         __syncthreads();  // sC is about to be overwritten by the next stream; X visible to the CTA
+        resident = tij;
+        PH(8)
       }
     }
 
@@ -565,31 +647,42 @@ __global__ void __launch_bounds__(CH_THREADS, 3) k_chol(const LargeArgs a) {
         sRhs[warp * 4 + lane] = a0;
         sRhs[32 + warp * 4 + lane] = a1;
       }
-      // diagonal block into the scratch (column-major, lower part)
+      PH(9)
+      // L(j,j) and the inverses of its 16x16 diagonal blocks back into shared memory
       {
         const double* Lt = Lsys + tb_tile_index(j, j) * TB_TILE_ELEMS;
 #pragma unroll 4
-        for (int q = 0; q < 16; ++q) {
-          const int idx = tid + q * 256;
-          const int l = idx & 31, slot = idx >> 5;
-          const int ks = slot & 7, rb = (slot >> 3) & 7, h = slot >> 6;
-          const int r = rb * 8 + (l >> 2), c = h * 32 + ks * 4 + (l & 3);
-          if (c <= r) sScr[r + c * SCR_LD] = __ldcg(Lt + idx);
+        for (int q = 0; q < 16; ++q) sLjj[tid + q * 256] = __ldcg(Lt + tid + q * 256);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) sWd[tid + q * 256] = __ldcg(wds + j * 1024 + tid + q * 256);
+      }
+      __syncthreads();
+      if (warp == 0) {  // L^T u = r block by block, last 16 first:  u_sb = W_sb^T (r_sb - L(below, sb)^T u_below)
+        sRv[lane] = __ldcg(ysys + j * T + lane) - sRhs[lane];
+        sRv[lane + 32] = __ldcg(ysys + j * T + lane + 32) - sRhs[lane + 32];
+        __syncwarp();
+        const int c = lane & 15, hh = lane >> 4;
+        for (int sb = 3; sb >= 0; --sb) {
+          double t = 0.0;
+          for (int rr = 16 * (sb + 1) + hh; rr < T; rr += 2) t = fma(sLjj[tb_tile_off(rr, 16 * sb + c)], sUb[rr], t);
+          t += __shfl_xor_sync(0xffffffffu, t, 16);
+          if (lane < 16) sT16[c] = sRv[16 * sb + c] - t;
+          __syncwarp();
+          double uv = 0.0;
+          for (int cc = c + hh; cc < 16; cc += 2)   // W^T: u[c] = sum_{cc >= c} W[cc][c] t[cc]
+            uv = fma(sWd[sb * 256 + ((((cc >> 3) << 2) + (c >> 2)) << 5) + ((cc & 7) << 2) + (c & 3)], sT16[cc], uv);
+          uv += __shfl_xor_sync(0xffffffffu, uv, 16);
+          if (lane < 16) {
+            sUb[16 * sb + c] = uv;
+            ysys[j * T + 16 * sb + c] = uv;
+          }
+          __syncwarp();
         }
       }
       __syncthreads();
-      if (tid < T) {  // two warps walk the 64 columns; the rest wait at the barrier below
-        const double rinv = 1.0 / sScr[tid + tid * SCR_LD];
-        double rp = __ldcg(ysys + j * T + tid) - sRhs[tid];
-        for (int k = T - 1; k >= 0; --k) {
-          if (tid == k) sUb[k] = rp * rinv;
-          asm volatile("bar.sync 2, 64;" ::: "memory");
-          if (tid < k) rp = fma(-sScr[k + tid * SCR_LD], sUb[k], rp);
-        }
-        ysys[j * T + tid] = sUb[tid];
-      }
-      __syncthreads();
+      PH(10)
     }
+    PH_FLUSH
     if (tid == 0) a.status[b] = 0;
   }
 }
@@ -732,7 +825,8 @@ __global__ void __launch_bounds__(256) k_recover(const LargeArgs a) {
 size_t tb_large_workspace_bytes(int batch, int dim, int M, int n_pad, int64_t nnz) {
   const int nt = n_pad / TB_TILE;
   const size_t ntiles = (size_t)nt * (nt + 1) / 2;
-  size_t doubles = (size_t)batch * ((size_t)M * (2 + dim) + ntiles * TB_TILE_ELEMS + (size_t)n_pad + (size_t)nnz);
+  size_t doubles = (size_t)batch * ((size_t)M * (2 + dim + dim * (dim + 1) / 2) + ntiles * TB_TILE_ELEMS + (size_t)n_pad + (size_t)nnz +
+                                    (size_t)nt * 1024);
   return doubles * 8 + (size_t)batch * 4 + 1024;
 }
 
@@ -744,7 +838,9 @@ void tb_large_carve(LargeArgs& a, void* ws) {
   a.mk = p; p += (size_t)a.batch * a.M;
   a.mc = p; p += (size_t)a.batch * a.M * a.dim;
   a.mw = p; p += (size_t)a.batch * a.M;
+  a.mkc = p; p += (size_t)a.batch * a.M * (a.dim * (a.dim + 1) / 2);
   a.kv = p; p += (size_t)a.batch * a.nnz;
+  a.wd = p; p += (size_t)a.batch * a.nt * 1024;
   a.status = (int32_t*)p;
 }
 
@@ -764,9 +860,7 @@ int tb_launch_large(const LargeArgs& a, int num_sm, cudaStream_t st) {
     tb_prof_end(TB_PROF_GEOM, st);
   }
   if (fused) {
-    const int64_t total = (int64_t)a.batch * a.nnz;
-    int grid = (int)((total + 255) / 256 < (int64_t)num_sm * 16 ? (total + 255) / 256 : (int64_t)num_sm * 16);
-    if (grid < 1) grid = 1;
+    int grid = a.batch < num_sm * 8 ? a.batch : num_sm * 8;
     tb_prof_begin(TB_PROF_ASSEMBLE, st);
     k_kval<<<grid, 256, 0, st>>>(a);
     tb_prof_end(TB_PROF_ASSEMBLE, st);

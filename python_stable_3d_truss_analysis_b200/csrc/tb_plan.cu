@@ -193,9 +193,18 @@ extern "C" int tb_plan_create(const tb_topology* topo, tb_plan** plan_out) {
     for (size_t e = 0; e < nnz; ++e)
       p->tile_ent[pos[tb_tile_index(p->ent_row[e] / TB_TILE, p->ent_col[e] / TB_TILE)]++] = (int32_t)e;
     p->tile_pos.assign(nnz, 0);
+    p->q_ptr.assign(nnz + 1, 0);
     for (size_t q = 0; q < nnz; ++q) {
       const int e = p->tile_ent[q];
       p->tile_pos[q] = tb_tile_off(p->ent_row[e] % TB_TILE, p->ent_col[e] % TB_TILE);
+      for (int64_t c = p->ent_ptr[e]; c < p->ent_ptr[e + 1]; ++c) {
+        const int loc = p->ctr_local[c], la = loc / (2 * d), lb = loc % (2 * d);
+        const int A = la / d, i = la % d, B = lb / d, j = lb % d;
+        const int lo = std::min(i, j), hi = std::max(i, j);
+        const int ij = lo * d - lo * (lo - 1) / 2 + (hi - lo);   // index of (lo,hi), lo <= hi, row-major upper triangle
+        p->q_pack.push_back((p->ctr_member[c] << 4) | ((A != B) << 3) | ij);
+      }
+      p->q_ptr[q + 1] = (int32_t)p->q_pack.size();
     }
   }
 
@@ -272,6 +281,8 @@ extern "C" int tb_plan_create(const tb_topology* topo, tb_plan** plan_out) {
   if (!rc) rc = upload(&p->d_tile_ent_ptr, p->tile_ent_ptr);
   if (!rc) rc = upload(&p->d_tile_ent, p->tile_ent);
   if (!rc) rc = upload(&p->d_tile_pos, p->tile_pos);
+  if (!rc) rc = upload(&p->d_q_ptr, p->q_ptr);
+  if (!rc) rc = upload(&p->d_q_pack, p->q_pack);
   if (!rc) rc = upload(&p->d_tile_nz, p->tile_nz);
   if (!rc) rc = upload(&p->d_prod_ptr, p->prod_ptr);
   if (!rc) rc = upload(&p->d_prod_k, p->prod_k);
@@ -304,6 +315,8 @@ extern "C" void tb_plan_destroy(tb_plan* p) {
   cudaFree(p->d_tile_ent_ptr);
   cudaFree(p->d_tile_ent);
   cudaFree(p->d_tile_pos);
+  cudaFree(p->d_q_ptr);
+  cudaFree(p->d_q_pack);
   cudaFree(p->d_tile_nz);
   cudaFree(p->d_prod_ptr);
   cudaFree(p->d_prod_k);
