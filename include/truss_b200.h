@@ -80,7 +80,7 @@ typedef struct {
   int32_t n_support;   /* s */
   int32_t n_resist;    /* Truss.nResistance, truss.py:154-156 */
   int32_t stable;      /* Truss.isStable, truss.py:158-164 */
-  int32_t path;        /* 0 = fused shared-memory kernel, 1 = blocked global-memory pipeline */
+  int32_t path;        /* 0 = fused shared-memory kernel, 1 = tiled (64x64) pipeline, 2 = band (16x16 blocks) pipeline */
   int32_t n_pad;       /* padded order used by the blocked pipeline (multiple of the tile) */
   int64_t nnz_lower;   /* structural non-zeros of the lower triangle of K_ff */
   int64_t n_contrib;   /* entries of the scatter map (member contributions to the lower triangle) */
@@ -90,6 +90,10 @@ typedef struct {
   int64_t n_tiles_nonzero;  /* tiles of L that are structurally non-zero (the only ones touched) */
   int64_t n_tile_products;  /* tile x tile^T updates the factorisation performs */
   double chol_flops;        /* flops of that block-sparse factorisation + the two triangular solves */
+  /* band path: 16x16 blocks */
+  int32_t band_blocks;      /* sub-diagonal 16x16 blocks per block column (the band path needs <= 8) */
+  int64_t envelope_size;    /* entries inside the row envelope of K_ff (fill stays inside it) */
+  double envelope_flops;    /* flops of an envelope Cholesky + two triangular solves: the algorithmic work */
 } tb_plan_info;
 
 /* Build the integer maps of truss.py:319-326 (free/supported DOF order = ascending DOF index)
@@ -99,8 +103,8 @@ typedef struct {
 int tb_plan_create(const tb_topology* topo, tb_plan** plan_out);
 void tb_plan_destroy(tb_plan* plan);
 int tb_plan_query(const tb_plan* plan, tb_plan_info* info_out);
-/* Override the automatic path choice (0 fused shared-memory kernel, 1 blocked pipeline);
- * used by the parity tests to push small trusses through the blocked pipeline too. */
+/* Override the automatic path choice (0 fused shared-memory kernel, 1 tiled pipeline, 2 band
+ * pipeline); used by the parity tests to push every truss through every pipeline. */
 int tb_plan_set_path(tb_plan* plan, int32_t path);
 
 /* Host copies of the DOF maps, for bit-exact checks against

@@ -17,7 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 LIB_PATH = os.path.join(CSRC, "libtruss_b200.so")
-SOURCES = ["tb_plan.cu", "tb_small.cu", "tb_large.cu", "tb_api.cu", "tb_peak.cu"]
+SOURCES = ["tb_plan.cu", "tb_small.cu", "tb_large.cu", "tb_band.cu", "tb_api.cu", "tb_peak.cu"]
 
 TB_ERR_NO_DEVICE = -7
 TB_ERR_TOO_LARGE = -6
@@ -63,7 +63,8 @@ class TbPlanInfo(C.Structure):
                 ("n_free", C.c_int32), ("n_support", C.c_int32), ("n_resist", C.c_int32), ("stable", C.c_int32),
                 ("path", C.c_int32), ("n_pad", C.c_int32), ("nnz_lower", C.c_int64), ("n_contrib", C.c_int64),
                 ("half_bandwidth", C.c_int64), ("n_tiles", C.c_int64), ("n_tiles_nonzero", C.c_int64),
-                ("n_tile_products", C.c_int64), ("chol_flops", C.c_double)]
+                ("n_tile_products", C.c_int64), ("chol_flops", C.c_double), ("band_blocks", C.c_int32),
+                ("envelope_size", C.c_int64), ("envelope_flops", C.c_double)]
 
 
 class TbBatchIn(C.Structure):

@@ -83,9 +83,10 @@ int run_plan(tb_plan* p, const tb_batch_in* in, const tb_batch_out* out, const t
   }
 
   // blocked path: process the batch in chunks that fit the workspace cap
-  const size_t per_sys = tb_large_workspace_bytes(1, p->dim, p->M, p->n_pad, (int64_t)p->ent_row.size());
+  const int64_t nnz = (int64_t)p->ent_row.size();
+  const size_t per_sys = tb_large_workspace_bytes(1, p->dim, p->M, p->n_pad, nnz, p->path, p->nb16, p->NB);
   int chunk = (int)std::min<size_t>((size_t)in->batch, std::max<size_t>(1, ws_cap_bytes() / per_sys));
-  const size_t need = tb_large_workspace_bytes(chunk, p->dim, p->M, p->n_pad, (int64_t)p->ent_row.size());
+  const size_t need = tb_large_workspace_bytes(chunk, p->dim, p->M, p->n_pad, nnz, p->path, p->nb16, p->NB);
   if (p->ws_bytes < need) {
     if (p->ws) {
       TB_CUDA(cudaStreamSynchronize(st));
@@ -132,14 +133,19 @@ int run_plan(tb_plan* p, const tb_batch_in* in, const tb_batch_out* out, const t
     a.tile_ent = p->d_tile_ent;
     a.tile_pos = p->d_tile_pos;
     a.nnz = (int64_t)p->ent_row.size();
-    a.q_ptr = p->d_q_ptr;
-    a.q_pack = p->d_q_pack;
+    a.q_ptr = p->path == 2 ? p->d_bq_ptr : p->d_q_ptr;
+    a.q_pack = p->path == 2 ? p->d_bq_pack : p->d_q_pack;
+    a.nb16 = p->nb16;
+    a.NB = p->NB;
+    a.b16_ptr = p->d_b16_ptr;
+    a.b16_pos = p->d_b16_pos;
+    if (p->path == 2) a.n_pad = p->nb16 * 16;
     a.tile_nz = p->d_tile_nz;
     a.prod_ptr = p->d_prod_ptr;
     a.prod_k = p->d_prod_k;
     a.inc_ptr = p->d_inc_ptr;
     a.inc_mem = p->d_inc_mem;
-    tb_large_carve(a, p->ws);
+    tb_large_carve(a, p->ws, p->path);
     a.u = out->u ? out->u + (int64_t)b0 * p->N : nullptr;
     a.ext = out->ext ? out->ext + (int64_t)b0 * p->N : nullptr;
     a.axial = out->axial ? out->axial + (int64_t)b0 * p->M : nullptr;
@@ -152,7 +158,7 @@ int run_plan(tb_plan* p, const tb_batch_in* in, const tb_batch_out* out, const t
     a.allow_displace = allow_d;
     a.fitness_mode = fitness_mode;
     a.plan_stable = p->stable;
-    int rc = tb_launch_large(a, p->num_sm, st);
+    int rc = tb_launch_large(a, p->num_sm, st, p->path);
     if (rc) return rc;
   }
   if (fit && fit->info && out->info) {

@@ -19,6 +19,10 @@ enum : int { SUP_NO = 0, SUP_PIN = 1, SUP_ROLLER_X = 2, SUP_ROLLER_Y = 3, SUP_RO
 constexpr int TB_TILE = 64;                     // tile order
 constexpr int TB_TILE_ELEMS = TB_TILE * TB_TILE;  // doubles per tile
 
+// band path (tb_band.cu): 16x16 blocks, at most TB_BAND_MAX_NB sub-diagonal blocks per block column
+constexpr int TB_BAND_THREADS = 128;
+constexpr int TB_BAND_MAX_NB = 8;
+
 // limits of the fused shared-memory path
 constexpr int TB_SMALL_MAX_DOF = 160;     // max d*nJ (bounds the free-DOF count)
 constexpr int TB_SMALL_MAX_MEMBER = 1024;
@@ -71,6 +75,13 @@ struct tb_plan {
   std::vector<int32_t> prod_ptr;           // [ntiles+1]
   std::vector<int32_t> prod_k;             // [n_prod]
   int64_t n_tiles_nz = 0;
+  // band view (16x16 blocks): nb16 block columns, NB sub-diagonal blocks; entries grouped per block column
+  int nb16 = 0, NB = 0;
+  std::vector<int32_t> b16_ptr;            // [nb16+1] entry ranges (band order) per block column
+  std::vector<int32_t> b16_pos;            // [nnz] (block offset e) << 8 | offset inside the 16x16 block
+  std::vector<int32_t> bq_ptr, bq_pack;    // contribution lists in band order (same encoding as q_ptr/q_pack)
+  int64_t envelope_size = 0;               // entries inside the row envelope of K_ff (= of L)
+  double envelope_flops = 0.0;             // flops of an envelope Cholesky + two triangular solves
   double chol_flops = 0.0;                 // flops of the block-sparse factorisation + two triangular solves
   // joint -> incident (member, end) lists, ascending member (recovery of reactions)
   std::vector<int32_t> inc_ptr;            // [nJ+1]
@@ -92,6 +103,10 @@ struct tb_plan {
   int32_t* d_tile_pos = nullptr;
   int32_t* d_q_ptr = nullptr;
   int32_t* d_q_pack = nullptr;
+  int32_t* d_b16_ptr = nullptr;
+  int32_t* d_b16_pos = nullptr;
+  int32_t* d_bq_ptr = nullptr;
+  int32_t* d_bq_pack = nullptr;
   uint8_t* d_tile_nz = nullptr;
   int32_t* d_prod_ptr = nullptr;
   int32_t* d_prod_k = nullptr;
@@ -144,6 +159,8 @@ struct LargeArgs {
   int64_t nnz;
   const uint8_t* tile_nz; const int32_t* prod_ptr; const int32_t* prod_k;
   const int32_t* q_ptr; const int32_t* q_pack;
+  int nb16, NB;
+  const int32_t* b16_ptr; const int32_t* b16_pos;
   const int32_t* inc_ptr; const int32_t* inc_mem;
   // workspace
   double* mk;      // [B][M]      EA/L
@@ -166,9 +183,11 @@ struct LargeArgs {
 // launchers (return cudaError_t as int)
 int tb_launch_small(const SmallArgs& a, int dim, cudaStream_t st);
 int tb_small_smem_bytes(int dim, int nJ, int M, int max_n, int* threads);
-int tb_launch_large(const LargeArgs& a, int num_sm, cudaStream_t st);
-size_t tb_large_workspace_bytes(int batch, int dim, int M, int n_pad, int64_t nnz);
-void tb_large_carve(LargeArgs& a, void* ws);
+int tb_launch_large(const LargeArgs& a, int num_sm, cudaStream_t st, int path);
+size_t tb_large_workspace_bytes(int batch, int dim, int M, int n_pad, int64_t nnz, int path, int nb16, int NB);
+void tb_large_carve(LargeArgs& a, void* ws, int path);
+int tb_launch_band_chol(const LargeArgs& a, int num_sm, cudaStream_t st);
+int tb_band_smem_bytes(int NB);
 
 // fragment-major offset of element (r, c) inside one 64x64 tile:
 //   [k-half 2][row-block 8][k-slab 8][lane 32], lane = (r%8)*4 + c%4

@@ -822,33 +822,41 @@ __global__ void __launch_bounds__(256) k_recover(const LargeArgs a) {
 
 }  // namespace
 
-size_t tb_large_workspace_bytes(int batch, int dim, int M, int n_pad, int64_t nnz) {
+size_t tb_large_workspace_bytes(int batch, int dim, int M, int n_pad, int64_t nnz, int path, int nb16, int NB) {
   const int nt = n_pad / TB_TILE;
   const size_t ntiles = (size_t)nt * (nt + 1) / 2;
-  size_t doubles = (size_t)batch * ((size_t)M * (2 + dim + dim * (dim + 1) / 2) + ntiles * TB_TILE_ELEMS + (size_t)n_pad + (size_t)nnz +
-                                    (size_t)nt * 1024);
-  return doubles * 8 + (size_t)batch * 4 + 1024;
+  size_t per = (size_t)M * (2 + dim + dim * (dim + 1) / 2) + (size_t)nnz;
+  if (path == 2) per += (size_t)nb16 * (NB + 1) * 256 + (size_t)nb16 * 256 + (size_t)nb16 * 16;
+  else per += ntiles * TB_TILE_ELEMS + (size_t)nt * 1024 + (size_t)n_pad;
+  return (size_t)batch * per * 8 + (size_t)batch * 4 + 1024;
 }
 
-void tb_large_carve(LargeArgs& a, void* ws) {
-  const size_t ntiles = (size_t)a.nt * (a.nt + 1) / 2;
+void tb_large_carve(LargeArgs& a, void* ws, int path) {
   double* p = (double*)ws;
-  a.L = p;  p += (size_t)a.batch * ntiles * TB_TILE_ELEMS;   // first: 32 KB-aligned tiles
-  a.y = p;  p += (size_t)a.batch * a.n_pad;
+  if (path == 2) {
+    a.L = p;  p += (size_t)a.batch * a.nb16 * (a.NB + 1) * 256;   // off-diagonal 16x16 blocks of L
+    a.wd = p; p += (size_t)a.batch * a.nb16 * 256;                // inverses of the diagonal blocks
+    a.y = p;  p += (size_t)a.batch * a.nb16 * 16;
+  } else {
+    const size_t ntiles = (size_t)a.nt * (a.nt + 1) / 2;
+    a.L = p;  p += (size_t)a.batch * ntiles * TB_TILE_ELEMS;      // first: 32 KB-aligned tiles
+    a.wd = p; p += (size_t)a.batch * a.nt * 1024;
+    a.y = p;  p += (size_t)a.batch * a.n_pad;
+  }
   a.mk = p; p += (size_t)a.batch * a.M;
   a.mc = p; p += (size_t)a.batch * a.M * a.dim;
   a.mw = p; p += (size_t)a.batch * a.M;
   a.mkc = p; p += (size_t)a.batch * a.M * (a.dim * (a.dim + 1) / 2);
   a.kv = p; p += (size_t)a.batch * a.nnz;
-  a.wd = p; p += (size_t)a.batch * a.nt * 1024;
   a.status = (int32_t*)p;
 }
 
-int tb_launch_large(const LargeArgs& a, int num_sm, cudaStream_t st) {
+int tb_launch_large(const LargeArgs& a, int num_sm, cudaStream_t st, int path) {
   if (a.batch <= 0) return 0;
   if (num_sm <= 0) num_sm = 148;
-  // TB_UNFUSED_ASSEMBLY=1 keeps the separate HBM-bound assembly kernel (A/B measurements)
-  static const bool fused = [] { const char* s = getenv("TB_UNFUSED_ASSEMBLY"); return !(s && s[0] == '1'); }();
+  // TB_UNFUSED_ASSEMBLY=1 keeps the separate HBM-bound assembly kernel (A/B measurements, tiled path only)
+  static const bool fused_env = [] { const char* s = getenv("TB_UNFUSED_ASSEMBLY"); return !(s && s[0] == '1'); }();
+  const bool fused = fused_env || path == 2;
   k_init_status<<<(a.batch + 255) / 256, 256, 0, st>>>(a.status, a.batch, 0);
   {
     const int64_t total = (int64_t)a.batch * a.M;
@@ -872,7 +880,10 @@ int tb_launch_large(const LargeArgs& a, int num_sm, cudaStream_t st) {
     else k_assemble<2><<<grid, 256, 0, st>>>(a);
     tb_prof_end(TB_PROF_ASSEMBLE, st);
   }
-  {
+  if (path == 2) {
+    int rc = tb_launch_band_chol(a, num_sm, st);
+    if (rc) return rc;
+  } else {
     auto kern = fused ? k_chol<true> : k_chol<false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CHOL_SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;

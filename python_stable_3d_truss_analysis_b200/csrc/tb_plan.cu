@@ -10,6 +10,7 @@
 #include <cstring>
 #include <new>
 #include <numeric>
+#include <tuple>
 
 #include "tb_common.cuh"
 
@@ -179,6 +180,7 @@ extern "C" int tb_plan_create(const tb_topology* topo, tb_plan** plan_out) {
 
   // ---- path + tile grouping of entries for the blocked path
   p->path = (p->N <= TB_SMALL_MAX_DOF && p->M <= TB_SMALL_MAX_MEMBER && p->nJ <= TB_SMALL_MAX_JOINT) ? 0 : 1;
+  // (a narrow band promotes path 1 to the band path 2 once the band view is known, below)
   p->n_pad = std::max(TB_TILE, (p->n + TB_TILE - 1) / TB_TILE * TB_TILE);
   p->nt = p->n_pad / TB_TILE;
   {
@@ -251,6 +253,49 @@ extern "C" int tb_plan_create(const tb_topology* topo, tb_plan** plan_out) {
     p->chol_flops = fl;
   }
 
+  // ---- band view: 16x16 blocks, entries grouped per block column (then block offset, row, column);
+  // row envelope of K_ff (fill stays inside it) and the flops an envelope Cholesky needs
+  {
+    const size_t nnz = p->ent_row.size();
+    p->nb16 = std::max(1, (p->n + 15) / 16);
+    int NB = 1;
+    for (size_t e = 0; e < nnz; ++e) NB = std::max(NB, p->ent_row[e] / 16 - p->ent_col[e] / 16);
+    p->NB = NB;
+    std::vector<int32_t> order(nnz);
+    std::iota(order.begin(), order.end(), 0);
+    auto key = [&](int e) { return std::make_tuple(p->ent_col[e] / 16, p->ent_row[e] / 16, p->ent_row[e], p->ent_col[e]); };
+    std::sort(order.begin(), order.end(), [&](int x, int y) { return key(x) < key(y); });
+    p->b16_ptr.assign(p->nb16 + 1, 0);
+    p->b16_pos.assign(nnz, 0);
+    p->bq_ptr.assign(nnz + 1, 0);
+    for (size_t q = 0; q < nnz; ++q) {
+      const int e = order[q], r = p->ent_row[e], c = p->ent_col[e];
+      p->b16_ptr[c / 16 + 1]++;
+      const int rr = r % 16, cc = c % 16;
+      p->b16_pos[q] = ((r / 16 - c / 16) << 8) | (((((rr >> 3) << 2) + (cc >> 2)) << 5) + ((rr & 7) << 2) + (cc & 3));
+      for (int64_t k = p->ent_ptr[e]; k < p->ent_ptr[e + 1]; ++k) {
+        const int loc = p->ctr_local[k], la = loc / (2 * d), lb = loc % (2 * d);
+        const int A = la / d, i = la % d, B = lb / d, j = lb % d;
+        const int lo = std::min(i, j), hi = std::max(i, j);
+        p->bq_pack.push_back((p->ctr_member[k] << 4) | ((A != B) << 3) | (lo * d - lo * (lo - 1) / 2 + (hi - lo)));
+      }
+      p->bq_ptr[q + 1] = (int32_t)p->bq_pack.size();
+    }
+    for (int c = 0; c < p->nb16; ++c) p->b16_ptr[c + 1] += p->b16_ptr[c];
+    std::vector<int32_t> first(p->n);
+    std::iota(first.begin(), first.end(), 0);
+    for (size_t e = 0; e < nnz; ++e) first[p->ent_row[e]] = std::min(first[p->ent_row[e]], p->ent_col[e]);
+    double fl = 0.0;
+    int64_t env = 0;
+    for (int i = 0; i < p->n; ++i) {
+      env += i - first[i] + 1;
+      for (int j = first[i]; j <= i; ++j) fl += 2.0 * (j - std::max(first[i], first[j])) + 1.0;   // dot + divide / sqrt
+      fl += 4.0 * (i - first[i]) + 2.0;                                                            // two triangular solves
+    }
+    p->envelope_size = env;
+    p->envelope_flops = fl;
+  }
+
   // ---- joint incidence lists (ascending member, then end)
   p->inc_ptr.assign(p->nJ + 1, 0);
   for (int m = 0; m < p->M; ++m)
@@ -263,6 +308,10 @@ extern "C" int tb_plan_create(const tb_topology* topo, tb_plan** plan_out) {
       for (int e = 0; e < 2; ++e) p->inc_mem[pos[p->conn[2 * m + e]]++] = m * 2 + e;
   }
 
+  if (p->path == 1 && p->NB <= TB_BAND_MAX_NB) {
+    const char* env = getenv("TB_NO_BAND");
+    if (!(env && env[0] == '1')) p->path = 2;
+  }
   if (!has_dev) {
     *plan_out = p;
     return TB_OK;
@@ -283,6 +332,10 @@ extern "C" int tb_plan_create(const tb_topology* topo, tb_plan** plan_out) {
   if (!rc) rc = upload(&p->d_tile_pos, p->tile_pos);
   if (!rc) rc = upload(&p->d_q_ptr, p->q_ptr);
   if (!rc) rc = upload(&p->d_q_pack, p->q_pack);
+  if (!rc) rc = upload(&p->d_b16_ptr, p->b16_ptr);
+  if (!rc) rc = upload(&p->d_b16_pos, p->b16_pos);
+  if (!rc) rc = upload(&p->d_bq_ptr, p->bq_ptr);
+  if (!rc) rc = upload(&p->d_bq_pack, p->bq_pack);
   if (!rc) rc = upload(&p->d_tile_nz, p->tile_nz);
   if (!rc) rc = upload(&p->d_prod_ptr, p->prod_ptr);
   if (!rc) rc = upload(&p->d_prod_k, p->prod_k);
@@ -317,6 +370,10 @@ extern "C" void tb_plan_destroy(tb_plan* p) {
   cudaFree(p->d_tile_pos);
   cudaFree(p->d_q_ptr);
   cudaFree(p->d_q_pack);
+  cudaFree(p->d_b16_ptr);
+  cudaFree(p->d_b16_pos);
+  cudaFree(p->d_bq_ptr);
+  cudaFree(p->d_bq_pack);
   cudaFree(p->d_tile_nz);
   cudaFree(p->d_prod_ptr);
   cudaFree(p->d_prod_k);
@@ -347,12 +404,16 @@ extern "C" int tb_plan_query(const tb_plan* p, tb_plan_info* o) {
   o->n_tiles_nonzero = p->n_tiles_nz;
   o->n_tile_products = (int64_t)p->prod_k.size();
   o->chol_flops = p->chol_flops;
+  o->band_blocks = p->NB;
+  o->envelope_size = p->envelope_size;
+  o->envelope_flops = p->envelope_flops;
   return TB_OK;
 }
 
 extern "C" int tb_plan_set_path(tb_plan* p, int32_t path) {
   if (!p) return TB_ERR_NULL;
-  if (path != 0 && path != 1) return TB_ERR_SIZE;
+  if (path < 0 || path > 2) return TB_ERR_SIZE;
+  if (path == 2 && p->NB > TB_BAND_MAX_NB) return TB_ERR_TOO_LARGE;
   if (path == 0 && !(p->N <= TB_SMALL_MAX_DOF && p->M <= TB_SMALL_MAX_MEMBER && p->nJ <= TB_SMALL_MAX_JOINT))
     return TB_ERR_TOO_LARGE;
   p->path = path;

@@ -127,8 +127,12 @@ def test_path_selection_and_padding():
         _, support, conn, _, _ = orc.arrays_from_json(data, dim)
         plan = _lib.Plan(dim, conn, support)
         big = name.startswith("bar-942")
-        assert plan.path == (1 if big else 0)
+        assert plan.path == (2 if big else 0)        # bar-942: half-bandwidth 56 -> band pipeline
         assert plan.info.n_pad % 64 == 0 and plan.info.n_pad >= plan.n
-        if not big:
-            plan.set_path(1)
-            assert plan.path == 1
+        assert plan.info.band_blocks >= 1 and plan.info.envelope_size <= plan.n * (plan.n + 1) // 2
+        if big:
+            assert plan.info.band_blocks == 4 and plan.info.half_bandwidth == 56
+            assert plan.info.n_tiles_nonzero == 21 and plan.info.n_tile_products == 10
+        for path in (1, 2, 0 if not big else 2):
+            plan.set_path(path)
+            assert plan.path == path

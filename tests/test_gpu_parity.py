@@ -22,14 +22,24 @@ def dense(t):
     return {"u": t._dense["u"], "ext": t._dense["ext"], "axial": t._dense["axial"], "weight": t.weight}
 
 
-@pytest.mark.parametrize("path", [0, 1], ids=["fused", "blocked"])
+PATHS = pytest.mark.parametrize("path", [0, 1, 2], ids=["fused", "tiled", "band"])
+
+
+def force_path(plan, path):
+    try:
+        plan.set_path(path)
+    except _lib.TrussLibError as exc:
+        if exc.code == _lib.TB_ERR_TOO_LARGE:
+            pytest.skip("system does not fit this pipeline")
+        raise
+
+
+@PATHS
 @pytest.mark.parametrize("name,dim,data,gold", H.shipped_cases(), ids=lambda v: v if isinstance(v, str) else None)
 def test_solve_vs_shipped_goldens(name, dim, data, gold, path):
     t = Truss(dim).LoadFromJSON(data=data)
     plan = t._get_plan()
-    if path == 0 and plan.path == 1:
-        pytest.skip("too large for the fused kernel")
-    plan.set_path(path)
+    force_path(plan, path)
     t.Solve()
     H.assert_close(dense(t), gold, what=f"{name} path{path}")
     for k in H.FIELDS:
@@ -48,12 +58,12 @@ def test_solve_vs_shipped_cube7(name, dim, data, gold):
     H.assert_close(dense(t), gold, what=name)
 
 
-@pytest.mark.parametrize("path", [0, 1], ids=["fused", "blocked"])
+@PATHS
 def test_solve_vs_live_random(path):
     for i, case in enumerate(H.load_json("live_random.json")):
         dim = case["dim"]
         t = Truss(dim).LoadFromJSON(data=case["data"])
-        t._get_plan().set_path(path)
+        force_path(t._get_plan(), path)
         t.Solve()
         want = {k: np.array(v) if k != "weight" else v for k, v in case["result"].items()}
         H.assert_close(dense(t), want, what=f"random[{i}] path{path}")
@@ -90,7 +100,7 @@ def test_ga_fitness_vs_live_reference():
     n_pen = 0
     for case, v, a_s, a_d in blocks:
         t = Truss(3).LoadFromJSON(f"{H.GOLDEN}/ref_data/{case}.json")
-        for path in (0, 1):
+        for path in (0, 1, 2):
             t._get_plan().set_path(path)
             out = FitnessBatch(t, v["genes"], types, a_s, a_d)
             assert not out["info"].any()
@@ -123,11 +133,13 @@ def test_ga_class_uses_batched_fitness():
 def test_load_cases_bar942_vs_live():
     z = np.load(f"{H.GOLDEN}/live_loadcases_bar942.npz")
     t = Truss(3).LoadFromJSON(f"{H.GOLDEN}/ref_data/bar-942_input_0.json")
-    out = SolveLoadCases(t, z["F"])
-    for b in range(z["F"].shape[0]):
-        for k in H.FIELDS:
-            err = orc.normwise_err(out[k][b], z[k][b])
-            assert err <= H.TOL, (b, k, err)
+    for path in (1, 2):
+        t._get_plan().set_path(path)
+        out = SolveLoadCases(t, z["F"])
+        for b in range(z["F"].shape[0]):
+            for k in H.FIELDS:
+                err = orc.normwise_err(out[k][b], z[k][b])
+                assert err <= H.TOL, (path, b, k, err)
 
 
 def test_member_type_batch_vs_oracle_bar942():
@@ -137,13 +149,15 @@ def test_member_type_batch_vs_oracle_bar942():
     types = [MemberType(a, 1e4, 0.1) for a in (0.5, 1.0, 2.0, 4.0)]
     genes = rng.integers(0, 4, size=(3, conn.shape[0]))
     t = Truss(3).LoadFromJSON(data=data)
-    out = SolveMemberTypes(t, genes, types)
     tab = type_table(types)
-    for b in range(3):
-        want = orc.solve_closed_form(3, joints, support, conn, tab[genes[b]], force)
-        for k in H.FIELDS:
-            assert orc.normwise_err(out[k][b], want[k]) <= H.TOL, (b, k)
-        assert abs(out["weight"][b] - want["weight"]) <= 1e-9 * want["weight"]
+    for path in (1, 2):
+        t._get_plan().set_path(path)
+        out = SolveMemberTypes(t, genes, types)
+        for b in range(3):
+            want = orc.solve_closed_form(3, joints, support, conn, tab[genes[b]], force)
+            for k in H.FIELDS:
+                assert orc.normwise_err(out[k][b], want[k]) <= H.TOL, (path, b, k)
+            assert abs(out["weight"][b] - want["weight"]) <= 1e-9 * want["weight"]
 
 
 def test_error_reporting_per_system():
