@@ -12,7 +12,7 @@ between the systems of a batch (the factor-once / 1024-right-hand-sides shortcut
 
 One JSON line on stdout (rank 0).  `value` = systems of all ranks / device time (inputs resident in HBM);
 `e2e` = same metric through the C ABI's host entry point (tb_solve_host) with pinned host buffers, H2D + D2H inside the
-timed region; `roofline` = the dominant kernel (k_chol) against the FP64 tensor (DMMA) peak measured in this run;
+timed region; `roofline` = the dominant kernel (k_band for bar-942) against the FP64 tensor (DMMA) peak measured in this run;
 `cpu_baseline` = the oracle port of the reference (numpy, per-member Python loops + LAPACK) on this box's cores.
 """
 from __future__ import annotations
@@ -285,16 +285,24 @@ def run_gpu(args):
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (k_chol) against the FP64 tensor peak measured on this GPU
+    # ---- roofline of the dominant kernel (factorisation + triangular solves) against the FP64 tensor peak measured
+    # on this GPU.  Algorithmic flops: the dense potrf count of SURVEY.md 8d when the tiled pipeline treats the
+    # matrix as dense; the envelope-Cholesky count (fill stays inside the row envelope of K_ff) when the plan
+    # exploits the sparsity -- counting the dense n^3/3 for work that is never done would inflate the fraction.
     peak_dmma, _ = _lib.fp64_peak(1, 8192)
     peak_dfma, _ = _lib.fp64_peak(0, 8192)
-    chol_ms, chol_n = prof["chol"]
-    flops_per_system = n ** 3 / 3.0 + n ** 2 / 2.0 + n / 6.0 + 2.0 * n * n        # potrf + two triangular solves
-    achieved = B * flops_per_system / (chol_ms / max(chol_n, 1) * 1e-3) / 1e12
+    path = plan.path
+    kname = {0: "k_small", 1: "k_chol", 2: "k_band"}[path]
+    chol_ms, chol_n = prof["small"] if path == 0 else prof["chol"]
+    dense_flops = n ** 3 / 3.0 + n ** 2 / 2.0 + n / 6.0 + 2.0 * n * n               # potrf + two triangular solves
+    dense_mode = os.environ.get("TB_DENSE_TILES") == "1" and path == 1
+    flops_per_system = dense_flops if dense_mode else float(plan.info.envelope_flops)
+    per_launch_s = chol_ms / max(chol_n, 1) * 1e-3
+    achieved = B * flops_per_system / per_launch_s / 1e12
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get("k_chol_dram_bytes_per_launch")
+        traffic = json.load(open(tpath)).get(f"{kname}_dram_bytes_per_launch")
     kernels = {k: {"ms_per_step": v[0] / args.steps, "launches": v[1]} for k, v in prof.items() if v[1]}
     peaks = {}
     try:
@@ -302,16 +310,25 @@ def run_gpu(args):
     except Exception:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    ntiles = (plan.info.n_pad // 64) * (plan.info.n_pad // 64 + 1) // 2
-    asm_bytes = B * (ntiles * 32768 + M * (2 + 3) * 8 + plan.info.n_pad * 8)
-    asm_ms = prof["assemble"][0] / max(prof["assemble"][1], 1)
-    if prof["assemble"][1]:
-        asm_gbs = asm_bytes / (asm_ms * 1e-3) / 1e9
-        roof_asm = {"kernel": "k_assemble", "bound": "hbm", "achieved": asm_gbs, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": asm_gbs / hbm_peak, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650"}
-    else:
-        roof_asm = {"kernel": "(none)", "note": "assembly is fused into k_chol: K_ff tiles are built in shared memory from "
-                    "the scatter map and never exist in HBM; run with TB_UNFUSED_ASSEMBLY=1 for the standalone kernel"}
+    hbm_src = "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650"
+    nnz = int(plan.info.nnz_lower)
+    # HBM view of the same kernel: compulsory bytes = K_ff non-zeros in, load vector in, displacements out
+    solve_bytes = B * (nnz * 8 + 2 * n * 8)
+    roof_hbm = {"kernel": kname, "bound": "hbm", "achieved": solve_bytes / per_launch_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                "frac": solve_bytes / per_launch_s / 1e9 / hbm_peak, "peak_source": hbm_src,
+                "bytes_per_system": nnz * 8 + 2 * n * 8}
+    # HBM-bound stages: member products + K_ff values (k_geom + k_kval), recovery (k_recover); SURVEY 8d byte counts
+    asm_bytes = B * (M * (2 * 4 + 3 * 8) + plan.nJ * 3 * 8 + plan.nJ + nnz * 8)
+    rec_bytes = B * (N * 8 + M * (2 * 4 + 8) + plan.nJ * 3 * 8 + (2 * N + M) * 8)
+    stages = {}
+    for key, byts in (("assemble", asm_bytes), ("recover", rec_bytes)):
+        ms_k, cnt = prof[key]
+        if key == "assemble":
+            ms_k += prof["geom"][0]
+        if cnt:
+            gbs = byts / (ms_k / cnt * 1e-3) / 1e9
+            stages[key] = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                           "bytes_per_launch": byts, "ms_per_launch": ms_k / cnt}
 
     cpu = cpu_port_throughput(6)
     line = {
@@ -319,19 +336,23 @@ def run_gpu(args):
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "batch_per_gpu": B, "n_free": n, "n_member": M, "mode": "independent K per system",
-                   "l2": "per-step working set (2.2 GB of factor tiles) >> 126 MB L2, plus an explicit 256 MB flush between steps",
+                   "pipeline": {0: "fused shared-memory kernel", 1: "tiled 64x64 block-sparse Cholesky", 2: "block-band Cholesky (16x16 blocks)"}[path],
+                   "l2": "explicit 256 MB flush (> 126 MB L2) between timed steps, outside the events",
                    "multi_gpu": "contiguous block partition of the batch, NCCL gather of u/ext/axial to rank 0 inside the step"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "tb_solve_host (C ABI) with pinned host buffers", "steps": e2e_steps},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"kernel": "k_chol (tiled left-looking Cholesky + forward/back substitution)", "bound": "tensor",
+        "roofline": {"kernel": kname + " (block Cholesky + forward/back substitution)", "bound": "tensor",
                      "achieved": achieved, "peak": peak_dmma, "unit": "TFLOP/s", "frac": achieved / peak_dmma,
                      "traffic": traffic, "flops_per_system": flops_per_system,
+                     "flops_model": "dense potrf (SURVEY 8d)" if dense_mode else "envelope Cholesky + two triangular solves (plan.envelope_flops)",
+                     "dense_potrf_equivalent_tflops": B * dense_flops / per_launch_s / 1e12,
                      "peak_source": "FP64 DMMA m8n8k4 microbenchmark (tb_fp64_peak) measured in this run; "
                                     "MEASURED_PEAKS.json has no FP64 entry", "peak_dfma": peak_dfma,
                      "share_of_step": chol_ms / dev_ms},
-        "roofline_assemble": roof_asm,
+        "roofline_hbm_view": roof_hbm,
+        "roofline_stages": stages,
         "kernels": kernels,
         "cpu_baseline": cpu,
         "wall_s_timed_region": wall,
