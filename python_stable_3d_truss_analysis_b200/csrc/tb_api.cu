@@ -139,6 +139,7 @@ int run_plan(tb_plan* p, const tb_batch_in* in, const tb_batch_out* out, const t
     a.NB = p->NB;
     a.b16_ptr = p->d_b16_ptr;
     a.b16_pos = p->d_b16_pos;
+    a.b16_nz = p->d_b16_nz;
     if (p->path == 2) a.n_pad = p->nb16 * 16;
     a.tile_nz = p->d_tile_nz;
     a.prod_ptr = p->d_prod_ptr;

@@ -1,21 +1,25 @@
 // Band path: block-band Cholesky for systems whose reduced stiffness matrix has a narrow
-// envelope (bar-942: n = 696, half-bandwidth 56).  The dense/tiled pipeline of tb_large.cu spends
-// its time on structurally zero 64x64 tiles and on latency between them; here the matrix is viewed
-// as a band of 16x16 blocks (NB sub-diagonal blocks per block column) and ONE small CTA (4 warps)
-// factorises one system with the active window of the band resident in shared memory:
+// envelope (bar-942: n = 696, half-bandwidth 56).  The matrix is viewed as a band of 16x16 blocks
+// (NB sub-diagonal blocks per block column) and ONE WARP factorises one system, start to finish,
+// with no block-level barrier anywhere:
 //
-//   per block column c:   assemble K blocks (c..c+NB, c) from the scatter map's values
-//                         update     P(R,c) -= sum_{d=1..NB} L(R,c-d) L(c,c-d)^T           (DMMA m8n8k4)
-//                         factor     16x16 diagonal block + its inverse W (one warp, in registers)
-//                         solve      L(R,c) = P(R,c) W^T for the NB blocks below            (DMMA)
-//                         forward    y_c = W (f_c - sum_d L(c,c-d) y_{c-d})
-//   then block back-substitution  u_c = W_c^T (y_c - sum_{rb} L(c+rb,c)^T u_{c+rb}).
+//   per block column c:   products   S(R,c)  = sum_{d=1..NB} L(R,c-d) L(c,c-d)^T   (DMMA m8n8k4; the accumulators
+//                                     of the whole block column live in registers; operands come from a ring of
+//                                     the previous NB block columns in shared memory)
+//                         assemble   P(R,c)  = K(R,c) - S(R,c)   (K values prefetched into registers before the
+//                                     products, scattered into the ring slots the products just released)
+//                         factor     16x16 diagonal block + its inverse W (in registers, lanes = rows)
+//                         solve      L(R,c)  = P(R,c) W^T                          (DMMA), kept in the ring + HBM
+//                         forward    y_c     = W (f_c - sum_d L(c,c-d) y_{c-d})    (rides on the operand registers)
+//   then block back-substitution  u_c = W_c^T (y_c - sum_rb L(c+rb,c)^T u_{c+rb}), the factor streamed back
+//   from HBM/L2 with cp.async one block column ahead.
 //
-// Only (NB+1)(NB+2)/2 blocks are alive at any time (block (p+e, p) lives on "diagonal e", which needs
-// a ring of e+1 slots), 30 KB for NB = 4, so seven CTAs share an SM and hide each other's pivot
-// latency.  HBM sees the K values once, the off-diagonal L blocks and the 16x16 inverses once out and
-// once back in (back-substitution), and u.  Replaces np.linalg.solve (slientruss3d/truss.py:343) for
-// this class of systems; results equal the dense factorisation's (zeros are skipped, nothing else).
+// Block (p+e, p) is alive from column p to column p+e, so "diagonal e" of the band needs e ring slots
+// (slot = e(e-1)/2 + p mod e): NB(NB+1)/2 blocks in all, 20 KB for NB = 4, and ten one-warp CTAs share an SM.
+// Structurally zero blocks (block-level symbolic factorisation, one bit mask per block column) are never
+// computed, stored or read.  HBM sees the K values once, the non-zero L blocks and the 16x16 inverses
+// once out and once back in, and u.  Replaces np.linalg.solve (slientruss3d/truss.py:343) for this class of
+// systems; results equal the dense factorisation's (zeros are skipped, nothing else).
 #include <math.h>
 
 #include "tb_common.cuh"
@@ -24,114 +28,203 @@ namespace {
 
 constexpr int BT = 16;    // block order
 constexpr int BE = 256;   // doubles per block, stored as [8-row block 2][k-slab 4][lane 32] (DMMA operand order)
+constexpr int PRE = 9;    // K entries per lane prefetched into registers per block column (288 per column)
 
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                : "+d"(c0), "+d"(c1)
                : "d"(a), "d"(b));
 }
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 __device__ __forceinline__ int b16_off(int r, int c) { return ((((r >> 3) << 2) + (c >> 2)) << 5) + ((r & 7) << 2) + (c & 3); }
-// ring slot (in doubles) of block (row block p+e, column block p): diagonal e keeps e+1 blocks alive
-__device__ __forceinline__ int slot(int e, int p) { return ((e * (e + 1)) / 2 + p % (e + 1)) * BE; }
 // this lane's accumulator pair of 8x8 block (mb, nbp) inside a 16x16 block
 __device__ __forceinline__ int cpair_off(int mb, int nbp, int lane) {
   return ((mb * 4 + nbp * 2 + ((lane & 3) >> 1)) << 5) + ((lane >> 2) << 2) + ((lane & 1) << 1);
 }
 
-__global__ void __launch_bounds__(TB_BAND_THREADS, 7) k_band(const LargeArgs a) {
+template <int NB>
+struct BandCfg {
+  static constexpr int RING = NB * (NB + 1) / 2;                                  // alive off-diagonal blocks
+  static constexpr int BUF = RING > 2 * (NB + 1) ? RING : 2 * (NB + 1);           // back substitution: two (NB+1)-block buffers
+  static constexpr int DOUBLES = BUF * BE + BE + (NB + 1) * BT + BT + 32 + 8;     // ring | scratch block | y ring | rhs | column | slot table
+};
+
+template <int NB>
+__global__ void __launch_bounds__(32) k_band(const LargeArgs a) {
   extern __shared__ __align__(16) double sm[];
-  const int NB = a.NB, ncol = a.nb16;
-  const int nring = (NB + 1) * (NB + 2) / 2;
-  double* sRing = sm;                          // alive blocks of the band (factorisation) | staging (back substitution)
-  double* sY = sRing + nring * BE;             // ring of the last NB+1 blocks of y (then u), 16 each
+  using Cfg = BandCfg<NB>;
+  double* sRing = sm;                          // blocks of the previous NB block columns | staging of K(:,c)
+  double* sScr = sRing + Cfg::BUF * BE;        // diagonal block P(c,c), then W_c
+  double* sY = sScr + BE;                      // ring of the last NB+1 blocks of y (then u), 16 each
   double* sT = sY + (NB + 1) * BT;             // [16] right-hand side of the current block
   double* sCol = sT + BT;                      // [32] base case: eliminated column, double buffered
-  int* sFlag = (int*)(sCol + 32);
-  double* sRed = sRing + (NB + 1) * BE;        // alias, back substitution only: [8][16] partial sums
+  int* sOff = (int*)(sCol + 32);               // [NB+1] staging slot (in doubles from sm) of block e of this column
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int lane = threadIdx.x;
+  const int ncol = a.nb16;
+  const int qr = lane >> 2, qc = lane & 3;     // this lane's (row, k) inside an operand fragment
 
   for (int b = blockIdx.x; b < a.batch; b += gridDim.x) {
     if (a.status[b] != 0) continue;            // input problem flagged by k_geom (uniform)
     const double* kvs = a.kv + (int64_t)b * a.nnz;
     const double* fsys = a.force + b * a.force_stride;
     double* ysys = a.y + (int64_t)b * a.n_pad;
-    double* Lb = a.L + (int64_t)b * ncol * (NB + 1) * BE;   // block (c+rb, c) at (c*(NB+1)+rb)*256, rb >= 1
-    double* Wb = a.wd + (int64_t)b * ncol * BE;
-    if (tid == 0) *sFlag = 0;
+    double* Lb = a.L + (int64_t)b * ncol * (NB + 1) * BE;   // column chunk c: [W_c | L(c+1,c) .. L(c+NB,c)]
     int fail = 0;
 
-    for (int c = 0; c < ncol; ++c) {
-      // ---------------- A: assemble the K blocks of block column c into their ring slots
-      for (int e = 0; e <= NB; ++e) {
-        double* blk = sRing + slot(e, c);
-        for (int i = tid; i < BE; i += TB_BAND_THREADS) blk[i] = 0.0;
-      }
-      __syncthreads();
-      {
-        const int q0 = a.b16_ptr[c], q1 = a.b16_ptr[c + 1];
-        for (int q = q0 + tid; q < q1; q += TB_BAND_THREADS) {
-          const int pos = a.b16_pos[q];        // e << 8 | offset inside the block
-          sRing[slot(pos >> 8, c) + (pos & 255)] += kvs[q];
-        }
-        if (tid < BT) {
-          const int row = c * BT + tid;
-          if (row >= a.n) sRing[slot(0, c) + b16_off(tid, tid)] += 1.0;   // identity on the padded diagonal
-        }
-      }
-      __syncthreads();
-
-      // ---------------- B: left-looking update with the previous NB block columns (DMMA)
-      for (int t = warp; t < 2 * (NB + 1); t += TB_BAND_THREADS / 32) {
-        const int rb = t >> 1, mb = t & 1;
-        double c0[2] = {0.0, 0.0}, c1[2] = {0.0, 0.0}, e0[2] = {0.0, 0.0}, e1[2] = {0.0, 0.0};
-        for (int d = 1; d <= NB - rb && d <= c; ++d) {
-          const double* A = sRing + slot(rb + d, c - d);   // L(c+rb, c-d)
-          const double* Bm = sRing + slot(d, c - d);       // L(c,    c-d)
+    int idx[NB + 1];                           // idx[e] = c mod e
+    unsigned nzprev[NB + 1];                   // nzprev[d] = block mask of column c-d
 #pragma unroll
-          for (int ks = 0; ks < 4; ks += 2) {
-            const double av0 = A[((mb * 4 + ks) << 5) + lane], av1 = A[((mb * 4 + ks + 1) << 5) + lane];
-            dmma(c0[0], c0[1], av0, Bm[(ks << 5) + lane]);
-            dmma(c1[0], c1[1], av0, Bm[((4 + ks) << 5) + lane]);
-            dmma(e0[0], e0[1], av1, Bm[((ks + 1) << 5) + lane]);
-            dmma(e1[0], e1[1], av1, Bm[((4 + ks + 1) << 5) + lane]);
+    for (int e = 0; e <= NB; ++e) { idx[e] = 0; nzprev[e] = 0u; }
+    int yslot = 0;                             // c mod (NB+1)
+
+    for (int c = 0; c < ncol; ++c) {
+      const unsigned nzc = (unsigned)__ldg(a.b16_nz + c);
+      // ---------------- prefetch this block column's K values and load-vector rows (consumed after the products)
+      const int q0 = __ldg(a.b16_ptr + c), q1 = __ldg(a.b16_ptr + c + 1);
+      double kvr[PRE];
+      int posr[PRE];
+#pragma unroll
+      for (int i = 0; i < PRE; ++i) {
+        const int q = q0 + lane + 32 * i;
+        kvr[i] = 0.0;
+        posr[i] = 0;
+        if (q < q1) {
+          kvr[i] = __ldg(kvs + q);
+          posr[i] = __ldg(a.b16_pos + q);      // e << 8 | offset inside the block
+        }
+      }
+      double fr[2];
+#pragma unroll
+      for (int mb = 0; mb < 2; ++mb) {
+        const int grow = c * BT + mb * 8 + qr;
+        fr[mb] = grow < a.n ? __ldg(fsys + __ldg(a.free_idx + grow)) : 0.0;
+      }
+
+      // ---------------- products with the previous NB block columns (DMMA), forward-substitution partial sums
+      double acc[NB + 1][2][2][2];
+#pragma unroll
+      for (int rb = 0; rb <= NB; ++rb)
+#pragma unroll
+        for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+          for (int nb = 0; nb < 2; ++nb) acc[rb][mb][nb][0] = acc[rb][mb][nb][1] = 0.0;
+      double tp[2] = {0.0, 0.0};
+#pragma unroll
+      for (int d = 1; d <= NB; ++d) {
+        const unsigned nzp = nzprev[d];
+        if (!((nzp >> d) & 1u)) continue;      // L(c, c-d) is structurally zero (or c-d < 0): uniform
+        const double* Bm = sRing + (d * (d - 1) / 2 + idx[d]) * BE;     // (c-d) mod d == c mod d
+        double bf[2][4];
+#pragma unroll
+        for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) bf[nb][ks] = Bm[((nb * 4 + ks) << 5) + lane];
+        {   // rows of L(c, c-d) times y_{c-d}: the operand registers are exactly the needed elements
+          int ys = yslot - d;
+          if (ys < 0) ys += NB + 1;
+          const double* yv = sY + ys * BT;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const double y4 = yv[ks * 4 + qc];
+            tp[0] = fma(bf[0][ks], y4, tp[0]);
+            tp[1] = fma(bf[1][ks], y4, tp[1]);
           }
         }
-        double* tgt = sRing + slot(rb, c);
-        double2* p0 = reinterpret_cast<double2*>(tgt + cpair_off(mb, 0, lane));
-        double2* p1 = reinterpret_cast<double2*>(tgt + cpair_off(mb, 1, lane));
-        double2 v0 = *p0, v1 = *p1;
-        v0.x -= c0[0] + e0[0]; v0.y -= c0[1] + e0[1];
-        v1.x -= c1[0] + e1[0]; v1.y -= c1[1] + e1[1];
-        *p0 = v0; *p1 = v1;
-      }
-      // right-hand side of this block: f_c - sum_d L(c,c-d) y_{c-d}   (last warp: it has the fewest update tasks)
-      if (warp == TB_BAND_THREADS / 32 - 1) {
-        const int row = lane & 15, hh = lane >> 4;
-        double tacc = 0.0;
-        for (int d = 1; d <= NB && d <= c; ++d) {
-          const double* Bm = sRing + slot(d, c - d);
-          const double* yv = sY + ((c - d) % (NB + 1)) * BT;
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk) tacc = fma(Bm[b16_off(row, 2 * kk + hh)], yv[2 * kk + hh], tacc);
-        }
-        tacc += __shfl_xor_sync(0xffffffffu, tacc, 16);
-        if (lane < 16) {
-          const int grow = c * BT + row;
-          sT[row] = (grow < a.n ? fsys[a.free_idx[grow]] : 0.0) - tacc;
+        for (int rb = 0; rb + d <= NB; ++rb) {
+          const int e = rb + d;
+          if (!((nzp >> e) & 1u)) continue;    // L(c+rb, c-d) structurally zero: uniform
+          int sl = idx[e] - d;                 // (c-d) mod e
+          if (sl < 0) sl += e;
+          const double* A = sRing + (e * (e - 1) / 2 + sl) * BE;
+          double af[2][4];
+#pragma unroll
+          for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) af[mb][ks] = A[((mb * 4 + ks) << 5) + lane];
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+            for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+              for (int nb = 0; nb < 2; ++nb)
+                if (rb > 0 || nb <= mb) dmma(acc[rb][mb][nb][0], acc[rb][mb][nb][1], af[mb][ks], bf[nb][ks]);
         }
       }
-      __syncthreads();
+#pragma unroll
+      for (int mb = 0; mb < 2; ++mb) {
+        tp[mb] += __shfl_xor_sync(0xffffffffu, tp[mb], 1);
+        tp[mb] += __shfl_xor_sync(0xffffffffu, tp[mb], 2);
+      }
+      __syncwarp();                            // every lane is done with the blocks (c, c-d): their slots are free
 
-      // ---------------- C: 16x16 diagonal block: L_D L_D^T = P, W = L_D^{-1}  (one warp, in registers)
-      if (warp == 0) {
-        double* blk = sRing + slot(0, c);
+      // ---------------- stage K(:,c) into the freed slots (block e -> slot of the dead block (c, c-e); e = 0 -> scratch)
+      if (lane == 0) sOff[0] = (int)(sScr - sm);
+#pragma unroll
+      for (int e = 1; e <= NB; ++e)
+        if (lane == e) sOff[e] = (e * (e - 1) / 2 + idx[e]) * BE;
+      {
+        const double2 z = make_double2(0.0, 0.0);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) reinterpret_cast<double2*>(sScr)[lane + 32 * i] = z;
+#pragma unroll
+        for (int e = 1; e <= NB; ++e)
+          if ((nzc >> e) & 1u) {
+            double2* blk = reinterpret_cast<double2*>(sRing + (e * (e - 1) / 2 + idx[e]) * BE);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) blk[lane + 32 * i] = z;
+          }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < PRE; ++i)
+        if (q0 + lane + 32 * i < q1) sm[sOff[posr[i] >> 8] + (posr[i] & 255)] = kvr[i];
+      for (int q = q0 + 32 * PRE + lane; q < q1; q += 32) {   // rare: more than 32*PRE entries in this block column
+        const int pos = __ldg(a.b16_pos + q);
+        sm[sOff[pos >> 8] + (pos & 255)] = __ldg(kvs + q);
+      }
+      if (lane < BT && c * BT + lane >= a.n) sScr[b16_off(lane, lane)] = 1.0;   // identity on the padded diagonal
+      __syncwarp();
+
+      // ---------------- P = K - S, in place in the staging slots (fragment layout: the next reads are operand reads)
+#pragma unroll
+      for (int rb = 0; rb <= NB; ++rb) {
+        if (rb > 0 && !((nzc >> rb) & 1u)) continue;
+        double* blk = rb == 0 ? sScr : sRing + (rb * (rb - 1) / 2 + idx[rb]) * BE;
+#pragma unroll
+        for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+          for (int nb = 0; nb < 2; ++nb) {
+            if (rb == 0 && nb > mb) continue;
+            double2* p = reinterpret_cast<double2*>(blk + cpair_off(mb, nb, lane));
+            double2 v = *p;
+            v.x -= acc[rb][mb][nb][0];
+            v.y -= acc[rb][mb][nb][1];
+            *p = v;
+          }
+      }
+      if (qc == 0) {
+        sT[qr] = fr[0] - tp[0];
+        sT[8 + qr] = fr[1] - tp[1];
+      }
+      __syncwarp();
+
+      // ---------------- 16x16 diagonal block: L_D L_D^T = P, W = L_D^{-1}  (in registers)
+      {
         const int r = lane & 15;
         const int rowpart = ((r >> 3) << 7) + ((r & 7) << 2);
         double row[16];
 #pragma unroll
         for (int cc = 0; cc < 16; ++cc) {
-          const double v = blk[rowpart + ((cc >> 2) << 5) + (cc & 3)];
+          const double v = sScr[rowpart + ((cc >> 2) << 5) + (cc & 3)];
           row[cc] = lane < 16 ? (cc <= r ? v : 0.0) : (cc == r ? 1.0 : 0.0);
         }
         __syncwarp();
@@ -160,117 +253,209 @@ __global__ void __launch_bounds__(TB_BAND_THREADS, 7) k_band(const LargeArgs a) 
           rinv = rinv_next;
         }
         if (bad) {
-          if (lane == 0) *sFlag = bad;
+          fail = bad;
         } else if (lane >= 16) {
-          // W[c'][kk] = Z[kk][c'] for kk <= c' (this lane: kk = r), as a DMMA B operand, over the slot of P
+          // W[c'][kk] = Z[kk][c'] for kk <= c' (this lane: kk = r), as a DMMA B operand, over P(c,c)
 #pragma unroll
-          for (int cp = 0; cp < 16; ++cp) blk[b16_off(cp, r)] = (cp >= r) ? row[cp] : 0.0;
+          for (int cp = 0; cp < 16; ++cp) sScr[b16_off(cp, r)] = (cp >= r) ? row[cp] : 0.0;
         }
       }
-      __syncthreads();
-      fail = *sFlag;
+      __syncwarp();
       if (fail) break;   // uniform
 
-      // ---------------- D: blocks below the diagonal block: L = P W^T (in place + to HBM), W to HBM, y_c
+      // ---------------- y_c = W t;  L(c+rb, c) = P W^T into the ring and to HBM;  W to HBM
+      double* chunk = Lb + (int64_t)c * (NB + 1) * BE;
       {
-        const double* W = sRing + slot(0, c);
-        for (int t = warp; t < 2 * NB; t += TB_BAND_THREADS / 32) {
-          const int rb = 1 + (t >> 1), mb = t & 1;
-          if (c + rb >= ncol) continue;        // below the last block row: nothing there
-          double* blk = sRing + slot(rb, c);
-          double a4[4];
+        double yp[2] = {0.0, 0.0};
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) a4[ks] = blk[((mb * 4 + ks) << 5) + lane];
-          __syncwarp();
-          double* g = Lb + ((int64_t)c * (NB + 1) + rb) * BE;
+        for (int ks = 0; ks < 4; ++ks) {
+          const double t4 = sT[ks * 4 + qc];
+          yp[0] = fma(sScr[(ks << 5) + lane], t4, yp[0]);
+          yp[1] = fma(sScr[((4 + ks) << 5) + lane], t4, yp[1]);
+        }
+#pragma unroll
+        for (int mb = 0; mb < 2; ++mb) {
+          yp[mb] += __shfl_xor_sync(0xffffffffu, yp[mb], 1);
+          yp[mb] += __shfl_xor_sync(0xffffffffu, yp[mb], 2);
+        }
+        if (qc == 0) {
+          sY[yslot * BT + qr] = yp[0];
+          sY[yslot * BT + 8 + qr] = yp[1];
+          ysys[c * BT + qr] = yp[0];
+          ysys[c * BT + 8 + qr] = yp[1];
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          reinterpret_cast<double2*>(chunk)[lane + 32 * i] = reinterpret_cast<const double2*>(sScr)[lane + 32 * i];
+      }
+      double wf[2][4];                          // W as the B operand: W[8 nbp + lane/4][4 ks + lane%4]
+#pragma unroll
+      for (int nbp = 0; nbp < 2; ++nbp)
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) wf[nbp][ks] = sScr[((nbp * 4 + ks) << 5) + lane];
+#pragma unroll
+      for (int rb = 1; rb <= NB; ++rb) {
+        if (!((nzc >> rb) & 1u)) continue;
+        double* blk = sRing + (rb * (rb - 1) / 2 + idx[rb]) * BE;
+        double a4[2][4];
+#pragma unroll
+        for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) a4[mb][ks] = blk[((mb * 4 + ks) << 5) + lane];
+        __syncwarp();                          // P(rb) fully read before L(rb) overwrites it
+        double* g = chunk + rb * BE;
+#pragma unroll
+        for (int mb = 0; mb < 2; ++mb)
 #pragma unroll
           for (int nbp = 0; nbp < 2; ++nbp) {
             double x0 = 0.0, x1 = 0.0;
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) dmma(x0, x1, a4[ks], W[((nbp * 4 + ks) << 5) + lane]);
+            for (int ks = 0; ks < 2 * nbp + 2; ++ks) dmma(x0, x1, a4[mb][ks], wf[nbp][ks]);   // W is lower triangular
             const int off = cpair_off(mb, nbp, lane);
             *reinterpret_cast<double2*>(blk + off) = make_double2(x0, x1);
             *reinterpret_cast<double2*>(g + off) = make_double2(x0, x1);
           }
-        }
-        for (int i = tid; i < BE; i += TB_BAND_THREADS) Wb[(int64_t)c * BE + i] = W[i];
-        if (warp == TB_BAND_THREADS / 32 - 1 && lane < 16) {   // y_c = W t  (W lower triangular)
-          double yv = 0.0;
-          for (int cc = 0; cc <= lane; ++cc) yv = fma(W[b16_off(lane, cc)], sT[cc], yv);
-          sY[(c % (NB + 1)) * BT + lane] = yv;
-          ysys[c * BT + lane] = yv;
-        }
       }
-      __syncthreads();
+      __syncwarp();
+
+      // ---------------- advance the ring counters
+#pragma unroll
+      for (int e = NB; e >= 2; --e) nzprev[e] = nzprev[e - 1];
+      nzprev[1] = nzc;
+#pragma unroll
+      for (int e = 1; e <= NB; ++e) idx[e] = (idx[e] + 1 == e) ? 0 : idx[e] + 1;
+      yslot = (yslot == NB) ? 0 : yslot + 1;
     }
 
     if (fail) {
-      if (tid == 0) a.status[b] = fail;
-      __syncthreads();
+      if (lane == 0) a.status[b] = fail;
+      __syncwarp();
       continue;
     }
 
-    // ---------------- back substitution: u_c = W_c^T (y_c - sum_rb L(c+rb,c)^T u_{c+rb}), last block first
-    for (int c = ncol - 1; c >= 0; --c) {
-      // stage W_c (slot 0) and the blocks below it (slots 1..NB) from HBM
-      for (int i = tid; i < BE; i += TB_BAND_THREADS) sRing[i] = __ldcg(Wb + (int64_t)c * BE + i);
-      for (int rb = 1; rb <= NB && c + rb < ncol; ++rb) {
-        const double* g = Lb + ((int64_t)c * (NB + 1) + rb) * BE;
-        for (int i = tid; i < BE; i += TB_BAND_THREADS) sRing[rb * BE + i] = __ldcg(g + i);
-      }
-      __syncthreads();
-      {
-        const int col = tid & 15, part = tid >> 4;   // 8 parts x 2 rows of every block
-        double tacc = 0.0;
-        for (int rb = 1; rb <= NB && c + rb < ncol; ++rb) {
-          const double* blk = sRing + rb * BE;
-          const double* uv = sY + ((c + rb) % (NB + 1)) * BT;
-          tacc = fma(blk[b16_off(2 * part, col)], uv[2 * part], tacc);
-          tacc = fma(blk[b16_off(2 * part + 1, col)], uv[2 * part + 1], tacc);
-        }
-        sRed[part * BT + col] = tacc;
-      }
-      __syncthreads();
-      if (warp == 0) {
-        if (lane < 16) {
-          double tsum = 0.0;
+    // ---------------- back substitution: u_c = W_c^T (y_c - sum_rb L(c+rb,c)^T u_{c+rb}), last block first.
+    // Column chunks come back from HBM/L2 through a two-buffer cp.async pipeline in the (now idle) ring.
+    auto fetch = [&](int c) {
+      const unsigned nz = (unsigned)__ldg(a.b16_nz + c) | 1u;     // bit 0: W_c
+      const double* src = Lb + (int64_t)c * (NB + 1) * BE;
+      double* dst = sRing + (c & 1) * (NB + 1) * BE;
 #pragma unroll
-          for (int p = 0; p < 8; ++p) tsum += sRed[p * BT + lane];
-          sT[lane] = __ldcg(ysys + c * BT + lane) - tsum;
+      for (int e = 0; e <= NB; ++e)
+        if ((nz >> e) & 1u) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) cp_async16(dst + e * BE + (lane + 32 * i) * 2, src + e * BE + (lane + 32 * i) * 2);
         }
-        __syncwarp();
-        if (lane < 16) {   // u = W^T r: u[col] = sum_{cc >= col} W[cc][col] r[cc]
-          double uvv = 0.0;
-          for (int cc = lane; cc < 16; ++cc) uvv = fma(sRing[b16_off(cc, lane)], sT[cc], uvv);
-          sY[(c % (NB + 1)) * BT + lane] = uvv;
-          ysys[c * BT + lane] = uvv;
+      cp_async_commit();
+    };
+    __syncwarp();
+    fetch(ncol - 1);
+    // after the factorisation yslot == ncol mod (NB+1); block column c of y sits in slot c mod (NB+1)
+    for (int c = ncol - 1; c >= 0; --c) {
+      yslot = (yslot == 0) ? NB : yslot - 1;   // slot of block c (the ring only keeps the last NB+1 blocks: y_c comes from HBM)
+      double yc[4] = {0.0, 0.0, 0.0, 0.0};
+      if (qr == 0) {
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) yc[ks] = __ldcg(ysys + c * BT + ks * 4 + qc);
+      }
+      if (c > 0) {
+        fetch(c - 1);
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
+      }
+      __syncwarp();
+      const unsigned nz = (unsigned)__ldg(a.b16_nz + c);
+      const double* buf = sRing + (c & 1) * (NB + 1) * BE;
+      // t[col] = sum_rb sum_r L(c+rb,c)[r][col] u_{c+rb}[r]; this lane: r = 8 mb + lane/4, col = 4 ks + lane%4
+      double tp[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+      for (int rb = 1; rb <= NB; ++rb) {
+        if (!((nz >> rb) & 1u)) continue;
+        int us = yslot + rb;
+        if (us > NB) us -= NB + 1;
+        const double* uv = sY + us * BT;
+        const double* blk = buf + rb * BE;
+#pragma unroll
+        for (int mb = 0; mb < 2; ++mb) {
+          const double ur = uv[mb * 8 + qr];
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) tp[ks] = fma(blk[((mb * 4 + ks) << 5) + lane], ur, tp[ks]);
         }
       }
-      __syncthreads();
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        tp[ks] += __shfl_xor_sync(0xffffffffu, tp[ks], 4);
+        tp[ks] += __shfl_xor_sync(0xffffffffu, tp[ks], 8);
+        tp[ks] += __shfl_xor_sync(0xffffffffu, tp[ks], 16);
+      }
+      if (qr == 0) {
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) sT[ks * 4 + qc] = yc[ks] - tp[ks];
+      }
+      __syncwarp();
+      // u = W^T r: u[col] = sum_{cc >= col} W[cc][col] r[cc]
+      double up[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+      for (int mb = 0; mb < 2; ++mb) {
+        const double rr = sT[mb * 8 + qr];
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) up[ks] = fma(buf[((mb * 4 + ks) << 5) + lane], rr, up[ks]);
+      }
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        up[ks] += __shfl_xor_sync(0xffffffffu, up[ks], 4);
+        up[ks] += __shfl_xor_sync(0xffffffffu, up[ks], 8);
+        up[ks] += __shfl_xor_sync(0xffffffffu, up[ks], 16);
+      }
+      if (qr == 0) {
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          sY[yslot * BT + ks * 4 + qc] = up[ks];
+          ysys[c * BT + ks * 4 + qc] = up[ks];
+        }
+      }
+      __syncwarp();
     }
-    if (tid == 0) a.status[b] = 0;
+    if (lane == 0) a.status[b] = 0;
+    __syncwarp();
   }
 }
 
-}  // namespace
-
-int tb_band_smem_bytes(int NB) {
-  const int nring = (NB + 1) * (NB + 2) / 2;
-  return (nring * BE + (NB + 1) * BT + BT + 32 + 2) * 8;
-}
-
-int tb_launch_band_chol(const LargeArgs& a, int num_sm, cudaStream_t st) {
-  const int smem = tb_band_smem_bytes(a.NB);
-  cudaError_t e = cudaFuncSetAttribute(k_band, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+template <int NB>
+int launch_band(const LargeArgs& a, int num_sm, cudaStream_t st) {
+  const int smem = BandCfg<NB>::DOUBLES * 8;
+  auto kern = k_band<NB>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return (int)e;
   int per_sm = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_band, TB_BAND_THREADS, smem);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, smem);
   if (e != cudaSuccess) return (int)e;
   if (per_sm < 1) per_sm = 1;
   int grid = num_sm * per_sm;
   if (grid > a.batch) grid = a.batch;
   tb_prof_begin(TB_PROF_CHOL, st);
-  k_band<<<grid, TB_BAND_THREADS, smem, st>>>(a);
+  kern<<<grid, 32, smem, st>>>(a);
   tb_prof_end(TB_PROF_CHOL, st);
   return (int)cudaGetLastError();
+}
+
+}  // namespace
+
+int tb_band_smem_bytes(int NB) {
+  const int ring = NB * (NB + 1) / 2, buf = ring > 2 * (NB + 1) ? ring : 2 * (NB + 1);
+  return (buf * BE + BE + (NB + 1) * BT + BT + 32 + 8) * 8;
+}
+
+int tb_launch_band_chol(const LargeArgs& a, int num_sm, cudaStream_t st) {
+  switch (a.NB) {
+    case 1: return launch_band<1>(a, num_sm, st);
+    case 2: return launch_band<2>(a, num_sm, st);
+    case 3: return launch_band<3>(a, num_sm, st);
+    case 4: return launch_band<4>(a, num_sm, st);
+    case 5: return launch_band<5>(a, num_sm, st);
+    case 6: return launch_band<6>(a, num_sm, st);
+    case 7: return launch_band<7>(a, num_sm, st);
+    case 8: return launch_band<8>(a, num_sm, st);
+    default: return TB_ERR_TOO_LARGE;
+  }
 }

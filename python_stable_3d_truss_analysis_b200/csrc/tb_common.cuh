@@ -20,7 +20,6 @@ constexpr int TB_TILE = 64;                     // tile order
 constexpr int TB_TILE_ELEMS = TB_TILE * TB_TILE;  // doubles per tile
 
 // band path (tb_band.cu): 16x16 blocks, at most TB_BAND_MAX_NB sub-diagonal blocks per block column
-constexpr int TB_BAND_THREADS = 128;
 constexpr int TB_BAND_MAX_NB = 8;
 
 // limits of the fused shared-memory path
@@ -79,6 +78,8 @@ struct tb_plan {
   int nb16 = 0, NB = 0;
   std::vector<int32_t> b16_ptr;            // [nb16+1] entry ranges (band order) per block column
   std::vector<int32_t> b16_pos;            // [nnz] (block offset e) << 8 | offset inside the 16x16 block
+  std::vector<int32_t> b16_nz;             // [nb16] bit e: block (c+e, c) of L is structurally non-zero (block symbolic factorisation)
+  int64_t b16_blocks_nz = 0, b16_products = 0;   // non-zero blocks of L, block products of the factorisation
   std::vector<int32_t> bq_ptr, bq_pack;    // contribution lists in band order (same encoding as q_ptr/q_pack)
   int64_t envelope_size = 0;               // entries inside the row envelope of K_ff (= of L)
   double envelope_flops = 0.0;             // flops of an envelope Cholesky + two triangular solves
@@ -105,6 +106,7 @@ struct tb_plan {
   int32_t* d_q_pack = nullptr;
   int32_t* d_b16_ptr = nullptr;
   int32_t* d_b16_pos = nullptr;
+  int32_t* d_b16_nz = nullptr;
   int32_t* d_bq_ptr = nullptr;
   int32_t* d_bq_pack = nullptr;
   uint8_t* d_tile_nz = nullptr;
@@ -160,7 +162,7 @@ struct LargeArgs {
   const uint8_t* tile_nz; const int32_t* prod_ptr; const int32_t* prod_k;
   const int32_t* q_ptr; const int32_t* q_pack;
   int nb16, NB;
-  const int32_t* b16_ptr; const int32_t* b16_pos;
+  const int32_t* b16_ptr; const int32_t* b16_pos; const int32_t* b16_nz;
   const int32_t* inc_ptr; const int32_t* inc_mem;
   // workspace
   double* mk;      // [B][M]      EA/L

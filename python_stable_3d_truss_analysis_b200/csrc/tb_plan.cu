@@ -282,6 +282,26 @@ extern "C" int tb_plan_create(const tb_topology* topo, tb_plan** plan_out) {
       p->bq_ptr[q + 1] = (int32_t)p->bq_pack.size();
     }
     for (int c = 0; c < p->nb16; ++c) p->b16_ptr[c + 1] += p->b16_ptr[c];
+    // block-level symbolic factorisation of the band: bit e of b16_nz[c] <=> block (c+e, c) of L is non-zero
+    p->b16_nz.assign(p->nb16, 1);
+    for (size_t e = 0; e < nnz; ++e) {
+      const int bc = p->ent_col[e] / 16, be = p->ent_row[e] / 16 - bc;
+      if (be < 31) p->b16_nz[bc] |= (1 << be);
+    }
+    p->b16_blocks_nz = 0;
+    p->b16_products = 0;
+    for (int c = 0; c < p->nb16; ++c) {
+      const unsigned m = (unsigned)p->b16_nz[c];
+      for (int e1 = 1; e1 <= NB && e1 < 31; ++e1) {
+        if (!((m >> e1) & 1u)) continue;
+        for (int e2 = e1; e2 <= NB && e2 < 31; ++e2)
+          if ((m >> e2) & 1u) {
+            p->b16_nz[c + e1] |= (1 << (e2 - e1));   // L(c+e2, c) L(c+e1, c)^T lands in block (c+e2, c+e1)
+            p->b16_products++;
+          }
+      }
+      for (int e = 0; e <= NB && e < 31; ++e) p->b16_blocks_nz += (m >> e) & 1u;
+    }
     std::vector<int32_t> first(p->n);
     std::iota(first.begin(), first.end(), 0);
     for (size_t e = 0; e < nnz; ++e) first[p->ent_row[e]] = std::min(first[p->ent_row[e]], p->ent_col[e]);
@@ -334,6 +354,7 @@ extern "C" int tb_plan_create(const tb_topology* topo, tb_plan** plan_out) {
   if (!rc) rc = upload(&p->d_q_pack, p->q_pack);
   if (!rc) rc = upload(&p->d_b16_ptr, p->b16_ptr);
   if (!rc) rc = upload(&p->d_b16_pos, p->b16_pos);
+  if (!rc) rc = upload(&p->d_b16_nz, p->b16_nz);
   if (!rc) rc = upload(&p->d_bq_ptr, p->bq_ptr);
   if (!rc) rc = upload(&p->d_bq_pack, p->bq_pack);
   if (!rc) rc = upload(&p->d_tile_nz, p->tile_nz);
@@ -372,6 +393,7 @@ extern "C" void tb_plan_destroy(tb_plan* p) {
   cudaFree(p->d_q_pack);
   cudaFree(p->d_b16_ptr);
   cudaFree(p->d_b16_pos);
+  cudaFree(p->d_b16_nz);
   cudaFree(p->d_bq_ptr);
   cudaFree(p->d_bq_pack);
   cudaFree(p->d_tile_nz);
