@@ -16,7 +16,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
-LIB_PATH = os.path.join(CSRC, "libtruss_b200.so")
+LIB_PATH = os.environ.get("TB_LIB_PATH") or os.path.join(CSRC, "libtruss_b200.so")   # TB_LIB_PATH: instrumented builds (tools/)
 SOURCES = ["tb_plan.cu", "tb_small.cu", "tb_large.cu", "tb_band.cu", "tb_api.cu", "tb_peak.cu"]
 
 TB_ERR_NO_DEVICE = -7
@@ -33,15 +33,22 @@ class NoCudaDeviceError(TrussLibError):
     pass
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, extra_flags=(), out: str | None = None) -> str:
     """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    if out is not None:
+        return _compile(out, verbose, list(extra_flags))
     srcs = [os.path.join(CSRC, s) for s in SOURCES]
     deps = srcs + [os.path.join(CSRC, "tb_common.cuh"), os.path.join(INCLUDE, "truss_b200.h")]
     if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
         return LIB_PATH
+    return _compile(LIB_PATH, verbose, list(extra_flags))
+
+
+def _compile(out_path: str, verbose: bool, extra_flags) -> str:
+    srcs = [os.path.join(CSRC, s) for s in SOURCES]
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-           "-Xcompiler", "-fPIC", "-shared", "-I", INCLUDE, "-o", LIB_PATH] + srcs
+           "-Xcompiler", "-fPIC", "-shared", "-I", INCLUDE, "-o", out_path] + extra_flags + srcs
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     res = subprocess.run(cmd, capture_output=True, text=True)
@@ -49,7 +56,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
     if verbose:
         print(res.stderr)
-    return LIB_PATH
+    return out_path
 
 
 # --------------------------------------------------------------------------- ctypes mirrors

@@ -21,8 +21,26 @@
 // once out and once back in, and u.  Replaces np.linalg.solve (slientruss3d/truss.py:343) for this class of
 // systems; results equal the dense factorisation's (zeros are skipped, nothing else).
 #include <math.h>
+#include <stdlib.h>
 
 #include "tb_common.cuh"
+
+#ifdef TB_PHASE_TIMING
+__device__ unsigned long long g_band_cycles[16];
+#define BPH_DECL long long _ph_t = clock64(); unsigned long long _ph_acc[16] = {0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0};
+#define BPH(i) { long long _n = clock64(); _ph_acc[i] += (unsigned long long)(_n - _ph_t); _ph_t = _n; }
+#define BPH_FLUSH(cond) if (cond) { for (int _i = 0; _i < 16; ++_i) atomicAdd(&g_band_cycles[_i], _ph_acc[_i]); }
+extern "C" int tb_band_phase_read(unsigned long long* out) {
+  cudaMemcpyFromSymbol(out, g_band_cycles, sizeof(unsigned long long) * 16);
+  unsigned long long z[16] = {0};
+  cudaMemcpyToSymbol(g_band_cycles, z, sizeof(z));
+  return 0;
+}
+#else
+#define BPH_DECL
+#define BPH(i) {}
+#define BPH_FLUSH(cond)
+#endif
 
 namespace {
 
@@ -43,10 +61,87 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+
+// Prefetch loads as volatile asm: the compiler keeps them in program order relative to the (volatile) DMMAs instead
+// of sinking them next to their first use, so the tensor work of a block column really covers their latency.
+__device__ __forceinline__ int ldg_i32(const int32_t* p) {
+  int v;
+  asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ double ldg_f64(const double* p) {
+  double v;
+  asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+
 __device__ __forceinline__ int b16_off(int r, int c) { return ((((r >> 3) << 2) + (c >> 2)) << 5) + ((r & 7) << 2) + (c & 3); }
 // this lane's accumulator pair of 8x8 block (mb, nbp) inside a 16x16 block
 __device__ __forceinline__ int cpair_off(int mb, int nbp, int lane) {
   return ((mb * 4 + nbp * 2 + ((lane & 3) >> 1)) << 5) + ((lane >> 2) << 2) + ((lane & 1) << 1);
+}
+
+
+// 1/sqrt(d) for a normal positive d: hardware seed (MUFU.RSQ64H) + two Newton steps, ~1 ulp.  The library
+// rsqrt() costs 18 instructions with its special-case handling; the pivots here are checked positive first.
+__device__ __forceinline__ double rsqrt_pos(double d) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+  const double h = 0.5 * d;
+  double e = fma(-h * y, y, 0.5);
+  y = fma(y, e, y);
+  e = fma(-h * y, y, 0.5);
+  y = fma(y, e, y);
+  return y;
+}
+
+// 16x16 diagonal block in shared memory (fragment layout): L_D L_D^T = P in registers, W = L_D^{-1} written back
+// over P as a DMMA B operand.  One warp: lanes 0-15 hold the rows of the block, lanes 16-31 the rows of
+// Z = L^{-T} (identity to start with).  The lane owning row k+1 forms the next pivot from its own registers,
+// one shuffle broadcasts it and the reciprocal square root of column k+1 is issued before the trailing update
+// of column k.  Returns 0 or the 1-based index (row0 + k + 1) of the first non-positive pivot.
+__device__ __forceinline__ int factor_diag16(double* sBlk, double* sCol, int lane, int row0) {
+  const int r = lane & 15;
+  const int rowpart = ((r >> 3) << 7) + ((r & 7) << 2);
+  double row[16];
+#pragma unroll
+  for (int cc = 0; cc < 16; ++cc) {
+    const double v = sBlk[rowpart + ((cc >> 2) << 5) + (cc & 3)];
+    row[cc] = lane < 16 ? (cc <= r ? v : 0.0) : (cc == r ? 1.0 : 0.0);
+  }
+  __syncwarp();
+  int bad = 0;
+  double d = __shfl_sync(0xffffffffu, row[0], 0);
+  if (!(d > 1e-290)) bad = row0 + 1;
+  double rinv = rsqrt_pos(bad ? 1.0 : d);
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const double lk = row[k] * rinv;                        // lane k: d * rsqrt(d) = sqrt(d)
+    row[k] = lk;
+    double rinv_next = 0.0;
+    if (k < 15) {
+      const double dn = __shfl_sync(0xffffffffu, fma(-lk, lk, row[k + 1]), k + 1);
+      if (!(dn > 1e-290) && !bad) bad = row0 + k + 2;       // same value in every lane
+      rinv_next = rsqrt_pos(bad ? 1.0 : dn);
+    }
+    double* col = sCol + ((k & 1) << 4);
+    if (lane < 16) col[lane] = lk;
+    __syncwarp();
+    const double2* col2 = reinterpret_cast<const double2*>(col);
+#pragma unroll
+    for (int p = (k + 1) >> 1; p < 8; ++p) {
+      const double2 cv = col2[p];
+      if (2 * p > k) row[2 * p] = fma(-lk, cv.x, row[2 * p]);
+      row[2 * p + 1] = fma(-lk, cv.y, row[2 * p + 1]);
+    }
+    rinv = rinv_next;
+  }
+  if (!bad && lane >= 16) {
+    // W[c'][kk] = Z[kk][c'] for kk <= c' (this lane: kk = r), as a DMMA B operand, over P
+#pragma unroll
+    for (int cp = 0; cp < 16; ++cp) sBlk[b16_off(cp, r)] = (cp >= r) ? row[cp] : 0.0;
+  }
+  return bad;
 }
 
 template <int NB>
@@ -56,10 +151,13 @@ struct BandCfg {
   static constexpr int DOUBLES = BUF * BE + BE + (NB + 1) * BT + BT + 32 + 8;     // ring | scratch block | y ring | rhs | column | slot table
 };
 
-template <int NB>
-__global__ void __launch_bounds__(32) k_band(const LargeArgs a) {
-  extern __shared__ __align__(16) double sm[];
+template <int NB, int NW>
+__global__ void __launch_bounds__(32 * NW) k_band1(const LargeArgs a) {
+  extern __shared__ __align__(16) double sm_all[];
   using Cfg = BandCfg<NB>;
+  // NW independent systems per CTA, one per warp, nothing shared between them: the CTA only exists so that the
+  // warps are spread over the four schedulers of the SM
+  double* sm = sm_all + (threadIdx.x >> 5) * Cfg::DOUBLES;
   double* sRing = sm;                          // blocks of the previous NB block columns | staging of K(:,c)
   double* sScr = sRing + Cfg::BUF * BE;        // diagonal block P(c,c), then W_c
   double* sY = sScr + BE;                      // ring of the last NB+1 blocks of y (then u), 16 each
@@ -67,12 +165,12 @@ __global__ void __launch_bounds__(32) k_band(const LargeArgs a) {
   double* sCol = sT + BT;                      // [32] base case: eliminated column, double buffered
   int* sOff = (int*)(sCol + 32);               // [NB+1] staging slot (in doubles from sm) of block e of this column
 
-  const int lane = threadIdx.x;
+  const int lane = threadIdx.x & 31;
   const int ncol = a.nb16;
   const int qr = lane >> 2, qc = lane & 3;     // this lane's (row, k) inside an operand fragment
 
-  for (int b = blockIdx.x; b < a.batch; b += gridDim.x) {
-    if (a.status[b] != 0) continue;            // input problem flagged by k_geom (uniform)
+  for (int b = blockIdx.x * NW + (threadIdx.x >> 5); b < a.batch; b += gridDim.x * NW) {
+    if (a.status[b] != 0) continue;            // input problem flagged by k_geom (uniform per warp)
     const double* kvs = a.kv + (int64_t)b * a.nnz;
     const double* fsys = a.force + b * a.force_stride;
     double* ysys = a.y + (int64_t)b * a.n_pad;
@@ -85,27 +183,40 @@ __global__ void __launch_bounds__(32) k_band(const LargeArgs a) {
     for (int e = 0; e <= NB; ++e) { idx[e] = 0; nzprev[e] = 0u; }
     int yslot = 0;                             // c mod (NB+1)
 
-    for (int c = 0; c < ncol; ++c) {
-      const unsigned nzc = (unsigned)__ldg(a.b16_nz + c);
-      // ---------------- prefetch this block column's K values and load-vector rows (consumed after the products)
-      const int q0 = __ldg(a.b16_ptr + c), q1 = __ldg(a.b16_ptr + c + 1);
-      double kvr[PRE];
-      int posr[PRE];
+    // column metadata and K values are fetched one block column ahead, so no load address ever waits on a load
+    unsigned nzn = (unsigned)ldg_i32(a.b16_nz);
+    int q0n = ldg_i32(a.b16_ptr), q1n = ldg_i32(a.b16_ptr + 2);
+    int fin[2];
 #pragma unroll
-      for (int i = 0; i < PRE; ++i) {
-        const int q = q0 + lane + 32 * i;
-        kvr[i] = 0.0;
-        posr[i] = 0;
-        if (q < q1) {
-          kvr[i] = __ldg(kvs + q);
-          posr[i] = __ldg(a.b16_pos + q);      // e << 8 | offset inside the block
-        }
+    for (int mb = 0; mb < 2; ++mb) fin[mb] = mb * 8 + qr < a.n ? ldg_i32(a.free_idx + mb * 8 + qr) : -1;
+    double kvr[PRE];
+    int posr[PRE];
+#pragma unroll
+    for (int i = 0; i < PRE; ++i) {
+      const int q = q0n + lane + 32 * i;
+      kvr[i] = 0.0;
+      posr[i] = 0;
+      if (q < q1n) {
+        kvr[i] = ldg_f64(kvs + q);
+        posr[i] = ldg_i32(a.b16_pos + q);        // e << 8 | offset inside the block
       }
+    }
+
+    for (int c = 0; c < ncol; ++c) {
+      const unsigned nzc = nzn;
+      const int q0 = q0n, q1 = q1n;
       double fr[2];
 #pragma unroll
-      for (int mb = 0; mb < 2; ++mb) {
-        const int grow = c * BT + mb * 8 + qr;
-        fr[mb] = grow < a.n ? __ldg(fsys + __ldg(a.free_idx + grow)) : 0.0;
+      for (int mb = 0; mb < 2; ++mb) fr[mb] = fin[mb] >= 0 ? ldg_f64(fsys + fin[mb]) : 0.0;
+      if (c + 1 < ncol) {
+        nzn = (unsigned)ldg_i32(a.b16_nz + c + 1);
+        q0n = ldg_i32(a.b16_ptr + 2 * (c + 1));
+        q1n = ldg_i32(a.b16_ptr + 2 * (c + 2));
+#pragma unroll
+        for (int mb = 0; mb < 2; ++mb) {
+          const int grow = (c + 1) * BT + mb * 8 + qr;
+          fin[mb] = grow < a.n ? ldg_i32(a.free_idx + grow) : -1;
+        }
       }
 
       // ---------------- products with the previous NB block columns (DMMA), forward-substitution partial sums
@@ -188,10 +299,20 @@ __global__ void __launch_bounds__(32) k_band(const LargeArgs a) {
       for (int i = 0; i < PRE; ++i)
         if (q0 + lane + 32 * i < q1) sm[sOff[posr[i] >> 8] + (posr[i] & 255)] = kvr[i];
       for (int q = q0 + 32 * PRE + lane; q < q1; q += 32) {   // rare: more than 32*PRE entries in this block column
-        const int pos = __ldg(a.b16_pos + q);
-        sm[sOff[pos >> 8] + (pos & 255)] = __ldg(kvs + q);
+        const int pos = ldg_i32(a.b16_pos + q);
+        sm[sOff[pos >> 8] + (pos & 255)] = ldg_f64(kvs + q);
       }
       if (lane < BT && c * BT + lane >= a.n) sScr[b16_off(lane, lane)] = 1.0;   // identity on the padded diagonal
+      if (c + 1 < ncol) {                      // the registers are free again: K values of the next block column
+#pragma unroll
+        for (int i = 0; i < PRE; ++i) {
+          const int q = q0n + lane + 32 * i;
+          if (q < q1n) {
+            kvr[i] = ldg_f64(kvs + q);
+            posr[i] = ldg_i32(a.b16_pos + q);
+          }
+        }
+      }
       __syncwarp();
 
       // ---------------- P = K - S, in place in the staging slots (fragment layout: the next reads are operand reads)
@@ -218,48 +339,7 @@ __global__ void __launch_bounds__(32) k_band(const LargeArgs a) {
       __syncwarp();
 
       // ---------------- 16x16 diagonal block: L_D L_D^T = P, W = L_D^{-1}  (in registers)
-      {
-        const int r = lane & 15;
-        const int rowpart = ((r >> 3) << 7) + ((r & 7) << 2);
-        double row[16];
-#pragma unroll
-        for (int cc = 0; cc < 16; ++cc) {
-          const double v = sScr[rowpart + ((cc >> 2) << 5) + (cc & 3)];
-          row[cc] = lane < 16 ? (cc <= r ? v : 0.0) : (cc == r ? 1.0 : 0.0);
-        }
-        __syncwarp();
-        // lanes 0-15: rows of the block; lanes 16-31: rows of Z = L^{-T} (identity to start with).  The
-        // lane owning row k+1 forms the next pivot from its own registers, one shuffle broadcasts it and
-        // the rsqrt of column k+1 is issued before the trailing update of column k.
-        int bad = 0;
-        double d = __shfl_sync(0xffffffffu, row[0], 0);
-        if (!(d > 0.0)) bad = c * BT + 1;
-        double rinv = rsqrt(bad ? 1.0 : d);
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-          const double lk = row[k] * rinv;                        // lane k: d * rsqrt(d) = sqrt(d)
-          row[k] = lk;
-          double rinv_next = 0.0;
-          if (k < 15) {
-            const double dn = __shfl_sync(0xffffffffu, fma(-lk, lk, row[k + 1]), k + 1);
-            if (!(dn > 0.0) && !bad) bad = c * BT + k + 2;         // same value in every lane
-            rinv_next = rsqrt(bad ? 1.0 : dn);
-          }
-          double* col = sCol + ((k & 1) << 4);
-          if (lane < 16) col[lane] = lk;
-          __syncwarp();
-#pragma unroll
-          for (int cc = k + 1; cc < 16; ++cc) row[cc] = fma(-lk, col[cc], row[cc]);
-          rinv = rinv_next;
-        }
-        if (bad) {
-          fail = bad;
-        } else if (lane >= 16) {
-          // W[c'][kk] = Z[kk][c'] for kk <= c' (this lane: kk = r), as a DMMA B operand, over P(c,c)
-#pragma unroll
-          for (int cp = 0; cp < 16; ++cp) sScr[b16_off(cp, r)] = (cp >= r) ? row[cp] : 0.0;
-        }
-      }
+      fail = factor_diag16(sScr, sCol, lane, c * BT);
       __syncwarp();
       if (fail) break;   // uniform
 
@@ -336,7 +416,7 @@ __global__ void __launch_bounds__(32) k_band(const LargeArgs a) {
     // ---------------- back substitution: u_c = W_c^T (y_c - sum_rb L(c+rb,c)^T u_{c+rb}), last block first.
     // Column chunks come back from HBM/L2 through a two-buffer cp.async pipeline in the (now idle) ring.
     auto fetch = [&](int c) {
-      const unsigned nz = (unsigned)__ldg(a.b16_nz + c) | 1u;     // bit 0: W_c
+      const unsigned nz = (unsigned)ldg_i32(a.b16_nz + c) | 1u;     // bit 0: W_c
       const double* src = Lb + (int64_t)c * (NB + 1) * BE;
       double* dst = sRing + (c & 1) * (NB + 1) * BE;
 #pragma unroll
@@ -364,7 +444,7 @@ __global__ void __launch_bounds__(32) k_band(const LargeArgs a) {
         cp_async_wait<0>();
       }
       __syncwarp();
-      const unsigned nz = (unsigned)__ldg(a.b16_nz + c);
+      const unsigned nz = (unsigned)ldg_i32(a.b16_nz + c);
       const double* buf = sRing + (c & 1) * (NB + 1) * BE;
       // t[col] = sum_rb sum_r L(c+rb,c)[r][col] u_{c+rb}[r]; this lane: r = 8 mb + lane/4, col = 4 ks + lane%4
       double tp[4] = {0.0, 0.0, 0.0, 0.0};
@@ -421,20 +501,458 @@ __global__ void __launch_bounds__(32) k_band(const LargeArgs a) {
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// Two warps per system (one CTA = one system), for batches too small to fill the GPU with one warp per system
+// (1024 systems on 148 SMs).  Same algorithm, data layout and arithmetic as k_band1; the block column is split
+// into the latency chain and the throughput work, which then overlap:
+//
+//   warp F  diagonal products S(c,c) -> P(c,c) -> 16x16 factorisation + W_c -> y_c        | X | L(c+1,c) = P W^T | Y |
+//   warp T  off-diagonal products S(c+rb,c) (96 of the 144 DMMAs) -> stage K -> P(c+rb,c) | X | L(c+rb,c), rb>=2 | Y |
+//
+// X and Y are CTA barriers (W_c and the P blocks exist / column c of L is in the ring); one more arrive/sync pair
+// (Z) tells T that F no longer reads the blocks (c, c-d) whose slots take the staged K blocks.  The back
+// substitution runs on warp F alone.  No instruction is duplicated between the warps except the operand loads of
+// L(c, c-d), so the instruction count per system stays that of k_band1 while the pivot chain of column c hides the
+// tensor work of the same column.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int PREF = 5;   // diagonal-block K entries per lane held in registers (<= 136 entries)
+constexpr int PRET = 6;   // off-diagonal K entries per lane held in registers
+
+__device__ __forceinline__ void bar_arrive_z() { asm volatile("bar.arrive 1, 64;" ::: "memory"); }
+__device__ __forceinline__ void bar_sync_z() { asm volatile("bar.sync 1, 64;" ::: "memory"); }
+
+template <int NB>
+__global__ void __launch_bounds__(64, 7) k_band2(const LargeArgs a) {
+  extern __shared__ __align__(16) double sm[];
+  using Cfg = BandCfg<NB>;
+  double* sRing = sm;
+  double* sScr = sRing + Cfg::BUF * BE;
+  double* sY = sScr + BE;
+  double* sT = sY + (NB + 1) * BT;
+  double* sCol = sT + BT;
+  int* sOff = (int*)(sCol + 32);               // [NB+1] staging slots, [NB+1] failure flag
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ncol = a.nb16;
+  const int qr = lane >> 2, qc = lane & 3;
+
+  for (int b = blockIdx.x; b < a.batch; b += gridDim.x) {
+    if (a.status[b] != 0) continue;            // input problem flagged by k_geom (uniform)
+    const bool isF = warp == (b & 1);          // alternate the roles so co-resident CTAs load the schedulers evenly
+    const double* kvs = a.kv + (int64_t)b * a.nnz;
+    const double* fsys = a.force + b * a.force_stride;
+    double* ysys = a.y + (int64_t)b * a.n_pad;
+    double* Lb = a.L + (int64_t)b * ncol * (NB + 1) * BE;
+    int fail = 0;
+    if (tid == 0) sOff[NB + 1] = 0;
+
+    int idx[NB + 1];
+    unsigned nzprev[NB + 1];
+#pragma unroll
+    for (int e = 0; e <= NB; ++e) { idx[e] = 0; nzprev[e] = 0u; }
+    int yslot = 0;
+    // column metadata is fetched one block column ahead, so that no load address waits on another load
+    const int part = isF ? 0 : 1;              // F: entries of the diagonal block; T: entries below it
+    unsigned nzn = (unsigned)ldg_i32(a.b16_nz);
+    int q0n = ldg_i32(a.b16_ptr + part), q1n = ldg_i32(a.b16_ptr + part + 1);
+    int fin[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) fin[h] = (isF && h * 8 + qr < a.n) ? ldg_i32(a.free_idx + h * 8 + qr) : -1;
+    BPH_DECL
+    __syncthreads();
+
+    for (int c = 0; c < ncol; ++c) {
+      const unsigned nzc = nzn;
+      const int q0 = q0n, q1 = q1n;
+      const int fi0 = fin[0], fi1 = fin[1];
+      if (c + 1 < ncol) {
+        nzn = (unsigned)ldg_i32(a.b16_nz + c + 1);
+        q0n = ldg_i32(a.b16_ptr + 2 * (c + 1) + part);
+        q1n = ldg_i32(a.b16_ptr + 2 * (c + 1) + part + 1);
+        if (isF) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int grow = (c + 1) * BT + h * 8 + qr;
+            fin[h] = grow < a.n ? ldg_i32(a.free_idx + grow) : -1;
+          }
+        }
+      }
+      double* chunk = Lb + (int64_t)c * (NB + 1) * BE;
+
+      if (isF) {
+        // ================= warp F: the latency chain of block column c =================
+        double kvf[PREF];
+        int posf[PREF];
+#pragma unroll
+        for (int i = 0; i < PREF; ++i) {
+          const int q = q0 + lane + 32 * i;
+          kvf[i] = 0.0;
+          posf[i] = 0;
+          if (q < q1) {
+            kvf[i] = ldg_f64(kvs + q);
+            posf[i] = ldg_i32(a.b16_pos + q);
+          }
+        }
+        double fr[2];
+        fr[0] = fi0 >= 0 ? ldg_f64(fsys + fi0) : 0.0;
+        fr[1] = fi1 >= 0 ? ldg_f64(fsys + fi1) : 0.0;
+        double acc[3][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};   // sub-blocks (0,0), (1,0), (1,1)
+        double tp[2] = {0.0, 0.0};
+#pragma unroll
+        for (int d = 1; d <= NB; ++d) {
+          if (!((nzprev[d] >> d) & 1u)) continue;
+          const double* Bm = sRing + (d * (d - 1) / 2 + idx[d]) * BE + lane;
+          double bf[2][4];
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) bf[h][ks] = Bm[(h * 4 + ks) << 5];
+          int ys = yslot - d;
+          if (ys < 0) ys += NB + 1;
+          const double* yv = sY + ys * BT;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const double y4 = yv[ks * 4 + qc];
+            tp[0] = fma(bf[0][ks], y4, tp[0]);
+            tp[1] = fma(bf[1][ks], y4, tp[1]);
+          }
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {     // L(c,c-d) L(c,c-d)^T: the operand fragments of A and B coincide
+            dmma(acc[0][0], acc[0][1], bf[0][ks], bf[0][ks]);
+            dmma(acc[1][0], acc[1][1], bf[1][ks], bf[0][ks]);
+            dmma(acc[2][0], acc[2][1], bf[1][ks], bf[1][ks]);
+          }
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          tp[h] += __shfl_xor_sync(0xffffffffu, tp[h], 1);
+          tp[h] += __shfl_xor_sync(0xffffffffu, tp[h], 2);
+        }
+        __syncwarp();
+        bar_arrive_z();                        // [Z] F no longer reads the blocks (c, c-d)
+        BPH(0)
+        {
+          const double2 z = make_double2(0.0, 0.0);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) reinterpret_cast<double2*>(sScr)[lane + 32 * i] = z;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < PREF; ++i)
+          if (q0 + lane + 32 * i < q1) sScr[posf[i] & 255] = kvf[i];
+        for (int q = q0 + 32 * PREF + lane; q < q1; q += 32) sScr[ldg_i32(a.b16_pos + q) & 255] = ldg_f64(kvs + q);
+        if (lane < BT && c * BT + lane >= a.n) sScr[b16_off(lane, lane)] = 1.0;   // identity on the padded diagonal
+        __syncwarp();
+        {
+          double2* p0 = reinterpret_cast<double2*>(sScr + cpair_off(0, 0, lane));
+          double2* p1 = reinterpret_cast<double2*>(sScr + cpair_off(1, 0, lane));
+          double2* p2 = reinterpret_cast<double2*>(sScr + cpair_off(1, 1, lane));
+          double2 v0 = *p0, v1 = *p1, v2 = *p2;
+          v0.x -= acc[0][0]; v0.y -= acc[0][1];
+          v1.x -= acc[1][0]; v1.y -= acc[1][1];
+          v2.x -= acc[2][0]; v2.y -= acc[2][1];
+          *p0 = v0; *p1 = v1; *p2 = v2;
+        }
+        if (qc == 0) {
+          sT[qr] = fr[0] - tp[0];
+          sT[8 + qr] = fr[1] - tp[1];
+        }
+        __syncwarp();
+        BPH(1)
+        const int bad = factor_diag16(sScr, sCol, lane, c * BT);
+        if (bad && lane == 0) sOff[NB + 1] = bad;
+        __syncwarp();
+        BPH(2)
+        if (!bad) {                            // y_c = W t, W_c to HBM
+          double yp[2] = {0.0, 0.0};
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const double t4 = sT[ks * 4 + qc];
+            yp[0] = fma(sScr[(ks << 5) + lane], t4, yp[0]);
+            yp[1] = fma(sScr[((4 + ks) << 5) + lane], t4, yp[1]);
+          }
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            yp[h] += __shfl_xor_sync(0xffffffffu, yp[h], 1);
+            yp[h] += __shfl_xor_sync(0xffffffffu, yp[h], 2);
+          }
+          if (qc == 0) {
+            sY[yslot * BT + qr] = yp[0];
+            sY[yslot * BT + 8 + qr] = yp[1];
+            ysys[c * BT + qr] = yp[0];
+            ysys[c * BT + 8 + qr] = yp[1];
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            reinterpret_cast<double2*>(chunk)[lane + 32 * i] = reinterpret_cast<const double2*>(sScr)[lane + 32 * i];
+        }
+        BPH(3)
+      } else {
+        // ================= warp T: the tensor work of block column c =================
+        double kvr[PRET];
+        int posr[PRET];
+#pragma unroll
+        for (int i = 0; i < PRET; ++i) {
+          const int q = q0 + lane + 32 * i;
+          kvr[i] = 0.0;
+          posr[i] = 0;
+          if (q < q1) {
+            kvr[i] = ldg_f64(kvs + q);
+            posr[i] = ldg_i32(a.b16_pos + q);
+          }
+        }
+#pragma unroll
+        for (int e = 1; e <= NB; ++e)
+          if (lane == e) sOff[e] = (e * (e - 1) / 2 + idx[e]) * BE;
+        double acc[NB + 1][2][2][2];
+#pragma unroll
+        for (int rb = 1; rb <= NB; ++rb)
+#pragma unroll
+          for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+            for (int nb = 0; nb < 2; ++nb) acc[rb][mb][nb][0] = acc[rb][mb][nb][1] = 0.0;
+#pragma unroll
+        for (int d = 1; d < NB; ++d) {
+          const unsigned nzp = nzprev[d];
+          if (!((nzp >> d) & 1u) || !(nzp >> (d + 1))) continue;   // L(c,c-d) zero, or nothing below it in that column
+          const double* Bm = sRing + (d * (d - 1) / 2 + idx[d]) * BE + lane;
+          double bf[2][4];
+#pragma unroll
+          for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) bf[nb][ks] = Bm[(nb * 4 + ks) << 5];
+#pragma unroll
+          for (int rb = 1; rb + d <= NB; ++rb) {
+            const int e = rb + d;
+            if (!((nzp >> e) & 1u)) continue;
+            int sl = idx[e] - d;               // (c-d) mod e
+            if (sl < 0) sl += e;
+            const double* A = sRing + (e * (e - 1) / 2 + sl) * BE + lane;
+            double af[2][4];
+#pragma unroll
+            for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) af[mb][ks] = A[(mb * 4 + ks) << 5];
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+              for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+                for (int nb = 0; nb < 2; ++nb) dmma(acc[rb][mb][nb][0], acc[rb][mb][nb][1], af[mb][ks], bf[nb][ks]);
+          }
+        }
+        __syncwarp();
+        bar_sync_z();                          // [Z] F is done with the blocks (c, c-d): their slots take K(c+e, c)
+        {
+          const double2 z = make_double2(0.0, 0.0);
+#pragma unroll
+          for (int e = 1; e <= NB; ++e)
+            if ((nzc >> e) & 1u) {
+              double2* blk = reinterpret_cast<double2*>(sRing + (e * (e - 1) / 2 + idx[e]) * BE);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) blk[lane + 32 * i] = z;
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < PRET; ++i)
+          if (q0 + lane + 32 * i < q1) sm[sOff[posr[i] >> 8] + (posr[i] & 255)] = kvr[i];
+        for (int q = q0 + 32 * PRET + lane; q < q1; q += 32) {
+          const int pos = ldg_i32(a.b16_pos + q);
+          sm[sOff[pos >> 8] + (pos & 255)] = ldg_f64(kvs + q);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int rb = 1; rb <= NB; ++rb) {
+          if (!((nzc >> rb) & 1u)) continue;
+          double* blk = sRing + (rb * (rb - 1) / 2 + idx[rb]) * BE;
+#pragma unroll
+          for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+            for (int nb = 0; nb < 2; ++nb) {
+              double2* p = reinterpret_cast<double2*>(blk + cpair_off(mb, nb, lane));
+              double2 v = *p;
+              v.x -= acc[rb][mb][nb][0];
+              v.y -= acc[rb][mb][nb][1];
+              *p = v;
+            }
+        }
+      }
+      __syncthreads();                         // [X] W_c is in the scratch block, P(c+rb, c) are in their slots
+      BPH(4)
+      fail = sOff[NB + 1];
+      if (fail) break;   // uniform
+
+      // ---------------- L(c+rb, c) = P W^T into the ring and to HBM: warp F takes rb = 1, warp T the rest
+      {
+        double wf[2][4];
+#pragma unroll
+        for (int nbp = 0; nbp < 2; ++nbp)
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) wf[nbp][ks] = sScr[((nbp * 4 + ks) << 5) + lane];
+#pragma unroll
+        for (int rb = 1; rb <= NB; ++rb) {
+          if ((rb == 1) != isF) continue;
+          if (!((nzc >> rb) & 1u)) continue;
+          double* blk = sRing + (rb * (rb - 1) / 2 + idx[rb]) * BE;
+          double a4[2][4];
+#pragma unroll
+          for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) a4[mb][ks] = blk[((mb * 4 + ks) << 5) + lane];
+          __syncwarp();                        // P(rb) fully read before L(rb) overwrites it
+          double* g = chunk + rb * BE;
+          double x[2][2][2] = {};
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+            for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+              for (int nbp = 0; nbp < 2; ++nbp)
+                if (ks < 2 * nbp + 2) dmma(x[mb][nbp][0], x[mb][nbp][1], a4[mb][ks], wf[nbp][ks]);   // W is lower triangular
+#pragma unroll
+          for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+            for (int nbp = 0; nbp < 2; ++nbp) {
+              const int off = cpair_off(mb, nbp, lane);
+              *reinterpret_cast<double2*>(blk + off) = make_double2(x[mb][nbp][0], x[mb][nbp][1]);
+              *reinterpret_cast<double2*>(g + off) = make_double2(x[mb][nbp][0], x[mb][nbp][1]);
+            }
+        }
+      }
+      BPH(5)
+      __syncthreads();                         // [Y] column c of L is in the ring
+      BPH(6)
+
+#pragma unroll
+      for (int e = NB; e >= 2; --e) nzprev[e] = nzprev[e - 1];
+      nzprev[1] = nzc;
+#pragma unroll
+      for (int e = 1; e <= NB; ++e) idx[e] = (idx[e] + 1 == e) ? 0 : idx[e] + 1;
+      yslot = (yslot == NB) ? 0 : yslot + 1;
+    }
+
+    if (fail) {
+      if (tid == 0) a.status[b] = fail;
+      __syncthreads();
+      continue;
+    }
+
+    // ---------------- back substitution on warp F: u_c = W_c^T (y_c - sum_rb L(c+rb,c)^T u_{c+rb}), last block first
+    if (isF) {
+      auto fetch = [&](int c) {
+        const unsigned nz = (unsigned)ldg_i32(a.b16_nz + c) | 1u;     // bit 0: W_c
+        const double* src = Lb + (int64_t)c * (NB + 1) * BE;
+        double* dst = sRing + (c & 1) * (NB + 1) * BE;
+#pragma unroll
+        for (int e = 0; e <= NB; ++e)
+          if ((nz >> e) & 1u) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) cp_async16(dst + e * BE + (lane + 32 * i) * 2, src + e * BE + (lane + 32 * i) * 2);
+          }
+        cp_async_commit();
+      };
+      fetch(ncol - 1);
+      for (int c = ncol - 1; c >= 0; --c) {
+        yslot = (yslot == 0) ? NB : yslot - 1;
+        double yc[4] = {0.0, 0.0, 0.0, 0.0};
+        if (qr == 0) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) yc[ks] = __ldcg(ysys + c * BT + ks * 4 + qc);
+        }
+        if (c > 0) {
+          fetch(c - 1);
+          cp_async_wait<1>();
+        } else {
+          cp_async_wait<0>();
+        }
+        __syncwarp();
+        const unsigned nz = (unsigned)ldg_i32(a.b16_nz + c);
+        const double* buf = sRing + (c & 1) * (NB + 1) * BE;
+        double tp[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int rb = 1; rb <= NB; ++rb) {
+          if (!((nz >> rb) & 1u)) continue;
+          int us = yslot + rb;
+          if (us > NB) us -= NB + 1;
+          const double* uv = sY + us * BT;
+          const double* blk = buf + rb * BE;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const double ur = uv[h * 8 + qr];
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) tp[ks] = fma(blk[((h * 4 + ks) << 5) + lane], ur, tp[ks]);
+          }
+        }
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          tp[ks] += __shfl_xor_sync(0xffffffffu, tp[ks], 4);
+          tp[ks] += __shfl_xor_sync(0xffffffffu, tp[ks], 8);
+          tp[ks] += __shfl_xor_sync(0xffffffffu, tp[ks], 16);
+        }
+        if (qr == 0) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) sT[ks * 4 + qc] = yc[ks] - tp[ks];
+        }
+        __syncwarp();
+        double up[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const double rr = sT[h * 8 + qr];
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) up[ks] = fma(buf[((h * 4 + ks) << 5) + lane], rr, up[ks]);
+        }
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          up[ks] += __shfl_xor_sync(0xffffffffu, up[ks], 4);
+          up[ks] += __shfl_xor_sync(0xffffffffu, up[ks], 8);
+          up[ks] += __shfl_xor_sync(0xffffffffu, up[ks], 16);
+        }
+        if (qr == 0) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            sY[yslot * BT + ks * 4 + qc] = up[ks];
+            ysys[c * BT + ks * 4 + qc] = up[ks];
+          }
+        }
+        __syncwarp();
+      }
+      BPH(7)
+      if (lane == 0) a.status[b] = 0;
+    }
+    BPH_FLUSH(lane == 0 && isF)
+    __syncthreads();
+  }
+}
+
 template <int NB>
 int launch_band(const LargeArgs& a, int num_sm, cudaStream_t st) {
-  const int smem = BandCfg<NB>::DOUBLES * 8;
-  auto kern = k_band<NB>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  // one warp per system when the batch alone fills the GPU (fewest instructions per system), else two warps per system
+  static const int force = [] { const char* s = getenv("TB_BAND_WARPS"); return s ? atoi(s) : 0; }();
+  constexpr int NW = 4;                        // k_band1 packs four independent systems (warps) into a CTA
+  const int smem1 = NW * BandCfg<NB>::DOUBLES * 8, smem2 = BandCfg<NB>::DOUBLES * 8;
+  int per1 = 0, per2 = 0;
+  cudaError_t e = cudaFuncSetAttribute(k_band1<NB, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_band2<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
+  if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per1, k_band1<NB, NW>, 32 * NW, smem1);
+  if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per2, k_band2<NB>, 64, smem2);
   if (e != cudaSuccess) return (int)e;
-  int per_sm = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, smem);
-  if (e != cudaSuccess) return (int)e;
-  if (per_sm < 1) per_sm = 1;
-  int grid = num_sm * per_sm;
-  if (grid > a.batch) grid = a.batch;
+  if (per1 < 1) per1 = 1;
+  if (per2 < 1) per2 = 1;
+  bool two = NB <= 5 && (int64_t)a.batch < (int64_t)2 * num_sm * per1 * NW;   // NB > 5: the trailing warp's accumulators spill
+  if (force == 1) two = false;
+  if (force == 2 && NB <= 5) two = true;
   tb_prof_begin(TB_PROF_CHOL, st);
-  kern<<<grid, 32, smem, st>>>(a);
+  if (two) {
+    int grid = num_sm * per2;
+    if (grid > a.batch) grid = a.batch;
+    k_band2<NB><<<grid, 64, smem2, st>>>(a);
+  } else {
+    int grid = num_sm * per1;
+    if (grid > (a.batch + NW - 1) / NW) grid = (a.batch + NW - 1) / NW;
+    k_band1<NB, NW><<<grid, 32 * NW, smem1, st>>>(a);
+  }
   tb_prof_end(TB_PROF_CHOL, st);
   return (int)cudaGetLastError();
 }

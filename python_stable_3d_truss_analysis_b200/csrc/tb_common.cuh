@@ -76,7 +76,7 @@ struct tb_plan {
   int64_t n_tiles_nz = 0;
   // band view (16x16 blocks): nb16 block columns, NB sub-diagonal blocks; entries grouped per block column
   int nb16 = 0, NB = 0;
-  std::vector<int32_t> b16_ptr;            // [nb16+1] entry ranges (band order) per block column
+  std::vector<int32_t> b16_ptr;            // [2 nb16+1] entry ranges (band order) per block column: diagonal block, blocks below it
   std::vector<int32_t> b16_pos;            // [nnz] (block offset e) << 8 | offset inside the 16x16 block
   std::vector<int32_t> b16_nz;             // [nb16] bit e: block (c+e, c) of L is structurally non-zero (block symbolic factorisation)
   int64_t b16_blocks_nz = 0, b16_products = 0;   // non-zero blocks of L, block products of the factorisation

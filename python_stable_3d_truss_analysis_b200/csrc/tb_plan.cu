@@ -263,14 +263,17 @@ extern "C" int tb_plan_create(const tb_topology* topo, tb_plan** plan_out) {
     p->NB = NB;
     std::vector<int32_t> order(nnz);
     std::iota(order.begin(), order.end(), 0);
+    // order: block column, then diagonal block before the blocks below it (the two-warp kernel gives the diagonal
+    // block to its factor warp and the rest to its trailing warp), then block row, row, column
+    auto sub = [&](int e) { return p->ent_row[e] / 16 == p->ent_col[e] / 16 ? 0 : 1; };
     auto key = [&](int e) { return std::make_tuple(p->ent_col[e] / 16, p->ent_row[e] / 16, p->ent_row[e], p->ent_col[e]); };
     std::sort(order.begin(), order.end(), [&](int x, int y) { return key(x) < key(y); });
-    p->b16_ptr.assign(p->nb16 + 1, 0);
+    p->b16_ptr.assign(2 * (size_t)p->nb16 + 1, 0);
     p->b16_pos.assign(nnz, 0);
     p->bq_ptr.assign(nnz + 1, 0);
     for (size_t q = 0; q < nnz; ++q) {
       const int e = order[q], r = p->ent_row[e], c = p->ent_col[e];
-      p->b16_ptr[c / 16 + 1]++;
+      p->b16_ptr[2 * (c / 16) + sub(e) + 1]++;
       const int rr = r % 16, cc = c % 16;
       p->b16_pos[q] = ((r / 16 - c / 16) << 8) | (((((rr >> 3) << 2) + (cc >> 2)) << 5) + ((rr & 7) << 2) + (cc & 3));
       for (int64_t k = p->ent_ptr[e]; k < p->ent_ptr[e + 1]; ++k) {
@@ -281,7 +284,7 @@ extern "C" int tb_plan_create(const tb_topology* topo, tb_plan** plan_out) {
       }
       p->bq_ptr[q + 1] = (int32_t)p->bq_pack.size();
     }
-    for (int c = 0; c < p->nb16; ++c) p->b16_ptr[c + 1] += p->b16_ptr[c];
+    for (int c = 0; c < 2 * p->nb16; ++c) p->b16_ptr[c + 1] += p->b16_ptr[c];
     // block-level symbolic factorisation of the band: bit e of b16_nz[c] <=> block (c+e, c) of L is non-zero
     p->b16_nz.assign(p->nb16, 1);
     for (size_t e = 0; e < nnz; ++e) {

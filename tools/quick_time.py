@@ -31,7 +31,7 @@ G = os.path.join(ROOT, "tests", "golden", "ref_data")
 t = Truss(3).LoadFromJSON(os.path.join(G, "bar-942_input_0.json"))
 xyz, sup, conn, aed, force = t._pack()
 plan = t._get_plan()
-for B in (148, 1024):
+for B in (1, 148, 1024, 8192):
     rng = np.random.default_rng(0)
     F = td(rng.uniform(-10, 10, size=(B, plan.N)))
     out = {k: torch.empty(B, plan.N if k in ("u", "ext") else plan.M, dtype=torch.float64, device=dev) for k in ("u", "ext", "axial")}
