@@ -167,6 +167,9 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------------ GPU arm
 def run_gpu(args):
+    # libraries (NCCL's version banner) may write to fd 1: keep the real stdout for the one JSON line
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
 
@@ -193,21 +196,21 @@ def run_gpu(args):
 
     td = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
     d_xyz, d_aed, d_F = td(xyz), td(aed), td(F)
-    out = {"u": torch.empty(B, N, dtype=torch.float64, device=dev), "ext": torch.empty(B, N, dtype=torch.float64, device=dev),
-           "axial": torch.empty(B, M, dtype=torch.float64, device=dev), "weight": torch.empty(B, dtype=torch.float64, device=dev),
-           "info": torch.empty(B, dtype=torch.int32, device=dev)}
+    # one flat result buffer per rank, [u | ext | axial]: the three outputs are views into it, so the multi-GPU gather
+    # ships it as it is (no packing kernel)
+    flat = torch.empty(B * (2 * N + M), dtype=torch.float64, device=dev)
+    out = {"u": flat[:B * N].view(B, N), "ext": flat[B * N:2 * B * N].view(B, N), "axial": flat[2 * B * N:].view(B, M),
+           "weight": torch.empty(B, dtype=torch.float64, device=dev), "info": torch.empty(B, dtype=torch.int32, device=dev)}
     gathered = None
     if world > 1:   # results go back to rank 0 over NCCL (north_star: gather only)
-        packed = torch.empty(B, 2 * N + M, dtype=torch.float64, device=dev)
-        gathered = [torch.empty_like(packed) for _ in range(world)] if rank == 0 else None
+        gathered = [torch.empty_like(flat) for _ in range(world)] if rank == 0 else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
     stream = torch.cuda.current_stream()
 
     def step():
         plan.solve_device(B, d_xyz, d_F, aed=d_aed, out=out, stream=stream)
         if world > 1:
-            torch.cat([out["u"], out["ext"], out["axial"]], dim=1, out=packed)
-            dist.gather(packed, gathered, dst=0)
+            dist.gather(flat, gathered, dst=0)
 
     def barrier():
         if world > 1:
@@ -357,7 +360,8 @@ def run_gpu(args):
         "cpu_baseline": cpu,
         "wall_s_timed_region": wall,
     }
-    print(json.dumps(line))
+    sys.stdout.flush()
+    os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 

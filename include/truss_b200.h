@@ -84,7 +84,7 @@ typedef struct {
   int32_t n_pad;       /* padded order used by the blocked pipeline (multiple of the tile) */
   int64_t nnz_lower;   /* structural non-zeros of the lower triangle of K_ff */
   int64_t n_contrib;   /* entries of the scatter map (member contributions to the lower triangle) */
-  int64_t half_bandwidth; /* max (row - col) over structural non-zeros of K_ff */
+  int64_t half_bandwidth; /* max (row - col) over structural non-zeros of K_ff in the internal elimination order */
   /* blocked pipeline: block-level symbolic factorisation over 64x64 tiles of the lower triangle */
   int64_t n_tiles;          /* nt(nt+1)/2 */
   int64_t n_tiles_nonzero;  /* tiles of L that are structurally non-zero (the only ones touched) */
@@ -94,6 +94,10 @@ typedef struct {
   int32_t band_blocks;      /* sub-diagonal 16x16 blocks per block column (the band path needs <= 8) */
   int64_t envelope_size;    /* entries inside the row envelope of K_ff (fill stays inside it) */
   double envelope_flops;    /* flops of an envelope Cholesky + two triangular solves: the algorithmic work */
+  int32_t reordered;        /* 1: the factorisation eliminates the free DOFs in reverse Cuthill-McKee order of the joints
+                               (internal only: tb_plan_get_maps / tb_plan_get_scatter stay in the reference's order) */
+  int64_t band_blocks_nonzero; /* band path: structurally non-zero 16x16 blocks of L */
+  int64_t band_products;       /* band path: 16x16 block products of the factorisation */
 } tb_plan_info;
 
 /* Build the integer maps of truss.py:319-326 (free/supported DOF order = ascending DOF index)

@@ -71,7 +71,8 @@ class TbPlanInfo(C.Structure):
                 ("path", C.c_int32), ("n_pad", C.c_int32), ("nnz_lower", C.c_int64), ("n_contrib", C.c_int64),
                 ("half_bandwidth", C.c_int64), ("n_tiles", C.c_int64), ("n_tiles_nonzero", C.c_int64),
                 ("n_tile_products", C.c_int64), ("chol_flops", C.c_double), ("band_blocks", C.c_int32),
-                ("envelope_size", C.c_int64), ("envelope_flops", C.c_double)]
+                ("envelope_size", C.c_int64), ("envelope_flops", C.c_double), ("reordered", C.c_int32),
+                ("band_blocks_nonzero", C.c_int64), ("band_products", C.c_int64)]
 
 
 class TbBatchIn(C.Structure):

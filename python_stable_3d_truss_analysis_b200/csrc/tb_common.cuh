@@ -58,6 +58,12 @@ struct tb_plan {
   std::vector<int32_t> free_idx;   // [n]
   std::vector<int32_t> dof2free;   // [N]
   std::vector<int32_t> sup_idx;    // [s]
+  // internal elimination order (reverse Cuthill-McKee over the joints when it shrinks the envelope)
+  int reordered = 0;
+  std::vector<int32_t> perm;       // [n] internal index -> reference free index
+  std::vector<int32_t> free_int;   // [n] DOF index of internal row i      (device: d_free_idx)
+  std::vector<int32_t> d2f_int;    // [N] internal row of a DOF, -1 at supports (device: d_dof2free)
+  std::vector<int32_t> int_row, int_col;   // [nnz] entry rows / columns in the internal order (row >= col)
   // scatter map over the lower triangle of K_ff (row-major order of entries)
   std::vector<int32_t> ent_row, ent_col;   // [nnz]
   std::vector<int64_t> ent_ptr;            // [nnz+1]

@@ -65,3 +65,30 @@ def key_sets_match(dense_got, dense_want, rel=1e-8):
     scale = max(np.abs(b).max(), 1e-300)
     sig = np.abs(b) > rel * scale
     return bool(np.all((np.abs(a[sig]) >= orc.ZERO_EPS) == (np.abs(b[sig]) >= orc.ZERO_EPS)))
+
+
+def cube_truss(n_side: int, seed: int = 1):
+    """Full n^3 cube-truss grid (n_side = 12 -> nJ 2197, M 14868, n 6084)."""
+    from python_stable_3d_truss_analysis_b200.generate import GenerateRandomCubeTrusses
+    from python_stable_3d_truss_analysis_b200.type import LinkType
+
+    ts = GenerateRandomCubeTrusses(gridRange=(n_side,) * 3, numCubeRange=(n_side ** 3,) * 2, numEachRange=(1, 1),
+                                   lengthRange=(100, 200), forceRange=[(-1000, 1000)] * 3,
+                                   linkType=LinkType.LeftBottom_RightTop, seed=seed, isPrintMessage=False)
+    return ts[0]
+
+
+def ragged_pool_arrays(pool, n_total: int, sigma: float = 10.0, seed: int = 1):
+    """Config 4 recipe: tile a pool of generated trusses to n_total systems with fresh Gaussian joint
+    jitter (AddJointNoise-style, sigma, default_rng(seed)).  Returns the tb_ragged_in arrays + the pool index of each system."""
+    packs = [t._pack() for t in pool]
+    which = np.arange(n_total) % len(pool)
+    nj = np.array([p[0].shape[0] for p in packs])[which]
+    nm = np.array([p[2].shape[0] for p in packs])[which]
+    joint_off = np.zeros(n_total + 1, np.int64); joint_off[1:] = np.cumsum(nj)
+    member_off = np.zeros(n_total + 1, np.int64); member_off[1:] = np.cumsum(nm)
+    cat = lambda i, dt: np.concatenate([np.asarray(packs[w][i]).reshape(-1) for w in which]).astype(dt)  # noqa: E731
+    xyz = cat(0, np.float64)
+    rng = np.random.default_rng(seed)
+    xyz = xyz + rng.normal(0.0, sigma, size=xyz.shape)
+    return joint_off, member_off, xyz, cat(1, np.uint8), cat(2, np.int32), cat(3, np.float64), cat(4, np.float64), which

@@ -83,7 +83,11 @@ def test_scatter_map_rebuilds_reference_K(name, dim, data):
     mask = orc.free_mask(dim, support)
     Kref = orc.assemble_K(dim, joints, conn, aed)[np.ix_(mask, mask)]
     assert np.array_equal(np.tril(Kref), K), "scatter map does not rebuild the reference matrix bit for bit"
-    assert plan.info.half_bandwidth == (np.abs(row - col).max() if len(row) else 0)
+    natural = int(np.abs(row - col).max()) if len(row) else 0
+    if plan.info.reordered:       # internal RCM elimination order: never wider than the reference's order
+        assert plan.info.half_bandwidth <= natural
+    else:
+        assert plan.info.half_bandwidth == natural
 
 
 def test_argument_errors():

@@ -282,3 +282,48 @@ def test_fp64_peaks_are_measurable():
     for which in (0, 1):
         tf, ms = _lib.fp64_peak(which, 1024)
         assert tf > 1.0 and ms > 0
+
+
+def test_config4_ragged_65536_properties():
+    """BASELINE configs[3] at full size: 65536 ragged cube-7 systems (pool tiled with joint jitter) in one call:
+    a sample against the oracle, determinism, and equality with the same systems solved in a smaller batch."""
+    pool = [Truss(3).LoadFromJSON(data={k: g[k] for k in ("joint", "force", "member")}) for g in H.load_json("live_cube7_aug.json")]
+    B = 65536
+    jo, mo, xyz, sup, conn, aed, force, which = H.ragged_pool_arrays(pool, B)
+    out = _lib.solve_ragged_host(3, jo, mo, xyz, sup, conn, aed, force)
+    assert not out["info"].any()
+    again = _lib.solve_ragged_host(3, jo, mo, xyz, sup, conn, aed, force)
+    for k in H.FIELDS:
+        assert np.array_equal(out[k], again[k]), k
+    # a slice of the batch solved on its own gives the same bits
+    lo, hi = 40000, 40064
+    sub = _lib.solve_ragged_host(3, jo[lo:hi + 1] - jo[lo], mo[lo:hi + 1] - mo[lo], xyz[jo[lo] * 3:jo[hi] * 3], sup[jo[lo]:jo[hi]],
+                                 conn[mo[lo] * 2:mo[hi] * 2], aed[mo[lo] * 3:mo[hi] * 3], force[jo[lo] * 3:jo[hi] * 3])
+    assert np.array_equal(sub["u"], out["u"][jo[lo] * 3:jo[hi] * 3]) and np.array_equal(sub["axial"], out["axial"][mo[lo]:mo[hi]])
+    for b in (0, 1, 12345, 65535):
+        j0, j1, m0, m1 = jo[b], jo[b + 1], mo[b], mo[b + 1]
+        want = orc.solve(3, xyz[j0 * 3:j1 * 3].reshape(-1, 3), sup[j0:j1], conn[m0 * 2:m1 * 2].reshape(-1, 2),
+                         aed[m0 * 3:m1 * 3].reshape(-1, 3), force[j0 * 3:j1 * 3])
+        got = {"u": out["u"][j0 * 3:j1 * 3], "ext": out["ext"][j0 * 3:j1 * 3], "axial": out["axial"][m0:m1], "weight": out["weight"][b]}
+        H.assert_close(got, want, what=f"config4[{b}]")
+
+
+def test_config5_cube12_tiled_vs_oracle():
+    """BASELINE configs[4] shape (12^3 cube truss: nJ 2197, M 14868, n 6084) through the tiled pipeline, two systems with
+    different member areas, against the oracle's dense solve; equilibrium of loads and reactions."""
+    t = H.cube_truss(12)
+    xyz, support, conn, aed, force = t._pack()
+    plan = t._get_plan()
+    assert plan.n == 6084 and plan.path == 1
+    rng = np.random.default_rng(5)
+    B = 2
+    aedb = np.repeat(aed[None], B, axis=0).copy()
+    aedb[:, :, 0] = rng.uniform(1.0, 20.0, size=(B, plan.M))
+    out = plan.solve_host(B, xyz, force, aed=aedb)
+    assert not out["info"].any()
+    mask = np.asarray(t.GetDisplacementUnknownMask())
+    for b in range(B):
+        want = orc.solve_closed_form(3, xyz, support, conn, aedb[b], force)
+        H.assert_close({k: out[k][b] for k in H.FIELDS} | {"weight": out["weight"][b]}, want, what=f"cube12[{b}]")
+        tot = (np.where(mask, force, 0.0) + np.where(~mask, out["ext"][b], 0.0)).reshape(-1, 3).sum(axis=0)
+        assert np.abs(tot).max() <= 1e-7 * np.abs(force).sum()
