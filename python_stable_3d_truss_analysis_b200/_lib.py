@@ -17,7 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 LIB_PATH = os.environ.get("TB_LIB_PATH") or os.path.join(CSRC, "libtruss_b200.so")   # TB_LIB_PATH: instrumented builds (tools/)
-SOURCES = ["tb_plan.cu", "tb_small.cu", "tb_large.cu", "tb_band.cu", "tb_api.cu", "tb_peak.cu"]
+SOURCES = ["tb_plan.cu", "tb_small.cu", "tb_dense16.cu", "tb_large.cu", "tb_band.cu", "tb_api.cu", "tb_peak.cu"]
 
 TB_ERR_NO_DEVICE = -7
 TB_ERR_TOO_LARGE = -6
@@ -38,7 +38,7 @@ def build(force: bool = False, verbose: bool = False, extra_flags=(), out: str |
     if out is not None:
         return _compile(out, verbose, list(extra_flags))
     srcs = [os.path.join(CSRC, s) for s in SOURCES]
-    deps = srcs + [os.path.join(CSRC, "tb_common.cuh"), os.path.join(INCLUDE, "truss_b200.h")]
+    deps = srcs + [os.path.join(CSRC, "tb_common.cuh"), os.path.join(CSRC, "tb_blocks.cuh"), os.path.join(INCLUDE, "truss_b200.h")]
     if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
         return LIB_PATH
     return _compile(LIB_PATH, verbose, list(extra_flags))

@@ -24,6 +24,7 @@
 #include <stdlib.h>
 
 #include "tb_common.cuh"
+#include "tb_blocks.cuh"
 
 #ifdef TB_PHASE_TIMING
 __device__ unsigned long long g_band_cycles[16];
@@ -44,105 +45,8 @@ extern "C" int tb_band_phase_read(unsigned long long* out) {
 
 namespace {
 
-constexpr int BT = 16;    // block order
-constexpr int BE = 256;   // doubles per block, stored as [8-row block 2][k-slab 4][lane 32] (DMMA operand order)
 constexpr int PRE = 9;    // K entries per lane prefetched into registers per block column (288 per column)
-
-__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-               : "+d"(c0), "+d"(c1)
-               : "d"(a), "d"(b));
-}
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-
-// Prefetch loads as volatile asm: the compiler keeps them in program order relative to the (volatile) DMMAs instead
-// of sinking them next to their first use, so the tensor work of a block column really covers their latency.
-__device__ __forceinline__ int ldg_i32(const int32_t* p) {
-  int v;
-  asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(p));
-  return v;
-}
-__device__ __forceinline__ double ldg_f64(const double* p) {
-  double v;
-  asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
-  return v;
-}
-
-__device__ __forceinline__ int b16_off(int r, int c) { return ((((r >> 3) << 2) + (c >> 2)) << 5) + ((r & 7) << 2) + (c & 3); }
-// this lane's accumulator pair of 8x8 block (mb, nbp) inside a 16x16 block
-__device__ __forceinline__ int cpair_off(int mb, int nbp, int lane) {
-  return ((mb * 4 + nbp * 2 + ((lane & 3) >> 1)) << 5) + ((lane >> 2) << 2) + ((lane & 1) << 1);
-}
-
-
-// 1/sqrt(d) for a normal positive d: hardware seed (MUFU.RSQ64H) + two Newton steps, ~1 ulp.  The library
-// rsqrt() costs 18 instructions with its special-case handling; the pivots here are checked positive first.
-__device__ __forceinline__ double rsqrt_pos(double d) {
-  double y;
-  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
-  const double h = 0.5 * d;
-  double e = fma(-h * y, y, 0.5);
-  y = fma(y, e, y);
-  e = fma(-h * y, y, 0.5);
-  y = fma(y, e, y);
-  return y;
-}
-
-// 16x16 diagonal block in shared memory (fragment layout): L_D L_D^T = P in registers, W = L_D^{-1} written back
-// over P as a DMMA B operand.  One warp: lanes 0-15 hold the rows of the block, lanes 16-31 the rows of
-// Z = L^{-T} (identity to start with).  The lane owning row k+1 forms the next pivot from its own registers,
-// one shuffle broadcasts it and the reciprocal square root of column k+1 is issued before the trailing update
-// of column k.  Returns 0 or the 1-based index (row0 + k + 1) of the first non-positive pivot.
-__device__ __forceinline__ int factor_diag16(double* sBlk, double* sCol, int lane, int row0) {
-  const int r = lane & 15;
-  const int rowpart = ((r >> 3) << 7) + ((r & 7) << 2);
-  double row[16];
-#pragma unroll
-  for (int cc = 0; cc < 16; ++cc) {
-    const double v = sBlk[rowpart + ((cc >> 2) << 5) + (cc & 3)];
-    row[cc] = lane < 16 ? (cc <= r ? v : 0.0) : (cc == r ? 1.0 : 0.0);
-  }
-  __syncwarp();
-  int bad = 0;
-  double d = __shfl_sync(0xffffffffu, row[0], 0);
-  if (!(d > 1e-290)) bad = row0 + 1;
-  double rinv = rsqrt_pos(bad ? 1.0 : d);
-#pragma unroll
-  for (int k = 0; k < 16; ++k) {
-    const double lk = row[k] * rinv;                        // lane k: d * rsqrt(d) = sqrt(d)
-    row[k] = lk;
-    double rinv_next = 0.0;
-    if (k < 15) {
-      const double dn = __shfl_sync(0xffffffffu, fma(-lk, lk, row[k + 1]), k + 1);
-      if (!(dn > 1e-290) && !bad) bad = row0 + k + 2;       // same value in every lane
-      rinv_next = rsqrt_pos(bad ? 1.0 : dn);
-    }
-    double* col = sCol + ((k & 1) << 4);
-    if (lane < 16) col[lane] = lk;
-    __syncwarp();
-    const double2* col2 = reinterpret_cast<const double2*>(col);
-#pragma unroll
-    for (int p = (k + 1) >> 1; p < 8; ++p) {
-      const double2 cv = col2[p];
-      if (2 * p > k) row[2 * p] = fma(-lk, cv.x, row[2 * p]);
-      row[2 * p + 1] = fma(-lk, cv.y, row[2 * p + 1]);
-    }
-    rinv = rinv_next;
-  }
-  if (!bad && lane >= 16) {
-    // W[c'][kk] = Z[kk][c'] for kk <= c' (this lane: kk = r), as a DMMA B operand, over P
-#pragma unroll
-    for (int cp = 0; cp < 16; ++cp) sBlk[b16_off(cp, r)] = (cp >= r) ? row[cp] : 0.0;
-  }
-  return bad;
-}
+using namespace tbblk;
 
 template <int NB>
 struct BandCfg {

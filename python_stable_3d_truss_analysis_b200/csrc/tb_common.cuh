@@ -191,6 +191,8 @@ struct LargeArgs {
 // launchers (return cudaError_t as int)
 int tb_launch_small(const SmallArgs& a, int dim, cudaStream_t st);
 int tb_small_smem_bytes(int dim, int nJ, int M, int max_n, int* threads);
+int tb_launch_dense16(const SmallArgs& a, int dim, cudaStream_t st);   // -1: does not fit, use the CTA-per-truss kernel
+int tb_dense16_smem_bytes(int dim, int nJ, int M, int max_n);
 int tb_launch_large(const LargeArgs& a, int num_sm, cudaStream_t st, int path);
 size_t tb_large_workspace_bytes(int batch, int dim, int M, int n_pad, int64_t nnz, int path, int nb16, int NB);
 void tb_large_carve(LargeArgs& a, void* ws, int path);

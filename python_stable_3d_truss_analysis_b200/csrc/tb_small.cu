@@ -15,6 +15,7 @@
 // ascending id, so every entry is summed in the reference's order (truss.py:310).  The right-hand
 // side rides along as row n of the factorisation (L y = f falls out of the same column loop).
 #include <math.h>
+#include <stdlib.h>
 
 #include "tb_common.cuh"
 
@@ -395,6 +396,12 @@ int tb_small_smem_bytes(int dim, int nJ, int M, int max_n, int* threads) {
 
 int tb_launch_small(const SmallArgs& a, int dim, cudaStream_t st) {
   if (a.batch <= 0) return 0;
+  // warp-per-system kernel (tb_dense16.cu) first; this CTA-per-truss kernel takes what does not fit its budget
+  static const bool legacy = [] { const char* s = getenv("TB_SMALL_LEGACY"); return s && s[0] == '1'; }();
+  if (!legacy) {
+    const int rc = tb_launch_dense16(a, dim, st);
+    if (rc != -1) return rc;
+  }
   int threads = 0;
   const int smem = tb_small_smem_bytes(dim, a.nJ, a.M, a.max_n, &threads);
   if (threads > SMALL_MAX_THREADS || smem > 227 * 1024) return TB_ERR_TOO_LARGE;
