@@ -135,6 +135,9 @@ int run_plan(tb_plan* p, const tb_batch_in* in, const tb_batch_out* out, const t
     a.nnz = (int64_t)p->ent_row.size();
     a.q_ptr = p->path == 2 ? p->d_bq_ptr : p->d_q_ptr;
     a.q_pack = p->path == 2 ? p->d_bq_pack : p->d_q_pack;
+    a.q_first = p->path == 2 ? p->d_bq_first : p->d_q_first;
+    a.q_multi = p->path == 2 ? p->d_bq_multi : p->d_q_multi;
+    a.n_multi = (int)(p->path == 2 ? p->bq_multi.size() : p->q_multi.size());
     a.nb16 = p->nb16;
     a.NB = p->NB;
     a.b16_ptr = p->d_b16_ptr;

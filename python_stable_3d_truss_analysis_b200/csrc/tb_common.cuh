@@ -74,6 +74,8 @@ struct tb_plan {
   std::vector<int32_t> tile_pos;           // [nnz] fragment-major offset inside the tile, same order
   std::vector<int32_t> q_ptr;              // [nnz+1] contribution ranges in tile_ent order
   std::vector<int32_t> q_pack;             // [n_contrib] member<<4 | negate<<3 | index of (i<=j) cosine product
+  std::vector<int32_t> q_multi, bq_multi;  // entries with more than one contribution (tile / band order positions)
+  std::vector<int32_t> q_first, bq_first;  // [nnz] first contribution of an entry (tile / band order) | bit 31: the entry has more
   // block-level symbolic factorisation: which 64x64 tiles of L are structurally non-zero, and for
   // each such tile (i,j) the list of k < j with L(i,k) and L(j,k) both non-zero
   std::vector<uint8_t> tile_nz;            // [ntiles]
@@ -110,6 +112,10 @@ struct tb_plan {
   int32_t* d_tile_pos = nullptr;
   int32_t* d_q_ptr = nullptr;
   int32_t* d_q_pack = nullptr;
+  int32_t* d_q_first = nullptr;
+  int32_t* d_bq_first = nullptr;
+  int32_t* d_q_multi = nullptr;
+  int32_t* d_bq_multi = nullptr;
   int32_t* d_b16_ptr = nullptr;
   int32_t* d_b16_pos = nullptr;
   int32_t* d_b16_nz = nullptr;
@@ -166,7 +172,7 @@ struct LargeArgs {
   const int64_t* tile_ent_ptr; const int32_t* tile_ent; const int32_t* tile_pos;
   int64_t nnz;
   const uint8_t* tile_nz; const int32_t* prod_ptr; const int32_t* prod_k;
-  const int32_t* q_ptr; const int32_t* q_pack;
+  const int32_t* q_ptr; const int32_t* q_pack; const int32_t* q_first; const int32_t* q_multi; int n_multi;
   int nb16, NB;
   const int32_t* b16_ptr; const int32_t* b16_pos; const int32_t* b16_nz;
   const int32_t* inc_ptr; const int32_t* inc_mem;

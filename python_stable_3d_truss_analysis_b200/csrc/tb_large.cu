@@ -113,6 +113,13 @@ __global__ void __launch_bounds__(256) k_kval(const LargeArgs a) {
     const double* mkc = a.mkc + (int64_t)b * a.M * nv;
     double* kv = a.kv + (int64_t)b * a.nnz;
     for (int q = threadIdx.x; q < a.nnz; q += 256) {
+      const int f = a.q_first[q];
+      if (f < 0) continue;                                          // several members contribute: second loop
+      const double t0 = mkc[(f >> 4) * nv + (f & 7)];
+      kv[q] = __dadd_rn(0.0, (f & 8) ? -t0 : t0);
+    }
+    for (int i = threadIdx.x; i < a.n_multi; i += 256) {             // same-joint entries: ascending member order
+      const int q = a.q_multi[i];
       double v = 0.0;
       for (int p = a.q_ptr[q]; p < a.q_ptr[q + 1]; ++p) {
         const int pk = a.q_pack[p];
@@ -121,6 +128,84 @@ __global__ void __launch_bounds__(256) k_kval(const LargeArgs a) {
       }
       kv[q] = v;
     }
+  }
+}
+
+// Fused k_geom + k_kval for systems whose member products fit in shared memory (M * d(d+1)/2 doubles): one CTA per
+// system computes the products k (c_i c_j) of every member into shared memory and gathers the K_ff non-zeros from there;
+// nothing but the K values goes to HBM (k_recover recomputes the member geometry it needs).
+template <int DIM>
+__global__ void __launch_bounds__(256) k_prep(const LargeArgs a) {
+  extern __shared__ __align__(16) double sMkc[];
+  constexpr int NV = DIM * (DIM + 1) / 2;
+  const int tid = threadIdx.x;
+  for (int b = blockIdx.x; b < a.batch; b += gridDim.x) {
+    const double* xyz = a.xyz + b * a.xyz_stride;
+    int flag = 0;
+    for (int m = tid; m < a.M; m += 256) {
+      double ar, e;
+      bool ok = true;
+      if (a.gene) {
+        const int g = a.gene[b * a.gene_stride + m];
+        if ((unsigned)g < (unsigned)a.n_type) {
+          ar = a.type_table[3 * g];
+          e = a.type_table[3 * g + 1];
+        } else {
+          ok = false;
+          ar = e = 0.0;
+        }
+      } else {
+        const double* t = a.aed + b * a.aed_stride + 3 * (int64_t)m;
+        ar = t[0];
+        e = t[1];
+      }
+      const int j0 = a.conn[2 * m], j1 = a.conn[2 * m + 1];
+      double dx[DIM], c[DIM];
+#pragma unroll
+      for (int i = 0; i < DIM; ++i) dx[i] = __dsub_rn(xyz[j1 * DIM + i], xyz[j0 * DIM + i]);
+      double l2 = __dmul_rn(dx[0], dx[0]);
+#pragma unroll
+      for (int i = 1; i < DIM; ++i) l2 = __dadd_rn(l2, __dmul_rn(dx[i], dx[i]));
+      const double len = __dsqrt_rn(l2);
+      double k = 0.0;
+#pragma unroll
+      for (int i = 0; i < DIM; ++i) c[i] = 0.0;
+      if (!ok) {
+        flag = min(flag, TB_INFO_BAD_INDEX);
+      } else if (!(len > 0.0)) {
+        flag = min(flag, TB_INFO_ZERO_LENGTH);
+      } else {
+        k = __ddiv_rn(__dmul_rn(e, ar), len);
+#pragma unroll
+        for (int i = 0; i < DIM; ++i) c[i] = __ddiv_rn(dx[i], len);
+      }
+      double* o = sMkc + m * NV;
+      int t = 0;
+#pragma unroll
+      for (int i = 0; i < DIM; ++i)
+#pragma unroll
+        for (int j = i; j < DIM; ++j) o[t++] = __dmul_rn(k, __dmul_rn(c[i], c[j]));   // truss.py:69-70 / 80-81
+    }
+    if (flag) atomicMin(&a.status[b], flag);
+    __syncthreads();
+    double* kv = a.kv + (int64_t)b * a.nnz;
+    for (int q = tid; q < a.nnz; q += 256) {
+      const int f = a.q_first[q];
+      if (f < 0) continue;                                          // several members contribute: second loop
+      const double t0 = sMkc[(f >> 4) * NV + (f & 7)];
+      kv[q] = __dadd_rn(0.0, (f & 8) ? -t0 : t0);
+    }
+    for (int i = tid; i < a.n_multi; i += 256) {             // same-joint entries: ascending member order
+      const int q = a.q_multi[i];
+      double v = 0.0;
+      for (int p = a.q_ptr[q]; p < a.q_ptr[q + 1]; ++p) {
+        const int pk = a.q_pack[p];
+        const double t = sMkc[(pk >> 4) * NV + (pk & 7)];
+        v = __dadd_rn(v, (pk & 8) ? -t : t);                       // truss.py:71-76 signs, :314 accumulation
+      }
+      kv[q] = v;
+    }
+    __syncthreads();
   }
 }
 
@@ -702,9 +787,12 @@ __device__ __forceinline__ double block_sum256(double v, double* sRed, int tid) 
   return t;
 }
 
-template <int DIM>
+// RECOMP: the member geometry (EA/L, cosines, weight term) is recomputed from the inputs instead of being read from the
+// k_geom arrays, and cosines / axial forces of the system live in shared memory (used with k_prep).
+template <int DIM, bool RECOMP>
 __global__ void __launch_bounds__(256) k_recover(const LargeArgs a) {
   __shared__ double sRed[8];
+  extern __shared__ __align__(16) double sRec[];   // RECOMP: [M] axial | [M][DIM] cosines
   const int tid = threadIdx.x;
   for (int b = blockIdx.x; b < a.batch; b += gridDim.x) {
     int status = a.status[b];
@@ -730,10 +818,11 @@ __global__ void __launch_bounds__(256) k_recover(const LargeArgs a) {
       continue;
     }
     const double* uf = a.y + (int64_t)b * a.n_pad;
-    const double* mk = a.mk + (int64_t)b * a.M;
-    const double* mc = a.mc + (int64_t)b * a.M * DIM;
-    const double* mw = a.mw + (int64_t)b * a.M;
-    double* axw = a.mw + (int64_t)b * a.M;  // reuse the weight terms' slot for axial after reading them
+    const double* mk = RECOMP ? nullptr : a.mk + (int64_t)b * a.M;
+    const double* mc = RECOMP ? sRec + a.M : a.mc + (int64_t)b * a.M * DIM;
+    const double* mw = RECOMP ? nullptr : a.mw + (int64_t)b * a.M;
+    double* axw = RECOMP ? sRec : a.mw + (int64_t)b * a.M;  // non-RECOMP: reuse the weight terms' slot for axial after reading them
+    const double* xyz = a.xyz + b * a.xyz_stride;
     double w = 0.0, vs = 0.0, vd = 0.0;
     for (int i = tid; i < a.N; i += 256) {
       const int fr = a.dof2free[i];
@@ -741,15 +830,45 @@ __global__ void __launch_bounds__(256) k_recover(const LargeArgs a) {
     }
     for (int m = tid; m < a.M; m += 256) {
       const int j0 = a.conn[2 * m], j1 = a.conn[2 * m + 1];
+      double km, wm, cm[DIM];
+      if (RECOMP) {   // same roundings as k_geom / k_prep (truss.py:19,56-63)
+        double ar, e, rho;
+        if (a.gene) {
+          const int g = a.gene[b * a.gene_stride + m];
+          ar = a.type_table[3 * g]; e = a.type_table[3 * g + 1]; rho = a.type_table[3 * g + 2];
+        } else {
+          const double* tt = a.aed + b * a.aed_stride + 3 * (int64_t)m;
+          ar = tt[0]; e = tt[1]; rho = tt[2];
+        }
+        double dx[DIM];
+#pragma unroll
+        for (int i = 0; i < DIM; ++i) dx[i] = __dsub_rn(xyz[j1 * DIM + i], xyz[j0 * DIM + i]);
+        double l2 = __dmul_rn(dx[0], dx[0]);
+#pragma unroll
+        for (int i = 1; i < DIM; ++i) l2 = __dadd_rn(l2, __dmul_rn(dx[i], dx[i]));
+        const double len = __dsqrt_rn(l2);
+        km = __ddiv_rn(__dmul_rn(e, ar), len);
+#pragma unroll
+        for (int i = 0; i < DIM; ++i) {
+          cm[i] = __ddiv_rn(dx[i], len);
+          sRec[a.M + m * DIM + i] = cm[i];
+        }
+        wm = __dmul_rn(__dmul_rn(ar, len), rho);
+      } else {
+        km = mk[m];
+        wm = mw[m];
+#pragma unroll
+        for (int i = 0; i < DIM; ++i) cm[i] = mc[m * DIM + i];
+      }
       double t = 0.0;
 #pragma unroll
       for (int i = 0; i < DIM; ++i) {
         const int f1 = a.dof2free[j1 * DIM + i], f0 = a.dof2free[j0 * DIM + i];
         const double u1 = f1 >= 0 ? uf[f1] : 0.0, u0 = f0 >= 0 ? uf[f0] : 0.0;
-        t = fma(mc[m * DIM + i], u1 - u0, t);
+        t = fma(cm[i], u1 - u0, t);
       }
-      const double nm = mk[m] * t;
-      w += mw[m];
+      const double nm = km * t;
+      w += wm;
       axw[m] = nm;
       if (ax_out) ax_out[m] = nm;
       if (a.fitness_mode) {
@@ -858,27 +977,41 @@ int tb_launch_large(const LargeArgs& a, int num_sm, cudaStream_t st, int path) {
   static const bool fused_env = [] { const char* s = getenv("TB_UNFUSED_ASSEMBLY"); return !(s && s[0] == '1'); }();
   const bool fused = fused_env || path == 2;
   k_init_status<<<(a.batch + 255) / 256, 256, 0, st>>>(a.status, a.batch, 0);
-  {
-    const int64_t total = (int64_t)a.batch * a.M;
-    int grid = (int)((total + 255) / 256 < (int64_t)num_sm * 8 ? (total + 255) / 256 : (int64_t)num_sm * 8);
-    if (grid < 1) grid = 1;
-    tb_prof_begin(TB_PROF_GEOM, st);
-    if (a.dim == 3) k_geom<3><<<grid, 256, 0, st>>>(a);
-    else k_geom<2><<<grid, 256, 0, st>>>(a);
-    tb_prof_end(TB_PROF_GEOM, st);
-  }
-  if (fused) {
+  // member products in shared memory (k_prep + recomputing k_recover) when they fit, else the k_geom arrays in HBM
+  const size_t prep_smem = (size_t)a.M * (a.dim * (a.dim + 1) / 2) * 8, rec_smem = (size_t)a.M * (1 + a.dim) * 8;
+  static const bool no_prep = [] { const char* s = getenv("TB_NO_PREP"); return s && s[0] == '1'; }();
+  const bool prep = fused && !no_prep && prep_smem <= 96 * 1024 && rec_smem <= 96 * 1024;
+  if (prep) {
+    auto kern = a.dim == 3 ? k_prep<3> : k_prep<2>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prep_smem);
+    if (e != cudaSuccess) return (int)e;
     int grid = a.batch < num_sm * 8 ? a.batch : num_sm * 8;
     tb_prof_begin(TB_PROF_ASSEMBLE, st);
-    k_kval<<<grid, 256, 0, st>>>(a);
+    kern<<<grid, 256, prep_smem, st>>>(a);
     tb_prof_end(TB_PROF_ASSEMBLE, st);
   } else {
-    const int64_t work = (int64_t)a.nt * (a.nt + 1) / 2 * a.batch;
-    int grid = (int)(work < (int64_t)num_sm * 16 ? work : (int64_t)num_sm * 16);
-    tb_prof_begin(TB_PROF_ASSEMBLE, st);
-    if (a.dim == 3) k_assemble<3><<<grid, 256, 0, st>>>(a);
-    else k_assemble<2><<<grid, 256, 0, st>>>(a);
-    tb_prof_end(TB_PROF_ASSEMBLE, st);
+    {
+      const int64_t total = (int64_t)a.batch * a.M;
+      int grid = (int)((total + 255) / 256 < (int64_t)num_sm * 8 ? (total + 255) / 256 : (int64_t)num_sm * 8);
+      if (grid < 1) grid = 1;
+      tb_prof_begin(TB_PROF_GEOM, st);
+      if (a.dim == 3) k_geom<3><<<grid, 256, 0, st>>>(a);
+      else k_geom<2><<<grid, 256, 0, st>>>(a);
+      tb_prof_end(TB_PROF_GEOM, st);
+    }
+    if (fused) {
+      int grid = a.batch < num_sm * 8 ? a.batch : num_sm * 8;
+      tb_prof_begin(TB_PROF_ASSEMBLE, st);
+      k_kval<<<grid, 256, 0, st>>>(a);
+      tb_prof_end(TB_PROF_ASSEMBLE, st);
+    } else {
+      const int64_t work = (int64_t)a.nt * (a.nt + 1) / 2 * a.batch;
+      int grid = (int)(work < (int64_t)num_sm * 16 ? work : (int64_t)num_sm * 16);
+      tb_prof_begin(TB_PROF_ASSEMBLE, st);
+      if (a.dim == 3) k_assemble<3><<<grid, 256, 0, st>>>(a);
+      else k_assemble<2><<<grid, 256, 0, st>>>(a);
+      tb_prof_end(TB_PROF_ASSEMBLE, st);
+    }
   }
   if (path == 2) {
     int rc = tb_launch_band_chol(a, num_sm, st);
@@ -900,10 +1033,18 @@ int tb_launch_large(const LargeArgs& a, int num_sm, cudaStream_t st, int path) {
   {
     int grid = a.batch < num_sm * 8 ? a.batch : num_sm * 8;
     tb_prof_begin(TB_PROF_RECOVER, st);
-    if (a.dim == 3) k_recover<3><<<grid, 256, 0, st>>>(a);
-    else k_recover<2><<<grid, 256, 0, st>>>(a);
+    if (prep) {
+      auto kern = a.dim == 3 ? k_recover<3, true> : k_recover<2, true>;
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rec_smem);
+      if (e != cudaSuccess) return (int)e;
+      kern<<<grid, 256, rec_smem, st>>>(a);
+    } else if (a.dim == 3) {
+      k_recover<3, false><<<grid, 256, 0, st>>>(a);
+    } else {
+      k_recover<2, false><<<grid, 256, 0, st>>>(a);
+    }
     tb_prof_end(TB_PROF_RECOVER, st);
   }
-  tb_count_launch(5);
+  tb_count_launch(prep ? 4 : 5);
   return (int)cudaGetLastError();
 }

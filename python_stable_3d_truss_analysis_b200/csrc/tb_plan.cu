@@ -425,6 +425,24 @@ extern "C" int tb_plan_create(const tb_topology* topo, tb_plan** plan_out) {
       for (int e = 0; e < 2; ++e) p->inc_mem[pos[p->conn[2 * m + e]]++] = m * 2 + e;
   }
 
+  // first contribution of every entry inline (85 % of the entries of a truss have exactly one: a member joining two
+  // different joints), so the K-value kernels need one coalesced load per entry instead of a pointer chase
+  // ... and the entries with several contributions (the same-joint entries: one per member at that joint) are listed
+  // separately, so that the lanes of a warp either all take the one-load path or all walk lists of similar length
+  auto firsts = [](const std::vector<int32_t>& ptr, const std::vector<int32_t>& pack, std::vector<int32_t>& first,
+                   std::vector<int32_t>& multi) {
+    const size_t nq = ptr.empty() ? 0 : ptr.size() - 1;
+    first.assign(nq, 0);
+    multi.clear();
+    for (size_t q = 0; q < nq; ++q) {
+      const int cnt = ptr[q + 1] - ptr[q];
+      first[q] = (cnt > 0 ? pack[ptr[q]] : 0) | (cnt > 1 ? (int32_t)0x80000000u : 0);
+      if (cnt > 1) multi.push_back((int32_t)q);
+    }
+  };
+  firsts(p->q_ptr, p->q_pack, p->q_first, p->q_multi);
+  firsts(p->bq_ptr, p->bq_pack, p->bq_first, p->bq_multi);
+
   if (p->path == 1 && p->NB <= TB_BAND_MAX_NB) {
     const char* env = getenv("TB_NO_BAND");
     if (!(env && env[0] == '1')) p->path = 2;
@@ -449,6 +467,10 @@ extern "C" int tb_plan_create(const tb_topology* topo, tb_plan** plan_out) {
   if (!rc) rc = upload(&p->d_tile_pos, p->tile_pos);
   if (!rc) rc = upload(&p->d_q_ptr, p->q_ptr);
   if (!rc) rc = upload(&p->d_q_pack, p->q_pack);
+  if (!rc) rc = upload(&p->d_q_first, p->q_first);
+  if (!rc) rc = upload(&p->d_bq_first, p->bq_first);
+  if (!rc) rc = upload(&p->d_q_multi, p->q_multi);
+  if (!rc) rc = upload(&p->d_bq_multi, p->bq_multi);
   if (!rc) rc = upload(&p->d_b16_ptr, p->b16_ptr);
   if (!rc) rc = upload(&p->d_b16_pos, p->b16_pos);
   if (!rc) rc = upload(&p->d_b16_nz, p->b16_nz);
@@ -488,6 +510,10 @@ extern "C" void tb_plan_destroy(tb_plan* p) {
   cudaFree(p->d_tile_pos);
   cudaFree(p->d_q_ptr);
   cudaFree(p->d_q_pack);
+  cudaFree(p->d_q_first);
+  cudaFree(p->d_bq_first);
+  cudaFree(p->d_q_multi);
+  cudaFree(p->d_bq_multi);
   cudaFree(p->d_b16_ptr);
   cudaFree(p->d_b16_pos);
   cudaFree(p->d_b16_nz);
