@@ -295,7 +295,7 @@ def run_gpu(args):
     peak_dmma, _ = _lib.fp64_peak(1, 8192)
     peak_dfma, _ = _lib.fp64_peak(0, 8192)
     path = plan.path
-    kname = {0: "k_small", 1: "k_chol", 2: "k_band"}[path]
+    kname = {0: "k_dense16", 1: "k_chol", 2: "k_band2"}[path]   # B = 1024 < 2368: the two-warp band kernel (tb_band.cu: launch_band)
     chol_ms, chol_n = prof["small"] if path == 0 else prof["chol"]
     dense_flops = n ** 3 / 3.0 + n ** 2 / 2.0 + n / 6.0 + 2.0 * n * n               # potrf + two triangular solves
     dense_mode = os.environ.get("TB_DENSE_TILES") == "1" and path == 1

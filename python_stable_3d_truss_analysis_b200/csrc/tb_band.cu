@@ -436,6 +436,8 @@ __global__ void __launch_bounds__(64, 7) k_band2(const LargeArgs a) {
   double* sT = sY + (NB + 1) * BT;
   double* sCol = sT + BT;
   int* sOff = (int*)(sCol + 32);               // [NB+1] staging slots, [NB+1] failure flag
+  double* sSd = sCol + 32 + 8;                 // [3][32][2] warp T's part of S(c+1,c+1) (terms d >= 2), accumulator layout
+  double* sTp = sSd + 192;                     // [16] warp T's part of sum_d L(c+1,c+1-d) y_{c+1-d} (terms d >= 2)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int ncol = a.nb16;
@@ -501,37 +503,50 @@ __global__ void __launch_bounds__(64, 7) k_band2(const LargeArgs a) {
         double fr[2];
         fr[0] = fi0 >= 0 ? ldg_f64(fsys + fi0) : 0.0;
         fr[1] = fi1 >= 0 ? ldg_f64(fsys + fi1) : 0.0;
-        double acc[3][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};   // sub-blocks (0,0), (1,0), (1,1)
+        // sub-blocks (0,0), (1,0), (1,1) of S(c,c) and the forward-substitution sums: warp T left the terms d >= 2 in
+        // shared memory during the previous block column (they only need columns <= c-2); the d = 1 term needs
+        // L(c,c-1), which this warp produced at the end of the previous block column
+        double acc[3][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
         double tp[2] = {0.0, 0.0};
+        if (c > 0) {
 #pragma unroll
-        for (int d = 1; d <= NB; ++d) {
-          if (!((nzprev[d] >> d) & 1u)) continue;
-          const double* Bm = sRing + (d * (d - 1) / 2 + idx[d]) * BE + lane;
+          for (int q = 0; q < 3; ++q) {
+            const double2 v = reinterpret_cast<const double2*>(sSd)[q * 32 + lane];
+            acc[q][0] = v.x;
+            acc[q][1] = v.y;
+          }
+          tp[0] = sTp[qr];
+          tp[1] = sTp[8 + qr];
+        }
+        if ((nzprev[1] >> 1) & 1u) {
+          const double* Bm = sRing + idx[1] * BE + lane;       // slot of block (c, c-1): diagonal 1 has one slot
           double bf[2][4];
 #pragma unroll
           for (int h = 0; h < 2; ++h)
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) bf[h][ks] = Bm[(h * 4 + ks) << 5];
-          int ys = yslot - d;
+          int ys = yslot - 1;
           if (ys < 0) ys += NB + 1;
           const double* yv = sY + ys * BT;
+          double t0 = 0.0, t1 = 0.0;
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
             const double y4 = yv[ks * 4 + qc];
-            tp[0] = fma(bf[0][ks], y4, tp[0]);
-            tp[1] = fma(bf[1][ks], y4, tp[1]);
+            t0 = fma(bf[0][ks], y4, t0);
+            t1 = fma(bf[1][ks], y4, t1);
           }
+          t0 += __shfl_xor_sync(0xffffffffu, t0, 1);
+          t0 += __shfl_xor_sync(0xffffffffu, t0, 2);
+          t1 += __shfl_xor_sync(0xffffffffu, t1, 1);
+          t1 += __shfl_xor_sync(0xffffffffu, t1, 2);
+          tp[0] += t0;
+          tp[1] += t1;
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {     // L(c,c-d) L(c,c-d)^T: the operand fragments of A and B coincide
+          for (int ks = 0; ks < 4; ++ks) {     // L(c,c-1) L(c,c-1)^T: the operand fragments of A and B coincide
             dmma(acc[0][0], acc[0][1], bf[0][ks], bf[0][ks]);
             dmma(acc[1][0], acc[1][1], bf[1][ks], bf[0][ks]);
             dmma(acc[2][0], acc[2][1], bf[1][ks], bf[1][ks]);
           }
-        }
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          tp[h] += __shfl_xor_sync(0xffffffffu, tp[h], 1);
-          tp[h] += __shfl_xor_sync(0xffffffffu, tp[h], 2);
         }
         __syncwarp();
         bar_arrive_z();                        // [Z] F no longer reads the blocks (c, c-d)
@@ -681,6 +696,51 @@ __global__ void __launch_bounds__(64, 7) k_band2(const LargeArgs a) {
               v.y -= acc[rb][mb][nb][1];
               *p = v;
             }
+        }
+        // ---- look-ahead for warp F: terms d >= 2 of S(c+1,c+1) and of the forward-substitution sum of block column
+        // c+1.  Block (c+1, c+1-d) is block (c + rb, c - dd) with rb = 1, dd = d - 1: slot and mask as seen from column c.
+        {
+          double sd[3][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
+          double tq[2] = {0.0, 0.0};
+#pragma unroll
+          for (int dd = 1; dd < NB; ++dd) {
+            const int e = dd + 1;
+            if (!((nzprev[dd] >> e) & 1u)) continue;
+            int sl = idx[e] - dd;              // (c-dd) mod e
+            if (sl < 0) sl += e;
+            const double* Bm = sRing + (e * (e - 1) / 2 + sl) * BE + lane;
+            double bf[2][4];
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) bf[h][ks] = Bm[(h * 4 + ks) << 5];
+            int ys = yslot - dd;               // y_{c-dd}
+            if (ys < 0) ys += NB + 1;
+            const double* yv = sY + ys * BT;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              const double y4 = yv[ks * 4 + qc];
+              tq[0] = fma(bf[0][ks], y4, tq[0]);
+              tq[1] = fma(bf[1][ks], y4, tq[1]);
+            }
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              dmma(sd[0][0], sd[0][1], bf[0][ks], bf[0][ks]);
+              dmma(sd[1][0], sd[1][1], bf[1][ks], bf[0][ks]);
+              dmma(sd[2][0], sd[2][1], bf[1][ks], bf[1][ks]);
+            }
+          }
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            tq[h] += __shfl_xor_sync(0xffffffffu, tq[h], 1);
+            tq[h] += __shfl_xor_sync(0xffffffffu, tq[h], 2);
+          }
+#pragma unroll
+          for (int q = 0; q < 3; ++q) reinterpret_cast<double2*>(sSd)[q * 32 + lane] = make_double2(sd[q][0], sd[q][1]);
+          if (qc == 0) {
+            sTp[qr] = tq[0];
+            sTp[8 + qr] = tq[1];
+          }
         }
       }
       __syncthreads();                         // [X] W_c is in the scratch block, P(c+rb, c) are in their slots
@@ -835,7 +895,7 @@ int launch_band(const LargeArgs& a, int num_sm, cudaStream_t st) {
   // one warp per system when the batch alone fills the GPU (fewest instructions per system), else two warps per system
   static const int force = [] { const char* s = getenv("TB_BAND_WARPS"); return s ? atoi(s) : 0; }();
   constexpr int NW = 4;                        // k_band1 packs four independent systems (warps) into a CTA
-  const int smem1 = NW * BandCfg<NB>::DOUBLES * 8, smem2 = BandCfg<NB>::DOUBLES * 8;
+  const int smem1 = NW * BandCfg<NB>::DOUBLES * 8, smem2 = (BandCfg<NB>::DOUBLES + 208) * 8;
   int per1 = 0, per2 = 0;
   cudaError_t e = cudaFuncSetAttribute(k_band1<NB, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_band2<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
