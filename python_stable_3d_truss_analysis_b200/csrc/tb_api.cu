@@ -38,80 +38,23 @@ int check_batch_in(const tb_plan* p, const tb_batch_in* in) {
   return TB_OK;
 }
 
-int run_plan(tb_plan* p, const tb_batch_in* in, const tb_batch_out* out, const tb_fit_out* fit, double allow_s,
-             double allow_d, cudaStream_t st) {
+// Systems [b0, b0 + nb) of a uniform batch on stream st; the blocked pipelines use the workspace slice `ws`.
+int run_plan_range(tb_plan* p, const tb_batch_in* in, const tb_batch_out* out, const tb_fit_out* fit, double allow_s,
+                   double allow_d, cudaStream_t st, int b0, int nb, void* ws) {
   const int fitness_mode = fit ? 1 : 0;
-  static const tb_batch_out none = {nullptr, nullptr, nullptr, nullptr, nullptr};
-  if (!out) out = &none;
+  int32_t* info = fit && fit->info ? fit->info : out->info;
   if (p->path == 0) {
     SmallArgs a;
     memset(&a, 0, sizeof(a));
-    a.batch = in->batch;
+    a.batch = nb;
     a.nJ = p->nJ;
     a.M = p->M;
-    a.xyz = in->joint_xyz;
+    a.xyz = in->joint_xyz + (int64_t)b0 * in->joint_stride;
     a.xyz_stride = in->joint_stride;
     a.support = p->d_support;
     a.support_stride = 0;
     a.conn = p->d_conn;
     a.conn_stride = 0;
-    a.aed = in->member_aed;
-    a.aed_stride = in->member_stride;
-    a.gene = in->member_aed ? nullptr : in->gene;
-    a.gene_stride = in->gene_stride;
-    a.type_table = in->type_table;
-    a.n_type = in->n_type;
-    a.force = in->force;
-    a.force_stride = in->force_stride;
-    a.u = out->u;
-    a.ext = out->ext;
-    a.axial = out->axial;
-    a.weight = out->weight;
-    a.info = fit && fit->info ? fit->info : out->info;
-    a.fitness = fit ? fit->fitness : nullptr;
-    a.flags = fit ? fit->flags : nullptr;
-    a.allow_stress = allow_s;
-    a.allow_displace = allow_d;
-    a.fitness_mode = fitness_mode;
-    a.max_n = p->n;
-    int rc = tb_launch_small(a, p->dim, st);
-    if (rc) return rc;
-    if (fit && fit->info && out->info) {
-      TB_CUDA(cudaMemcpyAsync(out->info, fit->info, sizeof(int32_t) * in->batch, cudaMemcpyDeviceToDevice, st));
-    }
-    return TB_OK;
-  }
-
-  // blocked path: process the batch in chunks that fit the workspace cap
-  const int64_t nnz = (int64_t)p->ent_row.size();
-  const size_t per_sys = tb_large_workspace_bytes(1, p->dim, p->M, p->n_pad, nnz, p->path, p->nb16, p->NB);
-  int chunk = (int)std::min<size_t>((size_t)in->batch, std::max<size_t>(1, ws_cap_bytes() / per_sys));
-  const size_t need = tb_large_workspace_bytes(chunk, p->dim, p->M, p->n_pad, nnz, p->path, p->nb16, p->NB);
-  if (p->ws_bytes < need) {
-    if (p->ws) {
-      TB_CUDA(cudaStreamSynchronize(st));
-      TB_CUDA(cudaFree(p->ws));
-      p->ws = nullptr;
-      p->ws_bytes = 0;
-    }
-    TB_CUDA(cudaMalloc(&p->ws, need));
-    p->ws_bytes = need;
-  }
-  for (int b0 = 0; b0 < in->batch; b0 += chunk) {
-    const int nb = std::min(chunk, in->batch - b0);
-    LargeArgs a;
-    memset(&a, 0, sizeof(a));
-    a.batch = nb;
-    a.dim = p->dim;
-    a.nJ = p->nJ;
-    a.M = p->M;
-    a.N = p->N;
-    a.n = p->n;
-    a.n_pad = p->n_pad;
-    a.nt = p->nt;
-    a.s = p->s;
-    a.xyz = in->joint_xyz + (int64_t)b0 * in->joint_stride;
-    a.xyz_stride = in->joint_stride;
     a.aed = in->member_aed ? in->member_aed + (int64_t)b0 * in->member_stride : nullptr;
     a.aed_stride = in->member_stride;
     a.gene = in->member_aed ? nullptr : in->gene + (int64_t)b0 * in->gene_stride;
@@ -120,50 +63,121 @@ int run_plan(tb_plan* p, const tb_batch_in* in, const tb_batch_out* out, const t
     a.n_type = in->n_type;
     a.force = in->force + (int64_t)b0 * in->force_stride;
     a.force_stride = in->force_stride;
-    a.conn = p->d_conn;
-    a.free_idx = p->d_free_idx;
-    a.dof2free = p->d_dof2free;
-    a.sup_idx = p->d_sup_idx;
-    a.ent_row = p->d_ent_row;
-    a.ent_col = p->d_ent_col;
-    a.ent_ptr = p->d_ent_ptr;
-    a.ctr_member = p->d_ctr_member;
-    a.ctr_local = p->d_ctr_local;
-    a.tile_ent_ptr = p->d_tile_ent_ptr;
-    a.tile_ent = p->d_tile_ent;
-    a.tile_pos = p->d_tile_pos;
-    a.nnz = (int64_t)p->ent_row.size();
-    a.q_ptr = p->path == 2 ? p->d_bq_ptr : p->d_q_ptr;
-    a.q_pack = p->path == 2 ? p->d_bq_pack : p->d_q_pack;
-    a.q_first = p->path == 2 ? p->d_bq_first : p->d_q_first;
-    a.q_multi = p->path == 2 ? p->d_bq_multi : p->d_q_multi;
-    a.n_multi = (int)(p->path == 2 ? p->bq_multi.size() : p->q_multi.size());
-    a.nb16 = p->nb16;
-    a.NB = p->NB;
-    a.b16_ptr = p->d_b16_ptr;
-    a.b16_pos = p->d_b16_pos;
-    a.b16_nz = p->d_b16_nz;
-    if (p->path == 2) a.n_pad = p->nb16 * 16;
-    a.tile_nz = p->d_tile_nz;
-    a.prod_ptr = p->d_prod_ptr;
-    a.prod_k = p->d_prod_k;
-    a.inc_ptr = p->d_inc_ptr;
-    a.inc_mem = p->d_inc_mem;
-    tb_large_carve(a, p->ws, p->path);
+    // the fused kernels address their outputs by (system index) * (row length)
     a.u = out->u ? out->u + (int64_t)b0 * p->N : nullptr;
     a.ext = out->ext ? out->ext + (int64_t)b0 * p->N : nullptr;
     a.axial = out->axial ? out->axial + (int64_t)b0 * p->M : nullptr;
     a.weight = out->weight ? out->weight + b0 : nullptr;
-    int32_t* info = fit && fit->info ? fit->info : out->info;
     a.info = info ? info + b0 : nullptr;
     a.fitness = fit && fit->fitness ? fit->fitness + b0 : nullptr;
     a.flags = fit && fit->flags ? fit->flags + 2 * (int64_t)b0 : nullptr;
     a.allow_stress = allow_s;
     a.allow_displace = allow_d;
     a.fitness_mode = fitness_mode;
-    a.plan_stable = p->stable;
-    int rc = tb_launch_large(a, p->num_sm, st, p->path);
+    a.max_n = p->n;
+    return tb_launch_small(a, p->dim, st);
+  }
+  LargeArgs a;
+  memset(&a, 0, sizeof(a));
+  a.batch = nb;
+  a.dim = p->dim;
+  a.nJ = p->nJ;
+  a.M = p->M;
+  a.N = p->N;
+  a.n = p->n;
+  a.n_pad = p->n_pad;
+  a.nt = p->nt;
+  a.s = p->s;
+  a.xyz = in->joint_xyz + (int64_t)b0 * in->joint_stride;
+  a.xyz_stride = in->joint_stride;
+  a.aed = in->member_aed ? in->member_aed + (int64_t)b0 * in->member_stride : nullptr;
+  a.aed_stride = in->member_stride;
+  a.gene = in->member_aed ? nullptr : in->gene + (int64_t)b0 * in->gene_stride;
+  a.gene_stride = in->gene_stride;
+  a.type_table = in->type_table;
+  a.n_type = in->n_type;
+  a.force = in->force + (int64_t)b0 * in->force_stride;
+  a.force_stride = in->force_stride;
+  a.conn = p->d_conn;
+  a.free_idx = p->d_free_idx;
+  a.dof2free = p->d_dof2free;
+  a.sup_idx = p->d_sup_idx;
+  a.ent_row = p->d_ent_row;
+  a.ent_col = p->d_ent_col;
+  a.ent_ptr = p->d_ent_ptr;
+  a.ctr_member = p->d_ctr_member;
+  a.ctr_local = p->d_ctr_local;
+  a.tile_ent_ptr = p->d_tile_ent_ptr;
+  a.tile_ent = p->d_tile_ent;
+  a.tile_pos = p->d_tile_pos;
+  a.nnz = (int64_t)p->ent_row.size();
+  a.q_ptr = p->path == 2 ? p->d_bq_ptr : p->d_q_ptr;
+  a.q_pack = p->path == 2 ? p->d_bq_pack : p->d_q_pack;
+  a.q_first = p->path == 2 ? p->d_bq_first : p->d_q_first;
+  a.q_multi = p->path == 2 ? p->d_bq_multi : p->d_q_multi;
+  a.n_multi = (int)(p->path == 2 ? p->bq_multi.size() : p->q_multi.size());
+  a.nb16 = p->nb16;
+  a.NB = p->NB;
+  a.b16_ptr = p->d_b16_ptr;
+  a.b16_pos = p->d_b16_pos;
+  a.b16_nz = p->d_b16_nz;
+  if (p->path == 2) a.n_pad = p->nb16 * 16;
+  a.tile_nz = p->d_tile_nz;
+  a.prod_ptr = p->d_prod_ptr;
+  a.prod_k = p->d_prod_k;
+  a.inc_ptr = p->d_inc_ptr;
+  a.inc_mem = p->d_inc_mem;
+  tb_large_carve(a, ws, p->path);
+  a.u = out->u ? out->u + (int64_t)b0 * p->N : nullptr;
+  a.ext = out->ext ? out->ext + (int64_t)b0 * p->N : nullptr;
+  a.axial = out->axial ? out->axial + (int64_t)b0 * p->M : nullptr;
+  a.weight = out->weight ? out->weight + b0 : nullptr;
+  a.info = info ? info + b0 : nullptr;
+  a.fitness = fit && fit->fitness ? fit->fitness + b0 : nullptr;
+  a.flags = fit && fit->flags ? fit->flags + 2 * (int64_t)b0 : nullptr;
+  a.allow_stress = allow_s;
+  a.allow_displace = allow_d;
+  a.fitness_mode = fitness_mode;
+  a.plan_stable = p->stable;
+  return tb_launch_large(a, p->num_sm, st, p->path);
+}
+
+size_t plan_ws_bytes(const tb_plan* p, int batch) {
+  if (p->path == 0) return 0;
+  return tb_large_workspace_bytes(batch, p->dim, p->M, p->n_pad, (int64_t)p->ent_row.size(), p->path, p->nb16, p->NB);
+}
+
+int ensure_ws(tb_plan* p, size_t need, cudaStream_t st) {
+  if (p->ws_bytes >= need) return TB_OK;
+  if (p->ws) {
+    TB_CUDA(cudaStreamSynchronize(st));
+    TB_CUDA(cudaDeviceSynchronize());
+    TB_CUDA(cudaFree(p->ws));
+    p->ws = nullptr;
+    p->ws_bytes = 0;
+  }
+  TB_CUDA(cudaMalloc(&p->ws, need));
+  p->ws_bytes = need;
+  return TB_OK;
+}
+
+int run_plan(tb_plan* p, const tb_batch_in* in, const tb_batch_out* out, const tb_fit_out* fit, double allow_s,
+             double allow_d, cudaStream_t st) {
+  static const tb_batch_out none = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  if (!out) out = &none;
+  if (p->path == 0) {
+    int rc = run_plan_range(p, in, out, fit, allow_s, allow_d, st, 0, in->batch, nullptr);
     if (rc) return rc;
+  } else {
+    // blocked paths: process the batch in chunks that fit the workspace cap
+    const size_t per_sys = plan_ws_bytes(p, 1);
+    int chunk = (int)std::min<size_t>((size_t)in->batch, std::max<size_t>(1, ws_cap_bytes() / per_sys));
+    int rc = ensure_ws(p, plan_ws_bytes(p, chunk), st);
+    if (rc) return rc;
+    for (int b0 = 0; b0 < in->batch; b0 += chunk) {
+      rc = run_plan_range(p, in, out, fit, allow_s, allow_d, st, b0, std::min(chunk, in->batch - b0), p->ws);
+      if (rc) return rc;
+    }
   }
   if (fit && fit->info && out->info) {
     TB_CUDA(cudaMemcpyAsync(out->info, fit->info, sizeof(int32_t) * in->batch, cudaMemcpyDeviceToDevice, st));
@@ -210,6 +224,25 @@ cudaStream_t host_stream() {
   return st;
 }
 
+constexpr int TB_HOST_STREAMS = 8;
+cudaStream_t* host_streams() {
+  static cudaStream_t sts[TB_HOST_STREAMS];
+  static bool init = [] {
+    for (int i = 0; i < TB_HOST_STREAMS; ++i) cudaStreamCreateWithFlags(&sts[i], cudaStreamNonBlocking);
+    return true;
+  }();
+  (void)init;
+  return sts;
+}
+cudaEvent_t host_event() {
+  static cudaEvent_t ev = [] {
+    cudaEvent_t e = nullptr;
+    cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    return e;
+  }();
+  return ev;
+}
+
 int stride_ok(int64_t stride, int64_t row) { return stride == 0 || stride == row; }
 
 int run_plan_host(tb_plan* p, const tb_batch_in* in, const tb_batch_out* out, const tb_fit_out* fit, double allow_s,
@@ -247,17 +280,12 @@ int run_plan_host(tb_plan* p, const tb_batch_in* in, const tb_batch_out* out, co
   double* daed = take<double>(cur, naed);
   int32_t* dgene = take<int32_t>(cur, ngene);
   double* dtab = take<double>(cur, ntab);
-  TB_CUDA(cudaMemcpyAsync(dxyz, in->joint_xyz, nxyz * 8, cudaMemcpyHostToDevice, st));
-  TB_CUDA(cudaMemcpyAsync(df, in->force, nf * 8, cudaMemcpyHostToDevice, st));
   din.joint_xyz = dxyz;
   din.force = df;
   if (in->member_aed) {
-    TB_CUDA(cudaMemcpyAsync(daed, in->member_aed, naed * 8, cudaMemcpyHostToDevice, st));
     din.member_aed = daed;
     din.gene = nullptr;
   } else {
-    TB_CUDA(cudaMemcpyAsync(dgene, in->gene, ngene * 4, cudaMemcpyHostToDevice, st));
-    TB_CUDA(cudaMemcpyAsync(dtab, in->type_table, ntab * 8, cudaMemcpyHostToDevice, st));
     din.gene = dgene;
     din.type_table = dtab;
   }
@@ -274,20 +302,71 @@ int run_plan_host(tb_plan* p, const tb_batch_in* in, const tb_batch_out* out, co
     dfit.info = dout.info;
     dout.info = nullptr;
   }
-  rc = run_plan(p, &din, &dout, fit ? &dfit : nullptr, allow_s, allow_d, st);
-  if (rc) return rc;
   int32_t* dinfo = fit ? dfit.info : dout.info;
-  if (out->u) TB_CUDA(cudaMemcpyAsync(out->u, dout.u, (size_t)B * rowN * 8, cudaMemcpyDeviceToHost, st));
-  if (out->ext) TB_CUDA(cudaMemcpyAsync(out->ext, dout.ext, (size_t)B * rowN * 8, cudaMemcpyDeviceToHost, st));
-  if (out->axial) TB_CUDA(cudaMemcpyAsync(out->axial, dout.axial, (size_t)B * rowM * 8, cudaMemcpyDeviceToHost, st));
-  if (out->weight) TB_CUDA(cudaMemcpyAsync(out->weight, dout.weight, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
-  if (out->info) TB_CUDA(cudaMemcpyAsync(out->info, dinfo, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
-  if (fit) {
-    if (fit->fitness) TB_CUDA(cudaMemcpyAsync(fit->fitness, dfit.fitness, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
-    if (fit->flags) TB_CUDA(cudaMemcpyAsync(fit->flags, dfit.flags, (size_t)B * 2, cudaMemcpyDeviceToHost, st));
-    if (fit->info) TB_CUDA(cudaMemcpyAsync(fit->info, dinfo, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+
+  // The batch is cut into chunks, each with its own stream and workspace slice: chunk j's results travel back
+  // (D2H) while chunk j+1 is still being solved, and the chunks' kernels share the GPU.  Arrays shared by the whole
+  // batch (stride 0) are copied once on the first stream; the other streams wait for that copy.
+  const size_t per_sys = plan_ws_bytes(p, 1);
+  int nch = 1;
+  {
+    static const int want = [] { const char* s = getenv("TB_HOST_CHUNKS"); int v = s ? atoi(s) : 4; return v < 1 ? 1 : (v > TB_HOST_STREAMS ? TB_HOST_STREAMS : v); }();
+    if (B >= 64 * want && (p->path == 0 || per_sys * (size_t)B <= ws_cap_bytes())) nch = want;
   }
-  TB_CUDA(cudaStreamSynchronize(st));
+  const int csz = (B + nch - 1) / nch;
+  if (p->path != 0) {
+    if (nch > 1) {
+      rc = ensure_ws(p, per_sys * (size_t)csz * nch + 4096 * nch, st);
+      if (rc) return rc;
+    }
+  }
+  cudaStream_t sts[TB_HOST_STREAMS];
+  for (int j = 0; j < TB_HOST_STREAMS; ++j) sts[j] = host_streams()[j];
+  cudaEvent_t shared_ready = host_event();
+  const bool sx = in->joint_stride == 0, sf = in->force_stride == 0;
+  const bool sm_ = in->member_aed ? in->member_stride == 0 : in->gene_stride == 0;
+  if (nch == 1) sts[0] = st;
+  // shared inputs first
+  if (sx) TB_CUDA(cudaMemcpyAsync(dxyz, in->joint_xyz, nxyz * 8, cudaMemcpyHostToDevice, sts[0]));
+  if (sf) TB_CUDA(cudaMemcpyAsync(df, in->force, nf * 8, cudaMemcpyHostToDevice, sts[0]));
+  if (in->member_aed) {
+    if (sm_) TB_CUDA(cudaMemcpyAsync(daed, in->member_aed, naed * 8, cudaMemcpyHostToDevice, sts[0]));
+  } else {
+    if (sm_) TB_CUDA(cudaMemcpyAsync(dgene, in->gene, ngene * 4, cudaMemcpyHostToDevice, sts[0]));
+    TB_CUDA(cudaMemcpyAsync(dtab, in->type_table, ntab * 8, cudaMemcpyHostToDevice, sts[0]));
+  }
+  if (nch > 1) TB_CUDA(cudaEventRecord(shared_ready, sts[0]));
+  for (int j = 0; j < nch; ++j) {
+    const int b0 = j * csz, nb = std::min(csz, B - b0);
+    if (nb <= 0) break;
+    cudaStream_t sj = sts[j];
+    if (j > 0) TB_CUDA(cudaStreamWaitEvent(sj, shared_ready, 0));
+    if (!sx) TB_CUDA(cudaMemcpyAsync(dxyz + (size_t)b0 * rowJ, in->joint_xyz + (size_t)b0 * rowJ, (size_t)nb * rowJ * 8, cudaMemcpyHostToDevice, sj));
+    if (!sf) TB_CUDA(cudaMemcpyAsync(df + (size_t)b0 * rowN, in->force + (size_t)b0 * rowN, (size_t)nb * rowN * 8, cudaMemcpyHostToDevice, sj));
+    if (in->member_aed) {
+      if (!sm_) TB_CUDA(cudaMemcpyAsync(daed + (size_t)b0 * rowM3, in->member_aed + (size_t)b0 * rowM3, (size_t)nb * rowM3 * 8, cudaMemcpyHostToDevice, sj));
+    } else {
+      if (!sm_) TB_CUDA(cudaMemcpyAsync(dgene + (size_t)b0 * rowM, in->gene + (size_t)b0 * rowM, (size_t)nb * rowM * 4, cudaMemcpyHostToDevice, sj));
+    }
+    if (nch == 1 && p->path != 0) {
+      rc = run_plan(p, &din, &dout, fit ? &dfit : nullptr, allow_s, allow_d, sj);   // handles the workspace cap itself
+    } else {
+      void* ws = p->path != 0 ? (void*)((char*)p->ws + ((per_sys * (size_t)csz + 4095) & ~(size_t)4095) * j) : nullptr;
+      rc = run_plan_range(p, &din, &dout, fit ? &dfit : nullptr, allow_s, allow_d, sj, b0, nb, ws);
+    }
+    if (rc) return rc;
+    if (out->u) TB_CUDA(cudaMemcpyAsync(out->u + (size_t)b0 * rowN, dout.u + (size_t)b0 * rowN, (size_t)nb * rowN * 8, cudaMemcpyDeviceToHost, sj));
+    if (out->ext) TB_CUDA(cudaMemcpyAsync(out->ext + (size_t)b0 * rowN, dout.ext + (size_t)b0 * rowN, (size_t)nb * rowN * 8, cudaMemcpyDeviceToHost, sj));
+    if (out->axial) TB_CUDA(cudaMemcpyAsync(out->axial + (size_t)b0 * rowM, dout.axial + (size_t)b0 * rowM, (size_t)nb * rowM * 8, cudaMemcpyDeviceToHost, sj));
+    if (out->weight) TB_CUDA(cudaMemcpyAsync(out->weight + b0, dout.weight + b0, (size_t)nb * 8, cudaMemcpyDeviceToHost, sj));
+    if (out->info) TB_CUDA(cudaMemcpyAsync(out->info + b0, dinfo + b0, (size_t)nb * 4, cudaMemcpyDeviceToHost, sj));
+    if (fit) {
+      if (fit->fitness) TB_CUDA(cudaMemcpyAsync(fit->fitness + b0, dfit.fitness + b0, (size_t)nb * 8, cudaMemcpyDeviceToHost, sj));
+      if (fit->flags) TB_CUDA(cudaMemcpyAsync(fit->flags + 2 * (size_t)b0, dfit.flags + 2 * (size_t)b0, (size_t)nb * 2, cudaMemcpyDeviceToHost, sj));
+      if (fit->info) TB_CUDA(cudaMemcpyAsync(fit->info + b0, dinfo + b0, (size_t)nb * 4, cudaMemcpyDeviceToHost, sj));
+    }
+  }
+  for (int j = 0; j < nch; ++j) TB_CUDA(cudaStreamSynchronize(sts[j]));
   return TB_OK;
 }
 

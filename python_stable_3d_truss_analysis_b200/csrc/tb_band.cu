@@ -131,9 +131,12 @@ __global__ void __launch_bounds__(32 * NW) k_band1(const LargeArgs a) {
         for (int mb = 0; mb < 2; ++mb)
 #pragma unroll
           for (int nb = 0; nb < 2; ++nb) acc[rb][mb][nb][0] = acc[rb][mb][nb][1] = 0.0;
-      double tp[2] = {0.0, 0.0};
+      // accumulation order of every sum over d: d = 2 .. NB, then d = 1 -- the order in which k_band2's two warps
+      // produce the same sums (its trailing warp looks ahead with the terms d >= 2), so both kernels give the same bits
+      double tp[2] = {0.0, 0.0}, tp1[2] = {0.0, 0.0};
 #pragma unroll
-      for (int d = 1; d <= NB; ++d) {
+      for (int dq = 0; dq < NB; ++dq) {
+        const int d = dq == NB - 1 ? 1 : dq + 2;
         const unsigned nzp = nzprev[d];
         if (!((nzp >> d) & 1u)) continue;      // L(c, c-d) is structurally zero (or c-d < 0): uniform
         const double* Bm = sRing + (d * (d - 1) / 2 + idx[d]) * BE;     // (c-d) mod d == c mod d
@@ -149,8 +152,13 @@ __global__ void __launch_bounds__(32 * NW) k_band1(const LargeArgs a) {
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
             const double y4 = yv[ks * 4 + qc];
-            tp[0] = fma(bf[0][ks], y4, tp[0]);
-            tp[1] = fma(bf[1][ks], y4, tp[1]);
+            if (d == 1) {
+              tp1[0] = fma(bf[0][ks], y4, tp1[0]);
+              tp1[1] = fma(bf[1][ks], y4, tp1[1]);
+            } else {
+              tp[0] = fma(bf[0][ks], y4, tp[0]);
+              tp[1] = fma(bf[1][ks], y4, tp[1]);
+            }
           }
         }
 #pragma unroll
@@ -178,6 +186,9 @@ __global__ void __launch_bounds__(32 * NW) k_band1(const LargeArgs a) {
       for (int mb = 0; mb < 2; ++mb) {
         tp[mb] += __shfl_xor_sync(0xffffffffu, tp[mb], 1);
         tp[mb] += __shfl_xor_sync(0xffffffffu, tp[mb], 2);
+        tp1[mb] += __shfl_xor_sync(0xffffffffu, tp1[mb], 1);
+        tp1[mb] += __shfl_xor_sync(0xffffffffu, tp1[mb], 2);
+        tp[mb] += tp1[mb];
       }
       __syncwarp();                            // every lane is done with the blocks (c, c-d): their slots are free
 
@@ -632,7 +643,8 @@ __global__ void __launch_bounds__(64, 7) k_band2(const LargeArgs a) {
 #pragma unroll
             for (int nb = 0; nb < 2; ++nb) acc[rb][mb][nb][0] = acc[rb][mb][nb][1] = 0.0;
 #pragma unroll
-        for (int d = 1; d < NB; ++d) {
+        for (int dq = 0; dq < NB - 1; ++dq) {    // d = 2 .. NB-1, then d = 1 (k_band1's order: same bits from both kernels)
+          const int d = dq == NB - 2 ? 1 : dq + 2;
           const unsigned nzp = nzprev[d];
           if (!((nzp >> d) & 1u) || !(nzp >> (d + 1))) continue;   // L(c,c-d) zero, or nothing below it in that column
           const double* Bm = sRing + (d * (d - 1) / 2 + idx[d]) * BE + lane;
@@ -896,14 +908,17 @@ int launch_band(const LargeArgs& a, int num_sm, cudaStream_t st) {
   static const int force = [] { const char* s = getenv("TB_BAND_WARPS"); return s ? atoi(s) : 0; }();
   constexpr int NW = 4;                        // k_band1 packs four independent systems (warps) into a CTA
   const int smem1 = NW * BandCfg<NB>::DOUBLES * 8, smem2 = (BandCfg<NB>::DOUBLES + 208) * 8;
-  int per1 = 0, per2 = 0;
-  cudaError_t e = cudaFuncSetAttribute(k_band1<NB, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_band2<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
-  if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per1, k_band1<NB, NW>, 32 * NW, smem1);
-  if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per2, k_band2<NB>, 64, smem2);
-  if (e != cudaSuccess) return (int)e;
-  if (per1 < 1) per1 = 1;
-  if (per2 < 1) per2 = 1;
+  static int per1 = 0, per2 = 0;               // attribute / occupancy queries once per instantiation (single device per process)
+  if (per1 == 0) {
+    int q1 = 0, q2 = 0;
+    cudaError_t e = cudaFuncSetAttribute(k_band1<NB, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_band2<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q1, k_band1<NB, NW>, 32 * NW, smem1);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q2, k_band2<NB>, 64, smem2);
+    if (e != cudaSuccess) return (int)e;
+    per2 = q2 < 1 ? 1 : q2;
+    per1 = q1 < 1 ? 1 : q1;
+  }
   bool two = NB <= 5 && (int64_t)a.batch < (int64_t)2 * num_sm * per1 * NW;   // NB > 5: the trailing warp's accumulators spill
   if (force == 1) two = false;
   if (force == 2 && NB <= 5) two = true;

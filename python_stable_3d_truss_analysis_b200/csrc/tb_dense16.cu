@@ -611,14 +611,22 @@ int tb_launch_dense16(const SmallArgs& a, int dim, cudaStream_t st) {
   if (nwarp > 4) nwarp = 4;
   const int smem = per * nwarp;
   auto kern = (dim == 3) ? k_dense16<3> : k_dense16<2>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  if (e != cudaSuccess) return (int)e;
-  int per_sm = 0, dev = 0, sms = 0;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * nwarp, smem);
-  if (e != cudaSuccess) return (int)e;
-  if (per_sm < 1) per_sm = 1;
+  // attribute / occupancy queries are cached per (instantiation, shared-memory size, warps): they cost more than the launch
+  static int c_smem[2] = {-1, -1}, c_nwarp[2] = {0, 0}, c_per_sm[2] = {0, 0}, c_sms = 0;
+  const int ci = dim - 2;
+  if (c_smem[ci] != smem || c_nwarp[ci] != nwarp) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return (int)e;
+    int dev = 0, q = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&c_sms, cudaDevAttrMultiProcessorCount, dev);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, kern, 32 * nwarp, smem);
+    if (e != cudaSuccess) return (int)e;
+    c_per_sm[ci] = q < 1 ? 1 : q;
+    c_smem[ci] = smem;
+    c_nwarp[ci] = nwarp;
+  }
+  const int per_sm = c_per_sm[ci], sms = c_sms;
   long long grid = (long long)sms * per_sm;    // persistent: a multiple of the SM count
   const long long need = (a.batch + nwarp - 1) / nwarp;
   if (grid > need) grid = need;

@@ -983,8 +983,12 @@ int tb_launch_large(const LargeArgs& a, int num_sm, cudaStream_t st, int path) {
   const bool prep = fused && !no_prep && prep_smem <= 96 * 1024 && rec_smem <= 96 * 1024;
   if (prep) {
     auto kern = a.dim == 3 ? k_prep<3> : k_prep<2>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prep_smem);
-    if (e != cudaSuccess) return (int)e;
+    static size_t prep_set[2] = {0, 0};        // largest dynamic shared-memory size already granted, per instantiation
+    if (prep_set[a.dim - 2] < prep_smem) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prep_smem);
+      if (e != cudaSuccess) return (int)e;
+      prep_set[a.dim - 2] = prep_smem;
+    }
     int grid = a.batch < num_sm * 8 ? a.batch : num_sm * 8;
     tb_prof_begin(TB_PROF_ASSEMBLE, st);
     kern<<<grid, 256, prep_smem, st>>>(a);
@@ -1018,12 +1022,16 @@ int tb_launch_large(const LargeArgs& a, int num_sm, cudaStream_t st, int path) {
     if (rc) return rc;
   } else {
     auto kern = fused ? k_chol<true> : k_chol<false>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CHOL_SMEM_BYTES);
-    if (e != cudaSuccess) return (int)e;
-    int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, CH_THREADS, CHOL_SMEM_BYTES);
-    if (e != cudaSuccess) return (int)e;
-    if (per_sm < 1) per_sm = 1;
+    static int chol_per_sm[2] = {0, 0};
+    if (chol_per_sm[fused] == 0) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CHOL_SMEM_BYTES);
+      if (e != cudaSuccess) return (int)e;
+      int q = 0;
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, kern, CH_THREADS, CHOL_SMEM_BYTES);
+      if (e != cudaSuccess) return (int)e;
+      chol_per_sm[fused] = q < 1 ? 1 : q;
+    }
+    const int per_sm = chol_per_sm[fused];
     int grid = num_sm * per_sm;
     if (grid > a.batch) grid = a.batch;
     tb_prof_begin(TB_PROF_CHOL, st);
@@ -1035,8 +1043,12 @@ int tb_launch_large(const LargeArgs& a, int num_sm, cudaStream_t st, int path) {
     tb_prof_begin(TB_PROF_RECOVER, st);
     if (prep) {
       auto kern = a.dim == 3 ? k_recover<3, true> : k_recover<2, true>;
-      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rec_smem);
-      if (e != cudaSuccess) return (int)e;
+      static size_t rec_set[2] = {0, 0};
+      if (rec_set[a.dim - 2] < rec_smem) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rec_smem);
+        if (e != cudaSuccess) return (int)e;
+        rec_set[a.dim - 2] = rec_smem;
+      }
       kern<<<grid, 256, rec_smem, st>>>(a);
     } else if (a.dim == 3) {
       k_recover<3, false><<<grid, 256, 0, st>>>(a);

@@ -327,3 +327,17 @@ def test_config5_cube12_tiled_vs_oracle():
         H.assert_close({k: out[k][b] for k in H.FIELDS} | {"weight": out["weight"][b]}, want, what=f"cube12[{b}]")
         tot = (np.where(mask, force, 0.0) + np.where(~mask, out["ext"][b], 0.0)).reshape(-1, 3).sum(axis=0)
         assert np.abs(tot).max() <= 1e-7 * np.abs(force).sum()
+
+
+def test_band_kernels_agree_bitwise_across_batch_sizes():
+    """The band path picks a two-warp-per-system kernel for small batches and a warp-per-system kernel for large ones
+    (tb_band.cu: launch_band); both sum in the same order, so a system's result does not depend on the batch it is in
+    (bit-identical per truss across GPU counts / shard sizes)."""
+    t = Truss(3).LoadFromJSON(f"{H.GOLDEN}/ref_data/bar-942_input_0.json")
+    rng = np.random.default_rng(3)
+    N = t.nJoint * 3
+    F = rng.uniform(-10, 10, size=(4096, N))
+    big = SolveLoadCases(t, F)                      # 4096 systems: warp-per-system kernel, chunked host pipeline
+    small = SolveLoadCases(t, F[1000:1032])         # 32 systems: two-warp kernel
+    for k in H.FIELDS:
+        assert np.array_equal(big[k][1000:1032], small[k]), k
