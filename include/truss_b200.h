@@ -202,6 +202,10 @@ int tb_small_path_limits(int32_t* max_dof, int32_t* max_member);
  * entry): which = 0 DFMA (vector), 1 DMMA m8n8k4 (tensor).  Returns TFLOP/s in *tflops. */
 int tb_fp64_peak(int32_t which, int32_t iters, double* tflops, float* ms);
 
+/* Accuracy probe of the reciprocal square root the 16x16 pivot blocks use (hardware seed + one third-order
+ * step): largest relative error against 1/sqrt(d) over n values spread log-uniformly over [1e-290, 1e300]. */
+int tb_rsqrt_probe(int32_t n, double* max_rel_err);
+
 /* Optional per-kernel CUDA-event timing on the launching stream (bench.py's roofline line).
  * tb_profile_read adds the milliseconds / launch counts recorded since the last read into
  * ms[8] / count[8]; slots: 0 member geometry, 1 assembly, 2 blocked Cholesky+solve, 3 recovery,

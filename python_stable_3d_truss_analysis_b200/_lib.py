@@ -99,7 +99,7 @@ class TbRaggedIn(C.Structure):
 
 EXPORTS = ["tb_plan_create", "tb_plan_destroy", "tb_plan_query", "tb_plan_set_path", "tb_plan_get_maps",
            "tb_plan_get_scatter", "tb_solve", "tb_solve_host", "tb_fitness", "tb_fitness_host", "tb_solve_ragged",
-           "tb_solve_ragged_host", "tb_pinned_alloc", "tb_pinned_free", "tb_small_path_limits", "tb_fp64_peak", "tb_profile_enable", "tb_profile_read",
+           "tb_solve_ragged_host", "tb_pinned_alloc", "tb_pinned_free", "tb_small_path_limits", "tb_fp64_peak", "tb_rsqrt_probe", "tb_profile_enable", "tb_profile_read",
            "tb_launch_count", "tb_strerror", "tb_version"]
 
 _lib = None
@@ -133,6 +133,7 @@ def lib():
     L.tb_pinned_free.argtypes = [vp]
     L.tb_small_path_limits.argtypes = [C.POINTER(i32), C.POINTER(i32)]
     L.tb_fp64_peak.argtypes = [i32, i32, C.POINTER(dbl), C.POINTER(C.c_float)]
+    L.tb_rsqrt_probe.argtypes = [i32, C.POINTER(dbl)]
     L.tb_profile_enable.argtypes = [i32]
     L.tb_profile_read.argtypes = [vp, vp]
     L.tb_launch_count.restype = i64
@@ -197,6 +198,13 @@ def fp64_peak(which: int, iters: int = 4096):
     t, ms = C.c_double(), C.c_float()
     check(lib().tb_fp64_peak(which, iters, C.byref(t), C.byref(ms)))
     return t.value, ms.value
+
+
+def rsqrt_probe(n: int = 1 << 22) -> float:
+    """Largest relative error of the pivot reciprocal square root against 1/sqrt(d) (see tb_rsqrt_probe)."""
+    e = C.c_double()
+    check(lib().tb_rsqrt_probe(n, C.byref(e)))
+    return e.value
 
 
 PROFILE_SLOTS = ("geom", "assemble", "chol", "recover", "small")

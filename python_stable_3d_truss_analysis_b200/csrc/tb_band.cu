@@ -21,6 +21,7 @@
 // once out and once back in, and u.  Replaces np.linalg.solve (slientruss3d/truss.py:343) for this class of
 // systems; results equal the dense factorisation's (zeros are skipped, nothing else).
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "tb_common.cuh"
@@ -69,7 +70,7 @@ __global__ void __launch_bounds__(32 * NW) k_band1(const LargeArgs a) {
   double* sCol = sT + BT;                      // [32] base case: eliminated column, double buffered
   int* sOff = (int*)(sCol + 32);               // [NB+1] staging slot (in doubles from sm) of block e of this column
 
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, lsw = lane_swz(lane);
   const int ncol = a.nb16;
   const int qr = lane >> 2, qc = lane & 3;     // this lane's (row, k) inside an operand fragment
 
@@ -144,7 +145,7 @@ __global__ void __launch_bounds__(32 * NW) k_band1(const LargeArgs a) {
 #pragma unroll
         for (int nb = 0; nb < 2; ++nb)
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) bf[nb][ks] = Bm[((nb * 4 + ks) << 5) + lane];
+          for (int ks = 0; ks < 4; ++ks) bf[nb][ks] = Bm[fo(nb * 4 + ks, lsw)];
         {   // rows of L(c, c-d) times y_{c-d}: the operand registers are exactly the needed elements
           int ys = yslot - d;
           if (ys < 0) ys += NB + 1;
@@ -172,7 +173,7 @@ __global__ void __launch_bounds__(32 * NW) k_band1(const LargeArgs a) {
 #pragma unroll
           for (int mb = 0; mb < 2; ++mb)
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) af[mb][ks] = A[((mb * 4 + ks) << 5) + lane];
+            for (int ks = 0; ks < 4; ++ks) af[mb][ks] = A[fo(mb * 4 + ks, lsw)];
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks)
 #pragma unroll
@@ -265,8 +266,8 @@ __global__ void __launch_bounds__(32 * NW) k_band1(const LargeArgs a) {
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
           const double t4 = sT[ks * 4 + qc];
-          yp[0] = fma(sScr[(ks << 5) + lane], t4, yp[0]);
-          yp[1] = fma(sScr[((4 + ks) << 5) + lane], t4, yp[1]);
+          yp[0] = fma(sScr[fo(ks, lsw)], t4, yp[0]);
+          yp[1] = fma(sScr[fo(4 + ks, lsw)], t4, yp[1]);
         }
 #pragma unroll
         for (int mb = 0; mb < 2; ++mb) {
@@ -287,7 +288,7 @@ __global__ void __launch_bounds__(32 * NW) k_band1(const LargeArgs a) {
 #pragma unroll
       for (int nbp = 0; nbp < 2; ++nbp)
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) wf[nbp][ks] = sScr[((nbp * 4 + ks) << 5) + lane];
+        for (int ks = 0; ks < 4; ++ks) wf[nbp][ks] = sScr[fo(nbp * 4 + ks, lsw)];
 #pragma unroll
       for (int rb = 1; rb <= NB; ++rb) {
         if (!((nzc >> rb) & 1u)) continue;
@@ -296,7 +297,7 @@ __global__ void __launch_bounds__(32 * NW) k_band1(const LargeArgs a) {
 #pragma unroll
         for (int mb = 0; mb < 2; ++mb)
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) a4[mb][ks] = blk[((mb * 4 + ks) << 5) + lane];
+          for (int ks = 0; ks < 4; ++ks) a4[mb][ks] = blk[fo(mb * 4 + ks, lsw)];
         __syncwarp();                          // P(rb) fully read before L(rb) overwrites it
         double* g = chunk + rb * BE;
 #pragma unroll
@@ -374,7 +375,7 @@ __global__ void __launch_bounds__(32 * NW) k_band1(const LargeArgs a) {
         for (int mb = 0; mb < 2; ++mb) {
           const double ur = uv[mb * 8 + qr];
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) tp[ks] = fma(blk[((mb * 4 + ks) << 5) + lane], ur, tp[ks]);
+          for (int ks = 0; ks < 4; ++ks) tp[ks] = fma(blk[fo(mb * 4 + ks, lsw)], ur, tp[ks]);
         }
       }
 #pragma unroll
@@ -394,7 +395,7 @@ __global__ void __launch_bounds__(32 * NW) k_band1(const LargeArgs a) {
       for (int mb = 0; mb < 2; ++mb) {
         const double rr = sT[mb * 8 + qr];
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) up[ks] = fma(buf[((mb * 4 + ks) << 5) + lane], rr, up[ks]);
+        for (int ks = 0; ks < 4; ++ks) up[ks] = fma(buf[fo(mb * 4 + ks, lsw)], rr, up[ks]);
       }
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {
@@ -450,7 +451,7 @@ __global__ void __launch_bounds__(64, 7) k_band2(const LargeArgs a) {
   double* sSd = sCol + 32 + 8;                 // [3][32][2] warp T's part of S(c+1,c+1) (terms d >= 2), accumulator layout
   double* sTp = sSd + 192;                     // [16] warp T's part of sum_d L(c+1,c+1-d) y_{c+1-d} (terms d >= 2)
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, lsw = lane_swz(lane);
   const int ncol = a.nb16;
   const int qr = lane >> 2, qc = lane & 3;
 
@@ -530,12 +531,12 @@ __global__ void __launch_bounds__(64, 7) k_band2(const LargeArgs a) {
           tp[1] = sTp[8 + qr];
         }
         if ((nzprev[1] >> 1) & 1u) {
-          const double* Bm = sRing + idx[1] * BE + lane;       // slot of block (c, c-1): diagonal 1 has one slot
+          const double* Bm = sRing + idx[1] * BE;       // slot of block (c, c-1): diagonal 1 has one slot
           double bf[2][4];
 #pragma unroll
           for (int h = 0; h < 2; ++h)
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) bf[h][ks] = Bm[(h * 4 + ks) << 5];
+            for (int ks = 0; ks < 4; ++ks) bf[h][ks] = Bm[fo(h * 4 + ks, lsw)];
           int ys = yslot - 1;
           if (ys < 0) ys += NB + 1;
           const double* yv = sY + ys * BT;
@@ -599,8 +600,8 @@ __global__ void __launch_bounds__(64, 7) k_band2(const LargeArgs a) {
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
             const double t4 = sT[ks * 4 + qc];
-            yp[0] = fma(sScr[(ks << 5) + lane], t4, yp[0]);
-            yp[1] = fma(sScr[((4 + ks) << 5) + lane], t4, yp[1]);
+            yp[0] = fma(sScr[fo(ks, lsw)], t4, yp[0]);
+            yp[1] = fma(sScr[fo(4 + ks, lsw)], t4, yp[1]);
           }
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
@@ -647,24 +648,24 @@ __global__ void __launch_bounds__(64, 7) k_band2(const LargeArgs a) {
           const int d = dq == NB - 2 ? 1 : dq + 2;
           const unsigned nzp = nzprev[d];
           if (!((nzp >> d) & 1u) || !(nzp >> (d + 1))) continue;   // L(c,c-d) zero, or nothing below it in that column
-          const double* Bm = sRing + (d * (d - 1) / 2 + idx[d]) * BE + lane;
+          const double* Bm = sRing + (d * (d - 1) / 2 + idx[d]) * BE;
           double bf[2][4];
 #pragma unroll
           for (int nb = 0; nb < 2; ++nb)
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) bf[nb][ks] = Bm[(nb * 4 + ks) << 5];
+            for (int ks = 0; ks < 4; ++ks) bf[nb][ks] = Bm[fo(nb * 4 + ks, lsw)];
 #pragma unroll
           for (int rb = 1; rb + d <= NB; ++rb) {
             const int e = rb + d;
             if (!((nzp >> e) & 1u)) continue;
             int sl = idx[e] - d;               // (c-d) mod e
             if (sl < 0) sl += e;
-            const double* A = sRing + (e * (e - 1) / 2 + sl) * BE + lane;
+            const double* A = sRing + (e * (e - 1) / 2 + sl) * BE;
             double af[2][4];
 #pragma unroll
             for (int mb = 0; mb < 2; ++mb)
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks) af[mb][ks] = A[(mb * 4 + ks) << 5];
+              for (int ks = 0; ks < 4; ++ks) af[mb][ks] = A[fo(mb * 4 + ks, lsw)];
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks)
 #pragma unroll
@@ -720,12 +721,12 @@ __global__ void __launch_bounds__(64, 7) k_band2(const LargeArgs a) {
             if (!((nzprev[dd] >> e) & 1u)) continue;
             int sl = idx[e] - dd;              // (c-dd) mod e
             if (sl < 0) sl += e;
-            const double* Bm = sRing + (e * (e - 1) / 2 + sl) * BE + lane;
+            const double* Bm = sRing + (e * (e - 1) / 2 + sl) * BE;
             double bf[2][4];
 #pragma unroll
             for (int h = 0; h < 2; ++h)
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks) bf[h][ks] = Bm[(h * 4 + ks) << 5];
+              for (int ks = 0; ks < 4; ++ks) bf[h][ks] = Bm[fo(h * 4 + ks, lsw)];
             int ys = yslot - dd;               // y_{c-dd}
             if (ys < 0) ys += NB + 1;
             const double* yv = sY + ys * BT;
@@ -766,7 +767,7 @@ __global__ void __launch_bounds__(64, 7) k_band2(const LargeArgs a) {
 #pragma unroll
         for (int nbp = 0; nbp < 2; ++nbp)
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) wf[nbp][ks] = sScr[((nbp * 4 + ks) << 5) + lane];
+          for (int ks = 0; ks < 4; ++ks) wf[nbp][ks] = sScr[fo(nbp * 4 + ks, lsw)];
 #pragma unroll
         for (int rb = 1; rb <= NB; ++rb) {
           if ((rb == 1) != isF) continue;
@@ -776,7 +777,7 @@ __global__ void __launch_bounds__(64, 7) k_band2(const LargeArgs a) {
 #pragma unroll
           for (int mb = 0; mb < 2; ++mb)
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) a4[mb][ks] = blk[((mb * 4 + ks) << 5) + lane];
+            for (int ks = 0; ks < 4; ++ks) a4[mb][ks] = blk[fo(mb * 4 + ks, lsw)];
           __syncwarp();                        // P(rb) fully read before L(rb) overwrites it
           double* g = chunk + rb * BE;
           double x[2][2][2] = {};
@@ -858,7 +859,7 @@ __global__ void __launch_bounds__(64, 7) k_band2(const LargeArgs a) {
           for (int h = 0; h < 2; ++h) {
             const double ur = uv[h * 8 + qr];
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) tp[ks] = fma(blk[((h * 4 + ks) << 5) + lane], ur, tp[ks]);
+            for (int ks = 0; ks < 4; ++ks) tp[ks] = fma(blk[fo(h * 4 + ks, lsw)], ur, tp[ks]);
           }
         }
 #pragma unroll
@@ -877,7 +878,518 @@ __global__ void __launch_bounds__(64, 7) k_band2(const LargeArgs a) {
         for (int h = 0; h < 2; ++h) {
           const double rr = sT[h * 8 + qr];
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) up[ks] = fma(buf[((h * 4 + ks) << 5) + lane], rr, up[ks]);
+          for (int ks = 0; ks < 4; ++ks) up[ks] = fma(buf[fo(h * 4 + ks, lsw)], rr, up[ks]);
+        }
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          up[ks] += __shfl_xor_sync(0xffffffffu, up[ks], 4);
+          up[ks] += __shfl_xor_sync(0xffffffffu, up[ks], 8);
+          up[ks] += __shfl_xor_sync(0xffffffffu, up[ks], 16);
+        }
+        if (qr == 0) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            sY[yslot * BT + ks * 4 + qc] = up[ks];
+            ysys[c * BT + ks * 4 + qc] = up[ks];
+          }
+        }
+        __syncwarp();
+      }
+      BPH(7)
+      if (lane == 0) a.status[b] = 0;
+    }
+    BPH_FLUSH(lane == 0 && isF)
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Three warps per system.  Same arithmetic, operand layout and summation orders as k_band1 / k_band2 (the three kernels
+// return the same bits); the block column is cut so that warp F carries the pivot chain and nothing else:
+//
+//   warp F  d = 1 term of S(c,c) -> P(c,c) = K - S -> 16x16 factorisation + W_c          | X | L(c+1,c) = P W^T     | Y |
+//   warp T  S(c+rb,c) -> [Z] -> -S into the staging slots -> [G] -> look-ahead S(c+1,c+1) | X | L(c+rb,c), rb >= 2   | Y |
+//   warp G  K values (global -> registers), column c-1 of L and W_{c-1} -> HBM, forward-substitution sums -> [Z]
+//           -> K(c+1,c+1) into the other scratch block -> [G] -> P(c+rb,c) = -S + K       | X | y_c = W_c t_c        | Y |
+//
+// X, Y: CTA barriers.  Z (named barrier 1): F and G no longer read the blocks (c, c-d) whose slots take column c.
+// G (named barrier 2): -S is in the staging slots.  Nothing from HBM, no zero fill and no scatter sits on warp F's
+// path any more; warp T no longer holds K values in registers; every global store is issued by warp G from shared
+// memory one block column later.
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bar_arrive_n(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_sync_n(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+template <int NB>
+struct Band3Cfg {
+  static constexpr int BUF = BandCfg<NB>::BUF;
+  // ring | two scratch blocks | y ring | rhs | column | slot table, failure flag | look-ahead part of S(c+1,c+1)
+  static constexpr int DOUBLES = BUF * BE + 2 * BE + (NB + 1) * BT + BT + 32 + 8 + 192;
+};
+
+template <int NB>
+__global__ void __maxnreg__(96) k_band3(const LargeArgs a) {
+  extern __shared__ __align__(16) double sm[];
+  using Cfg = Band3Cfg<NB>;
+  double* sRing = sm;
+  double* sScr0 = sRing + Cfg::BUF * BE;       // block column c uses scratch block (c & 1): P(c,c), then W_c
+  double* sY = sScr0 + 2 * BE;
+  double* sT = sY + (NB + 1) * BT;
+  double* sCol = sT + BT;
+  int* sOff = (int*)(sCol + 32);               // [1..NB] staging slots, [NB+1] failure flag
+  double* sSd = sCol + 32 + 8;                 // [3][32][2] terms d >= 2 of S(c+1,c+1), accumulator layout
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, lsw = lane_swz(lane);
+  const int ncol = a.nb16;
+  const int qr = lane >> 2, qc = lane & 3;
+
+  for (int b = blockIdx.x; b < a.batch; b += gridDim.x) {
+    if (a.status[b] != 0) continue;            // input problem flagged by k_geom (uniform)
+    int role = warp + (b % 3);                 // rotate the roles so co-resident CTAs load the schedulers evenly
+    if (role >= 3) role -= 3;
+    const bool isF = role == 0, isT = role == 1, isG = role == 2;
+    const double* kvs = a.kv + (int64_t)b * a.nnz;
+    const double* fsys = a.force + b * a.force_stride;
+    double* ysys = a.y + (int64_t)b * a.n_pad;
+    double* Lb = a.L + (int64_t)b * ncol * (NB + 1) * BE;
+    int fail = 0;
+    if (tid == 0) sOff[NB + 1] = 0;
+
+    int idx[NB + 1];
+    unsigned nzprev[NB + 1];
+#pragma unroll
+    for (int e = 0; e <= NB; ++e) { idx[e] = 0; nzprev[e] = 0u; }
+    int yslot = 0;
+    unsigned nzn = (unsigned)ldg_i32(a.b16_nz);
+    // warp G: entry ranges [po0, po1) below the diagonal block of column c, [po1, pd1) diagonal block of column c+1
+    int po0 = 0, po1 = 0, pd1 = 0, pn1 = 0, pn2 = 0;
+    int fin[2] = {-1, -1};
+    if (isG) {
+      const int d0 = ldg_i32(a.b16_ptr);
+      po0 = ldg_i32(a.b16_ptr + 1);
+      po1 = ldg_i32(a.b16_ptr + 2);
+      pd1 = ncol > 1 ? ldg_i32(a.b16_ptr + 3) : po1;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) fin[h] = h * 8 + qr < a.n ? ldg_i32(a.free_idx + h * 8 + qr) : -1;
+      // K(0,0) into scratch block 0
+      const double2 z = make_double2(0.0, 0.0);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) reinterpret_cast<double2*>(sScr0)[lane + 32 * i] = z;
+      __syncwarp();
+      for (int q = d0 + lane; q < po0; q += 32) sScr0[ldg_i32(a.b16_pos + q) & 255] = ldg_f64(kvs + q);
+      if (lane < BT && lane >= a.n) sScr0[b16_off(lane, lane)] = 1.0;
+    }
+    BPH_DECL
+    __syncthreads();
+
+    for (int c = 0; c < ncol; ++c) {
+      const unsigned nzc = nzn;
+      if (c + 1 < ncol) nzn = (unsigned)ldg_i32(a.b16_nz + c + 1);
+      double* scr = sScr0 + (c & 1) * BE;
+
+      if (isF) {
+        // ================= warp F: the pivot chain of block column c =================
+        double acc[3][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
+        if (c > 0) {
+#pragma unroll
+          for (int q = 0; q < 3; ++q) {
+            const double2 v = reinterpret_cast<const double2*>(sSd)[q * 32 + lane];
+            acc[q][0] = v.x;
+            acc[q][1] = v.y;
+          }
+        }
+        if ((nzprev[1] >> 1) & 1u) {
+          const double* Bm = sRing + idx[1] * BE;       // block (c, c-1): diagonal 1 has one slot
+          double bf[2][4];
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) bf[h][ks] = Bm[fo(h * 4 + ks, lsw)];
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {     // L(c,c-1) L(c,c-1)^T: the operand fragments of A and B coincide
+            dmma(acc[0][0], acc[0][1], bf[0][ks], bf[0][ks]);
+            dmma(acc[1][0], acc[1][1], bf[1][ks], bf[0][ks]);
+            dmma(acc[2][0], acc[2][1], bf[1][ks], bf[1][ks]);
+          }
+        }
+        __syncwarp();
+        bar_arrive_n(1, 96);                   // [Z] F no longer reads block (c, c-1)
+        BPH(0)
+        {
+          double2* p0 = reinterpret_cast<double2*>(scr + cpair_off(0, 0, lane));
+          double2* p1 = reinterpret_cast<double2*>(scr + cpair_off(1, 0, lane));
+          double2* p2 = reinterpret_cast<double2*>(scr + cpair_off(1, 1, lane));
+          double2 v0 = *p0, v1 = *p1, v2 = *p2;
+          v0.x -= acc[0][0]; v0.y -= acc[0][1];
+          v1.x -= acc[1][0]; v1.y -= acc[1][1];
+          v2.x -= acc[2][0]; v2.y -= acc[2][1];
+          *p0 = v0; *p1 = v1; *p2 = v2;
+        }
+        __syncwarp();
+        BPH(1)
+        const int bad = factor_diag16(scr, sCol, lane, c * BT);
+        if (bad && lane == 0) sOff[NB + 1] = bad;
+        __syncwarp();
+        BPH(2)
+      } else if (isT) {
+        // ================= warp T: the tensor work of block column c =================
+        double acc[NB + 1][2][2][2];
+#pragma unroll
+        for (int rb = 1; rb <= NB; ++rb)
+#pragma unroll
+          for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+            for (int nb = 0; nb < 2; ++nb) acc[rb][mb][nb][0] = acc[rb][mb][nb][1] = 0.0;
+#pragma unroll
+        for (int dq = 0; dq < NB - 1; ++dq) {    // d = 2 .. NB-1, then d = 1 (k_band1's order)
+          const int d = dq == NB - 2 ? 1 : dq + 2;
+          const unsigned nzp = nzprev[d];
+          if (!((nzp >> d) & 1u) || !(nzp >> (d + 1))) continue;   // L(c,c-d) zero, or nothing below it in that column
+          const double* Bm = sRing + (d * (d - 1) / 2 + idx[d]) * BE;
+          double bf[2][4];
+#pragma unroll
+          for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) bf[nb][ks] = Bm[fo(nb * 4 + ks, lsw)];
+#pragma unroll
+          for (int rb = 1; rb + d <= NB; ++rb) {
+            const int e = rb + d;
+            if (!((nzp >> e) & 1u)) continue;
+            int sl = idx[e] - d;               // (c-d) mod e
+            if (sl < 0) sl += e;
+            const double* A = sRing + (e * (e - 1) / 2 + sl) * BE;
+            double af[2][4];
+#pragma unroll
+            for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) af[mb][ks] = A[fo(mb * 4 + ks, lsw)];
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+              for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+                for (int nb = 0; nb < 2; ++nb) dmma(acc[rb][mb][nb][0], acc[rb][mb][nb][1], af[mb][ks], bf[nb][ks]);
+          }
+        }
+        __syncwarp();
+        bar_sync_n(1, 96);                     // [Z] the blocks (c, c-d) are dead: their slots take column c
+#pragma unroll
+        for (int rb = 1; rb <= NB; ++rb) {
+          if (!((nzc >> rb) & 1u)) continue;
+          double* blk = sRing + (rb * (rb - 1) / 2 + idx[rb]) * BE;
+#pragma unroll
+          for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+            for (int nb = 0; nb < 2; ++nb)
+              *reinterpret_cast<double2*>(blk + cpair_off(mb, nb, lane)) =
+                  make_double2(0.0 - acc[rb][mb][nb][0], 0.0 - acc[rb][mb][nb][1]);
+        }
+        __syncwarp();
+        bar_arrive_n(2, 64);                   // [G] -S is in the staging slots
+        // ---- look-ahead for warp F: terms d >= 2 of S(c+1,c+1).  Block (c+1, c+1-d) is block (c + 1, c - dd), dd = d - 1
+        {
+          double sd[3][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+          for (int dd = 1; dd < NB; ++dd) {
+            const int e = dd + 1;
+            if (!((nzprev[dd] >> e) & 1u)) continue;
+            int sl = idx[e] - dd;              // (c-dd) mod e
+            if (sl < 0) sl += e;
+            const double* Bm = sRing + (e * (e - 1) / 2 + sl) * BE;
+            double bf[2][4];
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) bf[h][ks] = Bm[fo(h * 4 + ks, lsw)];
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              dmma(sd[0][0], sd[0][1], bf[0][ks], bf[0][ks]);
+              dmma(sd[1][0], sd[1][1], bf[1][ks], bf[0][ks]);
+              dmma(sd[2][0], sd[2][1], bf[1][ks], bf[1][ks]);
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < 3; ++q) reinterpret_cast<double2*>(sSd)[q * 32 + lane] = make_double2(sd[q][0], sd[q][1]);
+        }
+      } else {
+        // ================= warp G: K values, forward substitution, stores =================
+        double kvo[PRET], kvd[PREF];
+        int poso[PRET], posd[PREF];
+#pragma unroll
+        for (int i = 0; i < PRET; ++i) {
+          const int q = po0 + lane + 32 * i;
+          kvo[i] = 0.0;
+          poso[i] = 0;
+          if (q < po1) {
+            kvo[i] = ldg_f64(kvs + q);
+            poso[i] = ldg_i32(a.b16_pos + q);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < PREF; ++i) {
+          const int q = po1 + lane + 32 * i;
+          kvd[i] = 0.0;
+          posd[i] = 0;
+          if (q < pd1) {
+            kvd[i] = ldg_f64(kvs + q);
+            posd[i] = ldg_i32(a.b16_pos + q);
+          }
+        }
+        double fr[2];
+        fr[0] = fin[0] >= 0 ? ldg_f64(fsys + fin[0]) : 0.0;
+        fr[1] = fin[1] >= 0 ? ldg_f64(fsys + fin[1]) : 0.0;
+        if (c + 1 < ncol) {                    // metadata of the next block column
+          pn1 = ldg_i32(a.b16_ptr + 2 * c + 4);
+          pn2 = c + 2 < ncol ? ldg_i32(a.b16_ptr + 2 * c + 5) : -1;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int grow = (c + 1) * BT + h * 8 + qr;
+            fin[h] = grow < a.n ? ldg_i32(a.free_idx + grow) : -1;
+          }
+        }
+#pragma unroll
+        for (int e = 1; e <= NB; ++e)
+          if (lane == e) sOff[e] = (e * (e - 1) / 2 + idx[e]) * BE;
+        // ---- block column c-1 of the factor -> HBM (its blocks are in the ring, W_{c-1} in the other scratch block)
+        if (c > 0) {
+          double* chunk = Lb + (int64_t)(c - 1) * (NB + 1) * BE;
+          const double* wsrc = sScr0 + ((c - 1) & 1) * BE;
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            reinterpret_cast<double2*>(chunk)[lane + 32 * i] = reinterpret_cast<const double2*>(wsrc)[lane + 32 * i];
+#pragma unroll
+          for (int rb = 1; rb <= NB; ++rb) {
+            if (!((nzprev[1] >> rb) & 1u)) continue;
+            const int sl = idx[rb] == 0 ? rb - 1 : idx[rb] - 1;          // (c-1) mod rb
+            const double* src = sRing + (rb * (rb - 1) / 2 + sl) * BE;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              reinterpret_cast<double2*>(chunk + rb * BE)[lane + 32 * i] = reinterpret_cast<const double2*>(src)[lane + 32 * i];
+          }
+        }
+        // ---- forward substitution: sum_d L(c,c-d) y_{c-d}, terms d = 2..NB then d = 1 (k_band1's order)
+        double tp[2] = {0.0, 0.0}, tp1[2] = {0.0, 0.0};
+#pragma unroll
+        for (int dq = 0; dq < NB; ++dq) {
+          const int d = dq == NB - 1 ? 1 : dq + 2;
+          if (!((nzprev[d] >> d) & 1u)) continue;
+          const double* Bm = sRing + (d * (d - 1) / 2 + idx[d]) * BE;
+          int ys = yslot - d;
+          if (ys < 0) ys += NB + 1;
+          const double* yv = sY + ys * BT;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const double y4 = yv[ks * 4 + qc];
+            const double b0 = Bm[fo(ks, lsw)], b1 = Bm[fo(4 + ks, lsw)];
+            if (d == 1) {
+              tp1[0] = fma(b0, y4, tp1[0]);
+              tp1[1] = fma(b1, y4, tp1[1]);
+            } else {
+              tp[0] = fma(b0, y4, tp[0]);
+              tp[1] = fma(b1, y4, tp[1]);
+            }
+          }
+        }
+        __syncwarp();
+        bar_arrive_n(1, 96);                   // [Z] G no longer reads the blocks (c, c-d)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          tp[h] += __shfl_xor_sync(0xffffffffu, tp[h], 1);
+          tp[h] += __shfl_xor_sync(0xffffffffu, tp[h], 2);
+          tp1[h] += __shfl_xor_sync(0xffffffffu, tp1[h], 1);
+          tp1[h] += __shfl_xor_sync(0xffffffffu, tp1[h], 2);
+          tp[h] += tp1[h];
+        }
+        if (qc == 0) {
+          sT[qr] = fr[0] - tp[0];
+          sT[8 + qr] = fr[1] - tp[1];
+        }
+        // ---- K(c+1,c+1) into the other scratch block (W_{c-1} has left it)
+        if (c + 1 < ncol) {
+          double* scn = sScr0 + ((c + 1) & 1) * BE;
+          const double2 z = make_double2(0.0, 0.0);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) reinterpret_cast<double2*>(scn)[lane + 32 * i] = z;
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < PREF; ++i)
+            if (po1 + lane + 32 * i < pd1) scn[posd[i] & 255] = kvd[i];
+          for (int q = po1 + 32 * PREF + lane; q < pd1; q += 32) scn[ldg_i32(a.b16_pos + q) & 255] = ldg_f64(kvs + q);
+          if (lane < BT && (c + 1) * BT + lane >= a.n) scn[b16_off(lane, lane)] = 1.0;   // identity on the padded diagonal
+        }
+        __syncwarp();
+        bar_sync_n(2, 64);                     // [G] -S is in the staging slots: P = -S + K
+#pragma unroll
+        for (int i = 0; i < PRET; ++i)
+          if (po0 + lane + 32 * i < po1) {
+            double* p = sm + sOff[poso[i] >> 8] + (poso[i] & 255);
+            *p += kvo[i];
+          }
+        for (int q = po0 + 32 * PRET + lane; q < po1; q += 32) {
+          const int pos = ldg_i32(a.b16_pos + q);
+          double* p = sm + sOff[pos >> 8] + (pos & 255);
+          *p += ldg_f64(kvs + q);
+        }
+      }
+      __syncthreads();                         // [X] W_c is in the scratch block, P(c+rb, c) are in their slots
+      BPH(4)
+      fail = sOff[NB + 1];
+      if (fail) break;   // uniform
+
+      if (isG) {
+        // ---------------- y_c = W_c t_c
+        double yp[2] = {0.0, 0.0};
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const double t4 = sT[ks * 4 + qc];
+          yp[0] = fma(scr[fo(ks, lsw)], t4, yp[0]);
+          yp[1] = fma(scr[fo(4 + ks, lsw)], t4, yp[1]);
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          yp[h] += __shfl_xor_sync(0xffffffffu, yp[h], 1);
+          yp[h] += __shfl_xor_sync(0xffffffffu, yp[h], 2);
+        }
+        if (qc == 0) {
+          sY[yslot * BT + qr] = yp[0];
+          sY[yslot * BT + 8 + qr] = yp[1];
+          ysys[c * BT + qr] = yp[0];
+          ysys[c * BT + 8 + qr] = yp[1];
+        }
+        po0 = pd1;
+        po1 = pn1;
+        pd1 = pn2 >= 0 ? pn2 : pn1;
+      } else {
+        // ---------------- L(c+rb, c) = P W^T into the ring: warp F takes rb = 1, warp T the rest
+        double wf[2][4];
+#pragma unroll
+        for (int nbp = 0; nbp < 2; ++nbp)
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) wf[nbp][ks] = scr[fo(nbp * 4 + ks, lsw)];
+#pragma unroll
+        for (int rb = 1; rb <= NB; ++rb) {
+          if ((rb == 1) != isF) continue;
+          if (!((nzc >> rb) & 1u)) continue;
+          double* blk = sRing + (rb * (rb - 1) / 2 + idx[rb]) * BE;
+          double a4[2][4];
+#pragma unroll
+          for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) a4[mb][ks] = blk[fo(mb * 4 + ks, lsw)];
+          __syncwarp();                        // P(rb) fully read before L(rb) overwrites it
+          double x[2][2][2] = {};
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+            for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+              for (int nbp = 0; nbp < 2; ++nbp)
+                if (ks < 2 * nbp + 2) dmma(x[mb][nbp][0], x[mb][nbp][1], a4[mb][ks], wf[nbp][ks]);   // W is lower triangular
+#pragma unroll
+          for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+            for (int nbp = 0; nbp < 2; ++nbp)
+              *reinterpret_cast<double2*>(blk + cpair_off(mb, nbp, lane)) = make_double2(x[mb][nbp][0], x[mb][nbp][1]);
+        }
+      }
+      BPH(5)
+      __syncthreads();                         // [Y] column c of L is in the ring, y_c in its slot
+      BPH(6)
+
+#pragma unroll
+      for (int e = NB; e >= 2; --e) nzprev[e] = nzprev[e - 1];
+      nzprev[1] = nzc;
+#pragma unroll
+      for (int e = 1; e <= NB; ++e) idx[e] = (idx[e] + 1 == e) ? 0 : idx[e] + 1;
+      yslot = (yslot == NB) ? 0 : yslot + 1;
+    }
+
+    if (fail) {
+      if (tid == 0) a.status[b] = fail;
+      __syncthreads();
+      continue;
+    }
+    if (isG) {                                 // the last block column of the factor -> HBM
+      double* chunk = Lb + (int64_t)(ncol - 1) * (NB + 1) * BE;
+      const double* wsrc = sScr0 + ((ncol - 1) & 1) * BE;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        reinterpret_cast<double2*>(chunk)[lane + 32 * i] = reinterpret_cast<const double2*>(wsrc)[lane + 32 * i];
+#pragma unroll
+      for (int rb = 1; rb <= NB; ++rb) {
+        if (!((nzprev[1] >> rb) & 1u)) continue;
+        const int sl = idx[rb] == 0 ? rb - 1 : idx[rb] - 1;
+        const double* src = sRing + (rb * (rb - 1) / 2 + sl) * BE;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          reinterpret_cast<double2*>(chunk + rb * BE)[lane + 32 * i] = reinterpret_cast<const double2*>(src)[lane + 32 * i];
+      }
+    }
+    __syncthreads();                           // the factor is in HBM/L2, the ring is free
+
+    // ---------------- back substitution on warp F: u_c = W_c^T (y_c - sum_rb L(c+rb,c)^T u_{c+rb}), last block first
+    if (isF) {
+      auto fetch = [&](int c) {
+        const unsigned nz = (unsigned)ldg_i32(a.b16_nz + c) | 1u;     // bit 0: W_c
+        const double* src = Lb + (int64_t)c * (NB + 1) * BE;
+        double* dst = sRing + (c & 1) * (NB + 1) * BE;
+#pragma unroll
+        for (int e = 0; e <= NB; ++e)
+          if ((nz >> e) & 1u) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) cp_async16(dst + e * BE + (lane + 32 * i) * 2, src + e * BE + (lane + 32 * i) * 2);
+          }
+        cp_async_commit();
+      };
+      fetch(ncol - 1);
+      for (int c = ncol - 1; c >= 0; --c) {
+        yslot = (yslot == 0) ? NB : yslot - 1;
+        double yc[4] = {0.0, 0.0, 0.0, 0.0};
+        if (qr == 0) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) yc[ks] = __ldcg(ysys + c * BT + ks * 4 + qc);
+        }
+        if (c > 0) {
+          fetch(c - 1);
+          cp_async_wait<1>();
+        } else {
+          cp_async_wait<0>();
+        }
+        __syncwarp();
+        const unsigned nz = (unsigned)ldg_i32(a.b16_nz + c);
+        const double* buf = sRing + (c & 1) * (NB + 1) * BE;
+        double tp[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int rb = 1; rb <= NB; ++rb) {
+          if (!((nz >> rb) & 1u)) continue;
+          int us = yslot + rb;
+          if (us > NB) us -= NB + 1;
+          const double* uv = sY + us * BT;
+          const double* blk = buf + rb * BE;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const double ur = uv[h * 8 + qr];
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) tp[ks] = fma(blk[fo(h * 4 + ks, lsw)], ur, tp[ks]);
+          }
+        }
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          tp[ks] += __shfl_xor_sync(0xffffffffu, tp[ks], 4);
+          tp[ks] += __shfl_xor_sync(0xffffffffu, tp[ks], 8);
+          tp[ks] += __shfl_xor_sync(0xffffffffu, tp[ks], 16);
+        }
+        if (qr == 0) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) sT[ks * 4 + qc] = yc[ks] - tp[ks];
+        }
+        __syncwarp();
+        double up[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const double rr = sT[h * 8 + qr];
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) up[ks] = fma(buf[fo(h * 4 + ks, lsw)], rr, up[ks]);
         }
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
@@ -904,26 +1416,38 @@ __global__ void __launch_bounds__(64, 7) k_band2(const LargeArgs a) {
 
 template <int NB>
 int launch_band(const LargeArgs& a, int num_sm, cudaStream_t st) {
-  // one warp per system when the batch alone fills the GPU (fewest instructions per system), else two warps per system
+  // one warp per system when the batch alone fills the GPU (fewest instructions per system), else several warps per
+  // system: TB_BAND_WARPS = 1 | 2 | 3 forces a kernel (parity tests, comparisons)
   static const int force = [] { const char* s = getenv("TB_BAND_WARPS"); return s ? atoi(s) : 0; }();
   constexpr int NW = 4;                        // k_band1 packs four independent systems (warps) into a CTA
-  const int smem1 = NW * BandCfg<NB>::DOUBLES * 8, smem2 = (BandCfg<NB>::DOUBLES + 208) * 8;
-  static int per1 = 0, per2 = 0;               // attribute / occupancy queries once per instantiation (single device per process)
+  const int smem1 = NW * BandCfg<NB>::DOUBLES * 8, smem2 = (BandCfg<NB>::DOUBLES + 208) * 8, smem3 = Band3Cfg<NB>::DOUBLES * 8;
+  static int per1 = 0, per2 = 0, per3 = 0;     // attribute / occupancy queries once per instantiation (single device per process)
   if (per1 == 0) {
-    int q1 = 0, q2 = 0;
+    int q1 = 0, q2 = 0, q3 = 0;
     cudaError_t e = cudaFuncSetAttribute(k_band1<NB, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_band2<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_band3<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3);
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q1, k_band1<NB, NW>, 32 * NW, smem1);
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q2, k_band2<NB>, 64, smem2);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q3, k_band3<NB>, 96, smem3);
     if (e != cudaSuccess) return (int)e;
+    per3 = q3 < 1 ? 1 : q3;
     per2 = q2 < 1 ? 1 : q2;
     per1 = q1 < 1 ? 1 : q1;
+    if (getenv("TB_BAND_DEBUG")) fprintf(stderr, "launch_band<%d>: CTAs/SM k_band1 %d, k_band2 %d, k_band3 %d\n", NB, q1, q2, q3);
   }
-  bool two = NB <= 5 && (int64_t)a.batch < (int64_t)2 * num_sm * per1 * NW;   // NB > 5: the trailing warp's accumulators spill
-  if (force == 1) two = false;
-  if (force == 2 && NB <= 5) two = true;
+  // NB > 5: the trailing warp's accumulators spill -> one warp per system.  Otherwise three warps per system (96
+  // registers per thread, six systems per SM) while the batch fits in one wave of that kernel, else two warps per
+  // system (eight systems per SM; measured faster than k_band1's eight one-warp systems per SM at every batch size:
+  // bar-942 x8192 in 2.73 ms against 2.96 ms)
+  int warps = NB > 5 ? 1 : (int64_t)a.batch <= (int64_t)num_sm * per3 ? 3 : 2;
+  if (force == 1 || (NB <= 5 && (force == 2 || force == 3))) warps = force;
   tb_prof_begin(TB_PROF_CHOL, st);
-  if (two) {
+  if (warps == 3) {
+    int grid = num_sm * per3;
+    if (grid > a.batch) grid = a.batch;
+    k_band3<NB><<<grid, 96, smem3, st>>>(a);
+  } else if (warps == 2) {
     int grid = num_sm * per2;
     if (grid > a.batch) grid = a.batch;
     k_band2<NB><<<grid, 64, smem2, st>>>(a);

@@ -37,24 +37,34 @@ __device__ __forceinline__ double ldg_f64(const double* p) {
   return v;
 }
 
-__device__ __forceinline__ int b16_off(int r, int c) { return ((((r >> 3) << 2) + (c >> 2)) << 5) + ((r & 7) << 2) + (c & 3); }
+// Block layout: 8 slabs (slab s = 4 * (row / 8) + k / 4) of 32 doubles; inside a slab element p = 4 * (row % 8) + k % 4
+// sits at p, so an operand read (lane = p, all 32 elements of one slab) is conflict free.  An XOR swizzle of p
+// (swz(s) = ((s & 1) << 3) | ((s & 2) << 1), plus bit 4 of p folded onto bit 1) removes the 2-way / 4-way conflicts of
+// the accumulator-pair, column and W-row accesses (12.1 M -> 3.2 M conflict wavefronts per 1024 bar-942 systems,
+// LSU pipe 69 % -> 55 %) but costs 7 % more instructions on the dependent chains and the kernel got 3 % slower
+// (profiles/r01g notes): the band kernels are bound by chain latency, not by the LSU pipe, so the plain layout stays.
+__host__ __device__ __forceinline__ constexpr int swz(int) { return 0; }
+__host__ __device__ __forceinline__ constexpr int slab_off(int s, int p) { return (s << 5) + (p ^ swz(s)); }
+__device__ __forceinline__ int lane_swz(int lane) { return lane; }
+// operand fragment element of this lane in slab s; lsw = lane_swz(lane)
+__device__ __forceinline__ int fo(int s, int lsw) { return (s << 5) + (lsw ^ swz(s)); }
+__host__ __device__ __forceinline__ constexpr int b16_off(int r, int c) { return slab_off(((r >> 3) << 2) + (c >> 2), ((r & 7) << 2) + (c & 3)); }
 // this lane's accumulator pair of 8x8 block (mb, nbp) inside a 16x16 block
 __device__ __forceinline__ int cpair_off(int mb, int nbp, int lane) {
-  return ((mb * 4 + nbp * 2 + ((lane & 3) >> 1)) << 5) + ((lane >> 2) << 2) + ((lane & 1) << 1);
+  return slab_off(mb * 4 + nbp * 2 + ((lane & 3) >> 1), ((lane >> 2) << 2) + ((lane & 1) << 1));
 }
 
 
-// 1/sqrt(d) for a normal positive d: hardware seed (MUFU.RSQ64H) + two Newton steps, ~1 ulp.  The library
-// rsqrt() costs 18 instructions with its special-case handling; the pivots here are checked positive first.
+// 1/sqrt(d) for a normal positive d: hardware seed (MUFU.RSQ64H, relative error e0 ~ 2^-22) + one third-order step
+// y (1 + e/2 + 3 e^2/8), e = 1 - d y^2: error O(e0^3), a dependent chain of four FP64 operations (two Newton steps
+// need six).  The library rsqrt() costs 18 instructions with its special-case handling; the pivots here are checked
+// positive beside the chain (a non-positive pivot yields NaNs that are discarded with the failure flag).
 __device__ __forceinline__ double rsqrt_pos(double d) {
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
-  const double h = 0.5 * d;
-  double e = fma(-h * y, y, 0.5);
-  y = fma(y, e, y);
-  e = fma(-h * y, y, 0.5);
-  y = fma(y, e, y);
-  return y;
+  const double e = fma(-d * y, y, 1.0);
+  const double t = fma(0.375, e, 0.5);
+  return fma(y * e, t, y);
 }
 
 // 16x16 diagonal block in shared memory (fragment layout): L_D L_D^T = P in registers, W = L_D^{-1} written back
@@ -64,18 +74,17 @@ __device__ __forceinline__ double rsqrt_pos(double d) {
 // of column k.  Returns 0 or the 1-based index (row0 + k + 1) of the first non-positive pivot.
 __device__ __forceinline__ int factor_diag16(double* sBlk, double* sCol, int lane, int row0) {
   const int r = lane & 15;
-  const int rowpart = ((r >> 3) << 7) + ((r & 7) << 2);
   double row[16];
 #pragma unroll
   for (int cc = 0; cc < 16; ++cc) {
-    const double v = sBlk[rowpart + ((cc >> 2) << 5) + (cc & 3)];
+    const double v = sBlk[b16_off(r, cc)];
     row[cc] = lane < 16 ? (cc <= r ? v : 0.0) : (cc == r ? 1.0 : 0.0);
   }
   __syncwarp();
   int bad = 0;
   double d = __shfl_sync(0xffffffffu, row[0], 0);
   if (!(d > 1e-290)) bad = row0 + 1;
-  double rinv = rsqrt_pos(bad ? 1.0 : d);
+  double rinv = rsqrt_pos(d);
 #pragma unroll
   for (int k = 0; k < 16; ++k) {
     const double lk = row[k] * rinv;                        // lane k: d * rsqrt(d) = sqrt(d)
@@ -83,8 +92,8 @@ __device__ __forceinline__ int factor_diag16(double* sBlk, double* sCol, int lan
     double rinv_next = 0.0;
     if (k < 15) {
       const double dn = __shfl_sync(0xffffffffu, fma(-lk, lk, row[k + 1]), k + 1);
-      if (!(dn > 1e-290) && !bad) bad = row0 + k + 2;       // same value in every lane
-      rinv_next = rsqrt_pos(bad ? 1.0 : dn);
+      rinv_next = rsqrt_pos(dn);
+      if (!(dn > 1e-290) && !bad) bad = row0 + k + 2;       // same value in every lane; off the pivot chain
     }
     double* col = sCol + ((k & 1) << 4);
     if (lane < 16) col[lane] = lk;

@@ -66,7 +66,7 @@ __device__ __forceinline__ double warp_sum(double v) {   // fixed-shape tree: sa
 template <int DIM>
 __global__ void __launch_bounds__(128) k_dense16(const SmallArgs a, const int nbm, const int nwarp) {
   extern __shared__ __align__(16) double sm_all[];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, lsw = lane_swz(lane);
   const int NJmax = a.nJ, Mmax = a.M;
   const D16Layout L = d16_layout(DIM, NJmax, Mmax, nbm);
   double* sm = sm_all + (size_t)wid * L.total;
@@ -315,12 +315,12 @@ __global__ void __launch_bounds__(128) k_dense16(const SmallArgs a, const int nb
           double acc[3][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
           double tp[2] = {0.0, 0.0};
           for (int d = 0; d < c; ++d) {
-            const double* Bm = sK + (c * (c + 1) / 2 + d) * BE + lane;
+            const double* Bm = sK + (c * (c + 1) / 2 + d) * BE;
             double bf[2][4];
 #pragma unroll
             for (int h = 0; h < 2; ++h)
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks) bf[h][ks] = Bm[(h * 4 + ks) << 5];
+              for (int ks = 0; ks < 4; ++ks) bf[h][ks] = Bm[fo(h * 4 + ks, lsw)];
             const double* yv = sY + d * BT;
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
@@ -361,7 +361,7 @@ __global__ void __launch_bounds__(128) k_dense16(const SmallArgs a, const int nb
 #pragma unroll
         for (int nbp = 0; nbp < 2; ++nbp)
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) wf[nbp][ks] = Dc[((nbp * 4 + ks) << 5) + lane];
+          for (int ks = 0; ks < 4; ++ks) wf[nbp][ks] = Dc[fo(nbp * 4 + ks, lsw)];
         {   // y_c = W t
           double yp[2] = {0.0, 0.0};
 #pragma unroll
@@ -386,15 +386,15 @@ __global__ void __launch_bounds__(128) k_dense16(const SmallArgs a, const int nb
           double* blk = sK + (i * (i + 1) / 2 + c) * BE;
           double acc[2][2][2] = {};
           for (int d = 0; d < c; ++d) {
-            const double* A = sK + (i * (i + 1) / 2 + d) * BE + lane;
-            const double* Bm = sK + (c * (c + 1) / 2 + d) * BE + lane;
+            const double* A = sK + (i * (i + 1) / 2 + d) * BE;
+            const double* Bm = sK + (c * (c + 1) / 2 + d) * BE;
             double af[2][4], bf[2][4];
 #pragma unroll
             for (int h = 0; h < 2; ++h)
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks) {
-                af[h][ks] = A[(h * 4 + ks) << 5];
-                bf[h][ks] = Bm[(h * 4 + ks) << 5];
+                af[h][ks] = A[fo(h * 4 + ks, lsw)];
+                bf[h][ks] = Bm[fo(h * 4 + ks, lsw)];
               }
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks)
@@ -418,7 +418,7 @@ __global__ void __launch_bounds__(128) k_dense16(const SmallArgs a, const int nb
 #pragma unroll
           for (int mb = 0; mb < 2; ++mb)
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) a4[mb][ks] = blk[((mb * 4 + ks) << 5) + lane];
+            for (int ks = 0; ks < 4; ++ks) a4[mb][ks] = blk[fo(mb * 4 + ks, lsw)];
           __syncwarp();
           double x[2][2][2] = {};
 #pragma unroll
@@ -448,7 +448,7 @@ __global__ void __launch_bounds__(128) k_dense16(const SmallArgs a, const int nb
             for (int h = 0; h < 2; ++h) {
               const double ur = uv[h * 8 + qr];
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks) tp[ks] = fma(blk[((h * 4 + ks) << 5) + lane], ur, tp[ks]);
+              for (int ks = 0; ks < 4; ++ks) tp[ks] = fma(blk[fo(h * 4 + ks, lsw)], ur, tp[ks]);
             }
           }
 #pragma unroll
@@ -468,7 +468,7 @@ __global__ void __launch_bounds__(128) k_dense16(const SmallArgs a, const int nb
           for (int h = 0; h < 2; ++h) {
             const double rr = sT[h * 8 + qr];
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) up[ks] = fma(W[((h * 4 + ks) << 5) + lane], rr, up[ks]);
+            for (int ks = 0; ks < 4; ++ks) up[ks] = fma(W[fo(h * 4 + ks, lsw)], rr, up[ks]);
           }
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {

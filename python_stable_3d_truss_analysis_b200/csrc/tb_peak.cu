@@ -1,6 +1,7 @@
 // FP64 pipe microbenchmarks.  MEASURED_PEAKS.json carries HBM and bf16 numbers only, so the
 // FP64 roofline denominators (vector DFMA, tensor DMMA) are measured on the box by these.
 #include "tb_common.cuh"
+#include "tb_blocks.cuh"
 
 namespace {
 
@@ -57,7 +58,35 @@ __global__ void __launch_bounds__(256) k_peak_dmma1688(double* out, int iters, d
   if (s == 123.456) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// accuracy probe of the pivot reciprocal square root (tb_blocks.cuh: rsqrt_pos): values log-uniform over
+// [1e-290, 1e300] (the range the factorisation accepts), error against 1 / sqrt(d) (correctly rounded steps)
+__global__ void k_rsqrt_probe(int n, double* worst) {
+  double w = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const double t = (i + 0.5) / n;
+    const double d = exp10(-290.0 + 590.0 * t) * (1.0 + 0.37 * t);
+    const double got = tbblk::rsqrt_pos(d), want = 1.0 / sqrt(d);
+    w = fmax(w, fabs(got - want) / want);
+  }
+  for (int o = 16; o > 0; o >>= 1) w = fmax(w, __shfl_xor_sync(0xffffffffu, w, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned long long*>(worst), (unsigned long long)__double_as_longlong(w));
+}
+
 }  // namespace
+
+extern "C" int tb_rsqrt_probe(int32_t n, double* max_rel_err) {
+  if (!max_rel_err) return TB_ERR_NULL;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return TB_ERR_NO_DEVICE;
+  double* d = nullptr;
+  TB_CUDA(cudaMalloc(&d, sizeof(double)));
+  TB_CUDA(cudaMemset(d, 0, sizeof(double)));
+  k_rsqrt_probe<<<256, 256>>>(n, d);
+  tb_count_launch(1);
+  cudaError_t e = cudaMemcpy(max_rel_err, d, sizeof(double), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  return (int)e;
+}
 
 extern "C" int tb_fp64_peak(int32_t which, int32_t iters, double* tflops, float* ms_out) {
   if (!tflops) return TB_ERR_NULL;

@@ -13,6 +13,7 @@
 #include <tuple>
 
 #include "tb_common.cuh"
+#include "tb_blocks.cuh"
 
 std::atomic<int64_t> g_tb_launches{0};
 
@@ -369,7 +370,7 @@ extern "C" int tb_plan_create(const tb_topology* topo, tb_plan** plan_out) {
       const int e = order[q], r = irow[e], c = icol[e];
       p->b16_ptr[2 * (c / 16) + sub(e) + 1]++;
       const int rr = r % 16, cc = c % 16;
-      p->b16_pos[q] = ((r / 16 - c / 16) << 8) | (((((rr >> 3) << 2) + (cc >> 2)) << 5) + ((rr & 7) << 2) + (cc & 3));
+      p->b16_pos[q] = ((r / 16 - c / 16) << 8) | tbblk::b16_off(rr, cc);   // tb_blocks.cuh: swizzled fragment layout
       for (int64_t k = p->ent_ptr[e]; k < p->ent_ptr[e + 1]; ++k) {
         const int loc = p->ctr_local[k], la = loc / (2 * d), lb = loc % (2 * d);
         const int A = la / d, i = la % d, B = lb / d, j = lb % d;

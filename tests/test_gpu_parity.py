@@ -330,14 +330,50 @@ def test_config5_cube12_tiled_vs_oracle():
 
 
 def test_band_kernels_agree_bitwise_across_batch_sizes():
-    """The band path picks a two-warp-per-system kernel for small batches and a warp-per-system kernel for large ones
-    (tb_band.cu: launch_band); both sum in the same order, so a system's result does not depend on the batch it is in
-    (bit-identical per truss across GPU counts / shard sizes)."""
+    """The band path picks a three-warp-per-system kernel while the batch fits in one wave and a two-warp-per-system
+    kernel beyond (tb_band.cu: launch_band); both sum in the same order, so a system's result does not depend on the
+    batch it is in (bit-identical per truss across GPU counts / shard sizes)."""
     t = Truss(3).LoadFromJSON(f"{H.GOLDEN}/ref_data/bar-942_input_0.json")
     rng = np.random.default_rng(3)
     N = t.nJoint * 3
     F = rng.uniform(-10, 10, size=(4096, N))
-    big = SolveLoadCases(t, F)                      # 4096 systems: warp-per-system kernel, chunked host pipeline
-    small = SolveLoadCases(t, F[1000:1032])         # 32 systems: two-warp kernel
+    big = SolveLoadCases(t, F)                      # 4096 systems: two-warp kernel, chunked host pipeline
+    small = SolveLoadCases(t, F[1000:1032])         # 32 systems: three-warp kernel
     for k in H.FIELDS:
         assert np.array_equal(big[k][1000:1032], small[k]), k
+
+
+_BAND_VARIANT_SCRIPT = """
+import sys, numpy as np
+sys.path.insert(0, {root!r})
+from python_stable_3d_truss_analysis_b200.truss import Truss
+from python_stable_3d_truss_analysis_b200.batch import SolveLoadCases
+t = Truss(3).LoadFromJSON({inp!r})
+F = np.random.default_rng(5).uniform(-10, 10, size=(40, t.nJoint * 3))
+out = SolveLoadCases(t, F)
+np.savez({dst!r}, u=out["u"], ext=out["ext"], axial=out["axial"])
+"""
+
+
+def test_band_kernel_variants_agree_bitwise(tmp_path):
+    """k_band1 (one warp per system), k_band2 (two) and k_band3 (three) are the same arithmetic in the same order:
+    forced one after the other through TB_BAND_WARPS (read once per process, hence the subprocesses) they return the
+    same bits."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = {}
+    for w in (1, 2, 3):
+        dst = str(tmp_path / f"w{w}.npz")
+        code = _BAND_VARIANT_SCRIPT.format(root=root, inp=f"{H.GOLDEN}/ref_data/bar-942_input_0.json", dst=dst)
+        subprocess.run([sys.executable, "-c", code], check=True, env=dict(os.environ, TB_BAND_WARPS=str(w)), timeout=600)
+        res[w] = np.load(dst)
+    for w in (2, 3):
+        for k in ("u", "ext", "axial"):
+            assert np.array_equal(res[1][k], res[w][k]), (w, k)
+
+
+def test_pivot_rsqrt_accuracy():
+    """The 16x16 pivot blocks take 1/sqrt(pivot) from the hardware seed plus one third-order correction
+    (tb_blocks.cuh: rsqrt_pos); it must stay within 2 ulp of 1/sqrt(d) over the whole accepted pivot range."""
+    from python_stable_3d_truss_analysis_b200 import _lib
+    assert _lib.rsqrt_probe(1 << 22) <= 4.5e-16

@@ -12,7 +12,7 @@ from python_stable_3d_truss_analysis_b200.truss import Truss
 dev = torch.device("cuda:0"); td = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
 t = Truss(3).LoadFromJSON(os.path.join(ROOT, "tests/golden/ref_data/bar-942_input_0.json"))
 xyz, sup, conn, aed, force = t._pack(); plan = t._get_plan()
-names = ["F: prefetch + diagonal products", "F: stage K, P = K - S", "F: 16x16 factor + W", "F: y_c, W store", "wait X (for warp T)",
+names = ["F: diagonal products (d=1)", "F: P = K - S", "F: 16x16 factor + W", "-", "wait X",
          "trsm rb=1", "wait Y (for warp T)", "back substitution (all columns)"]
 L = _lib.lib()
 for B in [int(x) for x in sys.argv[1:]] or (1, 148, 1024):
