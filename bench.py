@@ -260,6 +260,31 @@ def run_gpu(args):
     ms_per_step = dev_ms / args.steps
     value = B * world / (ms_per_step * 1e-3)
 
+    # ---- same 1024 load cases with the factorisation shared (SURVEY.md 8d asks for both timings): K assembled and
+    # factorised once, 1024 substitutions + recoveries (tb_solve_loadcases).  Reported beside the headline, never as it.
+    shared = None
+    if plan.path == 2:
+        flat2 = torch.empty_like(flat)
+        out2 = {"u": flat2[:B * N].view(B, N), "ext": flat2[B * N:2 * B * N].view(B, N), "axial": flat2[2 * B * N:].view(B, M),
+                "weight": torch.empty(B, dtype=torch.float64, device=dev), "info": torch.empty(B, dtype=torch.int32, device=dev)}
+        for _ in range(3):
+            plan.solve_device(B, d_xyz, d_F, aed=d_aed, out=out2, stream=stream, shared_factor=True)
+        torch.cuda.synchronize()
+        worst = max(float((out2[k] - out[k]).abs().max() / out[k].abs().max()) for k in ("u", "ext", "axial"))
+        assert worst <= 1e-10, f"shared-factor results differ from the independent ones: {worst:.3e}"
+        ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        for e0, e1 in ev2:
+            flush.zero_()
+            e0.record(stream)
+            plan.solve_device(B, d_xyz, d_F, aed=d_aed, out=out2, stream=stream, shared_factor=True)
+            e1.record(stream)
+        torch.cuda.synchronize()
+        ms2 = sum(e0.elapsed_time(e1) for e0, e1 in ev2) / args.steps
+        shared = {"value": B / (ms2 * 1e-3), "unit": "load cases/s per GPU", "ms_per_step": ms2,
+                  "max_rel_diff_vs_independent": worst,
+                  "what": "tb_solve_loadcases: one assembly + one factorisation (k_prep, k_band3 on one system), "
+                          "k_band_subst (a warp per load case against the shared factor), k_recover"}
+
     # ---- end to end through the C ABI host entry point: pinned host buffers, H2D + D2H inside the timed region
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()  # noqa: E731
     h_xyz, h_aed, h_F = pin(xyz), pin(aed), pin(F)
@@ -358,6 +383,7 @@ def run_gpu(args):
         "roofline_stages": stages,
         "kernels": kernels,
         "cpu_baseline": cpu,
+        "shared_k": shared,
         "wall_s_timed_region": wall,
     }
     sys.stdout.flush()

@@ -164,6 +164,14 @@ typedef struct {
 int tb_solve(tb_plan* plan, const tb_batch_in* in, const tb_batch_out* out, void* cuda_stream);
 int tb_solve_host(tb_plan* plan, const tb_batch_in* in, const tb_batch_out* out);
 
+/* B load cases of ONE truss: `for f in F: truss.SetForces(f); truss.Solve()` (truss.py:329-364 called B times on
+ * the same joints and members).  joint_stride and member_stride (or gene_stride) must be 0; only `force` varies.
+ * On the band path the stiffness matrix is assembled and factorised ONCE and every load case runs the two triangular
+ * substitutions and the recovery against that factor; plans on the other paths factorise per system as tb_solve does.
+ * tb_solve on the same arguments factorises every system independently (the bench's headline mode). */
+int tb_solve_loadcases(tb_plan* plan, const tb_batch_in* in, const tb_batch_out* out, void* cuda_stream);
+int tb_solve_loadcases_host(tb_plan* plan, const tb_batch_in* in, const tb_batch_out* out);
+
 /* GA.GetFitness for B genes (ga.py:139-149); `full` may be NULL or receive the full results. */
 int tb_fitness(tb_plan* plan, const tb_batch_in* in, double allow_stress, double allow_displace,
                const tb_fit_out* fit, const tb_batch_out* full, void* cuda_stream);

@@ -98,7 +98,7 @@ class TbRaggedIn(C.Structure):
 
 
 EXPORTS = ["tb_plan_create", "tb_plan_destroy", "tb_plan_query", "tb_plan_set_path", "tb_plan_get_maps",
-           "tb_plan_get_scatter", "tb_solve", "tb_solve_host", "tb_fitness", "tb_fitness_host", "tb_solve_ragged",
+           "tb_plan_get_scatter", "tb_solve", "tb_solve_host", "tb_solve_loadcases", "tb_solve_loadcases_host", "tb_fitness", "tb_fitness_host", "tb_solve_ragged",
            "tb_solve_ragged_host", "tb_pinned_alloc", "tb_pinned_free", "tb_small_path_limits", "tb_fp64_peak", "tb_rsqrt_probe", "tb_profile_enable", "tb_profile_read",
            "tb_launch_count", "tb_strerror", "tb_version"]
 
@@ -125,6 +125,8 @@ def lib():
     L.tb_plan_get_scatter.argtypes = [vp, vp, vp, vp, vp, vp]
     L.tb_solve.argtypes = [vp, C.POINTER(TbBatchIn), C.POINTER(TbBatchOut), vp]
     L.tb_solve_host.argtypes = [vp, C.POINTER(TbBatchIn), C.POINTER(TbBatchOut)]
+    L.tb_solve_loadcases.argtypes = [vp, C.POINTER(TbBatchIn), C.POINTER(TbBatchOut), vp]
+    L.tb_solve_loadcases_host.argtypes = [vp, C.POINTER(TbBatchIn), C.POINTER(TbBatchOut)]
     L.tb_fitness.argtypes = [vp, C.POINTER(TbBatchIn), dbl, dbl, C.POINTER(TbFitOut), C.POINTER(TbBatchOut), vp]
     L.tb_fitness_host.argtypes = [vp, C.POINTER(TbBatchIn), dbl, dbl, C.POINTER(TbFitOut), C.POINTER(TbBatchOut)]
     L.tb_solve_ragged.argtypes = [C.POINTER(TbRaggedIn), C.POINTER(TbBatchOut), vp]
@@ -207,7 +209,7 @@ def rsqrt_probe(n: int = 1 << 22) -> float:
     return e.value
 
 
-PROFILE_SLOTS = ("geom", "assemble", "chol", "recover", "small")
+PROFILE_SLOTS = ("geom", "assemble", "chol", "recover", "small", "subst")
 
 
 def profile_enable(on: bool):
@@ -309,8 +311,9 @@ class Plan:
         return bi
 
     def solve_host(self, B, xyz, force, aed=None, gene=None, type_table=None, want=("u", "ext", "axial", "weight"),
-                   out=None):
-        """Truss.Solve() for B systems, host (numpy) buffers; H2D/D2H happen inside the library."""
+                   out=None, shared_factor=False):
+        """Truss.Solve() for B systems, host (numpy) buffers; H2D/D2H happen inside the library.
+        ``shared_factor``: the B systems are load cases of one truss (tb_solve_loadcases_host)."""
         keep = []
         bi = self._batch_in(B, xyz, aed, gene, type_table, force, keep)
         out = {} if out is None else out
@@ -322,7 +325,8 @@ class Plan:
             out["info"] = np.empty(B, np.int32)
         bo = TbBatchOut(_ptr(out.get("u")), _ptr(out.get("ext")), _ptr(out.get("axial")), _ptr(out.get("weight")),
                         _ptr(out["info"]))
-        check(lib().tb_solve_host(self._h, C.byref(bi), C.byref(bo)))
+        fn = lib().tb_solve_loadcases_host if shared_factor else lib().tb_solve_host
+        check(fn(self._h, C.byref(bi), C.byref(bo)))
         return out
 
     def fitness_host(self, B, xyz, force, gene, type_table, allow_stress, allow_displace, aed=None, full=False,
@@ -342,8 +346,10 @@ class Plan:
         check(lib().tb_fitness_host(self._h, C.byref(bi), float(allow_stress), float(allow_displace), C.byref(fo), bo))
         return out
 
-    def solve_device(self, B, xyz, force, aed=None, gene=None, type_table=None, out=None, stream=None):
-        """Device pointers (torch CUDA tensors); enqueues on ``stream`` (a torch stream or None = current)."""
+    def solve_device(self, B, xyz, force, aed=None, gene=None, type_table=None, out=None, stream=None,
+                     shared_factor=False):
+        """Device pointers (torch CUDA tensors); enqueues on ``stream`` (a torch stream or None = current).
+        ``shared_factor``: the B systems are load cases of one truss (tb_solve_loadcases)."""
         import torch
 
         keep = []
@@ -351,7 +357,8 @@ class Plan:
         st = torch.cuda.current_stream() if stream is None else stream
         bo = TbBatchOut(_ptr(out.get("u")), _ptr(out.get("ext")), _ptr(out.get("axial")), _ptr(out.get("weight")),
                         _ptr(out.get("info")))
-        check(lib().tb_solve(self._h, C.byref(bi), C.byref(bo), C.c_void_p(st.cuda_stream)))
+        fn = lib().tb_solve_loadcases if shared_factor else lib().tb_solve
+        check(fn(self._h, C.byref(bi), C.byref(bo), C.c_void_p(st.cuda_stream)))
         return out
 
     def fitness_device(self, B, xyz, force, gene, type_table, allow_stress, allow_displace, out, aed=None, stream=None):

@@ -34,12 +34,16 @@ def _check_infos(info, raise_on_error):
             raise_for_info(int(info[bad[0]]))
 
 
-def SolveLoadCases(truss: Truss, forces, raise_on_error=True):
-    """One truss under B load cases.  ``forces`` is [B, N] dense (index jointID*dim + axis)."""
+def SolveLoadCases(truss: Truss, forces, raise_on_error=True, independent=False):
+    """One truss under B load cases.  ``forces`` is [B, N] dense (index jointID*dim + axis).
+
+    Equivalent to ``for f in forces: truss.SetForces(f); truss.Solve()`` (truss.py:329-364).  The stiffness matrix is the
+    same for every load case, so on the band path it is assembled and factorised once (tb_solve_loadcases_host);
+    ``independent=True`` factorises every system on its own, as a batch of unrelated trusses would (tb_solve_host)."""
     xyz, support, conn, aed, _ = truss._pack()
     forces = np.ascontiguousarray(forces, dtype=np.float64).reshape(-1, truss.nJoint * truss.dim)
     plan = truss._get_plan(support, conn)
-    out = plan.solve_host(forces.shape[0], xyz, forces, aed=aed)
+    out = plan.solve_host(forces.shape[0], xyz, forces, aed=aed, shared_factor=not independent)
     _check_infos(out["info"], raise_on_error)
     return out
 

@@ -40,7 +40,7 @@ int check_batch_in(const tb_plan* p, const tb_batch_in* in) {
 
 // Systems [b0, b0 + nb) of a uniform batch on stream st; the blocked pipelines use the workspace slice `ws`.
 int run_plan_range(tb_plan* p, const tb_batch_in* in, const tb_batch_out* out, const tb_fit_out* fit, double allow_s,
-                   double allow_d, cudaStream_t st, int b0, int nb, void* ws) {
+                   double allow_d, cudaStream_t st, int b0, int nb, void* ws, int shared_k = 0) {
   const int fitness_mode = fit ? 1 : 0;
   int32_t* info = fit && fit->info ? fit->info : out->info;
   if (p->path == 0) {
@@ -139,6 +139,7 @@ int run_plan_range(tb_plan* p, const tb_batch_in* in, const tb_batch_out* out, c
   a.allow_displace = allow_d;
   a.fitness_mode = fitness_mode;
   a.plan_stable = p->stable;
+  a.shared_k = shared_k;
   return tb_launch_large(a, p->num_sm, st, p->path);
 }
 
@@ -162,7 +163,7 @@ int ensure_ws(tb_plan* p, size_t need, cudaStream_t st) {
 }
 
 int run_plan(tb_plan* p, const tb_batch_in* in, const tb_batch_out* out, const tb_fit_out* fit, double allow_s,
-             double allow_d, cudaStream_t st) {
+             double allow_d, cudaStream_t st, int shared_k = 0) {
   static const tb_batch_out none = {nullptr, nullptr, nullptr, nullptr, nullptr};
   if (!out) out = &none;
   if (p->path == 0) {
@@ -175,7 +176,7 @@ int run_plan(tb_plan* p, const tb_batch_in* in, const tb_batch_out* out, const t
     int rc = ensure_ws(p, plan_ws_bytes(p, chunk), st);
     if (rc) return rc;
     for (int b0 = 0; b0 < in->batch; b0 += chunk) {
-      rc = run_plan_range(p, in, out, fit, allow_s, allow_d, st, b0, std::min(chunk, in->batch - b0), p->ws);
+      rc = run_plan_range(p, in, out, fit, allow_s, allow_d, st, b0, std::min(chunk, in->batch - b0), p->ws, shared_k);
       if (rc) return rc;
     }
   }
@@ -246,7 +247,7 @@ cudaEvent_t host_event() {
 int stride_ok(int64_t stride, int64_t row) { return stride == 0 || stride == row; }
 
 int run_plan_host(tb_plan* p, const tb_batch_in* in, const tb_batch_out* out, const tb_fit_out* fit, double allow_s,
-                  double allow_d) {
+                  double allow_d, int shared_k = 0) {
   int rc = check_batch_in(p, in);
   if (rc) return rc;
   const int B = in->batch;
@@ -349,10 +350,10 @@ int run_plan_host(tb_plan* p, const tb_batch_in* in, const tb_batch_out* out, co
       if (!sm_) TB_CUDA(cudaMemcpyAsync(dgene + (size_t)b0 * rowM, in->gene + (size_t)b0 * rowM, (size_t)nb * rowM * 4, cudaMemcpyHostToDevice, sj));
     }
     if (nch == 1 && p->path != 0) {
-      rc = run_plan(p, &din, &dout, fit ? &dfit : nullptr, allow_s, allow_d, sj);   // handles the workspace cap itself
+      rc = run_plan(p, &din, &dout, fit ? &dfit : nullptr, allow_s, allow_d, sj, shared_k);   // handles the workspace cap itself
     } else {
       void* ws = p->path != 0 ? (void*)((char*)p->ws + ((per_sys * (size_t)csz + 4095) & ~(size_t)4095) * j) : nullptr;
-      rc = run_plan_range(p, &din, &dout, fit ? &dfit : nullptr, allow_s, allow_d, sj, b0, nb, ws);
+      rc = run_plan_range(p, &din, &dout, fit ? &dfit : nullptr, allow_s, allow_d, sj, b0, nb, ws, shared_k);
     }
     if (rc) return rc;
     if (out->u) TB_CUDA(cudaMemcpyAsync(out->u + (size_t)b0 * rowN, dout.u + (size_t)b0 * rowN, (size_t)nb * rowN * 8, cudaMemcpyDeviceToHost, sj));
@@ -420,6 +421,33 @@ extern "C" int tb_solve(tb_plan* plan, const tb_batch_in* in, const tb_batch_out
 
 extern "C" int tb_solve_host(tb_plan* plan, const tb_batch_in* in, const tb_batch_out* out) {
   return run_plan_host(plan, in, out, nullptr, 0.0, 0.0);
+}
+
+namespace {
+// load cases of one truss: geometry and member properties must be shared by the whole batch
+int check_loadcases(const tb_batch_in* in) {
+  if (in->joint_stride != 0) return TB_ERR_SIZE;
+  if (in->member_aed ? in->member_stride != 0 : in->gene_stride != 0) return TB_ERR_SIZE;
+  return TB_OK;
+}
+}  // namespace
+
+extern "C" int tb_solve_loadcases(tb_plan* plan, const tb_batch_in* in, const tb_batch_out* out, void* cuda_stream) {
+  int rc = check_batch_in(plan, in);
+  if (rc) return rc;
+  if (in->batch == 0) return TB_OK;
+  rc = check_loadcases(in);
+  if (rc) return rc;
+  return run_plan(plan, in, out, nullptr, 0.0, 0.0, (cudaStream_t)cuda_stream, 1);
+}
+
+extern "C" int tb_solve_loadcases_host(tb_plan* plan, const tb_batch_in* in, const tb_batch_out* out) {
+  int rc = check_batch_in(plan, in);
+  if (rc) return rc;
+  if (in->batch == 0) return TB_OK;
+  rc = check_loadcases(in);
+  if (rc) return rc;
+  return run_plan_host(plan, in, out, nullptr, 0.0, 0.0, 1);
 }
 
 extern "C" int tb_fitness(tb_plan* plan, const tb_batch_in* in, double allow_stress, double allow_displace,

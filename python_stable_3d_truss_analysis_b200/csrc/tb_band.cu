@@ -1414,6 +1414,209 @@ __global__ void __maxnreg__(96) k_band3(const LargeArgs a) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Load cases of one truss (LargeArgs::shared_k): the stiffness matrix is assembled and factorised once (system 0, by the
+// kernels above) and every load case only runs the two substitutions against that factor, one warp per load case:
+//   forward (right-looking)   y_c = W_c t_c,   t_{c+rb} -= L(c+rb,c) y_c        t = the load vector at the free DOFs
+//   backward                  u_c = W_c^T (y_c - sum_rb L(c+rb,c)^T u_{c+rb})
+// Both sweeps stream the column chunks [W_c | L(c+1,c) .. L(c+NB,c)] of the shared factor from L2 through a two-buffer
+// cp.async pipeline.  Replaces the 1024 identical factorisations a loop over Truss.Solve() would do.
+// ------------------------------------------------------------------------------------------------------------
+template <int NB>
+struct SubstCfg {
+  static constexpr int DOUBLES = 2 * (NB + 1) * BE + (NB + 1) * BT + BT;   // two chunk buffers | t / u ring | block rhs
+};
+
+template <int NB, int NW>
+__global__ void __launch_bounds__(32 * NW) k_band_subst(const LargeArgs a) {
+  extern __shared__ __align__(16) double sm_all[];
+  double* sm = sm_all + (threadIdx.x >> 5) * SubstCfg<NB>::DOUBLES;
+  double* sBuf = sm;
+  double* sY = sBuf + 2 * (NB + 1) * BE;       // ring: block c of t (then y), later of u, in slot c mod (NB+1)
+  double* sT = sY + (NB + 1) * BT;
+  const int lane = threadIdx.x & 31, lsw = lane_swz(lane);
+  const int ncol = a.nb16;
+  const int qr = lane >> 2, qc = lane & 3;
+  const int st0 = a.status[0];                 // outcome of the shared factorisation
+  const double* Lb = a.L;                      // factor of system 0
+
+  for (int b = blockIdx.x * NW + (threadIdx.x >> 5); b < a.batch; b += gridDim.x * NW) {
+    if (b > 0 && lane == 0) a.status[b] = st0;
+    if (st0 != 0) continue;
+    const double* fsys = a.force + b * a.force_stride;
+    double* ysys = a.y + (int64_t)b * a.n_pad;
+    auto fetch = [&](int c) {
+      const unsigned nz = (unsigned)ldg_i32(a.b16_nz + c) | 1u;     // bit 0: W_c
+      const double* src = Lb + (int64_t)c * (NB + 1) * BE;
+      double* dst = sBuf + (c & 1) * (NB + 1) * BE;
+#pragma unroll
+      for (int e = 0; e <= NB; ++e)
+        if ((nz >> e) & 1u) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) cp_async16(dst + e * BE + (lane + 32 * i) * 2, src + e * BE + (lane + 32 * i) * 2);
+        }
+      cp_async_commit();
+    };
+    auto load_rhs = [&](int c, int slot) {     // t_c = f at the free DOFs of block c (0 on the padding)
+      if (lane < BT) {
+        const int row = c * BT + lane;
+        sY[slot * BT + lane] = (c < ncol && row < a.n) ? __ldg(fsys + __ldg(a.free_idx + row)) : 0.0;
+      }
+    };
+    __syncwarp();
+    fetch(0);
+#pragma unroll
+    for (int e = 0; e < NB; ++e) load_rhs(e, e);
+    int slot = 0;                              // c mod (NB+1)
+    // ---------------- forward sweep
+    for (int c = 0; c < ncol; ++c) {
+      {
+        int sl = slot + NB;
+        if (sl > NB) sl -= NB + 1;
+        load_rhs(c + NB, sl);                  // block c+NB enters the window
+      }
+      if (c + 1 < ncol) {
+        fetch(c + 1);
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
+      }
+      __syncwarp();
+      const unsigned nz = (unsigned)ldg_i32(a.b16_nz + c);
+      const double* buf = sBuf + (c & 1) * (NB + 1) * BE;
+      double yp[2] = {0.0, 0.0};               // y_c = W_c t_c
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const double t4 = sY[slot * BT + ks * 4 + qc];
+        yp[0] = fma(buf[fo(ks, lsw)], t4, yp[0]);
+        yp[1] = fma(buf[fo(4 + ks, lsw)], t4, yp[1]);
+      }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        yp[h] += __shfl_xor_sync(0xffffffffu, yp[h], 1);
+        yp[h] += __shfl_xor_sync(0xffffffffu, yp[h], 2);
+      }
+      __syncwarp();
+      if (qc == 0) {
+        sT[qr] = yp[0];
+        sT[8 + qr] = yp[1];
+        ysys[c * BT + qr] = yp[0];
+        ysys[c * BT + 8 + qr] = yp[1];
+      }
+      __syncwarp();
+#pragma unroll
+      for (int rb = 1; rb <= NB; ++rb) {       // t_{c+rb} -= L(c+rb,c) y_c
+        if (!((nz >> rb) & 1u)) continue;
+        const double* blk = buf + rb * BE;
+        double tq[2] = {0.0, 0.0};
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const double y4 = sT[ks * 4 + qc];
+          tq[0] = fma(blk[fo(ks, lsw)], y4, tq[0]);
+          tq[1] = fma(blk[fo(4 + ks, lsw)], y4, tq[1]);
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          tq[h] += __shfl_xor_sync(0xffffffffu, tq[h], 1);
+          tq[h] += __shfl_xor_sync(0xffffffffu, tq[h], 2);
+        }
+        int sl = slot + rb;
+        if (sl > NB) sl -= NB + 1;
+        if (qc == 0) {
+          sY[sl * BT + qr] -= tq[0];
+          sY[sl * BT + 8 + qr] -= tq[1];
+        }
+      }
+      __syncwarp();
+      slot = (slot == NB) ? 0 : slot + 1;
+    }
+    // ---------------- backward sweep (the ring now collects u; block c in slot c mod (NB+1))
+    fetch(ncol - 1);
+    for (int c = ncol - 1; c >= 0; --c) {
+      slot = (slot == 0) ? NB : slot - 1;
+      double yc[4] = {0.0, 0.0, 0.0, 0.0};
+      if (qr == 0) {
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) yc[ks] = __ldcg(ysys + c * BT + ks * 4 + qc);
+      }
+      if (c > 0) {
+        fetch(c - 1);
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
+      }
+      __syncwarp();
+      const unsigned nz = (unsigned)ldg_i32(a.b16_nz + c);
+      const double* buf = sBuf + (c & 1) * (NB + 1) * BE;
+      double tp[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+      for (int rb = 1; rb <= NB; ++rb) {
+        if (!((nz >> rb) & 1u)) continue;
+        int us = slot + rb;
+        if (us > NB) us -= NB + 1;
+        const double* uv = sY + us * BT;
+        const double* blk = buf + rb * BE;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const double ur = uv[h * 8 + qr];
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) tp[ks] = fma(blk[fo(h * 4 + ks, lsw)], ur, tp[ks]);
+        }
+      }
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        tp[ks] += __shfl_xor_sync(0xffffffffu, tp[ks], 4);
+        tp[ks] += __shfl_xor_sync(0xffffffffu, tp[ks], 8);
+        tp[ks] += __shfl_xor_sync(0xffffffffu, tp[ks], 16);
+      }
+      if (qr == 0) {
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) sT[ks * 4 + qc] = yc[ks] - tp[ks];
+      }
+      __syncwarp();
+      double up[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const double rr = sT[h * 8 + qr];
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) up[ks] = fma(buf[fo(h * 4 + ks, lsw)], rr, up[ks]);
+      }
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        up[ks] += __shfl_xor_sync(0xffffffffu, up[ks], 4);
+        up[ks] += __shfl_xor_sync(0xffffffffu, up[ks], 8);
+        up[ks] += __shfl_xor_sync(0xffffffffu, up[ks], 16);
+      }
+      if (qr == 0) {
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          sY[slot * BT + ks * 4 + qc] = up[ks];
+          ysys[c * BT + ks * 4 + qc] = up[ks];
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+template <int NB>
+int launch_subst(const LargeArgs& a, int num_sm, cudaStream_t st) {
+  constexpr int NW = 4;
+  const int smem = NW * SubstCfg<NB>::DOUBLES * 8;
+  static bool set = false;
+  if (!set) {
+    cudaError_t e = cudaFuncSetAttribute(k_band_subst<NB, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return (int)e;
+    set = true;
+  }
+  // spread the load cases over all SMs first: one warp per CTA slot until every SM has one
+  const int grid = (a.batch + NW - 1) / NW;
+  tb_prof_begin(TB_PROF_SUBST, st);
+  k_band_subst<NB, NW><<<grid, 32 * NW, smem, st>>>(a);
+  tb_prof_end(TB_PROF_SUBST, st);
+  return (int)cudaGetLastError();
+}
+
 template <int NB>
 int launch_band(const LargeArgs& a, int num_sm, cudaStream_t st) {
   // one warp per system when the batch alone fills the GPU (fewest instructions per system), else several warps per
@@ -1465,6 +1668,20 @@ int launch_band(const LargeArgs& a, int num_sm, cudaStream_t st) {
 int tb_band_smem_bytes(int NB) {
   const int ring = NB * (NB + 1) / 2, buf = ring > 2 * (NB + 1) ? ring : 2 * (NB + 1);
   return (buf * BE + BE + (NB + 1) * BT + BT + 32 + 8) * 8;
+}
+
+int tb_launch_band_subst(const LargeArgs& a, int num_sm, cudaStream_t st) {
+  switch (a.NB) {
+    case 1: return launch_subst<1>(a, num_sm, st);
+    case 2: return launch_subst<2>(a, num_sm, st);
+    case 3: return launch_subst<3>(a, num_sm, st);
+    case 4: return launch_subst<4>(a, num_sm, st);
+    case 5: return launch_subst<5>(a, num_sm, st);
+    case 6: return launch_subst<6>(a, num_sm, st);
+    case 7: return launch_subst<7>(a, num_sm, st);
+    case 8: return launch_subst<8>(a, num_sm, st);
+    default: return TB_ERR_TOO_LARGE;
+  }
 }
 
 int tb_launch_band_chol(const LargeArgs& a, int num_sm, cudaStream_t st) {

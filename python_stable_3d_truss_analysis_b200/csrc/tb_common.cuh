@@ -31,7 +31,7 @@ extern std::atomic<int64_t> g_tb_launches;
 inline void tb_count_launch(int n = 1) { g_tb_launches.fetch_add(n, std::memory_order_relaxed); }
 
 // optional per-kernel CUDA-event timing (bench.py's roofline line); slots:
-enum : int { TB_PROF_GEOM = 0, TB_PROF_ASSEMBLE = 1, TB_PROF_CHOL = 2, TB_PROF_RECOVER = 3, TB_PROF_SMALL = 4, TB_PROF_SLOTS = 8 };
+enum : int { TB_PROF_GEOM = 0, TB_PROF_ASSEMBLE = 1, TB_PROF_CHOL = 2, TB_PROF_RECOVER = 3, TB_PROF_SMALL = 4, TB_PROF_SUBST = 5, TB_PROF_SLOTS = 8 };
 bool tb_prof_on();
 void tb_prof_begin(int slot, cudaStream_t st);
 void tb_prof_end(int slot, cudaStream_t st);
@@ -192,6 +192,7 @@ struct LargeArgs {
   double allow_stress, allow_displace;
   int fitness_mode;
   int plan_stable;
+  int shared_k;     // band path: every system of the batch has the stiffness matrix of system 0 (load cases of one truss)
 };
 
 // launchers (return cudaError_t as int)
@@ -203,6 +204,7 @@ int tb_launch_large(const LargeArgs& a, int num_sm, cudaStream_t st, int path);
 size_t tb_large_workspace_bytes(int batch, int dim, int M, int n_pad, int64_t nnz, int path, int nb16, int NB);
 void tb_large_carve(LargeArgs& a, void* ws, int path);
 int tb_launch_band_chol(const LargeArgs& a, int num_sm, cudaStream_t st);
+int tb_launch_band_subst(const LargeArgs& a, int num_sm, cudaStream_t st);   // load cases against the factor of system 0
 int tb_band_smem_bytes(int NB);
 
 // fragment-major offset of element (r, c) inside one 64x64 tile:

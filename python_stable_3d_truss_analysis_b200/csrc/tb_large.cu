@@ -981,6 +981,10 @@ int tb_launch_large(const LargeArgs& a, int num_sm, cudaStream_t st, int path) {
   const size_t prep_smem = (size_t)a.M * (a.dim * (a.dim + 1) / 2) * 8, rec_smem = (size_t)a.M * (1 + a.dim) * 8;
   static const bool no_prep = [] { const char* s = getenv("TB_NO_PREP"); return s && s[0] == '1'; }();
   const bool prep = fused && !no_prep && prep_smem <= 96 * 1024 && rec_smem <= 96 * 1024;
+  // load cases of one truss (shared_k): assembly and factorisation run for system 0 only
+  const bool shared = a.shared_k && path == 2 && prep && a.batch > 1;
+  LargeArgs a1 = a;
+  a1.batch = 1;
   if (prep) {
     auto kern = a.dim == 3 ? k_prep<3> : k_prep<2>;
     static size_t prep_set[2] = {0, 0};        // largest dynamic shared-memory size already granted, per instantiation
@@ -991,7 +995,8 @@ int tb_launch_large(const LargeArgs& a, int num_sm, cudaStream_t st, int path) {
     }
     int grid = a.batch < num_sm * 8 ? a.batch : num_sm * 8;
     tb_prof_begin(TB_PROF_ASSEMBLE, st);
-    kern<<<grid, 256, prep_smem, st>>>(a);
+    if (shared) kern<<<1, 256, prep_smem, st>>>(a1);
+    else kern<<<grid, 256, prep_smem, st>>>(a);
     tb_prof_end(TB_PROF_ASSEMBLE, st);
   } else {
     {
@@ -1018,8 +1023,12 @@ int tb_launch_large(const LargeArgs& a, int num_sm, cudaStream_t st, int path) {
     }
   }
   if (path == 2) {
-    int rc = tb_launch_band_chol(a, num_sm, st);
+    int rc = tb_launch_band_chol(shared ? a1 : a, num_sm, st);
     if (rc) return rc;
+    if (shared) {                              // every load case against the factor of system 0
+      rc = tb_launch_band_subst(a, num_sm, st);
+      if (rc) return rc;
+    }
   } else {
     auto kern = fused ? k_chol<true> : k_chol<false>;
     static int chol_per_sm[2] = {0, 0};
@@ -1057,6 +1066,6 @@ int tb_launch_large(const LargeArgs& a, int num_sm, cudaStream_t st, int path) {
     }
     tb_prof_end(TB_PROF_RECOVER, st);
   }
-  tb_count_launch(prep ? 4 : 5);
+  tb_count_launch((prep ? 4 : 5) + (shared ? 1 : 0));
   return (int)cudaGetLastError();
 }

@@ -133,13 +133,13 @@ def test_ga_class_uses_batched_fitness():
 def test_load_cases_bar942_vs_live():
     z = np.load(f"{H.GOLDEN}/live_loadcases_bar942.npz")
     t = Truss(3).LoadFromJSON(f"{H.GOLDEN}/ref_data/bar-942_input_0.json")
-    for path in (1, 2):
+    for path, independent in ((1, True), (2, True), (2, False)):   # (2, False): one factorisation, 16 substitutions
         t._get_plan().set_path(path)
-        out = SolveLoadCases(t, z["F"])
+        out = SolveLoadCases(t, z["F"], independent=independent)
         for b in range(z["F"].shape[0]):
             for k in H.FIELDS:
                 err = orc.normwise_err(out[k][b], z[k][b])
-                assert err <= H.TOL, (path, b, k, err)
+                assert err <= H.TOL, (path, independent, b, k, err)
 
 
 def test_member_type_batch_vs_oracle_bar942():
@@ -224,11 +224,15 @@ def test_full_size_properties_bar942_x1024():
     base = rng.uniform(-10, 10, size=(4, N))
     coef = rng.uniform(-2, 2, size=(1024, 4))
     F = coef @ base
-    out = SolveLoadCases(t, F)
-    again = SolveLoadCases(t, F)
+    out = SolveLoadCases(t, F, independent=True)
+    again = SolveLoadCases(t, F, independent=True)
     for k in H.FIELDS:
         assert np.array_equal(out[k], again[k]), k                       # deterministic
-    basis = SolveLoadCases(t, base)
+    shared = SolveLoadCases(t, F)                                        # one factorisation, 1024 substitutions
+    for k in H.FIELDS:
+        assert orc.normwise_err(shared[k], out[k]) <= 1e-11, k
+        assert np.array_equal(shared[k][100:140], SolveLoadCases(t, F[100:140])[k]), k   # batch-size independent
+    basis = SolveLoadCases(t, base, independent=True)
     mask = t.GetDisplacementUnknownMask()
     for k in ("u", "axial"):
         want = coef @ basis[k]
@@ -337,8 +341,8 @@ def test_band_kernels_agree_bitwise_across_batch_sizes():
     rng = np.random.default_rng(3)
     N = t.nJoint * 3
     F = rng.uniform(-10, 10, size=(4096, N))
-    big = SolveLoadCases(t, F)                      # 4096 systems: two-warp kernel, chunked host pipeline
-    small = SolveLoadCases(t, F[1000:1032])         # 32 systems: three-warp kernel
+    big = SolveLoadCases(t, F, independent=True)                 # 4096 systems: two-warp kernel, chunked host pipeline
+    small = SolveLoadCases(t, F[1000:1032], independent=True)    # 32 systems: three-warp kernel
     for k in H.FIELDS:
         assert np.array_equal(big[k][1000:1032], small[k]), k
 
@@ -350,7 +354,7 @@ from python_stable_3d_truss_analysis_b200.truss import Truss
 from python_stable_3d_truss_analysis_b200.batch import SolveLoadCases
 t = Truss(3).LoadFromJSON({inp!r})
 F = np.random.default_rng(5).uniform(-10, 10, size=(40, t.nJoint * 3))
-out = SolveLoadCases(t, F)
+out = SolveLoadCases(t, F, independent=True)
 np.savez({dst!r}, u=out["u"], ext=out["ext"], axial=out["axial"])
 """
 

@@ -41,6 +41,17 @@ for B in (1, 148, 1024, 8192):
     fl = B * (696**3 / 3 + 2 * 696**2)
     print(f"bar-942 x{B}: best {best:.3f} ms  median {med:.3f} ms  -> {B/best*1e3:.0f} trusses/s, {fl/best/1e9:.2f} TFLOP/s potrf-equivalent; info any={bool(out['info'].any())}")
 
+for B in (1024, 8192):
+    F = td(np.random.default_rng(0).uniform(-10, 10, size=(B, plan.N)))
+    out = {k: torch.empty(B, plan.N if k in ("u", "ext") else plan.M, dtype=torch.float64, device=dev) for k in ("u", "ext", "axial")}
+    out["weight"] = torch.empty(B, dtype=torch.float64, device=dev); out["info"] = torch.empty(B, dtype=torch.int32, device=dev)
+    dx, da = td(xyz), td(aed)
+    _lib.profile_enable(True); _lib.profile_read()
+    best, med = timeit(lambda: plan.solve_device(B, dx, F, aed=da, out=out, shared_factor=True))
+    pr = _lib.profile_read(); _lib.profile_enable(False)
+    print(f"bar-942 x{B} load cases, shared factor: best {best:.3f} ms -> {B/best*1e3:.0f} load cases/s; kernels(ms) " +
+          str({k: round(v[0] / max(v[1], 1), 4) for k, v in pr.items() if v[1]}) + f"; info any={bool(out['info'].any())}")
+
 # config 3: bar-72 x 8192 genes fitness
 import random
 random.seed(0)
