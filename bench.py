@@ -263,7 +263,7 @@ def run_gpu(args):
     # ---- same 1024 load cases with the factorisation shared (SURVEY.md 8d asks for both timings): K assembled and
     # factorised once, 1024 substitutions + recoveries (tb_solve_loadcases).  Reported beside the headline, never as it.
     shared = None
-    if plan.path == 2:
+    if plan.path == 2 and not args.headline_only:
         flat2 = torch.empty_like(flat)
         out2 = {"u": flat2[:B * N].view(B, N), "ext": flat2[B * N:2 * B * N].view(B, N), "axial": flat2[2 * B * N:].view(B, M),
                 "weight": torch.empty(B, dtype=torch.float64, device=dev), "info": torch.empty(B, dtype=torch.int32, device=dev)}
@@ -398,6 +398,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--headline-only", action="store_true",
+                    help="skip the shared-factor extra (profiler runs: the launch list then holds the headline step only)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -1599,20 +1599,216 @@ __global__ void __launch_bounds__(32 * NW) k_band_subst(const LargeArgs a) {
   }
 }
 
+// Eight load cases per warp on the FP64 tensor cores: the substitutions of a tile of load cases are 16x16 by 16x8
+// block products (DMMA m8n8k4, the load cases in the n dimension), so one pass over the factor serves eight load cases
+// (an eighth of k_band_subst's L2 traffic) and a block column costs a few dependent DMMA chains instead of shuffle
+// reductions.  Columns of a DMMA product do not interact: a load case's result does not depend on its tile mates.
+//   forward   Y_c = W_c T_c,  T_{c+rb} += (-L(c+rb,c)) Y_c      T (accumulator layout) lives in registers
+//   backward  R = Y_c + sum_rb (-L(c+rb,c)^T) U_{c+rb},  U_c = W_c^T R
+// Accumulator -> B-operand layout changes go through a 16x8 shared-memory scratch; all of y stays in shared memory.
+template <int NB>
+__global__ void __launch_bounds__(32) k_band_subst8(const LargeArgs a) {
+  extern __shared__ __align__(16) double sm[];
+  constexpr int NBUF = 2;                      // chunk buffers [W_c | L(c+1,c) .. L(c+NB,c)]: one block column in flight (more did not help)
+  double* sBuf = sm;
+  double* sU = sBuf + NBUF * (NB + 1) * BE;       // ring of NB+1 blocks of u as [16][8] arrays (block c in slot c mod (NB+1))
+  double* sX = sU + (NB + 1) * 128;            // [16][8] transpose scratch
+  double* sYall = sX + 128;                    // [ncol][2][32][2] y, accumulator layout
+  const int lane = threadIdx.x, lsw = lane_swz(lane);
+  const int ncol = a.nb16;
+  const int qr = lane >> 2, qc = lane & 3;
+  const int st0 = a.status[0];                 // outcome of the shared factorisation
+  const double* Lb = a.L;
+  int tro[2][4];                               // element (4 ks + qc, 8 mb + qr) of a block: A operand of the transposed block
+#pragma unroll
+  for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) tro[mb][ks] = b16_off(4 * ks + qc, 8 * mb + qr);
+
+  for (int tile = blockIdx.x; tile * 8 < a.batch; tile += gridDim.x) {
+    const int b0 = tile * 8;
+    if (lane < 8 && b0 + lane < a.batch && b0 + lane > 0) a.status[b0 + lane] = st0;
+    if (st0 != 0) continue;
+    const int n0 = b0 + 2 * qc, n1 = n0 + 1;   // this lane's accumulator columns
+    const bool v0 = n0 < a.batch, v1 = n1 < a.batch;
+    const double* f0 = a.force + (int64_t)(v0 ? n0 : b0) * a.force_stride;
+    const double* f1 = a.force + (int64_t)(v1 ? n1 : b0) * a.force_stride;
+    auto fetch = [&](int c) {                  // out of range: an empty group, so the wait counts stay uniform
+      if (c < 0 || c >= ncol) { cp_async_commit(); return; }
+      const unsigned nz = (unsigned)ldg_i32(a.b16_nz + c) | 1u;     // bit 0: W_c
+      const double* src = Lb + (int64_t)c * (NB + 1) * BE;
+      double* dst = sBuf + (c & (NBUF - 1)) * (NB + 1) * BE;
+#pragma unroll
+      for (int e = 0; e <= NB; ++e)
+        if ((nz >> e) & 1u) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) cp_async16(dst + e * BE + (lane + 32 * i) * 2, src + e * BE + (lane + 32 * i) * 2);
+        }
+      cp_async_commit();
+    };
+    auto load_idx = [&](int c, int (&fi)[2]) {      // free-DOF -> DOF index of rows 8 mb + qr of block c (-1 on the padding)
+#pragma unroll
+      for (int mb = 0; mb < 2; ++mb) {
+        const int row = c * BT + 8 * mb + qr;
+        fi[mb] = (c < ncol && row < a.n) ? __ldg(a.free_idx + row) : -1;
+      }
+    };
+    auto load_t = [&](const int (&fi)[2], double (&t)[2][2]) {   // the load vectors at those rows
+#pragma unroll
+      for (int mb = 0; mb < 2; ++mb) {
+        t[mb][0] = (v0 && fi[mb] >= 0) ? __ldg(f0 + fi[mb]) : 0.0;
+        t[mb][1] = (v1 && fi[mb] >= 0) ? __ldg(f1 + fi[mb]) : 0.0;
+      }
+    };
+    auto to_b = [&](const double (&x)[2][2], double (&bfrag)[4]) {   // accumulator layout -> B operand (k = row, n = load case)
+      __syncwarp();
+#pragma unroll
+      for (int mb = 0; mb < 2; ++mb)
+        *reinterpret_cast<double2*>(sX + (8 * mb + qr) * 8 + 2 * qc) = make_double2(x[mb][0], x[mb][1]);
+      __syncwarp();
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) bfrag[ks] = sX[(4 * ks + qc) * 8 + qr];
+    };
+
+    double t[NB + 1][2][2];
+    int fin[2];                                // indices of the block that enters the window next: fetched a column ahead
+#pragma unroll
+    for (int e = 0; e <= NB; ++e) {
+      load_idx(e, fin);
+      load_t(fin, t[e]);
+    }
+    load_idx(NB + 1, fin);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < NBUF - 1; ++i) fetch(i);
+    // ---------------- forward sweep
+    for (int c = 0; c < ncol; ++c) {
+      double tn[2][2];
+      load_t(fin, tn);                         // block c+NB+1 enters the window after this column; its loads fly meanwhile
+      load_idx(c + NB + 2, fin);
+      __syncwarp();                            // every lane is done with the buffer of column c-1, which takes column c+NBUF-1
+      fetch(c + NBUF - 1);
+      cp_async_wait<NBUF - 1>();
+      __syncwarp();
+      const unsigned nz = (unsigned)ldg_i32(a.b16_nz + c);
+      const double* buf = sBuf + (c & (NBUF - 1)) * (NB + 1) * BE;
+      double bf[4];
+      to_b(t[0], bf);
+      double y[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+        for (int mb = 0; mb < 2; ++mb) dmma(y[mb][0], y[mb][1], buf[fo(mb * 4 + ks, lsw)], bf[ks]);
+#pragma unroll
+      for (int mb = 0; mb < 2; ++mb)
+        reinterpret_cast<double2*>(sYall)[(c * 2 + mb) * 32 + lane] = make_double2(y[mb][0], y[mb][1]);
+      double yf[4];
+      to_b(y, yf);
+#pragma unroll
+      for (int rb = 1; rb <= NB; ++rb) {
+        if (!((nz >> rb) & 1u)) continue;
+        const double* blk = buf + rb * BE;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+          for (int mb = 0; mb < 2; ++mb) dmma(t[rb][mb][0], t[rb][mb][1], -blk[fo(mb * 4 + ks, lsw)], yf[ks]);
+      }
+#pragma unroll
+      for (int e = 0; e < NB; ++e)
+#pragma unroll
+        for (int mb = 0; mb < 2; ++mb) { t[e][mb][0] = t[e + 1][mb][0]; t[e][mb][1] = t[e + 1][mb][1]; }
+#pragma unroll
+      for (int mb = 0; mb < 2; ++mb) { t[NB][mb][0] = tn[mb][0]; t[NB][mb][1] = tn[mb][1]; }
+      __syncwarp();
+    }
+    // ---------------- backward sweep
+    cp_async_wait<0>();
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < NBUF - 1; ++i) fetch(ncol - 1 - i);
+    int slot = (ncol - 1) % (NB + 1);
+    for (int c = ncol - 1; c >= 0; --c) {
+      __syncwarp();
+      fetch(c - (NBUF - 1));
+      cp_async_wait<NBUF - 1>();
+      __syncwarp();
+      const unsigned nz = (unsigned)ldg_i32(a.b16_nz + c);
+      const double* buf = sBuf + (c & (NBUF - 1)) * (NB + 1) * BE;
+      double r[2][2][2];                       // two partial sums (odd / even rb) keep the dependent DMMA chains short
+#pragma unroll
+      for (int mb = 0; mb < 2; ++mb) {
+        const double2 v = reinterpret_cast<const double2*>(sYall)[(c * 2 + mb) * 32 + lane];
+        r[0][mb][0] = v.x;
+        r[0][mb][1] = v.y;
+        r[1][mb][0] = r[1][mb][1] = 0.0;
+      }
+#pragma unroll
+      for (int rb = 1; rb <= NB; ++rb) {
+        if (!((nz >> rb) & 1u)) continue;
+        int us = slot + rb;
+        if (us > NB) us -= NB + 1;
+        const double* ub = sU + us * 128;
+        const double* blk = buf + rb * BE;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const double bu = ub[(4 * ks + qc) * 8 + qr];
+#pragma unroll
+          for (int mb = 0; mb < 2; ++mb) dmma(r[rb & 1][mb][0], r[rb & 1][mb][1], -blk[tro[mb][ks]], bu);
+        }
+      }
+      double rs[2][2];
+#pragma unroll
+      for (int mb = 0; mb < 2; ++mb) {
+        rs[mb][0] = r[0][mb][0] + r[1][mb][0];
+        rs[mb][1] = r[0][mb][1] + r[1][mb][1];
+      }
+      double rf[4];
+      to_b(rs, rf);
+      double u[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+        for (int mb = 0; mb < 2; ++mb) dmma(u[mb][0], u[mb][1], buf[tro[mb][ks]], rf[ks]);
+      double* ub = sU + slot * 128;
+#pragma unroll
+      for (int mb = 0; mb < 2; ++mb) {
+        *reinterpret_cast<double2*>(ub + (8 * mb + qr) * 8 + 2 * qc) = make_double2(u[mb][0], u[mb][1]);
+        const int row = c * BT + 8 * mb + qr;
+        if (v0) a.y[(int64_t)n0 * a.n_pad + row] = u[mb][0];
+        if (v1) a.y[(int64_t)n1 * a.n_pad + row] = u[mb][1];
+      }
+      __syncwarp();
+      slot = (slot == 0) ? NB : slot - 1;
+    }
+  }
+}
+
 template <int NB>
 int launch_subst(const LargeArgs& a, int num_sm, cudaStream_t st) {
-  constexpr int NW = 4;
-  const int smem = NW * SubstCfg<NB>::DOUBLES * 8;
-  static bool set = false;
-  if (!set) {
-    cudaError_t e = cudaFuncSetAttribute(k_band_subst<NB, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return (int)e;
-    set = true;
-  }
-  // spread the load cases over all SMs first: one warp per CTA slot until every SM has one
-  const int grid = (a.batch + NW - 1) / NW;
+  static const int force = [] { const char* s = getenv("TB_SUBST_TILE"); return s ? atoi(s) : 0; }();   // 1 | 8: force a kernel
+  const int smem8 = (2 * (NB + 1) * BE + (NB + 1) * 128 + 128 + a.nb16 * 128) * 8;
   tb_prof_begin(TB_PROF_SUBST, st);
-  k_band_subst<NB, NW><<<grid, 32 * NW, smem, st>>>(a);
+  if (force != 1 && smem8 <= 200 * 1024) {
+    // tiles of eight load cases on the tensor cores; y of the whole system stays in shared memory
+    static int granted = 0;
+    if (granted < smem8) {
+      cudaError_t e = cudaFuncSetAttribute(k_band_subst8<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem8);
+      if (e != cudaSuccess) return (int)e;
+      granted = smem8;
+    }
+    const int tiles = (a.batch + 7) / 8, cap = num_sm * (int)((220 * 1024) / (smem8 + 1024));
+    k_band_subst8<NB><<<tiles < cap ? tiles : cap, 32, smem8, st>>>(a);
+  } else {
+    constexpr int NW = 4;
+    const int smem = NW * SubstCfg<NB>::DOUBLES * 8;
+    static bool set = false;
+    if (!set) {
+      cudaError_t e = cudaFuncSetAttribute(k_band_subst<NB, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      if (e != cudaSuccess) return (int)e;
+      set = true;
+    }
+    k_band_subst<NB, NW><<<(a.batch + NW - 1) / NW, 32 * NW, smem, st>>>(a);
+  }
   tb_prof_end(TB_PROF_SUBST, st);
   return (int)cudaGetLastError();
 }
