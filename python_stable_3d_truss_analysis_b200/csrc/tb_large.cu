@@ -142,66 +142,105 @@ __global__ void __launch_bounds__(256) k_prep(const LargeArgs a) {
   for (int b = blockIdx.x; b < a.batch; b += gridDim.x) {
     const double* xyz = a.xyz + b * a.xyz_stride;
     int flag = 0;
-    for (int m = tid; m < a.M; m += 256) {
-      double ar, e;
-      bool ok = true;
-      if (a.gene) {
-        const int g = a.gene[b * a.gene_stride + m];
-        if ((unsigned)g < (unsigned)a.n_type) {
-          ar = a.type_table[3 * g];
-          e = a.type_table[3 * g + 1];
+    if (tid == 0) a.status[b] = 0;             // no separate initialisation kernel on this path
+    __syncthreads();
+    // two members per thread and pass: the connectivity / property loads of both, then the joint positions of both
+    // (which wait on the connectivity), then the arithmetic -- half as many exposed load latencies
+    for (int mbase = tid; mbase < a.M; mbase += 2 * 256) {
+      double ar[2], e[2], x0[2][DIM], x1[2][DIM];
+      int j0[2], j1[2];
+      bool ok[2], live[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int m = mbase + 256 * u;
+        live[u] = m < a.M;
+        ok[u] = true;
+        ar[u] = e[u] = 0.0;
+        j0[u] = j1[u] = 0;
+        if (!live[u]) continue;
+        if (a.gene) {
+          const int g = a.gene[b * a.gene_stride + m];
+          if ((unsigned)g < (unsigned)a.n_type) {
+            ar[u] = a.type_table[3 * g];
+            e[u] = a.type_table[3 * g + 1];
+          } else {
+            ok[u] = false;
+          }
         } else {
-          ok = false;
-          ar = e = 0.0;
+          const double* t = a.aed + b * a.aed_stride + 3 * (int64_t)m;
+          ar[u] = t[0];
+          e[u] = t[1];
         }
-      } else {
-        const double* t = a.aed + b * a.aed_stride + 3 * (int64_t)m;
-        ar = t[0];
-        e = t[1];
+        j0[u] = a.conn[2 * m];
+        j1[u] = a.conn[2 * m + 1];
       }
-      const int j0 = a.conn[2 * m], j1 = a.conn[2 * m + 1];
-      double dx[DIM], c[DIM];
 #pragma unroll
-      for (int i = 0; i < DIM; ++i) dx[i] = __dsub_rn(xyz[j1 * DIM + i], xyz[j0 * DIM + i]);
-      double l2 = __dmul_rn(dx[0], dx[0]);
+      for (int u = 0; u < 2; ++u)
 #pragma unroll
-      for (int i = 1; i < DIM; ++i) l2 = __dadd_rn(l2, __dmul_rn(dx[i], dx[i]));
-      const double len = __dsqrt_rn(l2);
-      double k = 0.0;
+        for (int i = 0; i < DIM; ++i) {
+          x0[u][i] = live[u] ? xyz[j0[u] * DIM + i] : 0.0;
+          x1[u][i] = live[u] ? xyz[j1[u] * DIM + i] : 0.0;
+        }
 #pragma unroll
-      for (int i = 0; i < DIM; ++i) c[i] = 0.0;
-      if (!ok) {
-        flag = min(flag, TB_INFO_BAD_INDEX);
-      } else if (!(len > 0.0)) {
-        flag = min(flag, TB_INFO_ZERO_LENGTH);
-      } else {
-        k = __ddiv_rn(__dmul_rn(e, ar), len);
+      for (int u = 0; u < 2; ++u) {
+        if (!live[u]) continue;
+        const int m = mbase + 256 * u;
+        double dx[DIM], c[DIM];
 #pragma unroll
-        for (int i = 0; i < DIM; ++i) c[i] = __ddiv_rn(dx[i], len);
+        for (int i = 0; i < DIM; ++i) dx[i] = __dsub_rn(x1[u][i], x0[u][i]);
+        double l2 = __dmul_rn(dx[0], dx[0]);
+#pragma unroll
+        for (int i = 1; i < DIM; ++i) l2 = __dadd_rn(l2, __dmul_rn(dx[i], dx[i]));
+        const double len = __dsqrt_rn(l2);
+        double k = 0.0;
+#pragma unroll
+        for (int i = 0; i < DIM; ++i) c[i] = 0.0;
+        if (!ok[u]) {
+          flag = min(flag, TB_INFO_BAD_INDEX);
+        } else if (!(len > 0.0)) {
+          flag = min(flag, TB_INFO_ZERO_LENGTH);
+        } else {
+          k = __ddiv_rn(__dmul_rn(e[u], ar[u]), len);
+#pragma unroll
+          for (int i = 0; i < DIM; ++i) c[i] = __ddiv_rn(dx[i], len);
+        }
+        double* o = sMkc + m * NV;
+        int t = 0;
+#pragma unroll
+        for (int i = 0; i < DIM; ++i)
+#pragma unroll
+          for (int j = i; j < DIM; ++j) o[t++] = __dmul_rn(k, __dmul_rn(c[i], c[j]));   // truss.py:69-70 / 80-81
       }
-      double* o = sMkc + m * NV;
-      int t = 0;
-#pragma unroll
-      for (int i = 0; i < DIM; ++i)
-#pragma unroll
-        for (int j = i; j < DIM; ++j) o[t++] = __dmul_rn(k, __dmul_rn(c[i], c[j]));   // truss.py:69-70 / 80-81
     }
     if (flag) atomicMin(&a.status[b], flag);
     __syncthreads();
     double* kv = a.kv + (int64_t)b * a.nnz;
-    for (int q = tid; q < a.nnz; q += 256) {
-      const int f = a.q_first[q];
-      if (f < 0) continue;                                          // several members contribute: second loop
-      const double t0 = sMkc[(f >> 4) * NV + (f & 7)];
-      kv[q] = __dadd_rn(0.0, (f & 8) ? -t0 : t0);
+    // the map loads of four entries are issued together: one exposed L2 latency per four entries instead of per entry
+    for (int q = tid; q < a.nnz; q += 4 * 256) {
+      int f[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) f[u] = q + 256 * u < a.nnz ? a.q_first[q + 256 * u] : -1;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (f[u] < 0) continue;                                     // several members contribute: second loop
+        const double t0 = sMkc[(f[u] >> 4) * NV + (f[u] & 7)];
+        kv[q + 256 * u] = __dadd_rn(0.0, (f[u] & 8) ? -t0 : t0);
+      }
     }
     for (int i = tid; i < a.n_multi; i += 256) {             // same-joint entries: ascending member order
       const int q = a.q_multi[i];
+      const int p0 = a.q_ptr[q], p1 = a.q_ptr[q + 1];
       double v = 0.0;
-      for (int p = a.q_ptr[q]; p < a.q_ptr[q + 1]; ++p) {
-        const int pk = a.q_pack[p];
-        const double t = sMkc[(pk >> 4) * NV + (pk & 7)];
-        v = __dadd_rn(v, (pk & 8) ? -t : t);                       // truss.py:71-76 signs, :314 accumulation
+      for (int p = p0; p < p1; p += 8) {                     // eight contributions' map loads in flight, summed in order
+        int pk[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) pk[u] = p + u < p1 ? a.q_pack[p + u] : -1;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          if (pk[u] < 0) continue;
+          const double t = sMkc[(pk[u] >> 4) * NV + (pk[u] & 7)];
+          v = __dadd_rn(v, (pk[u] & 8) ? -t : t);                  // truss.py:71-76 signs, :314 accumulation
+        }
       }
       kv[q] = v;
     }
@@ -976,11 +1015,11 @@ int tb_launch_large(const LargeArgs& a, int num_sm, cudaStream_t st, int path) {
   // TB_UNFUSED_ASSEMBLY=1 keeps the separate HBM-bound assembly kernel (A/B measurements, tiled path only)
   static const bool fused_env = [] { const char* s = getenv("TB_UNFUSED_ASSEMBLY"); return !(s && s[0] == '1'); }();
   const bool fused = fused_env || path == 2;
-  k_init_status<<<(a.batch + 255) / 256, 256, 0, st>>>(a.status, a.batch, 0);
   // member products in shared memory (k_prep + recomputing k_recover) when they fit, else the k_geom arrays in HBM
   const size_t prep_smem = (size_t)a.M * (a.dim * (a.dim + 1) / 2) * 8, rec_smem = (size_t)a.M * (1 + a.dim) * 8;
   static const bool no_prep = [] { const char* s = getenv("TB_NO_PREP"); return s && s[0] == '1'; }();
   const bool prep = fused && !no_prep && prep_smem <= 96 * 1024 && rec_smem <= 96 * 1024;
+  if (!prep) k_init_status<<<(a.batch + 255) / 256, 256, 0, st>>>(a.status, a.batch, 0);   // k_prep clears its own
   // load cases of one truss (shared_k): assembly and factorisation run for system 0 only
   const bool shared = a.shared_k && path == 2 && prep && a.batch > 1;
   LargeArgs a1 = a;
@@ -1066,6 +1105,6 @@ int tb_launch_large(const LargeArgs& a, int num_sm, cudaStream_t st, int path) {
     }
     tb_prof_end(TB_PROF_RECOVER, st);
   }
-  tb_count_launch((prep ? 4 : 5) + (shared ? 1 : 0));
+  tb_count_launch((prep ? 3 : 5) + (shared ? 1 : 0));
   return (int)cudaGetLastError();
 }
