@@ -196,20 +196,38 @@ def run_gpu(args):
 
     td = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
     d_xyz, d_aed, d_F = td(xyz), td(aed), td(F)
-    # one flat result buffer per rank, [u | ext | axial]: the three outputs are views into it, so the multi-GPU gather
-    # ships it as it is (no packing kernel)
-    flat = torch.empty(B * (2 * N + M), dtype=torch.float64, device=dev)
+    # one flat result buffer per rank, [u | ext | axial]: the three outputs are views into it.  With several GPUs the
+    # results go back to rank 0 (north_star: gather only).  Preferred: rank r's flat buffer IS slice r of a buffer in
+    # rank 0's HBM, mapped into every process (symmetric memory over NVLink / NVSwitch), so k_recover's stores are the
+    # gather -- compute and transfer in one kernel, one device-side barrier after it.  TB_BENCH_GATHER=nccl (or a
+    # failed rendezvous) falls back to a separate NCCL gather of the local flat buffer.
+    per_rank = B * (2 * N + M)
+    gathered, symm, gather_mode = None, None, "single GPU"
+    if world > 1 and os.environ.get("TB_BENCH_GATHER", "peer") == "peer":
+        try:
+            from python_stable_3d_truss_analysis_b200.parallel import PeerGather
+            symm = PeerGather(per_rank, torch.float64, dev, dst=0)
+            flat = symm.local                                   # my slice of rank 0's buffer
+            gathered = symm.slices
+            gather_mode = "k_recover stores straight into rank 0's buffer (peer-mapped symmetric memory over NVLink), one signal barrier"
+        except Exception as exc:   # noqa: BLE001
+            print(f"bench.py: symmetric-memory rendezvous failed ({exc!r}); using the NCCL gather", file=sys.stderr)
+            symm = None
+    if symm is None:
+        flat = torch.empty(per_rank, dtype=torch.float64, device=dev)
+        if world > 1:
+            gathered = [torch.empty_like(flat) for _ in range(world)] if rank == 0 else None
+            gather_mode = "NCCL gather of u/ext/axial to rank 0 inside the step"
     out = {"u": flat[:B * N].view(B, N), "ext": flat[B * N:2 * B * N].view(B, N), "axial": flat[2 * B * N:].view(B, M),
            "weight": torch.empty(B, dtype=torch.float64, device=dev), "info": torch.empty(B, dtype=torch.int32, device=dev)}
-    gathered = None
-    if world > 1:   # results go back to rank 0 over NCCL (north_star: gather only)
-        gathered = [torch.empty_like(flat) for _ in range(world)] if rank == 0 else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
     stream = torch.cuda.current_stream()
 
     def step():
         plan.solve_device(B, d_xyz, d_F, aed=d_aed, out=out, stream=stream)
-        if world > 1:
+        if symm is not None:
+            symm.barrier()                     # every rank's results have landed in rank 0's buffer
+        elif world > 1:
             dist.gather(flat, gathered, dst=0)
 
     def barrier():
@@ -221,6 +239,17 @@ def run_gpu(args):
         step()
     barrier()
     assert not bool(out["info"].any().item()), "a system failed to factorise"
+
+    # ---- multi-GPU: what rank 0 received from the last rank equals what it computes itself for those load cases
+    if world > 1 and rank == 0:
+        chk = torch.empty(per_rank, dtype=torch.float64, device=dev)
+        chk_out = {"u": chk[:B * N].view(B, N), "ext": chk[B * N:2 * B * N].view(B, N), "axial": chk[2 * B * N:].view(B, M),
+                   "weight": torch.empty(B, dtype=torch.float64, device=dev), "info": torch.empty(B, dtype=torch.int32, device=dev)}
+        plan.solve_device(B, d_xyz, td(F_all[(world - 1) * B:world * B]), aed=d_aed, out=chk_out, stream=stream)
+        torch.cuda.synchronize()
+        assert torch.equal(chk, gathered[world - 1]), "gathered results of the last rank differ from a local solve"
+        del chk, chk_out
+    barrier()
 
     # ---- parity gate on the timed batch (oracle = checker only): 2 sampled systems, 1e-9 norm-wise
     if rank == 0:
@@ -366,7 +395,7 @@ def run_gpu(args):
         "config": {"workload": WORKLOAD, "batch_per_gpu": B, "n_free": n, "n_member": M, "mode": "independent K per system",
                    "pipeline": {0: "fused shared-memory kernel", 1: "tiled 64x64 block-sparse Cholesky", 2: "block-band Cholesky (16x16 blocks)"}[path],
                    "l2": "explicit 256 MB flush (> 126 MB L2) between timed steps, outside the events",
-                   "multi_gpu": "contiguous block partition of the batch, NCCL gather of u/ext/axial to rank 0 inside the step"},
+                   "multi_gpu": "contiguous block partition of the batch; " + gather_mode},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "tb_solve_host (C ABI) with pinned host buffers", "steps": e2e_steps},
         "gpu_launches": int(launches),

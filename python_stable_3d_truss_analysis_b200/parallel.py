@@ -75,6 +75,35 @@ def gather_rows(local_rows, n_total: int, dst: int = 0):
     return torch.cat([b[:s] for b, s in zip(bufs, sizes)], dim=0)
 
 
+class PeerGather:
+    """Gather without a collective: every rank's result buffer IS a slice of one buffer in rank ``dst``'s HBM.
+
+    The buffer is allocated as symmetric memory and mapped into every process of the node (NVLink 5 / NVSwitch peer
+    access), so the stores of the recovery kernel (k_recover / the fused kernels) travel to rank ``dst`` as they are
+    issued -- compute and transfer are one kernel -- and ``barrier()`` (a device-side signal barrier on the current
+    stream) is all that follows.  ``local`` is this rank's slice (pass views of it as the solver's outputs);
+    ``slices`` on rank ``dst`` lists every rank's slice.  Requires one process per GPU on one node (NCCL group)."""
+
+    def __init__(self, per_rank_elems: int, dtype=None, device=None, dst: int = 0, group=None):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+
+        dtype = torch.float64 if dtype is None else dtype
+        group = dist.group.WORLD if group is None else group
+        self.rank, self.world, self.dst = dist.get_rank(group), dist.get_world_size(group), dst
+        self.per_rank = int(per_rank_elems)
+        self._pool = symm_mem.empty(self.world * self.per_rank, dtype=dtype, device=device)
+        self._hdl = symm_mem.rendezvous(self._pool, group)
+        self.local = self._hdl.get_buffer(dst, (self.per_rank,), dtype, self.rank * self.per_rank)
+        self.slices = ([self._pool[r * self.per_rank:(r + 1) * self.per_rank] for r in range(self.world)]
+                       if self.rank == dst else None)
+
+    def barrier(self):
+        """Enqueue the device-side barrier: after it, rank ``dst`` holds every rank's results."""
+        self._hdl.barrier()
+
+
 def gather_results(local: dict, n_total: int, dst: int = 0):
     """Gather a dict of row-sharded arrays (u, ext, axial, weight, info, fitness, flags ...) to rank ``dst``."""
     out = {k: gather_rows(v, n_total, dst) for k, v in sorted(local.items()) if v is not None}
