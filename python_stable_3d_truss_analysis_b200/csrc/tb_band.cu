@@ -345,13 +345,26 @@ __global__ void __launch_bounds__(32 * NW) k_band1(const LargeArgs a) {
     };
     __syncwarp();
     fetch(ncol - 1);
+    // y_c and the block mask of column c are fetched one block column ahead (they come from L2)
+    double ycn[4] = {0.0, 0.0, 0.0, 0.0};
+    if (qr == 0) {
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) ycn[ks] = __ldcg(ysys + (ncol - 1) * BT + ks * 4 + qc);
+    }
+    unsigned nzb = (unsigned)ldg_i32(a.b16_nz + ncol - 1);
     // after the factorisation yslot == ncol mod (NB+1); block column c of y sits in slot c mod (NB+1)
     for (int c = ncol - 1; c >= 0; --c) {
       yslot = (yslot == 0) ? NB : yslot - 1;   // slot of block c (the ring only keeps the last NB+1 blocks: y_c comes from HBM)
-      double yc[4] = {0.0, 0.0, 0.0, 0.0};
-      if (qr == 0) {
+      double yc[4];
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) yc[ks] = __ldcg(ysys + c * BT + ks * 4 + qc);
+      for (int ks = 0; ks < 4; ++ks) yc[ks] = ycn[ks];
+      const unsigned nz = nzb;
+      if (c > 0) {
+        nzb = (unsigned)ldg_i32(a.b16_nz + c - 1);
+        if (qr == 0) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) ycn[ks] = __ldcg(ysys + (c - 1) * BT + ks * 4 + qc);
+        }
       }
       if (c > 0) {
         fetch(c - 1);
@@ -360,7 +373,6 @@ __global__ void __launch_bounds__(32 * NW) k_band1(const LargeArgs a) {
         cp_async_wait<0>();
       }
       __syncwarp();
-      const unsigned nz = (unsigned)ldg_i32(a.b16_nz + c);
       const double* buf = sRing + (c & 1) * (NB + 1) * BE;
       // t[col] = sum_rb sum_r L(c+rb,c)[r][col] u_{c+rb}[r]; this lane: r = 8 mb + lane/4, col = 4 ks + lane%4
       double tp[4] = {0.0, 0.0, 0.0, 0.0};
@@ -831,12 +843,25 @@ __global__ void __launch_bounds__(64, 7) k_band2(const LargeArgs a) {
         cp_async_commit();
       };
       fetch(ncol - 1);
+      // y_c and the block mask of column c are fetched one block column ahead (they come from L2)
+      double ycn[4] = {0.0, 0.0, 0.0, 0.0};
+      if (qr == 0) {
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) ycn[ks] = __ldcg(ysys + (ncol - 1) * BT + ks * 4 + qc);
+      }
+      unsigned nzb = (unsigned)ldg_i32(a.b16_nz + ncol - 1);
       for (int c = ncol - 1; c >= 0; --c) {
         yslot = (yslot == 0) ? NB : yslot - 1;
-        double yc[4] = {0.0, 0.0, 0.0, 0.0};
-        if (qr == 0) {
+        double yc[4];
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) yc[ks] = __ldcg(ysys + c * BT + ks * 4 + qc);
+        for (int ks = 0; ks < 4; ++ks) yc[ks] = ycn[ks];
+        const unsigned nz = nzb;
+        if (c > 0) {
+          nzb = (unsigned)ldg_i32(a.b16_nz + c - 1);
+          if (qr == 0) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) ycn[ks] = __ldcg(ysys + (c - 1) * BT + ks * 4 + qc);
+          }
         }
         if (c > 0) {
           fetch(c - 1);
@@ -845,7 +870,6 @@ __global__ void __launch_bounds__(64, 7) k_band2(const LargeArgs a) {
           cp_async_wait<0>();
         }
         __syncwarp();
-        const unsigned nz = (unsigned)ldg_i32(a.b16_nz + c);
         const double* buf = sRing + (c & 1) * (NB + 1) * BE;
         double tp[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
@@ -1342,12 +1366,25 @@ __global__ void __maxnreg__(96) k_band3(const LargeArgs a) {
         cp_async_commit();
       };
       fetch(ncol - 1);
+      // y_c and the block mask of column c are fetched one block column ahead (they come from L2)
+      double ycn[4] = {0.0, 0.0, 0.0, 0.0};
+      if (qr == 0) {
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) ycn[ks] = __ldcg(ysys + (ncol - 1) * BT + ks * 4 + qc);
+      }
+      unsigned nzb = (unsigned)ldg_i32(a.b16_nz + ncol - 1);
       for (int c = ncol - 1; c >= 0; --c) {
         yslot = (yslot == 0) ? NB : yslot - 1;
-        double yc[4] = {0.0, 0.0, 0.0, 0.0};
-        if (qr == 0) {
+        double yc[4];
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) yc[ks] = __ldcg(ysys + c * BT + ks * 4 + qc);
+        for (int ks = 0; ks < 4; ++ks) yc[ks] = ycn[ks];
+        const unsigned nz = nzb;
+        if (c > 0) {
+          nzb = (unsigned)ldg_i32(a.b16_nz + c - 1);
+          if (qr == 0) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) ycn[ks] = __ldcg(ysys + (c - 1) * BT + ks * 4 + qc);
+          }
         }
         if (c > 0) {
           fetch(c - 1);
@@ -1356,7 +1393,6 @@ __global__ void __maxnreg__(96) k_band3(const LargeArgs a) {
           cp_async_wait<0>();
         }
         __syncwarp();
-        const unsigned nz = (unsigned)ldg_i32(a.b16_nz + c);
         const double* buf = sRing + (c & 1) * (NB + 1) * BE;
         double tp[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
