@@ -951,8 +951,13 @@ struct Band3Cfg {
   static constexpr int DOUBLES = BUF * BE + 2 * BE + (NB + 1) * BT + BT + 32 + 8 + 192;
 };
 
+#ifdef TB_BAND3_80   // experiment: cap at 80 registers so that seven (eight) systems fit an SM
+#define TB_BAND3_ATTR __launch_bounds__(96, 7)
+#else
+#define TB_BAND3_ATTR __maxnreg__(96)
+#endif
 template <int NB>
-__global__ void __maxnreg__(96) k_band3(const LargeArgs a) {
+__global__ void TB_BAND3_ATTR k_band3(const LargeArgs a) {
   extern __shared__ __align__(16) double sm[];
   using Cfg = Band3Cfg<NB>;
   double* sRing = sm;
@@ -1284,17 +1289,14 @@ __global__ void __maxnreg__(96) k_band3(const LargeArgs a) {
         po1 = pn1;
         pd1 = pn2 >= 0 ? pn2 : pn1;
       } else {
-        // ---------------- L(c+rb, c) = P W^T into the ring: warp F takes rb = 1, warp T the rest
+        // ---------------- L(c+rb, c) = P W^T into the ring: warp F takes rb = 1, warp T the rest (two separate code
+        // paths, so that the chain warp's one block solve does not inherit the trailing warp's register pressure)
         double wf[2][4];
 #pragma unroll
         for (int nbp = 0; nbp < 2; ++nbp)
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) wf[nbp][ks] = scr[fo(nbp * 4 + ks, lsw)];
-#pragma unroll
-        for (int rb = 1; rb <= NB; ++rb) {
-          if ((rb == 1) != isF) continue;
-          if (!((nzc >> rb) & 1u)) continue;
-          double* blk = sRing + (rb * (rb - 1) / 2 + idx[rb]) * BE;
+        auto solve_block = [&](double* blk) {
           double a4[2][4];
 #pragma unroll
           for (int mb = 0; mb < 2; ++mb)
@@ -1314,6 +1316,13 @@ __global__ void __maxnreg__(96) k_band3(const LargeArgs a) {
 #pragma unroll
             for (int nbp = 0; nbp < 2; ++nbp)
               *reinterpret_cast<double2*>(blk + cpair_off(mb, nbp, lane)) = make_double2(x[mb][nbp][0], x[mb][nbp][1]);
+        };
+        if (isF) {
+          if ((nzc >> 1) & 1u) solve_block(sRing + idx[1] * BE);
+        } else {
+#pragma unroll
+          for (int rb = 2; rb <= NB; ++rb)
+            if ((nzc >> rb) & 1u) solve_block(sRing + (rb * (rb - 1) / 2 + idx[rb]) * BE);
         }
       }
       BPH(5)
