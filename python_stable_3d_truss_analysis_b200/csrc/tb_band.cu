@@ -1863,7 +1863,9 @@ int launch_band(const LargeArgs& a, int num_sm, cudaStream_t st) {
   // one warp per system when the batch alone fills the GPU (fewest instructions per system), else several warps per
   // system: TB_BAND_WARPS = 1 | 2 | 3 forces a kernel (parity tests, comparisons)
   static const int force = [] { const char* s = getenv("TB_BAND_WARPS"); return s ? atoi(s) : 0; }();
-  constexpr int NW = 4;                        // k_band1 packs four independent systems (warps) into a CTA
+  // k_band1 packs independent systems (one warp each) into a CTA: four while four rings fit the 227 KB of an SM's
+  // shared memory (NB <= 6), two for the widest bands (NB = 7, 8: 59 / 76 KB per system)
+  constexpr int NW = NB <= 6 ? 4 : 2;
   const int smem1 = NW * BandCfg<NB>::DOUBLES * 8, smem2 = (BandCfg<NB>::DOUBLES + 208) * 8, smem3 = Band3Cfg<NB>::DOUBLES * 8;
   static int per1 = 0, per2 = 0, per3 = 0;     // attribute / occupancy queries once per instantiation (single device per process)
   if (per1 == 0) {

@@ -381,3 +381,67 @@ def test_pivot_rsqrt_accuracy():
     (tb_blocks.cuh: rsqrt_pos); it must stay within 2 ulp of 1/sqrt(d) over the whole accepted pivot range."""
     from python_stable_3d_truss_analysis_b200 import _lib
     assert _lib.rsqrt_probe(1 << 22) <= 4.5e-16
+
+
+def _tower(dim, per_level, levels, seed):
+    """A lattice tower: `per_level` joints per level on a ring (2D: a ladder), every level braced to the next; the bottom
+    level is pinned.  Half-bandwidth of K_ff ~ 2 * dim * per_level, so per_level sweeps the band width."""
+    rng = np.random.default_rng(seed)
+    joints, members = [], []
+    for lv in range(levels):
+        for k in range(per_level):
+            if dim == 2:
+                p = [float(k) * 2.0 + 0.1 * rng.standard_normal(), float(lv) * 1.5]
+            else:
+                ang = 2 * np.pi * k / per_level
+                p = [3.0 * np.cos(ang) + 0.1 * rng.standard_normal(), 3.0 * np.sin(ang) + 0.1 * rng.standard_normal(), 2.0 * lv]
+            joints.append([p, "PIN" if lv == 0 else "NO"])
+    jid = lambda lv, k: lv * per_level + (k % per_level)
+    mt = lambda: [float(rng.uniform(0.5, 2.0)), 1e4, 0.1]
+    for lv in range(levels):
+        ring = per_level if (dim == 3 and per_level > 2) else per_level - 1
+        for k in range(ring):
+            if lv > 0:
+                members.append([[jid(lv, k), jid(lv, k + 1)], mt()])
+        if dim == 3 and per_level > 3 and lv > 0:                  # cross bracing inside the level
+            for k in range(per_level - 2):
+                members.append([[jid(lv, 0), jid(lv, k + 2)], mt()]) if k + 2 != per_level - 1 or per_level == 4 else None
+        if lv + 1 < levels:
+            for k in range(per_level):
+                members.append([[jid(lv, k), jid(lv + 1, k)], mt()])
+                members.append([[jid(lv, k), jid(lv + 1, k + 1)], mt()])
+                if dim == 3:
+                    members.append([[jid(lv, k + 1), jid(lv + 1, k)], mt()])
+    members = [m for m in members if m is not None and m[0][0] != m[0][1]]
+    seen, uniq = set(), []
+    for m in members:
+        key = tuple(sorted(m[0]))
+        if key not in seen:
+            seen.add(key)
+            uniq.append(m)
+    forces = [[jid(levels - 1, k), [float(x) for x in rng.uniform(-5, 5, size=dim)]] for k in range(per_level)]
+    return {"joint": joints, "force": forces, "member": uniq}
+
+
+@pytest.mark.parametrize("dim,per_level,levels", [(2, 2, 40), (3, 3, 30), (3, 5, 24), (3, 8, 16), (3, 11, 12), (3, 13, 10),
+                                                   (3, 15, 9), (3, 19, 8), (3, 21, 7)])
+def test_band_path_every_band_width_vs_oracle(dim, per_level, levels):
+    """Towers of growing cross-section sweep the number of sub-diagonal 16x16 blocks of the band path (1 .. 8: the
+    three-warp / two-warp kernels up to 5, the one-warp kernel beyond), each against the oracle, with a factorisation
+    per load case and with the shared one."""
+    data = _tower(dim, per_level, levels, seed=per_level)
+    t = Truss(dim).LoadFromJSON(data=data)
+    plan = t._get_plan()
+    if plan.info.band_blocks > 8:
+        pytest.skip(f"band of {plan.info.band_blocks} blocks: not a band-path system")
+    plan.set_path(2)
+    joints, support, conn, aed, force = orc.arrays_from_json(data, dim)
+    rng = np.random.default_rng(1)
+    F = np.stack([force, -0.5 * force, force * rng.uniform(0.5, 2.0, size=force.shape)])
+    for independent in (True, False):
+        out = SolveLoadCases(t, F, independent=independent)
+        for b in range(3):
+            want = orc.solve(dim, joints, support, conn, aed, F[b])
+            for k in H.FIELDS:
+                err = orc.normwise_err(out[k][b], want[k])
+                assert err <= H.TOL, (plan.info.band_blocks, independent, b, k, err)
