@@ -445,3 +445,40 @@ def test_band_path_every_band_width_vs_oracle(dim, per_level, levels):
             for k in H.FIELDS:
                 err = orc.normwise_err(out[k][b], want[k])
                 assert err <= H.TOL, (plan.info.band_blocks, independent, b, k, err)
+
+
+@pytest.mark.parametrize("dim,per_level,levels,path", [(2, 4, 40, 2), (2, 9, 30, 2), (2, 9, 30, 1), (3, 8, 16, 1), (3, 13, 10, 1)])
+def test_towers_2d_and_tiled_path_vs_oracle(dim, per_level, levels, path):
+    """2D band systems and the same kind of tower through the tiled (64x64 block-sparse) pipeline."""
+    data = _tower(dim, per_level, levels, seed=100 + per_level)
+    t = Truss(dim).LoadFromJSON(data=data)
+    t._get_plan().set_path(path)
+    t.Solve()
+    want = orc.solve(dim, *orc.arrays_from_json(data, dim))
+    for k in H.FIELDS:
+        err = orc.normwise_err(t._dense[k], want[k])
+        assert err <= H.TOL, (path, k, err)
+
+
+def test_long_tower_shared_factor_falls_back_to_warp_per_load_case():
+    """A band system too long for y to stay in shared memory (196 block columns): tb_solve_loadcases uses the
+    warp-per-load-case substitution kernel instead of the tensor-core tile kernel.  The tower (pinned at both ends, loaded
+    at mid-height) is slender: cond(K_ff) = 1.8e8, where the reference's LU and a Cholesky factorisation on the CPU already
+    differ by ~1e-9, so this test checks the kernels at 1e-7 instead of the 1e-9 of the well-conditioned fixtures."""
+    data = _tower(3, 3, 350, seed=7)
+    for j in data["joint"][-3:]:
+        j[1] = "PIN"
+    rng = np.random.default_rng(9)
+    data["force"] = [[3 * lv + k, [float(x) for x in rng.uniform(-5, 5, size=3)]] for lv in (120, 175, 230) for k in range(3)]
+    t = Truss(3).LoadFromJSON(data=data)
+    plan = t._get_plan()
+    assert plan.info.path == 2 and plan.info.n_free > 3040
+    joints, support, conn, aed, force = orc.arrays_from_json(data, 3)
+    F = np.stack([force, 2.0 * force, -force, 0.25 * force, force[::-1].copy()])
+    shared = SolveLoadCases(t, F)
+    indep = SolveLoadCases(t, F, independent=True)
+    for b in (0, 4):
+        want = orc.solve(3, joints, support, conn, aed, F[b])
+        for k in H.FIELDS:
+            assert orc.normwise_err(shared[k][b], want[k]) <= 1e-7, ("shared", b, k)
+            assert orc.normwise_err(indep[k][b], want[k]) <= 1e-7, ("independent", b, k)
