@@ -482,3 +482,27 @@ def test_long_tower_shared_factor_falls_back_to_warp_per_load_case():
         for k in H.FIELDS:
             assert orc.normwise_err(shared[k][b], want[k]) <= 1e-7, ("shared", b, k)
             assert orc.normwise_err(indep[k][b], want[k]) <= 1e-7, ("independent", b, k)
+
+
+@pytest.mark.parametrize("path", [1, 2], ids=["tiled", "band"])
+def test_blocked_paths_report_failures_per_system(path):
+    """A system whose stiffness matrix is not positive definite (all members of zero stiffness) fails alone: info > 0
+    (first non-positive pivot, 1-based) and zero-filled outputs for it, correct results for its batch mates; with the
+    factorisation shared, the failure reaches every load case."""
+    data = _tower(3, 5, 24, seed=3)
+    t = Truss(3).LoadFromJSON(data=data)
+    t._get_plan().set_path(path)
+    types = [MemberType(1.0, 1e4, 0.1), MemberType(1.0, 0.0, 0.1)]
+    genes = np.zeros((3, t.nMember), dtype=np.int32)
+    genes[1, :] = 1
+    out = SolveMemberTypes(t, genes, types, raise_on_error=False)
+    assert out["info"][0] == 0 and out["info"][2] == 0 and out["info"][1] > 0
+    assert not np.any(out["u"][1]) and not np.any(out["axial"][1]) and not np.any(out["ext"][1])
+    assert np.array_equal(out["u"][0], out["u"][2]) and np.any(out["u"][0])
+    with pytest.raises(np.linalg.LinAlgError):
+        SolveMemberTypes(t, genes, types)
+    for m in range(t.nMember):                 # the truss itself with zero stiffness: every load case fails
+        t.SetMemberType(m, types[1])
+    N = t.nJoint * 3
+    res = SolveLoadCases(t, np.ones((4, N)), raise_on_error=False)
+    assert np.all(res["info"] > 0) and not np.any(res["u"])
