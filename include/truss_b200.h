@@ -178,6 +178,37 @@ int tb_fitness(tb_plan* plan, const tb_batch_in* in, double allow_stress, double
 int tb_fitness_host(tb_plan* plan, const tb_batch_in* in, double allow_stress, double allow_displace,
                     const tb_fit_out* fit, const tb_batch_out* full);
 
+/* ---- GA generation step on the device (slientruss3d/ga.py:151-190) -------------------------
+ * One generation = tb_fitness on the gene matrix, then tb_ga_step: rank the population by fitness (stable, like
+ * sorted() in GA.Select ga.py:155-160), copy the nElite best genes to the front and fill the rest by the reference's
+ * UpdatePop rules (crossover of two distinct elites / mutation of one elite / keep pop[j] / fresh random gene,
+ * ga.py:172-190).  Random numbers are counter-based (Philox4x32-10 keyed by `seed`, counter = individual, generation),
+ * so a run is reproducible from (seed, generation) but does NOT replay Python's `random` stream -- the host GA class
+ * keeps that property.  All pointers are device pointers; n_pop <= 16384. */
+typedef struct {
+  int32_t n_pop, n_elite, n_member, n_type;
+  double p_crossover, p_mutate, p_origin;   /* GA(pCrossover, pMutate, pOrigin); the rest re-seeds */
+  uint64_t seed;
+} tb_ga_params;
+
+typedef struct {
+  int32_t best_index;         /* individual with the lowest fitness (rank 0) */
+  int32_t feasible_index;     /* first individual in rank order with both flags set, -1 if none (_RecordFeasible, ga.py:101-108) */
+  double best_fitness;
+  double feasible_fitness;
+  uint8_t best_stress_ok, best_displace_ok;
+  uint8_t pad_[6];
+} tb_ga_report;
+
+/* GA.Initialize (ga.py:151-153): gene[n_pop][n_member] drawn from the member-type distribution; type_cum = normalised
+ * cumulative weights [n_type] (device) or NULL for uniform. */
+int tb_ga_init(const tb_ga_params* params, const double* type_cum, int32_t* gene, void* cuda_stream);
+
+/* GA.Select + GA.UpdatePop (ga.py:155-190).  order[n_pop] receives the ranking (individual indices, best first);
+ * gene_out may be NULL (ranking and report only, e.g. the last Select of a run); report may be NULL. */
+int tb_ga_step(const tb_ga_params* params, uint64_t generation, const double* fitness, const uint8_t* flags,
+               const int32_t* gene_in, int32_t* gene_out, int32_t* order, tb_ga_report* report, void* cuda_stream);
+
 /* Ragged batch: B independent trusses with their own topology (the generator's solve site,
  * generate.py:354-357).  Arrays are packed back to back; system b owns joints
  * joint_off[b]..joint_off[b+1]-1 and members member_off[b]..member_off[b+1]-1; conn holds

@@ -17,7 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 LIB_PATH = os.environ.get("TB_LIB_PATH") or os.path.join(CSRC, "libtruss_b200.so")   # TB_LIB_PATH: instrumented builds (tools/)
-SOURCES = ["tb_plan.cu", "tb_small.cu", "tb_dense16.cu", "tb_large.cu", "tb_band.cu", "tb_api.cu", "tb_peak.cu"]
+SOURCES = ["tb_plan.cu", "tb_small.cu", "tb_dense16.cu", "tb_large.cu", "tb_band.cu", "tb_api.cu", "tb_peak.cu", "tb_ga.cu"]
 
 TB_ERR_NO_DEVICE = -7
 TB_ERR_TOO_LARGE = -6
@@ -75,6 +75,17 @@ class TbPlanInfo(C.Structure):
                 ("band_blocks_nonzero", C.c_int64), ("band_products", C.c_int64)]
 
 
+class TbGaParams(C.Structure):
+    _fields_ = [("n_pop", C.c_int32), ("n_elite", C.c_int32), ("n_member", C.c_int32), ("n_type", C.c_int32),
+                ("p_crossover", C.c_double), ("p_mutate", C.c_double), ("p_origin", C.c_double), ("seed", C.c_uint64)]
+
+
+class TbGaReport(C.Structure):
+    _fields_ = [("best_index", C.c_int32), ("feasible_index", C.c_int32), ("best_fitness", C.c_double),
+                ("feasible_fitness", C.c_double), ("best_stress_ok", C.c_uint8), ("best_displace_ok", C.c_uint8),
+                ("pad_", C.c_uint8 * 6)]
+
+
 class TbBatchIn(C.Structure):
     _fields_ = [("batch", C.c_int32), ("joint_xyz", C.c_void_p), ("joint_stride", C.c_int64),
                 ("member_aed", C.c_void_p), ("member_stride", C.c_int64), ("gene", C.c_void_p),
@@ -99,7 +110,7 @@ class TbRaggedIn(C.Structure):
 
 EXPORTS = ["tb_plan_create", "tb_plan_destroy", "tb_plan_query", "tb_plan_set_path", "tb_plan_get_maps",
            "tb_plan_get_scatter", "tb_solve", "tb_solve_host", "tb_solve_loadcases", "tb_solve_loadcases_host", "tb_fitness", "tb_fitness_host", "tb_solve_ragged",
-           "tb_solve_ragged_host", "tb_pinned_alloc", "tb_pinned_free", "tb_small_path_limits", "tb_fp64_peak", "tb_rsqrt_probe", "tb_profile_enable", "tb_profile_read",
+           "tb_solve_ragged_host", "tb_ga_init", "tb_ga_step", "tb_pinned_alloc", "tb_pinned_free", "tb_small_path_limits", "tb_fp64_peak", "tb_rsqrt_probe", "tb_profile_enable", "tb_profile_read",
            "tb_launch_count", "tb_strerror", "tb_version"]
 
 _lib = None
@@ -136,6 +147,8 @@ def lib():
     L.tb_small_path_limits.argtypes = [C.POINTER(i32), C.POINTER(i32)]
     L.tb_fp64_peak.argtypes = [i32, i32, C.POINTER(dbl), C.POINTER(C.c_float)]
     L.tb_rsqrt_probe.argtypes = [i32, C.POINTER(dbl)]
+    L.tb_ga_init.argtypes = [C.POINTER(TbGaParams), vp, vp, vp]
+    L.tb_ga_step.argtypes = [C.POINTER(TbGaParams), C.c_uint64, vp, vp, vp, vp, vp, vp, vp]
     L.tb_profile_enable.argtypes = [i32]
     L.tb_profile_read.argtypes = [vp, vp]
     L.tb_launch_count.restype = i64
@@ -200,6 +213,21 @@ def fp64_peak(which: int, iters: int = 4096):
     t, ms = C.c_double(), C.c_float()
     check(lib().tb_fp64_peak(which, iters, C.byref(t), C.byref(ms)))
     return t.value, ms.value
+
+
+def ga_init(params: TbGaParams, gene, type_cum=None, stream=None):
+    """GA.Initialize on the device: fills the int32 CUDA tensor ``gene`` [n_pop, n_member]."""
+    import torch
+    st = torch.cuda.current_stream() if stream is None else stream
+    check(lib().tb_ga_init(C.byref(params), _ptr(type_cum), _ptr(gene), C.c_void_p(st.cuda_stream)))
+
+
+def ga_step(params: TbGaParams, generation: int, fitness, flags, gene_in, gene_out, order, report, stream=None):
+    """GA.Select + GA.UpdatePop on the device (all arguments CUDA tensors; gene_out / report may be None)."""
+    import torch
+    st = torch.cuda.current_stream() if stream is None else stream
+    check(lib().tb_ga_step(C.byref(params), int(generation), _ptr(fitness), _ptr(flags), _ptr(gene_in), _ptr(gene_out),
+                           _ptr(order), _ptr(report), C.c_void_p(st.cuda_stream)))
 
 
 def rsqrt_probe(n: int = 1 << 22) -> float:

@@ -202,3 +202,92 @@ class GA:
             if isPrintMessage:
                 print('-' * 50 + '\n' + "Warning: Cannot find any feasible result, so only return the gene which has lowest fitness." + '\n' + '-' * 50)
         return minGene, minGeneInfo, pop, history
+
+    # ------------------------------------------------------------------ the whole loop on the device
+    def EvolveOnDevice(self, isPrintMessage=True, seed=None, device=None):
+        """``Evolve`` with the population resident on the GPU: every generation is one ``tb_fitness`` launch on the gene
+        matrix plus one ``tb_ga_step`` (ranking, elitism, crossover, mutation, re-seeding -- the operators of
+        ``UpdatePop`` / ``Crossover`` / ``Mutate`` / ``Select``, ga.py:155-190, written as CUDA kernels); the host reads one
+        40-byte report per generation for the early-stopping rule.  Same return value as ``Evolve``.
+
+        The random numbers come from a counter-based generator on the device (reproducible from ``seed``), not from
+        Python's ``random`` stream, so the trajectory differs from ``Evolve``'s while the operators and their
+        probabilities are the same.  Needs the stock ``GetFitness`` (a Python override cannot run on the device)."""
+        import ctypes as C
+
+        import numpy as np
+        import torch
+
+        from . import _lib
+        from .batch import type_table
+
+        if not self._stock_fitness():
+            raise TypeError("EvolveOnDevice needs the stock GetFitness; use Evolve() with an overridden fitness")
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        seed = random.getrandbits(63) if seed is None else int(seed)
+        nPop, M = self.nPop, self.nMember
+        prm = _lib.TbGaParams(nPop, self.nElite, M, self.nType, self.pCrossover, self.pMutate, self.pOrigin, seed)
+        xyz, support, conn, _, force = self.truss._pack()
+        plan = self.truss._get_plan(support, conn)
+        td = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+        d_xyz, d_force, d_tab = td(xyz), td(force), td(type_table(self.typeList))
+        w = np.asarray(self.memberTypeWeightedInitProb, dtype=np.float64)
+        d_cum = None if np.all(w == w[0]) else td(np.cumsum(w) / w.sum())
+        genes = [torch.empty((nPop, M), dtype=torch.int32, device=dev) for _ in range(2)]
+        out = {"fitness": torch.empty(nPop, dtype=torch.float64, device=dev),
+               "flags": torch.empty((nPop, 2), dtype=torch.uint8, device=dev),
+               "info": torch.empty(nPop, dtype=torch.int32, device=dev)}
+        order = torch.empty(nPop, dtype=torch.int32, device=dev)
+        rep_dev = torch.zeros(C.sizeof(_lib.TbGaReport), dtype=torch.uint8, device=dev)
+        rep_host = torch.zeros(C.sizeof(_lib.TbGaReport), dtype=torch.uint8).pin_memory()
+
+        def evaluate_and_rank(cur, nxt, generation):
+            plan.fitness_device(nPop, d_xyz, d_force, genes[cur], d_tab, self.allowStress, self.allowDisplace, out)
+            _lib.ga_step(prm, generation, out["fitness"], out["flags"], genes[cur], None if nxt is None else genes[nxt],
+                         order, rep_dev)
+            rep_host.copy_(rep_dev, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return _lib.TbGaReport.from_buffer_copy(rep_host.numpy().tobytes())
+
+        def record_feasible(rep, cur):
+            if rep.feasible_index >= 0 and (self._lastFeasibleFitness is None or rep.feasible_fitness < self._lastFeasibleFitness):
+                self._lastFeasibleGene[:] = genes[cur][rep.feasible_index].tolist()
+                self._lastFeasibleFitness = float(rep.feasible_fitness)
+
+        _lib.ga_init(prm, genes[0], d_cum)
+        cur = 0
+        bestFitness, history, nWait, earlyStop = INF, [], 0, False
+        for i in (range(self.nIteration) if self.nIteration is not None else InfinteLoop()):
+            rep = evaluate_and_rank(cur, 1 - cur, i)          # Select + UpdatePop of generation i
+            if i == 0 and bool(out["info"].any().item()):     # topology / input problems show in the first generation
+                from .truss import raise_for_info             # (a gene that makes K singular ranks last: fitness inf)
+                raise_for_info(int(out["info"][out["info"].nonzero()[0, 0]].item()))
+            record_feasible(rep, cur)
+            minFitness = float(rep.best_fitness)
+            if minFitness < bestFitness:
+                bestFitness, nWait = minFitness, 0
+            else:
+                nWait += 1
+                if nWait >= self.nPatience:
+                    earlyStop = True
+                    break
+            history.append(bestFitness)
+            if isPrintMessage:
+                print(f"\rIteration: {i :6d}, nWaitBestIter: {nWait :3d}, minFitness: {minFitness :12.4f}, "
+                      f"isInternalAllowed: {str(bool(rep.best_stress_ok)) :5s}, isDisplaceAllowed: {str(bool(rep.best_displace_ok)) :5s}", end='')
+            cur = 1 - cur                                      # the updated population becomes the current one
+        if isPrintMessage:
+            print('...Early stoping !' if earlyStop else "")
+
+        # GetBestFeasibleGene (ga.py:110-123): the record when early-stopped, else the best feasible gene of the final population
+        pop = genes[cur].cpu().numpy().tolist()
+        if earlyStop and self._lastFeasibleFitness is not None:
+            return self._lastFeasibleGene, (self._lastFeasibleFitness, True, True), pop, history
+        rep = evaluate_and_rank(cur, None, 0)
+        if rep.feasible_index >= 0:
+            return pop[rep.feasible_index], (float(rep.feasible_fitness), True, True), pop, history
+        if self._lastFeasibleFitness is not None:
+            return self._lastFeasibleGene, (self._lastFeasibleFitness, True, True), pop, history
+        if isPrintMessage:
+            print('-' * 50 + '\n' + "Warning: Cannot find any feasible result, so only return the gene which has lowest fitness." + '\n' + '-' * 50)
+        return pop[0], self.GetFitness(pop[0]), pop, history

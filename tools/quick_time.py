@@ -69,3 +69,17 @@ for path in (1, 2):
     plan.set_path(path)
     best, med = timeit(lambda: plan.fitness_device(B, dx, df, dg, dt, 30000.0, 10.0, o), n=5)
     print(f"bar-72 GA x{B} (path {path}): best {best:.3f} ms -> {B/best*1e3:.0f} fitness/s")
+
+# config 3 as a loop: GA generations on the device (tb_fitness + tb_ga_step per generation) vs the host GA class
+from python_stable_3d_truss_analysis_b200.ga import GA
+import time as _t
+for nPop, nElite in ((8192, 1024),):
+    ga = GA(t, types, allowStress=30000., allowDisplace=10., nIteration=40, nPatience=1000, nPop=nPop, nElite=nElite)
+    ga.EvolveOnDevice(isPrintMessage=False, seed=1)
+    torch.cuda.synchronize(); t0 = _t.perf_counter()
+    g, info, pop, hist = ga.EvolveOnDevice(isPrintMessage=False, seed=1)
+    dt = _t.perf_counter() - t0
+    print(f"bar-72 GA nPop={nPop}: device loop {dt/40*1e3:.3f} ms per generation ({40/dt:.0f} generations/s, {nPop*40/dt/1e6:.1f} M fitness/s incl. ranking + update); best {hist[0]:.1f} -> {hist[-1]:.1f}")
+    ga2 = GA(t, types, allowStress=30000., allowDisplace=10., nIteration=3, nPatience=1000, nPop=nPop, nElite=nElite)
+    random.seed(1); t0 = _t.perf_counter(); ga2.Evolve(isPrintMessage=False); dt2 = _t.perf_counter() - t0
+    print(f"bar-72 GA nPop={nPop}: host loop (GA.Evolve, batched fitness, Python operators) {dt2/3*1e3:.1f} ms per generation")
