@@ -230,6 +230,27 @@ typedef struct {
 int tb_solve_ragged(const tb_ragged_in* in, const tb_batch_out* out, void* cuda_stream);
 int tb_solve_ragged_host(const tb_ragged_in* in, const tb_batch_out* out);
 
+/* ---- Dataset generation on the device (slientruss3d/generate.py:12-148) ------------------
+ * Expands a pool of trusses (a tb_ragged_in with DEVICE pointers) into n_out augmented trusses in the same packed layout,
+ * ready for tb_solve_ragged: output truss o is pool truss src[o] after MoveToCentroid, RandomTranslation, AddJointNoise,
+ * RandomResetPin (each optional, applied in this order).  out_joint_off / out_member_off [n_out+1] are the prefix sums of
+ * the chosen pool trusses' sizes (device).  Counter-based random numbers keyed by `seed`. */
+typedef struct {
+  int32_t move_to_centroid;
+  int32_t random_translation;
+  double translate_lo, translate_hi;     /* RandomTranslation(translateRange) */
+  int32_t joint_noise;
+  double noise_mean[3], noise_std[3];    /* AddJointNoise(noiseMeans, noiseStds) */
+  int32_t reset_pin;
+  int32_t min_pin;                       /* RandomResetPin(minNumPin, maxNumPinRatio); ratio <= 0: up to every joint */
+  double max_pin_ratio;
+  uint64_t seed;
+} tb_augment_params;
+
+int tb_augment_ragged(const tb_ragged_in* pool, int32_t n_out, const int32_t* src, const int64_t* out_joint_off,
+                      const int64_t* out_member_off, const tb_augment_params* params, double* out_xyz,
+                      uint8_t* out_support, int32_t* out_conn, double* out_aed, double* out_force, void* cuda_stream);
+
 /* Page-locked host buffers for callers of the *_host entry points (full-speed H2D/D2H). */
 int tb_pinned_alloc(void** ptr, size_t bytes);
 int tb_pinned_free(void* ptr);

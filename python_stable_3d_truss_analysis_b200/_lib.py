@@ -17,7 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 LIB_PATH = os.environ.get("TB_LIB_PATH") or os.path.join(CSRC, "libtruss_b200.so")   # TB_LIB_PATH: instrumented builds (tools/)
-SOURCES = ["tb_plan.cu", "tb_small.cu", "tb_dense16.cu", "tb_large.cu", "tb_band.cu", "tb_api.cu", "tb_peak.cu", "tb_ga.cu"]
+SOURCES = ["tb_plan.cu", "tb_small.cu", "tb_dense16.cu", "tb_large.cu", "tb_band.cu", "tb_api.cu", "tb_peak.cu", "tb_ga.cu", "tb_augment.cu"]
 
 TB_ERR_NO_DEVICE = -7
 TB_ERR_TOO_LARGE = -6
@@ -75,6 +75,13 @@ class TbPlanInfo(C.Structure):
                 ("band_blocks_nonzero", C.c_int64), ("band_products", C.c_int64)]
 
 
+class TbAugmentParams(C.Structure):
+    _fields_ = [("move_to_centroid", C.c_int32), ("random_translation", C.c_int32), ("translate_lo", C.c_double),
+                ("translate_hi", C.c_double), ("joint_noise", C.c_int32), ("noise_mean", C.c_double * 3),
+                ("noise_std", C.c_double * 3), ("reset_pin", C.c_int32), ("min_pin", C.c_int32),
+                ("max_pin_ratio", C.c_double), ("seed", C.c_uint64)]
+
+
 class TbGaParams(C.Structure):
     _fields_ = [("n_pop", C.c_int32), ("n_elite", C.c_int32), ("n_member", C.c_int32), ("n_type", C.c_int32),
                 ("p_crossover", C.c_double), ("p_mutate", C.c_double), ("p_origin", C.c_double), ("seed", C.c_uint64)]
@@ -110,7 +117,7 @@ class TbRaggedIn(C.Structure):
 
 EXPORTS = ["tb_plan_create", "tb_plan_destroy", "tb_plan_query", "tb_plan_set_path", "tb_plan_get_maps",
            "tb_plan_get_scatter", "tb_solve", "tb_solve_host", "tb_solve_loadcases", "tb_solve_loadcases_host", "tb_fitness", "tb_fitness_host", "tb_solve_ragged",
-           "tb_solve_ragged_host", "tb_ga_init", "tb_ga_step", "tb_pinned_alloc", "tb_pinned_free", "tb_small_path_limits", "tb_fp64_peak", "tb_rsqrt_probe", "tb_profile_enable", "tb_profile_read",
+           "tb_solve_ragged_host", "tb_ga_init", "tb_ga_step", "tb_augment_ragged", "tb_pinned_alloc", "tb_pinned_free", "tb_small_path_limits", "tb_fp64_peak", "tb_rsqrt_probe", "tb_profile_enable", "tb_profile_read",
            "tb_launch_count", "tb_strerror", "tb_version"]
 
 _lib = None
