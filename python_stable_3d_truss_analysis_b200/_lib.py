@@ -154,6 +154,7 @@ def lib():
     L.tb_small_path_limits.argtypes = [C.POINTER(i32), C.POINTER(i32)]
     L.tb_fp64_peak.argtypes = [i32, i32, C.POINTER(dbl), C.POINTER(C.c_float)]
     L.tb_rsqrt_probe.argtypes = [i32, C.POINTER(dbl)]
+    L.tb_augment_ragged.argtypes = [C.POINTER(TbRaggedIn), i32, vp, vp, vp, C.POINTER(TbAugmentParams), vp, vp, vp, vp, vp, vp]
     L.tb_ga_init.argtypes = [C.POINTER(TbGaParams), vp, vp, vp]
     L.tb_ga_step.argtypes = [C.POINTER(TbGaParams), C.c_uint64, vp, vp, vp, vp, vp, vp, vp]
     L.tb_profile_enable.argtypes = [i32]
@@ -437,6 +438,50 @@ def solve_ragged_host(dim, joint_off, member_off, xyz, support, conn, aed, force
     bo = TbBatchOut(_ptr(out.get("u")), _ptr(out.get("ext")), _ptr(out.get("axial")), _ptr(out.get("weight")),
                     _ptr(out["info"]))
     check(lib().tb_solve_ragged_host(C.byref(ri), C.byref(bo)))
+    return out
+
+
+def augment_and_solve_device(dim, pool, n_out, params: "TbAugmentParams", src=None, solve=True, device=None):
+    """Dataset generation on the device: expand the packed pool (dict of numpy arrays: joint_off, member_off, xyz,
+    support, conn, aed, force) into ``n_out`` augmented trusses (tb_augment_ragged) and, if ``solve``, run
+    tb_solve_ragged on them without leaving the GPU.  Returns a dict of torch CUDA tensors in the packed layout
+    (joint_off, member_off, src, xyz, support, conn, aed, force [, u, ext, axial, weight, info])."""
+    import torch
+
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    jo, mo = _np(pool["joint_off"], np.int64), _np(pool["member_off"], np.int64)
+    P = jo.shape[0] - 1
+    src = (np.arange(n_out) % P).astype(np.int32) if src is None else _np(src, np.int32)
+    nj, nm = np.diff(jo), np.diff(mo)
+    ojo = np.zeros(n_out + 1, np.int64)
+    omo = np.zeros(n_out + 1, np.int64)
+    ojo[1:] = np.cumsum(nj[src])
+    omo[1:] = np.cumsum(nm[src])
+    td = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(dev)  # noqa: E731
+    d = {"p_jo": td(jo, np.int64), "p_mo": td(mo, np.int64), "p_xyz": td(pool["xyz"], np.float64),
+         "p_sup": td(pool["support"], np.uint8), "p_conn": td(pool["conn"], np.int32), "p_aed": td(pool["aed"], np.float64),
+         "p_force": td(pool["force"], np.float64)}
+    SJ, SM = int(ojo[-1]), int(omo[-1])
+    out = {"joint_off": td(ojo, np.int64), "member_off": td(omo, np.int64), "src": td(src, np.int32),
+           "xyz": torch.empty(SJ * dim, dtype=torch.float64, device=dev), "support": torch.empty(SJ, dtype=torch.uint8, device=dev),
+           "conn": torch.empty(SM * 2, dtype=torch.int32, device=dev), "aed": torch.empty(SM * 3, dtype=torch.float64, device=dev),
+           "force": torch.empty(SJ * dim, dtype=torch.float64, device=dev)}
+    maxj, maxm = int(nj.max()), int(nm.max())
+    ri = TbRaggedIn(int(dim), int(P), _ptr(d["p_jo"]), _ptr(d["p_mo"]), _ptr(d["p_xyz"]), _ptr(d["p_sup"]), _ptr(d["p_conn"]),
+                    _ptr(d["p_aed"]), _ptr(d["p_force"]), maxj, maxm)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    check(lib().tb_augment_ragged(C.byref(ri), int(n_out), _ptr(out["src"]), _ptr(out["joint_off"]), _ptr(out["member_off"]),
+                                  C.byref(params), _ptr(out["xyz"]), _ptr(out["support"]), _ptr(out["conn"]), _ptr(out["aed"]),
+                                  _ptr(out["force"]), st))
+    if solve:
+        out.update({"u": torch.empty(SJ * dim, dtype=torch.float64, device=dev), "ext": torch.empty(SJ * dim, dtype=torch.float64, device=dev),
+                    "axial": torch.empty(SM, dtype=torch.float64, device=dev), "weight": torch.empty(n_out, dtype=torch.float64, device=dev),
+                    "info": torch.empty(n_out, dtype=torch.int32, device=dev)})
+        ro = TbRaggedIn(int(dim), int(n_out), _ptr(out["joint_off"]), _ptr(out["member_off"]), _ptr(out["xyz"]), _ptr(out["support"]),
+                        _ptr(out["conn"]), _ptr(out["aed"]), _ptr(out["force"]), maxj, maxm)
+        bo = TbBatchOut(_ptr(out["u"]), _ptr(out["ext"]), _ptr(out["axial"]), _ptr(out["weight"]), _ptr(out["info"]))
+        check(lib().tb_solve_ragged(C.byref(ro), C.byref(bo), st))
+    out["_keep"] = d
     return out
 
 

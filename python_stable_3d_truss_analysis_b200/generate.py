@@ -312,3 +312,47 @@ def GenerateRandomCubeTrusses(gridRange=(5, 5, 5), numCubeRange=(5, 5), numEachR
     if isPlotTruss and isPrintMessage:
         print("\n[generate] isPlotTruss is not supported by the B200 build (plotting is outside the solve path).")
     return trussList
+
+
+def GenerateAugmentedDataset(pool, nOut, moveToCentroid=False, translateRange=None, noiseMeans=None, noiseStds=None,
+                             resetPin=None, seed=0, isDoStructuralAnalysis=True, asNumpy=True):
+    """Bulk dataset generation on the GPU: ``pool`` (a list of Truss objects, e.g. from
+    ``GenerateRandomCubeTrusses``) is expanded into ``nOut`` augmented trusses -- output truss ``o`` is pool truss
+    ``o % len(pool)`` after MoveToCentroid, RandomTranslation(translateRange), AddJointNoise(noiseMeans, noiseStds) and
+    RandomResetPin(*resetPin) (each optional, in this order: the order of the reference's recipe, example.py:239-267) --
+    and solved in the same GPU pass (``tb_augment_ragged`` + ``tb_solve_ragged``).
+
+    Returns the packed arrays (``joint_off``, ``member_off``, ``src``, ``xyz``, ``support``, ``conn``, ``aed``, ``force`` and,
+    when solved, ``u``, ``ext``, ``axial``, ``weight``, ``info``; ``info[o] == -1`` marks a truss that fails the counting rule
+    of truss.py:158-164, which the reference's generator would have re-drawn).  The host augmenter classes above follow
+    Python's ``random`` stream; this path uses counter-based random numbers keyed by ``seed``."""
+    from . import _lib
+    from .batch import pack_ragged
+
+    pool = list(pool)
+    dim, jo, mo, xyz, sup, conn, aed, force = pack_ragged(pool)
+    prm = _lib.TbAugmentParams()
+    prm.move_to_centroid = 1 if moveToCentroid else 0
+    if translateRange is not None:
+        prm.random_translation, prm.translate_lo, prm.translate_hi = 1, float(translateRange[0]), float(translateRange[1])
+    if noiseStds is not None or noiseMeans is not None:
+        prm.joint_noise = 1
+        means = [0., 0., 0.] if noiseMeans is None else list(noiseMeans)
+        stds = [1., 1., 1.] if noiseStds is None else list(noiseStds)
+        for i in range(dim):
+            prm.noise_mean[i], prm.noise_std[i] = float(means[i]), float(stds[i])
+    if resetPin is not None:
+        minNumPin, maxNumPinRatio = resetPin
+        if minNumPin < 3:
+            from .utils import PinNotEnoughError
+            raise PinNotEnoughError("Number of pins must >= 3.")
+        prm.reset_pin, prm.min_pin = 1, int(minNumPin)
+        prm.max_pin_ratio = 0.0 if maxNumPinRatio is None else float(maxNumPinRatio)
+    prm.seed = int(seed)
+    out = _lib.augment_and_solve_device(dim, {"joint_off": jo, "member_off": mo, "xyz": xyz, "support": sup, "conn": conn,
+                                               "aed": aed, "force": force}, int(nOut), prm, solve=isDoStructuralAnalysis)
+    out.pop("_keep", None)
+    out["dim"] = dim
+    if asNumpy:
+        out = {k: (v.cpu().numpy() if hasattr(v, "cpu") else v) for k, v in out.items()}
+    return out

@@ -83,3 +83,13 @@ for nPop, nElite in ((8192, 1024),):
     ga2 = GA(t, types, allowStress=30000., allowDisplace=10., nIteration=3, nPatience=1000, nPop=nPop, nElite=nElite)
     random.seed(1); t0 = _t.perf_counter(); ga2.Evolve(isPrintMessage=False); dt2 = _t.perf_counter() - t0
     print(f"bar-72 GA nPop={nPop}: host loop (GA.Evolve, batched fitness, Python operators) {dt2/3*1e3:.1f} ms per generation")
+
+# config 4 as a pipeline: a pool of cube-7 trusses expanded to 65536 augmented trusses and solved, all on the device
+import copy as _copy, glob as _glob
+from python_stable_3d_truss_analysis_b200.generate import GenerateAugmentedDataset
+pool = [Truss(3).LoadFromJSON(data=json.load(open(f))) for f in sorted(_glob.glob(os.path.join(ROOT, "tests", "golden", "ref_generate", "cube-7_case_*.json")))]
+kw = dict(moveToCentroid=True, translateRange=(-30., 30.), noiseStds=[10., 10., 10.], resetPin=(5, 0.6), seed=42, asNumpy=False)
+GenerateAugmentedDataset(pool, 65536, **kw); torch.cuda.synchronize()
+t0 = _t.perf_counter(); ds = GenerateAugmentedDataset(pool, 65536, **kw); torch.cuda.synchronize(); dt = _t.perf_counter() - t0
+ok = int((ds["info"] == 0).sum().item())
+print(f"cube-7 pool of {len(pool)} -> 65536 augmented trusses generated + solved on the device: {dt*1e3:.2f} ms wall ({65536/dt/1e6:.2f} M trusses/s incl. pool upload and offsets), {ok} solved, {65536-ok} fail the counting rule")
