@@ -171,6 +171,22 @@ class Truss:
         self._displace = self._external = self._internal = None
         self._solved = True
 
+    def _dense_or_from_sparse(self, key):
+        """Dense result array ``key`` (u | ext | axial), rebuilt from the sparse dicts when the truss was loaded from an
+        output JSON (the entries the reference dropped under its 1e-10 filter come back as zeros)."""
+        if self._dense is not None:
+            return np.asarray(self._dense[key], dtype=np.float64).reshape(-1)
+        d = self._dim
+        if key == "axial":
+            v = np.zeros(self.nMember)
+            for m, f in (self._internal or {}).items():
+                v[m] = f
+            return v
+        v = np.zeros(self.nJoint * d)
+        for j, vec in ((self._displace if key == "u" else self._external) or {}).items():
+            v[j * d:(j + 1) * d] = vec
+        return v
+
     def _sparse(self, key):
         """Build (once) the reference's sparse dict view of a dense result."""
         attr = {"u": "_displace", "ext": "_external", "axial": "_internal"}[key]

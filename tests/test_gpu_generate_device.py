@@ -102,3 +102,12 @@ def test_full_recipe_solved_on_the_device_matches_the_oracle():
             assert orc.normwise_err(got[k], want[k]) <= H.TOL, (o, k)
         checked += 1
     assert checked >= 12
+    # the packed result goes into the binary container as it is, and comes back as Truss objects / reference JSON
+    from python_stable_3d_truss_analysis_b200.dataset import PackedDataset
+    pd_ = PackedDataset(3, ds)
+    o = int(np.nonzero(ds["info"] == 0)[0][5])
+    t = pd_.truss(o)
+    j0, j1 = ds["joint_off"][o], ds["joint_off"][o + 1]
+    assert t.isSolved and np.array_equal(t._dense["u"], ds["u"][3 * j0:3 * j1])
+    again = Truss(3).LoadFromJSON(data=pd_.json(o), isOutputFile=True)
+    assert again.GetInternalForces() == t.GetInternalForces()
