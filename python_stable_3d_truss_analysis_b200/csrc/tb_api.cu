@@ -235,15 +235,6 @@ cudaStream_t* host_streams() {
   (void)init;
   return sts;
 }
-cudaEvent_t host_event() {
-  static cudaEvent_t ev = [] {
-    cudaEvent_t e = nullptr;
-    cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
-    return e;
-  }();
-  return ev;
-}
-
 int stride_ok(int64_t stride, int64_t row) { return stride == 0 || stride == row; }
 
 int run_plan_host(tb_plan* p, const tb_batch_in* in, const tb_batch_out* out, const tb_fit_out* fit, double allow_s,

@@ -140,3 +140,23 @@ def test_path_selection_and_padding():
         for path in (1, 2, 0 if not big else 2):
             plan.set_path(path)
             assert plan.path == path
+
+
+def test_ga_and_augment_argument_errors_without_a_device():
+    """tb_ga_* / tb_augment_ragged validate their arguments before touching the GPU, and fail loudly without one."""
+    import ctypes as C
+    L = _lib.lib()
+    ok = _lib.TbGaParams(64, 8, 12, 3, 0.7, 0.1, 0.1, 1)
+    dummy = np.zeros(64 * 12, np.int32)
+    assert L.tb_ga_init(None, None, dummy.ctypes.data, None) == -1                      # TB_ERR_NULL
+    bad = _lib.TbGaParams(64, 80, 12, 3, 0.7, 0.1, 0.1, 1)                               # more elites than population
+    assert L.tb_ga_init(C.byref(bad), None, dummy.ctypes.data, None) == -3               # TB_ERR_SIZE
+    bad = _lib.TbGaParams(64, 8, 12, 1, 0.7, 0.1, 0.1, 1)                                # one member type (OnlyOneMemberTypeError)
+    assert L.tb_ga_init(C.byref(bad), None, dummy.ctypes.data, None) == -3
+    bad = _lib.TbGaParams(64, 8, 12, 3, 0.7, 0.3, 0.1, 1)                                # probabilities above one
+    assert L.tb_ga_step(C.byref(bad), 0, dummy.ctypes.data, None, dummy.ctypes.data, None, dummy.ctypes.data, None, None) == -3
+    assert L.tb_ga_step(C.byref(ok), 0, None, None, dummy.ctypes.data, None, dummy.ctypes.data, None, None) == -1
+    prm = _lib.TbAugmentParams()
+    assert L.tb_augment_ragged(None, 4, None, None, None, C.byref(prm), None, None, None, None, None, None) == -1
+    if not _has_cuda():
+        assert L.tb_ga_init(C.byref(ok), None, dummy.ctypes.data, None) == _lib.TB_ERR_NO_DEVICE
