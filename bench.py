@@ -223,8 +223,8 @@ def run_gpu(args):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
     stream = torch.cuda.current_stream()
 
-    def step():
-        plan.solve_device(B, d_xyz, d_F, aed=d_aed, out=out, stream=stream)
+    def step(st=None):
+        plan.solve_device(B, d_xyz, d_F, aed=d_aed, out=out, stream=stream if st is None else st)
         if symm is not None:
             symm.barrier()                     # every rank's results have landed in rank 0's buffer
         elif world > 1:
@@ -261,26 +261,55 @@ def run_gpu(args):
                 err = orc.normwise_err(out[k][b].cpu().numpy(), want[k])
                 assert err <= 1e-9, f"parity gate failed: system {b} field {k} err {err:.3e}"
 
-    # ---- timed region: K steps, each timed on the device; L2 flushed between steps (outside the events)
+    # ---- timed region: K steps, each timed on the device; L2 flushed between steps (outside the events).  On one GPU the
+    # step (three kernel launches through tb_solve) is captured once into a CUDA graph and replayed (TB_BENCH_GRAPH=0:
+    # plain launches); the per-kernel times of the roofline come from a second, instrumented pass of K steps.
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    _lib.profile_enable(True)
-    _lib.profile_read()
     launches0 = _lib.launch_count()
+    step()
+    launches_per_step = _lib.launch_count() - launches0
+    graph = None
+    if world == 1 and os.environ.get("TB_BENCH_GRAPH", "1") == "1":
+        try:
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                step(torch.cuda.current_stream())
+            graph.replay()
+            torch.cuda.synchronize()
+        except Exception as exc:   # noqa: BLE001
+            print(f"bench.py: CUDA graph capture failed ({exc!r}); plain launches", file=sys.stderr)
+            graph = None
+            torch.cuda.synchronize()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
     wall0 = time.perf_counter()
     for e0, e1 in ev:
         flush.zero_()
         e0.record(stream)
-        step()
+        if graph is not None:
+            graph.replay()
+        else:
+            step()
         e1.record(stream)
     barrier()
     wall = time.perf_counter() - wall0
-    launches = _lib.launch_count() - launches0
+    launches = launches_per_step * args.steps
+    # instrumented pass: CUDA events around every kernel (they cost a few microseconds per step, hence not in the timed pass)
+    _lib.profile_enable(True)
+    _lib.profile_read()
+    evp = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for e0, e1 in evp:
+        flush.zero_()
+        e0.record(stream)
+        step()
+        e1.record(stream)
+    barrier()
     prof = _lib.profile_read()
     _lib.profile_enable(False)
+    prof_ms = sum(e0.elapsed_time(e1) for e0, e1 in evp)
     dev_ms = sum(e0.elapsed_time(e1) for e0, e1 in ev)
     t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -395,6 +424,7 @@ def run_gpu(args):
         "config": {"workload": WORKLOAD, "batch_per_gpu": B, "n_free": n, "n_member": M, "mode": "independent K per system",
                    "pipeline": {0: "fused shared-memory kernel", 1: "tiled 64x64 block-sparse Cholesky", 2: "block-band Cholesky (16x16 blocks)"}[path],
                    "l2": "explicit 256 MB flush (> 126 MB L2) between timed steps, outside the events",
+                   "launch": "CUDA graph replay of the step" if graph is not None else "plain stream launches",
                    "multi_gpu": "contiguous block partition of the batch; " + gather_mode},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "tb_solve_host (C ABI) with pinned host buffers", "steps": e2e_steps},
@@ -407,7 +437,7 @@ def run_gpu(args):
                      "dense_potrf_equivalent_tflops": B * dense_flops / per_launch_s / 1e12,
                      "peak_source": "FP64 DMMA m8n8k4 microbenchmark (tb_fp64_peak) measured in this run; "
                                     "MEASURED_PEAKS.json has no FP64 entry", "peak_dfma": peak_dfma,
-                     "share_of_step": chol_ms / dev_ms},
+                     "share_of_step": chol_ms / prof_ms},
         "roofline_hbm_view": roof_hbm,
         "roofline_stages": stages,
         "kernels": kernels,
