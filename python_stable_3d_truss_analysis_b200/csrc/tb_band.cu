@@ -1887,6 +1887,7 @@ int launch_band(const LargeArgs& a, int num_sm, cudaStream_t st) {
   // system (eight systems per SM; measured faster than k_band1's eight one-warp systems per SM at every batch size:
   // bar-942 x8192 in 2.73 ms against 2.96 ms)
   int warps = NB > 5 ? 1 : (int64_t)a.batch <= (int64_t)num_sm * per3 ? 3 : 2;
+  if (NB <= 5 && a.band_warps == 2) warps = 2;
   if (force == 1 || (NB <= 5 && (force == 2 || force == 3))) warps = force;
   tb_prof_begin(TB_PROF_CHOL, st);
   if (warps == 3) {

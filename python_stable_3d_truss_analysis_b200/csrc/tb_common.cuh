@@ -192,6 +192,8 @@ struct LargeArgs {
   double allow_stress, allow_displace;
   int fitness_mode;
   int plan_stable;
+  int band_warps;   // band path: 0 = choose by batch size, 2 = force the two-warp kernel (halves of a split batch share the SMs)
+  int no_split;     // internal: this call is one half of a split batch
   int shared_k;     // band path: every system of the batch has the stiffness matrix of system 0 (load cases of one truss)
 };
 

@@ -1019,6 +1019,62 @@ int tb_launch_large(const LargeArgs& a, int num_sm, cudaStream_t st, int path) {
   const size_t prep_smem = (size_t)a.M * (a.dim * (a.dim + 1) / 2) * 8, rec_smem = (size_t)a.M * (1 + a.dim) * 8;
   static const bool no_prep = [] { const char* s = getenv("TB_NO_PREP"); return s && s[0] == '1'; }();
   const bool prep = fused && !no_prep && prep_smem <= 96 * 1024 && rec_smem <= 96 * 1024;
+  // Two half-batches on two streams (band path, a batch of a few systems per SM): assembly is two waves of CTAs, so
+  // the first half's factorisation starts while the second half is still being assembled, and the first half's
+  // recovery runs under the second half's factorisation.  Both halves use the two-warp band kernel (eight systems per
+  // SM), so together they occupy the SMs like the unsplit batch.  Not under per-kernel profiling (one stream there).
+  static const bool split_env = [] { const char* s = getenv("TB_LARGE_SPLIT"); return !(s && s[0] == '0'); }();
+  if (split_env && !a.no_split && !tb_prof_on() && path == 2 && prep && !a.shared_k && a.NB <= 5 &&
+      a.batch > num_sm * 6 && a.batch <= num_sm * 8) {
+    static cudaStream_t aux = nullptr;
+    static cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    if (!aux) {
+      cudaError_t e = cudaStreamCreateWithFlags(&aux, cudaStreamNonBlocking);
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming);
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming);
+      if (e != cudaSuccess) return (int)e;
+    }
+    static const int n0_env = [] { const char* s = getenv("TB_LARGE_SPLIT_N0"); return s ? atoi(s) : 0; }();
+    const int n0 = n0_env > 0 && n0_env < a.batch ? n0_env : num_sm * 4;   // default: one wave of the assembly kernel
+    auto slice = [&](int b0, int nb) {
+      LargeArgs h = a;
+      h.batch = nb;
+      h.no_split = 1;
+      h.band_warps = 2;
+      h.xyz = a.xyz + (int64_t)b0 * a.xyz_stride;
+      if (a.aed) h.aed = a.aed + (int64_t)b0 * a.aed_stride;
+      if (a.gene) h.gene = a.gene + (int64_t)b0 * a.gene_stride;
+      h.force = a.force + (int64_t)b0 * a.force_stride;
+      const int nv = a.dim * (a.dim + 1) / 2;
+      h.mk = a.mk + (int64_t)b0 * a.M;
+      h.mc = a.mc + (int64_t)b0 * a.M * a.dim;
+      h.mw = a.mw + (int64_t)b0 * a.M;
+      h.mkc = a.mkc + (int64_t)b0 * a.M * nv;
+      h.kv = a.kv + (int64_t)b0 * a.nnz;
+      h.wd = a.wd + (int64_t)b0 * a.nb16 * 256;
+      h.L = a.L + (int64_t)b0 * a.nb16 * (a.NB + 1) * 256;
+      h.y = a.y + (int64_t)b0 * a.n_pad;
+      h.status = a.status + b0;
+      if (a.u) h.u = a.u + (int64_t)b0 * a.N;
+      if (a.ext) h.ext = a.ext + (int64_t)b0 * a.N;
+      if (a.axial) h.axial = a.axial + (int64_t)b0 * a.M;
+      if (a.weight) h.weight = a.weight + b0;
+      if (a.info) h.info = a.info + b0;
+      if (a.fitness) h.fitness = a.fitness + b0;
+      if (a.flags) h.flags = a.flags + 2 * (int64_t)b0;
+      return h;
+    };
+    const LargeArgs hA = slice(0, n0), hB = slice(n0, a.batch - n0);
+    TB_CUDA(cudaEventRecord(ev_fork, st));
+    TB_CUDA(cudaStreamWaitEvent(aux, ev_fork, 0));
+    int rc = tb_launch_large(hA, num_sm, st, path);
+    if (rc) return rc;
+    rc = tb_launch_large(hB, num_sm, aux, path);
+    if (rc) return rc;
+    TB_CUDA(cudaEventRecord(ev_join, aux));
+    TB_CUDA(cudaStreamWaitEvent(st, ev_join, 0));
+    return (int)cudaGetLastError();
+  }
   if (!prep) k_init_status<<<(a.batch + 255) / 256, 256, 0, st>>>(a.status, a.batch, 0);   // k_prep clears its own
   // load cases of one truss (shared_k): assembly and factorisation run for system 0 only
   const bool shared = a.shared_k && path == 2 && prep && a.batch > 1;
