@@ -15,6 +15,8 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <mutex>
+
 #include "tb_common.cuh"
 
 #ifdef TB_PHASE_TIMING
@@ -1026,6 +1028,8 @@ int tb_launch_large(const LargeArgs& a, int num_sm, cudaStream_t st, int path) {
   static const bool split_env = [] { const char* s = getenv("TB_LARGE_SPLIT"); return !(s && s[0] == '0'); }();
   if (split_env && !a.no_split && !tb_prof_on() && path == 2 && prep && !a.shared_k && a.NB <= 5 &&
       a.batch > num_sm * 6 && a.batch <= num_sm * 8) {
+    static std::mutex split_mu;                // the second stream and its events are shared by every plan of the process:
+    std::lock_guard<std::mutex> split_lock(split_mu);   // fork .. join is enqueued as one unit
     static cudaStream_t aux = nullptr;
     static cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     if (!aux) {
