@@ -313,6 +313,10 @@ int run_plan_host(tb_plan* p, const tb_batch_in* in, const tb_batch_out* out, co
     nch = want > 0 ? want : (fit_ < 1 ? 1 : fit_);
     if (nch > B) nch = B;
     if (p->path != 0 && per_sys * (size_t)B > ws_cap_bytes()) nch = 1;   // run_plan cuts the batch to the workspace cap itself
+    // chunking a blocked path only pays through the D2H it hides (each chunk is a latency-bound wave of its own):
+    // with little to copy back (fitness only, weights only) one launch over the whole batch is faster
+    const size_t d2h_bytes = ((out->u ? rowN : 0) + (out->ext ? rowN : 0) + (out->axial ? rowM : 0)) * (size_t)B * 8;
+    if (want == 0 && p->path != 0 && d2h_bytes < ((size_t)4 << 20)) nch = 1;
   }
   // chunk boundaries: equal parts (a 3:1 split, to shrink the D2H of the last chunk that nothing hides, measured slower:
   // 0.89 ms against 0.82 ms for 1024 bar-942 systems -- the larger first wave costs more than the copy saves)
