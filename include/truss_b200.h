@@ -273,6 +273,22 @@ int tb_rsqrt_probe(int32_t n, double* max_rel_err);
 int tb_profile_enable(int32_t on);
 int tb_profile_read(float* ms, int64_t* count);
 
+/* ---- Introspection of the fused band kernel's program (tests and tools only) ---------------------------------------
+ * The band path runs one fused kernel per batch (csrc/tb_bandts.cu): 8x8 blocks, two-sided elimination (the free DOFs
+ * are split into a top part, a separator and a bottom part; two warps eliminate towards the separator).  The integer
+ * program it executes is built on the host with the plan; these calls expose it so that the CPU tests can replay it in
+ * numpy against the oracle (tests/test_ts_program_cpu.py).
+ * tb_plan_ts_info: out[16] = {exists, block columns, padded order, first separator block, separator blocks, bottom
+ *   blocks, sub-diagonal blocks top / bottom, largest factor chunk, factor doubles per system, block products, block
+ *   solves, entries / contributions of the top side, of the bottom side}.
+ * tb_plan_ts_array: copies array `which` of side `side` (0 colmask, 1 srcmask, 2 xmask, 3 chunk_ptr, 4 mem_ptr,
+ *   5 mem[.][4], 6 ent_ptr, 7 ent[.][2], 8 pack, 9 rowdof, 10 rownat, 11 lofs, 12 ent_src) into out (may be NULL) and
+ *   returns its length in int32 elements, -1 if there is no program.
+ * tb_ts_phase_read: cycles per kernel phase accumulated by an instrumented build (-DTB_PHASE_TIMING), zeros otherwise. */
+int tb_plan_ts_info(const tb_plan* plan, int32_t* out);
+int64_t tb_plan_ts_array(const tb_plan* plan, int32_t side, int32_t which, int32_t* out);
+int tb_ts_phase_read(unsigned long long* out);
+
 /* Kernel launches issued by this library since load (bench.py's gpu_launches). */
 int64_t tb_launch_count(void);
 const char* tb_strerror(int code);

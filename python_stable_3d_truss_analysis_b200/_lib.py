@@ -17,7 +17,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 LIB_PATH = os.environ.get("TB_LIB_PATH") or os.path.join(CSRC, "libtruss_b200.so")   # TB_LIB_PATH: instrumented builds (tools/)
-SOURCES = ["tb_plan.cu", "tb_small.cu", "tb_dense16.cu", "tb_large.cu", "tb_band.cu", "tb_api.cu", "tb_peak.cu", "tb_ga.cu", "tb_augment.cu"]
+SOURCES = ["tb_plan.cu", "tb_tsplan.cu", "tb_small.cu", "tb_dense16.cu", "tb_large.cu", "tb_band.cu", "tb_bandts.cu", "tb_api.cu", "tb_peak.cu",
+           "tb_ga.cu", "tb_augment.cu"]
 
 TB_ERR_NO_DEVICE = -7
 TB_ERR_TOO_LARGE = -6
@@ -33,29 +34,60 @@ class NoCudaDeviceError(TrussLibError):
     pass
 
 
+HEADERS = ("tb_common.cuh", "tb_blocks.cuh", "tb_ts.cuh")
+
+
 def build(force: bool = False, verbose: bool = False, extra_flags=(), out: str | None = None) -> str:
-    """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU).
+
+    Every source is compiled to an object file on its own (in parallel, rebuilt only when it or a header changed) and
+    the objects are linked into ``csrc/libtruss_b200.so``; ``out`` builds a separate (e.g. instrumented) library from
+    scratch with ``extra_flags``."""
     if out is not None:
-        return _compile(out, verbose, list(extra_flags))
+        return _compile(out, verbose, list(extra_flags), objdir=None)
     srcs = [os.path.join(CSRC, s) for s in SOURCES]
-    deps = srcs + [os.path.join(CSRC, "tb_common.cuh"), os.path.join(CSRC, "tb_blocks.cuh"), os.path.join(INCLUDE, "truss_b200.h")]
+    deps = srcs + [os.path.join(CSRC, h) for h in HEADERS] + [os.path.join(INCLUDE, "truss_b200.h")]
     if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
         return LIB_PATH
-    return _compile(LIB_PATH, verbose, list(extra_flags))
+    return _compile(LIB_PATH, verbose, list(extra_flags), objdir=os.path.join(CSRC, "build"), force=force)
 
 
-def _compile(out_path: str, verbose: bool, extra_flags) -> str:
-    srcs = [os.path.join(CSRC, s) for s in SOURCES]
+def _compile(out_path: str, verbose: bool, extra_flags, objdir, force: bool = True) -> str:
+    from concurrent.futures import ThreadPoolExecutor
+    import tempfile
+
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-           "-Xcompiler", "-fPIC", "-shared", "-I", INCLUDE, "-o", out_path] + extra_flags + srcs
+    base = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+            "-Xcompiler", "-fPIC", "-I", INCLUDE] + list(extra_flags)
     if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    res = subprocess.run(cmd, capture_output=True, text=True)
+        base.insert(1, "-Xptxas=-v")
+    tmp = None
+    if objdir is None:
+        tmp = tempfile.TemporaryDirectory()
+        objdir = tmp.name
+    os.makedirs(objdir, exist_ok=True)
+    hdr_time = max(os.path.getmtime(p) for p in [os.path.join(CSRC, h) for h in HEADERS] + [os.path.join(INCLUDE, "truss_b200.h")])
+
+    def one(src):
+        obj = os.path.join(objdir, os.path.splitext(src)[0] + ".o")
+        path = os.path.join(CSRC, src)
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) >= max(os.path.getmtime(path), hdr_time):
+            return obj, ""
+        res = subprocess.run(base + ["-c", path, "-o", obj], capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n" + res.stdout + res.stderr)
+        return obj, res.stderr
+
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 4)) as ex:
+        done = list(ex.map(one, SOURCES))
+    if verbose:
+        print("".join(err for _, err in done))
+    res = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", out_path] + [o for o, _ in done],
+                         capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    if verbose:
-        print(res.stderr)
+        raise RuntimeError("link failed:\n" + res.stdout + res.stderr)
+    if tmp is not None:
+        tmp.cleanup()
     return out_path
 
 
@@ -118,7 +150,7 @@ class TbRaggedIn(C.Structure):
 EXPORTS = ["tb_plan_create", "tb_plan_destroy", "tb_plan_query", "tb_plan_set_path", "tb_plan_get_maps",
            "tb_plan_get_scatter", "tb_solve", "tb_solve_host", "tb_solve_loadcases", "tb_solve_loadcases_host", "tb_fitness", "tb_fitness_host", "tb_solve_ragged",
            "tb_solve_ragged_host", "tb_ga_init", "tb_ga_step", "tb_augment_ragged", "tb_pinned_alloc", "tb_pinned_free", "tb_small_path_limits", "tb_fp64_peak", "tb_rsqrt_probe", "tb_profile_enable", "tb_profile_read",
-           "tb_launch_count", "tb_strerror", "tb_version"]
+           "tb_launch_count", "tb_strerror", "tb_version", "tb_plan_ts_info", "tb_plan_ts_array", "tb_ts_phase_read"]
 
 _lib = None
 
@@ -160,6 +192,10 @@ def lib():
     L.tb_profile_enable.argtypes = [i32]
     L.tb_profile_read.argtypes = [vp, vp]
     L.tb_launch_count.restype = i64
+    L.tb_plan_ts_info.argtypes = [vp, vp]
+    L.tb_plan_ts_array.argtypes = [vp, i32, i32, vp]
+    L.tb_plan_ts_array.restype = i64
+    L.tb_ts_phase_read.argtypes = [vp]
     L.tb_strerror.argtypes = [C.c_int]
     L.tb_strerror.restype = C.c_char_p
     _lib = L
@@ -317,6 +353,32 @@ class Plan:
         check(lib().tb_plan_get_scatter(self._h, row.ctypes.data, col.ctypes.data, ptr.ctypes.data,
                                         mem.ctypes.data, loc.ctypes.data))
         return row, col, ptr, mem, loc
+
+    TS_ARRAYS = ("colmask", "srcmask", "xmask", "chunk_ptr", "mem_ptr", "mem", "ent_ptr", "ent", "pack", "rowdof",
+                 "rownat", "lofs", "ent_src")
+
+    def ts_program(self):
+        """The two-sided band program of the fused band kernel as host arrays (None when the band is too wide for it):
+        ``{"info": {...}, "side": [{name: int32 array}, {...}]}`` -- replayed in numpy by the CPU tests."""
+        L = lib()
+        raw = np.zeros(16, np.int32)
+        check(L.tb_plan_ts_info(self._h, raw.ctypes.data))
+        if not raw[0]:
+            return None
+        keys = ("ok", "nblk", "n_pad", "bT", "nS", "nB", "nb_top", "nb_bottom", "chunk_max", "l_per_sys", "products", "solves")
+        out = {"info": {k: int(raw[i]) for i, k in enumerate(keys)}, "side": []}
+        for s in range(2):
+            d = {}
+            for w, name in enumerate(self.TS_ARRAYS):
+                cnt = L.tb_plan_ts_array(self._h, s, w, None)
+                a = np.zeros(max(int(cnt), 0), np.int32)
+                if cnt > 0:
+                    L.tb_plan_ts_array(self._h, s, w, a.ctypes.data)
+                d[name] = a
+            d["mem"] = d["mem"].reshape(-1, 4)
+            d["ent"] = d["ent"].reshape(-1, 2)
+            out["side"].append(d)
+        return out
 
     # ------------------------------------------------------------------ batch packing
     def _batch_in(self, B, xyz, aed, gene, type_table, force, keep):

@@ -6,6 +6,7 @@
 #include <mutex>
 
 #include "tb_common.cuh"
+#include "tb_ts.cuh"
 
 namespace {
 
@@ -140,12 +141,18 @@ int run_plan_range(tb_plan* p, const tb_batch_in* in, const tb_batch_out* out, c
   a.fitness_mode = fitness_mode;
   a.plan_stable = p->stable;
   a.shared_k = shared_k;
+  if (p->path == 2 && p->ts && p->ts->ok) {      // fused two-sided band kernel: its slice follows the 16x16 pipeline's
+    a.ts = p->ts;
+    a.ts_ws = (char*)ws + ((tb_large_workspace_bytes(nb, p->dim, p->M, p->n_pad, a.nnz, p->path, p->nb16, p->NB) + 255) & ~(size_t)255);
+  }
   return tb_launch_large(a, p->num_sm, st, p->path);
 }
 
 size_t plan_ws_bytes(const tb_plan* p, int batch) {
   if (p->path == 0) return 0;
-  return tb_large_workspace_bytes(batch, p->dim, p->M, p->n_pad, (int64_t)p->ent_row.size(), p->path, p->nb16, p->NB);
+  size_t need = tb_large_workspace_bytes(batch, p->dim, p->M, p->n_pad, (int64_t)p->ent_row.size(), p->path, p->nb16, p->NB);
+  if (p->path == 2 && p->ts) need = ((need + 255) & ~(size_t)255) + tb_ts_workspace_bytes(p, batch);
+  return need;
 }
 
 int ensure_ws(tb_plan* p, size_t need, cudaStream_t st) {

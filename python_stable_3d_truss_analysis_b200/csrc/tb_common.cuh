@@ -9,6 +9,8 @@
 
 #include "truss_b200.h"
 
+struct TsPlan;   // two-sided band program (tb_ts.cuh)
+
 // SupportType codes, slientruss3d/type.py:30-35
 enum : int { SUP_NO = 0, SUP_PIN = 1, SUP_ROLLER_X = 2, SUP_ROLLER_Y = 3, SUP_ROLLER_Z = 4 };
 
@@ -127,6 +129,9 @@ struct tb_plan {
   int32_t* d_inc_ptr = nullptr;
   int32_t* d_inc_mem = nullptr;
 
+  // two-sided band program of the fused band kernel (tb_tsplan.cu); ts->ok == 0 when the band is too wide for it
+  TsPlan* ts = nullptr;
+
   // grow-only device workspace of the blocked path
   void* ws = nullptr;
   size_t ws_bytes = 0;
@@ -195,6 +200,10 @@ struct LargeArgs {
   int band_warps;   // band path: 0 = choose by batch size, 2 = force the two-warp kernel (halves of a split batch share the SMs)
   int no_split;     // internal: this call is one half of a split batch
   int shared_k;     // band path: every system of the batch has the stiffness matrix of system 0 (load cases of one truss)
+  // two-sided fused band kernel (tb_bandts.cu): program + its slice of the workspace; null = the 16x16 band kernels
+  const TsPlan* ts;
+  void* ts_ws;
+  double* kdebug;   // optional debug export of the assembled K values (tb_debug_assemble)
 };
 
 // launchers (return cudaError_t as int)

@@ -14,10 +14,12 @@
 // shared-memory read, and a 64-row x 32-k half tile is one contiguous 16 KB chunk in HBM.
 #include <math.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <mutex>
 
 #include "tb_common.cuh"
+#include "tb_ts.cuh"
 
 #ifdef TB_PHASE_TIMING
 __device__ unsigned long long g_phase_cycles[16];
@@ -1011,9 +1013,95 @@ void tb_large_carve(LargeArgs& a, void* ws, int path) {
   a.status = (int32_t*)p;
 }
 
+namespace {
+
+// largest dynamic shared-memory size already granted to a kernel instantiation, per device (cudaFuncSetAttribute is a
+// per-device setting: a process that solves on cuda:0 and then on cuda:1 has to opt in on both)
+constexpr int TB_MAX_DEV = 64;
+struct SmemGrant {
+  std::mutex mu;
+  size_t granted[TB_MAX_DEV] = {};
+  template <typename K>
+  int ensure(K kern, size_t bytes) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    std::lock_guard<std::mutex> lock(mu);
+    size_t& g = granted[dev & (TB_MAX_DEV - 1)];
+    if (g >= bytes) return 0;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return (int)e;
+    g = bytes;
+    return 0;
+  }
+};
+SmemGrant g_prep_grant[2], g_rec_grant[2], g_chol_grant[2];
+
+// recovery of one batch (truss.py:344-361): member geometry recomputed in shared memory when it fits, else from the k_geom arrays
+int launch_recover(const LargeArgs& a, int num_sm, cudaStream_t st, bool recomp) {
+  const size_t rec_smem = (size_t)a.M * (1 + a.dim) * 8;
+  int grid = a.batch < num_sm * 8 ? a.batch : num_sm * 8;
+  tb_prof_begin(TB_PROF_RECOVER, st);
+  if (recomp) {
+    auto kern = a.dim == 3 ? k_recover<3, true> : k_recover<2, true>;
+    const int rc = g_rec_grant[a.dim - 2].ensure(kern, rec_smem);
+    if (rc) return rc;
+    kern<<<grid, 256, rec_smem, st>>>(a);
+  } else if (a.dim == 3) {
+    k_recover<3, false><<<grid, 256, 0, st>>>(a);
+  } else {
+    k_recover<2, false><<<grid, 256, 0, st>>>(a);
+  }
+  tb_prof_end(TB_PROF_RECOVER, st);
+  return 0;
+}
+
+// Fused two-sided band kernel (tb_bandts.cu) + recovery: two launches per batch, K never leaves the SM
+int launch_ts_path(const LargeArgs& a, int num_sm, cudaStream_t st) {
+  TsArgs t;
+  memset(&t, 0, sizeof(t));
+  t.batch = a.batch; t.dim = a.dim; t.nJ = a.nJ; t.M = a.M; t.N = a.N; t.n = a.n;
+  t.xyz = a.xyz; t.xyz_stride = a.xyz_stride;
+  t.aed = a.aed; t.aed_stride = a.aed_stride;
+  t.gene = a.gene; t.gene_stride = a.gene_stride;
+  t.type_table = a.type_table; t.n_type = a.n_type;
+  t.force = a.force; t.force_stride = a.force_stride;
+  tb_ts_fill_sides(t, a.ts);
+  tb_ts_carve(t, a.ts, a.ts_ws, a.batch);
+  t.kdebug = a.kdebug;
+  LargeArgs r = a;
+  r.y = t.uf;
+  r.n_pad = t.n_pad;
+  r.status = t.status;
+  const size_t rec_smem = (size_t)a.M * (1 + a.dim) * 8;
+  const bool recomp = rec_smem <= 96 * 1024;
+  int launches = 2;
+  if (!recomp) {                                 // very many members: the recovery reads the k_geom arrays
+    k_init_status<<<(a.batch + 255) / 256, 256, 0, st>>>(r.status, a.batch, 0);
+    const int64_t total = (int64_t)a.batch * a.M;
+    int grid = (int)((total + 255) / 256 < (int64_t)num_sm * 8 ? (total + 255) / 256 : (int64_t)num_sm * 8);
+    if (grid < 1) grid = 1;
+    tb_prof_begin(TB_PROF_GEOM, st);
+    if (a.dim == 3) k_geom<3><<<grid, 256, 0, st>>>(r);
+    else k_geom<2><<<grid, 256, 0, st>>>(r);
+    tb_prof_end(TB_PROF_GEOM, st);
+    launches += 2;
+  }
+  int rc = tb_launch_band_ts(t, tb_ts_smem_bytes(a.ts), num_sm, st);
+  if (rc) return rc;
+  rc = launch_recover(r, num_sm, st, recomp);
+  if (rc) return rc;
+  tb_count_launch(launches - 1);                 // (the band kernel counted itself)
+  return (int)cudaGetLastError();
+}
+
+}  // namespace
+
 int tb_launch_large(const LargeArgs& a, int num_sm, cudaStream_t st, int path) {
   if (a.batch <= 0) return 0;
   if (num_sm <= 0) num_sm = 148;
+  static const bool ts_legacy = [] { const char* s = getenv("TB_BAND_LEGACY"); return s && s[0] == '1'; }();
+  if (path == 2 && a.ts && a.ts_ws && !a.shared_k && !ts_legacy) return launch_ts_path(a, num_sm, st);
   // TB_UNFUSED_ASSEMBLY=1 keeps the separate HBM-bound assembly kernel (A/B measurements, tiled path only)
   static const bool fused_env = [] { const char* s = getenv("TB_UNFUSED_ASSEMBLY"); return !(s && s[0] == '1'); }();
   const bool fused = fused_env || path == 2;
@@ -1086,11 +1174,9 @@ int tb_launch_large(const LargeArgs& a, int num_sm, cudaStream_t st, int path) {
   a1.batch = 1;
   if (prep) {
     auto kern = a.dim == 3 ? k_prep<3> : k_prep<2>;
-    static size_t prep_set[2] = {0, 0};        // largest dynamic shared-memory size already granted, per instantiation
-    if (prep_set[a.dim - 2] < prep_smem) {
-      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prep_smem);
-      if (e != cudaSuccess) return (int)e;
-      prep_set[a.dim - 2] = prep_smem;
+    {
+      const int rcg = g_prep_grant[a.dim - 2].ensure(kern, prep_smem);
+      if (rcg) return rcg;
     }
     int grid = a.batch < num_sm * 8 ? a.batch : num_sm * 8;
     tb_prof_begin(TB_PROF_ASSEMBLE, st);
@@ -1130,16 +1216,18 @@ int tb_launch_large(const LargeArgs& a, int num_sm, cudaStream_t st, int path) {
     }
   } else {
     auto kern = fused ? k_chol<true> : k_chol<false>;
-    static int chol_per_sm[2] = {0, 0};
-    if (chol_per_sm[fused] == 0) {
-      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CHOL_SMEM_BYTES);
-      if (e != cudaSuccess) return (int)e;
-      int q = 0;
-      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, kern, CH_THREADS, CHOL_SMEM_BYTES);
-      if (e != cudaSuccess) return (int)e;
-      chol_per_sm[fused] = q < 1 ? 1 : q;
+    {
+      const int rcg = g_chol_grant[fused].ensure(kern, CHOL_SMEM_BYTES);
+      if (rcg) return rcg;
     }
-    const int per_sm = chol_per_sm[fused];
+    static std::atomic<int> chol_per_sm[2];    // blocks per SM: a property of the kernel and the architecture, not of the device ordinal
+    if (chol_per_sm[fused].load() == 0) {
+      int q = 0;
+      cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, kern, CH_THREADS, CHOL_SMEM_BYTES);
+      if (e != cudaSuccess) return (int)e;
+      chol_per_sm[fused].store(q < 1 ? 1 : q);
+    }
+    const int per_sm = chol_per_sm[fused].load();
     int grid = num_sm * per_sm;
     if (grid > a.batch) grid = a.batch;
     tb_prof_begin(TB_PROF_CHOL, st);
@@ -1147,23 +1235,8 @@ int tb_launch_large(const LargeArgs& a, int num_sm, cudaStream_t st, int path) {
     tb_prof_end(TB_PROF_CHOL, st);
   }
   {
-    int grid = a.batch < num_sm * 8 ? a.batch : num_sm * 8;
-    tb_prof_begin(TB_PROF_RECOVER, st);
-    if (prep) {
-      auto kern = a.dim == 3 ? k_recover<3, true> : k_recover<2, true>;
-      static size_t rec_set[2] = {0, 0};
-      if (rec_set[a.dim - 2] < rec_smem) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rec_smem);
-        if (e != cudaSuccess) return (int)e;
-        rec_set[a.dim - 2] = rec_smem;
-      }
-      kern<<<grid, 256, rec_smem, st>>>(a);
-    } else if (a.dim == 3) {
-      k_recover<3, false><<<grid, 256, 0, st>>>(a);
-    } else {
-      k_recover<2, false><<<grid, 256, 0, st>>>(a);
-    }
-    tb_prof_end(TB_PROF_RECOVER, st);
+    const int rcr = launch_recover(a, num_sm, st, prep);
+    if (rcr) return rcr;
   }
   tb_count_launch((prep ? 3 : 5) + (shared ? 1 : 0));
   return (int)cudaGetLastError();

@@ -13,6 +13,7 @@
 #include <tuple>
 
 #include "tb_common.cuh"
+#include "tb_ts.cuh"
 #include "tb_blocks.cuh"
 
 std::atomic<int64_t> g_tb_launches{0};
@@ -444,6 +445,13 @@ extern "C" int tb_plan_create(const tb_topology* topo, tb_plan** plan_out) {
   firsts(p->q_ptr, p->q_pack, p->q_first, p->q_multi);
   firsts(p->bq_ptr, p->bq_pack, p->bq_first, p->bq_multi);
 
+  {   // two-sided 8x8 band program of the fused band kernel (host arrays always; device mirrors with a device)
+    const int rc_ts = tb_ts_build(p);
+    if (rc_ts) {
+      tb_plan_destroy(p);
+      return rc_ts;
+    }
+  }
   if (p->path == 1 && p->NB <= TB_BAND_MAX_NB) {
     const char* env = getenv("TB_NO_BAND");
     if (!(env && env[0] == '1')) p->path = 2;
@@ -492,6 +500,8 @@ extern "C" int tb_plan_create(const tb_topology* topo, tb_plan** plan_out) {
 
 extern "C" void tb_plan_destroy(tb_plan* p) {
   if (!p) return;
+  tb_ts_destroy(p->ts, p->device >= 0);
+  p->ts = nullptr;
   if (p->device < 0) {
     delete p;
     return;

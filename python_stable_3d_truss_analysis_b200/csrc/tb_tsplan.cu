@@ -1,0 +1,409 @@
+// Host-side builder of the two-sided band program (tb_ts.cuh).  Pure integer work on the plan's scatter map
+// (Truss.GetKMatrix's "+=" loop, slientruss3d/truss.py:307-316, restricted to the free DOFs of truss.py:343).
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <numeric>
+
+#include "tb_common.cuh"
+#include "tb_ts.cuh"
+
+namespace {
+
+template <typename T>
+int up(T** dptr, const std::vector<T>& h) {
+  *dptr = nullptr;
+  size_t bytes = std::max<size_t>(h.size(), 1) * sizeof(T);
+  cudaError_t e = cudaMalloc((void**)dptr, bytes);
+  if (e != cudaSuccess) return (int)e;
+  if (!h.empty()) {
+    e = cudaMemcpy(*dptr, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return (int)e;
+  }
+  return 0;
+}
+
+inline int popc(uint32_t x) { return __builtin_popcount(x); }
+inline int topbit(uint32_t x) { return x ? 31 - __builtin_clz(x) : 0; }
+
+struct Masks {
+  bool valid = false;
+  int nb[2] = {0, 0};
+  std::vector<uint32_t> col[2], src[2], xm[2];
+  double t_own[2] = {0, 0}, t_sep = 0, t_x = 0;
+  int64_t products = 0, solves = 0;
+};
+
+// cost model of one block column (cycles of one warp, calibrated on B200: see DESIGN.md): fixed part (assembly, staging,
+// 8 pivots, stores), 8x8 block products (two DMMAs + operand loads), block solves; back substitution per column
+constexpr double C_COL = 900.0, C_PROD = 45.0, C_SOLVE = 50.0, C_BACK = 260.0;
+
+// Block masks of both sides for the split (bT, nS): kblk[bj] bit e <=> K_ff has an entry in block (bj+e, bj)
+Masks make_masks(const std::vector<uint32_t>& kblk, int nblk, int bT, int nS) {
+  Masks m;
+  const int nB = nblk - bT - nS;
+  const int tot0 = bT + nS, tot1 = nB > 0 ? nB + nS : 0;
+  m.col[0].assign(tot0, 0); m.src[0].assign(tot0, 0); m.xm[0].assign(tot0, 0);
+  m.col[1].assign(tot1, 0); m.src[1].assign(tot1, 0); m.xm[1].assign(tot1, 0);
+  for (int bj = 0; bj < nblk; ++bj)
+    for (int e = 0; e <= TS_NBX + 1 && bj + e < nblk; ++e) {
+      if (!((kblk[bj] >> e) & 1u) && e != 0) continue;
+      const int bi = bj + e;
+      if (bi < tot0) {
+        m.col[0][bj] |= 1u << e;
+      } else {
+        if (bj < bT) return m;                 // a row of B coupled to T: not a separator
+        m.col[1][nblk - 1 - bi] |= 1u << e;    // virtual column of the bottom side, same block distance
+      }
+    }
+  auto symbolic = [&](int s, int ncol_src, int tot) -> bool {
+    for (int c = 0; c < tot; ++c) {
+      const uint32_t mc = c < ncol_src ? m.col[s][c] : 0u;
+      m.src[s][c] = mc;
+      if (topbit(m.col[s][c]) > TS_NBX) return false;
+      for (int e1 = 1; e1 <= TS_NBX; ++e1) {
+        if (!((mc >> e1) & 1u)) continue;
+        for (int e2 = e1; e2 <= TS_NBX; ++e2)
+          if ((mc >> e2) & 1u) {
+            if (c + e1 >= tot) return false;
+            m.col[s][c + e1] |= 1u << (e2 - e1);
+          }
+      }
+    }
+    return true;
+  };
+  if (nB > 0) {
+    for (int c = 0; c < nB; ++c) m.col[1][c] |= 1u;
+    if (!symbolic(1, nB, tot1)) return m;
+    // hand-over: virtual block (nB + j' + rb', nB + j') of the bottom side is the separator block (row J + rb', column J),
+    // J = nS - 1 - j' - rb', of the top side
+    for (int jq = 0; jq < nS; ++jq) {
+      const uint32_t mx = m.col[1][nB + jq];
+      for (int rb = 0; rb <= TS_NBX; ++rb)
+        if ((mx >> rb) & 1u) {
+          const int J = nS - 1 - jq - rb;
+          if (J < 0) return m;
+          m.xm[0][bT + J] |= 1u << rb;
+          m.col[0][bT + J] |= 1u << rb;
+        }
+    }
+  }
+  for (int c = 0; c < tot0; ++c) m.col[0][c] |= 1u;
+  if (!symbolic(0, tot0, tot0)) return m;
+  for (int s = 0; s < 2; ++s) {
+    int nb = 1;
+    for (uint32_t x : m.col[s]) nb = std::max(nb, topbit(x));
+    m.nb[s] = nb;
+    if (nb > TS_NBX) return m;
+  }
+  // cost: products counted at the column that receives them
+  for (int s = 0; s < 2; ++s) {
+    const int tot = s == 0 ? tot0 : tot1, own = s == 0 ? bT : nB;
+    std::vector<double> prod(tot, 0.0);
+    for (int c = 0; c < tot; ++c) {
+      const uint32_t mc = m.src[s][c];
+      for (int e1 = 1; e1 <= TS_NBX; ++e1)
+        if ((mc >> e1) & 1u)
+          for (int e2 = e1; e2 <= TS_NBX; ++e2)
+            if ((mc >> e2) & 1u) { prod[c + e1] += 1.0; m.products++; }
+    }
+    for (int c = 0; c < tot; ++c) {
+      const int sol = std::max(0, popc(m.col[s][c] >> 2));
+      if (c < own) {
+        m.t_own[s] += C_COL + C_PROD * prod[c] + C_SOLVE * sol + C_BACK;
+        m.solves += popc(m.col[s][c] >> 2);
+      } else if (s == 0) {
+        m.t_sep += C_COL + C_PROD * prod[c] + C_SOLVE * sol + C_BACK;
+        m.solves += popc(m.col[s][c] >> 2);
+      } else {
+        m.t_x += 150.0 + C_PROD * prod[c];
+      }
+    }
+  }
+  m.valid = true;
+  return m;
+}
+
+}  // namespace
+
+void tb_ts_destroy(TsPlan* ts, bool device) {
+  if (!ts) return;
+  if (device)
+    for (int s = 0; s < 2; ++s) {
+      TsSideHost& h = ts->side[s];
+      cudaFree(h.d_colinfo); cudaFree(h.d_colent); cudaFree(h.d_mem0); cudaFree(h.d_mem_ptr);
+      cudaFree(h.d_ent_ptr); cudaFree(h.d_pack); cudaFree(h.d_rowdof); cudaFree(h.d_rownat); cudaFree(h.d_lofs);
+      cudaFree(h.d_mem); cudaFree(h.d_ent);
+    }
+  delete ts;
+}
+
+int tb_ts_build(tb_plan* p) {
+  TsPlan* ts = new TsPlan();
+  p->ts = ts;
+  const int n = p->n, d = p->dim;
+  if (n <= 0 || p->M <= 0) return 0;
+  const size_t nnz = p->int_row.size();
+  const int nblk = (n + TS_BT - 1) / TS_BT;
+  ts->nblk = nblk;
+  ts->n_pad = nblk * TS_BT;
+  // block structure of K_ff and the reach of every block row (first block column of its envelope)
+  std::vector<uint32_t> kblk(nblk, 0u);
+  for (size_t e = 0; e < nnz; ++e) {
+    const int bi = p->int_row[e] / TS_BT, bj = p->int_col[e] / TS_BT;
+    if (bi - bj > TS_NBX) return 0;              // band too wide for this kernel: the other pipelines take it
+    kblk[bj] |= 1u << (bi - bj);
+  }
+  std::vector<int> reach(nblk);                  // lowest block column touched by block row i
+  std::iota(reach.begin(), reach.end(), 0);
+  for (int bj = 0; bj < nblk; ++bj)
+    for (int e = 0; e <= TS_NBX && bj + e < nblk; ++e)
+      if ((kblk[bj] >> e) & 1u) reach[bj + e] = std::min(reach[bj + e], bj);
+
+  // ---- choose the split: one-sided (everything on the top side), or the two-sided split with the smallest critical path
+  Masks best = make_masks(kblk, nblk, nblk, 0);
+  if (!best.valid) return 0;
+  int best_bT = nblk, best_nS = 0;
+  const double t_one = best.t_own[0];
+  double best_t = t_one;
+  const char* env1 = getenv("TB_TS_ONE_SIDED");
+  const bool allow_two = !(env1 && env1[0] == '1');
+  const char* envs = getenv("TB_TS_SPLIT");       // force the first separator block (experiments)
+  const int force_bT = envs ? atoi(envs) : -1;
+  if (allow_two)
+    for (int bT = 1; bT + 2 <= nblk; ++bT) {
+      if (force_bT >= 0 && bT != force_bT) continue;
+      int last = bT - 1;                           // last block row whose envelope reaches into T
+      for (int bi = bT; bi < nblk; ++bi)
+        if (reach[bi] < bT) last = bi;
+      const int nS = last - bT + 1;
+      if (nS < 1 || nS > TS_NBX || bT + nS >= nblk) continue;
+      Masks m = make_masks(kblk, nblk, bT, nS);
+      if (!m.valid) continue;
+      const double t = std::max(m.t_own[0], m.t_own[1] + m.t_x) + m.t_sep;
+      if (t < (force_bT >= 0 ? 1e300 : 0.9 * t_one) && (t < best_t || best_nS == 0)) {
+        best = m; best_bT = bT; best_nS = nS; best_t = t;
+      }
+    }
+  const int bT = best_bT, nS = best_nS, nB = nblk - bT - nS;
+  ts->bT = bT; ts->nS = nS; ts->nB = nB;
+  ts->products = best.products;
+  ts->solves = best.solves;
+  // executed tensor work: two DMMA (512 flop each) per block product and per block solve
+  ts->dmma_flops = 1024.0 * (double)(best.products + best.solves);
+
+  const int n_pad = ts->n_pad;
+  for (int s = 0; s < 2; ++s) {
+    TsSideHost& h = ts->side[s];
+    h.ncol_own = s == 0 ? bT : nB;
+    h.ncol_tot = s == 0 ? bT + nS : (nB > 0 ? nB + nS : 0);
+    h.nb = best.nb[s];
+    h.colmask = best.col[s];
+    h.srcmask = best.src[s];
+    h.xmask = best.xm[s];
+    h.rowdof.assign((size_t)h.ncol_tot * TS_BT, -1);
+    h.rownat.assign((size_t)h.ncol_tot * TS_BT, -1);
+    for (int v = 0; v < h.ncol_tot * TS_BT; ++v) {
+      const int nat = s == 0 ? v : n_pad - 1 - v;
+      if (nat >= 0 && nat < n) {
+        h.rownat[v] = nat;
+        h.rowdof[v] = p->free_int[nat];
+      }
+    }
+  }
+  // ---- factor storage: top columns (separator included), then the bottom's own columns
+  {
+    int64_t off = 0;
+    int cmax = 0;
+    for (int s = 0; s < 2; ++s) {
+      TsSideHost& h = ts->side[s];
+      const int ncol = s == 0 ? h.ncol_tot : h.ncol_own;
+      h.lofs.assign((size_t)h.ncol_tot + 1, 0);
+      for (int c = 0; c < h.ncol_tot; ++c) {
+        h.lofs[c] = (int32_t)off;
+        if (c < ncol) {
+          const int sz = TS_BE + TS_BT + TS_BE * popc(h.colmask[c] >> 1);
+          off += sz;
+          cmax = std::max(cmax, sz);
+        }
+      }
+      h.lofs[h.ncol_tot] = (int32_t)off;
+    }
+    ts->l_per_sys = off;
+    ts->chunk_max = cmax;
+  }
+  // ---- entries and members per side / block column / chunk
+  struct Ent { int vr, vc; int32_t src; };
+  std::vector<std::vector<Ent>> colent[2];
+  colent[0].resize(ts->side[0].ncol_tot);
+  colent[1].resize(ts->side[1].ncol_tot);
+  for (size_t e = 0; e < nnz; ++e) {
+    const int i = p->int_row[e], j = p->int_col[e];
+    if (i / TS_BT < bT + nS) {
+      colent[0][j / TS_BT].push_back({i, j, (int32_t)e});
+    } else {
+      const int vr = n_pad - 1 - j, vc = n_pad - 1 - i;
+      colent[1][vc / TS_BT].push_back({vr, vc, (int32_t)e});
+    }
+  }
+  for (int s = 0; s < 2; ++s) {
+    TsSideHost& h = ts->side[s];
+    h.chunk_ptr.assign((size_t)h.ncol_tot + 1, 0);
+    h.mem_ptr.assign(1, 0);
+    h.ent_ptr.assign(1, 0);
+    for (int c = 0; c < h.ncol_tot; ++c) {
+      std::vector<Ent>& ev = colent[s][c];
+      // members of this block column, ascending
+      std::vector<int32_t> mem;
+      for (const Ent& en : ev)
+        for (int64_t k = p->ent_ptr[en.src]; k < p->ent_ptr[en.src + 1]; ++k) mem.push_back(p->ctr_member[k]);
+      std::sort(mem.begin(), mem.end());
+      mem.erase(std::unique(mem.begin(), mem.end()), mem.end());
+      const int nchunk = ((int)mem.size() + TS_CHUNK - 1) / TS_CHUNK;
+      for (int q = 0; q < nchunk; ++q) {
+        const int m0 = q * TS_CHUNK, m1 = std::min((int)mem.size(), m0 + TS_CHUNK);
+        for (int t = m0; t < m1; ++t) h.mem.push_back(make_int4(mem[t], p->conn[2 * mem[t]], p->conn[2 * mem[t] + 1], 0));
+        h.mem_ptr.push_back((int32_t)h.mem.size());
+        // entries with contributions from this chunk (the scatter map lists contributions in ascending member order)
+        struct CE { int pos; int32_t src; std::vector<int32_t> pk; };
+        std::vector<CE> ces;
+        for (const Ent& en : ev) {
+          CE ce;
+          ce.pos = ((en.vr / TS_BT - en.vc / TS_BT) << 6) | ((((en.vc % TS_BT) >> 2) << 5) + ((en.vr % TS_BT) << 2) + (en.vc & 3));
+          ce.src = en.src;
+          for (int64_t k = p->ent_ptr[en.src]; k < p->ent_ptr[en.src + 1]; ++k) {
+            const int slot = (int)(std::lower_bound(mem.begin(), mem.end(), p->ctr_member[k]) - mem.begin());
+            if (slot < m0 || slot >= m1) continue;
+            const int loc = p->ctr_local[k], la = loc / (2 * d), lb = loc % (2 * d);
+            const int A = la / d, i = la % d, B = lb / d, j = lb % d;
+            const int lo = std::min(i, j), hi = std::max(i, j);
+            ce.pk.push_back(((slot - m0) << 4) | ((A != B) << 3) | (lo * d - lo * (lo - 1) / 2 + (hi - lo)));
+          }
+          if (!ce.pk.empty()) ces.push_back(std::move(ce));
+        }
+        // heaviest entries first: entry i goes to lane i % 32, so every lane gets a similar mix
+        std::stable_sort(ces.begin(), ces.end(), [](const CE& a, const CE& b) { return a.pk.size() > b.pk.size(); });
+        for (const CE& ce : ces) {
+          const int cnt = (int)ce.pk.size();
+          int2 dsc;
+          dsc.x = ce.pos | (cnt << 10);
+          if (cnt == 1) {
+            dsc.y = ce.pk[0];
+          } else {
+            dsc.y = (int32_t)h.pack.size();
+            h.pack.insert(h.pack.end(), ce.pk.begin(), ce.pk.end());
+          }
+          h.ent.push_back(dsc);
+          h.ent_src.push_back(ce.src);
+        }
+        h.ent_ptr.push_back((int32_t)h.ent.size());
+      }
+      h.chunk_ptr[c + 1] = h.chunk_ptr[c] + nchunk;
+    }
+    // flat per-column views: nothing the kernel needs at the top of a block column hangs on another load
+    h.colinfo.resize(h.ncol_tot);
+    h.colent.resize(h.ncol_tot);
+    h.mem0.assign((size_t)h.ncol_tot * TS_CHUNK, make_int4(-1, 0, 0, 0));
+    for (int c = 0; c < h.ncol_tot; ++c) {
+      h.colinfo[c] = make_int4((int)h.colmask[c], (int)h.srcmask[c], (int)h.xmask[c], 0);
+      const int q0 = h.chunk_ptr[c], q1 = h.chunk_ptr[c + 1];
+      h.colent[c] = make_int4(q1 > q0 ? h.ent_ptr[q0] : 0, q1 > q0 ? h.ent_ptr[q0 + 1] : 0, q0, q1);
+      if (q1 > q0)
+        for (int t = h.mem_ptr[q0]; t < h.mem_ptr[q0 + 1]; ++t) h.mem0[(size_t)c * TS_CHUNK + (t - h.mem_ptr[q0])] = h.mem[t];
+    }
+  }
+  ts->ok = 1;
+  if (p->device < 0) return 0;
+  int rc = 0;
+  for (int s = 0; s < 2 && !rc; ++s) {
+    TsSideHost& h = ts->side[s];
+    if (!rc) rc = up(&h.d_colinfo, h.colinfo);
+    if (!rc) rc = up(&h.d_colent, h.colent);
+    if (!rc) rc = up(&h.d_mem0, h.mem0);
+    if (!rc) rc = up(&h.d_mem_ptr, h.mem_ptr);
+    if (!rc) rc = up(&h.d_ent_ptr, h.ent_ptr);
+    if (!rc) rc = up(&h.d_pack, h.pack);
+    if (!rc) rc = up(&h.d_rowdof, h.rowdof);
+    if (!rc) rc = up(&h.d_rownat, h.rownat);
+    if (!rc) rc = up(&h.d_lofs, h.lofs);
+    if (!rc) rc = up(&h.d_mem, h.mem);
+    if (!rc) rc = up(&h.d_ent, h.ent);
+  }
+  return rc;
+}
+
+size_t tb_ts_workspace_bytes(const tb_plan* p, int batch) {
+  const TsPlan* ts = p->ts;
+  if (!ts || !ts->ok) return 0;
+  const size_t per = (size_t)ts->l_per_sys + (size_t)ts->nS * ts->nS * TS_BE + (size_t)ts->nS * TS_BT + (size_t)ts->n_pad;
+  return (size_t)batch * per * 8 + (size_t)batch * 4 + 4096;
+}
+
+void tb_ts_carve(TsArgs& t, const TsPlan* ts, void* ws, int batch) {
+  double* p = (double*)ws;
+  t.L = p;  p += (size_t)batch * ts->l_per_sys;
+  t.X = p;  p += (size_t)batch * ts->nS * ts->nS * TS_BE;
+  t.Z = p;  p += (size_t)batch * ts->nS * TS_BT;
+  t.uf = p; p += (size_t)batch * ts->n_pad;
+  t.status = (int32_t*)p;
+}
+
+void tb_ts_fill_sides(TsArgs& t, const TsPlan* ts) {
+  for (int s = 0; s < 2; ++s) {
+    const TsSideHost& h = ts->side[s];
+    TsSideDev& d = t.side[s];
+    d.ncol_own = h.ncol_own; d.ncol_tot = h.ncol_tot; d.nb = h.nb;
+    d.colinfo = h.d_colinfo; d.colent = h.d_colent; d.mem0 = h.d_mem0; d.mem_ptr = h.d_mem_ptr; d.mem = h.d_mem;
+    d.ent_ptr = h.d_ent_ptr; d.ent = h.d_ent; d.pack = h.d_pack; d.rowdof = h.d_rowdof; d.rownat = h.d_rownat;
+    d.lofs = h.d_lofs;
+  }
+  t.nS = ts->nS;
+  t.chunk_max = ts->chunk_max;
+  t.l_per_sys = ts->l_per_sys;
+  t.n_pad = ts->n_pad;
+  t.kdbg_stride = (int64_t)(ts->side[0].ent.size() + ts->side[1].ent.size());
+  t.kdbg_off1 = (int)ts->side[0].ent.size();
+}
+
+// ---- debug / test exports: the program as flat host arrays (tests/test_ts_program_cpu.py replays it in numpy)
+extern "C" int tb_plan_ts_info(const tb_plan* p, int32_t* out /*[16]*/) {
+  if (!p || !out) return TB_ERR_NULL;
+  const TsPlan* ts = p->ts;
+  for (int i = 0; i < 16; ++i) out[i] = 0;
+  if (!ts || !ts->ok) return TB_OK;
+  out[0] = 1; out[1] = ts->nblk; out[2] = ts->n_pad; out[3] = ts->bT; out[4] = ts->nS; out[5] = ts->nB;
+  out[6] = ts->side[0].nb; out[7] = ts->side[1].nb; out[8] = ts->chunk_max; out[9] = (int32_t)ts->l_per_sys;
+  out[10] = (int32_t)ts->products; out[11] = (int32_t)ts->solves;
+  for (int s = 0; s < 2; ++s) {
+    out[12 + 2 * s] = (int32_t)ts->side[s].ent.size();
+    out[13 + 2 * s] = (int32_t)ts->side[s].pack.size();
+  }
+  return TB_OK;
+}
+
+// which = 0 colmask, 1 srcmask, 2 xmask, 3 chunk_ptr, 4 mem_ptr, 5 mem (4 ints each), 6 ent_ptr, 7 ent (2 ints each),
+// 8 pack, 9 rowdof, 10 rownat, 11 lofs, 12 ent_src.  Returns the element count (ints); copies when out != NULL.
+extern "C" int64_t tb_plan_ts_array(const tb_plan* p, int32_t side, int32_t which, int32_t* out) {
+  if (!p || !p->ts || !p->ts->ok || side < 0 || side > 1) return -1;
+  const TsSideHost& h = p->ts->side[side];
+  const void* src = nullptr;
+  size_t cnt = 0;
+  switch (which) {
+    case 0: src = h.colmask.data(); cnt = h.colmask.size(); break;
+    case 1: src = h.srcmask.data(); cnt = h.srcmask.size(); break;
+    case 2: src = h.xmask.data(); cnt = h.xmask.size(); break;
+    case 3: src = h.chunk_ptr.data(); cnt = h.chunk_ptr.size(); break;
+    case 4: src = h.mem_ptr.data(); cnt = h.mem_ptr.size(); break;
+    case 5: src = h.mem.data(); cnt = h.mem.size() * 4; break;
+    case 6: src = h.ent_ptr.data(); cnt = h.ent_ptr.size(); break;
+    case 7: src = h.ent.data(); cnt = h.ent.size() * 2; break;
+    case 8: src = h.pack.data(); cnt = h.pack.size(); break;
+    case 9: src = h.rowdof.data(); cnt = h.rowdof.size(); break;
+    case 10: src = h.rownat.data(); cnt = h.rownat.size(); break;
+    case 11: src = h.lofs.data(); cnt = h.lofs.size(); break;
+    case 12: src = h.ent_src.data(); cnt = h.ent_src.size(); break;
+    default: return -1;
+  }
+  if (out && cnt) memcpy(out, src, cnt * 4);
+  return (int64_t)cnt;
+}

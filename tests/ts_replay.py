@@ -1,0 +1,201 @@
+"""numpy replay of the two-sided band program (csrc/tb_ts.cuh) -- test infrastructure only.
+
+Executes, block by block and with the kernel's own ring-slot arithmetic, what ``k_band_ts`` (csrc/tb_bandts.cu) does with
+the program ``Plan.ts_program()`` returns: per-column assembly from member products (truss.py:56-86, 307-316), left-looking
+block products driven by the structural masks, the hand-over of the bottom side's Schur complement to the separator,
+the chunk layout of the factor and the two back substitutions.  It checks the integer program (orders, flips, masks,
+slots, chunk offsets) on the CPU; the thread-level layout of the kernel is covered by the GPU parity tests.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+BT = 8
+
+
+def member_products(dim, xyz, conn_pair, a, e):
+    """(k, c) of one member with the reference's roundings (truss.py:19, 56-63)."""
+    j0, j1 = conn_pair
+    dx = [xyz[j1][i] - xyz[j0][i] for i in range(dim)]
+    l2 = dx[0] * dx[0]
+    for i in range(1, dim):
+        l2 = l2 + dx[i] * dx[i]
+    length = float(np.sqrt(l2))
+    k = e * a / length
+    c = [dx[i] / length for i in range(dim)]
+    return k, c
+
+
+def _term(dim, prod, pk):
+    k, c = prod[pk >> 4]
+    ij = pk & 7
+    if dim == 3:
+        i = (ij >= 3) + (ij >= 5)
+        j = ij if ij < 3 else (ij - 2 if ij < 5 else 2)
+    else:
+        i = int(ij >= 2)
+        j = int(ij >= 1)
+    t = k * (c[i] * c[j])
+    return -t if (pk & 8) else t
+
+
+def _unpack_pos(pos):
+    rb, off = pos >> 6, pos & 63
+    k = ((off >> 5) << 2) | (off & 3)
+    r = (off >> 2) & 7
+    return rb, r, k
+
+
+class _Side:
+    def __init__(self, prog, s):
+        d = prog["side"][s]
+        self.d = d
+        self.s = s
+        self.nb = prog["info"]["nb_top" if s == 0 else "nb_bottom"]
+        self.tot = len(d["colmask"])
+        nS = prog["info"]["nS"]
+        self.own = self.tot - nS if self.tot else 0
+        self.ring = {}          # slot -> 8x8 block
+        self.idx = [0] * 10
+        self.nzprev = [0] * 10
+        self.ys = []            # y blocks of the processed columns (virtual order)
+        self.chunks = {}        # c -> dict(Z, y, blocks{rb})
+        self.kvals = {}         # program entry index -> assembled value
+
+    def slot(self, e, p):
+        return e * (e - 1) // 2 + p % e
+
+
+def replay(prog, dim, xyz, aed, force, n_dof):
+    """Returns (u per DOF, dict with debug data).  ``aed`` is [M,3]."""
+    info = prog["info"]
+    nS = info["nS"]
+    sides = [_Side(prog, 0), _Side(prog, 1)]
+    X = {}
+    Zx = np.zeros((max(nS, 1), BT))
+    two = sides[1].tot > 0
+
+    def forward_column(S, c):
+        d = S.d
+        nb = S.nb
+        own = c < S.own
+        xcol = S.s == 1 and not own
+        nzc, srcc, xm = int(d["colmask"][c]), int(d["srcmask"][c]), int(d["xmask"][c])
+        acc = {rb: np.zeros((BT, BT)) for rb in range(nb + 1)}
+        tp = np.zeros(BT)
+        for dd in range(1, nb + 1):
+            nzp = S.nzprev[dd]
+            if not (nzp >> dd) & 1:
+                continue
+            Bm = S.ring[dd * (dd - 1) // 2 + S.idx[dd]]
+            tp += Bm @ S.ys[c - dd]
+            for rb in range(0, nb - dd + 1):
+                e = rb + dd
+                if not (nzp >> e) & 1:
+                    continue
+                sl = S.idx[e] - dd
+                if sl < 0:
+                    sl += e
+                A = S.ring[e * (e - 1) // 2 + sl]
+                acc[rb] += A @ Bm.T
+        if xcol:
+            jq = c - S.own
+            for rb in range(nb + 1):
+                if (nzc >> rb) & 1:
+                    J = nS - 1 - jq - rb
+                    assert J >= 0
+                    X[(J, rb)] = acc[rb][::-1, ::-1].T.copy()     # element (r, k) -> (7-k, 7-r)
+            Zx[nS - 1 - jq] = tp[::-1]
+            S.ys.append(np.zeros(BT))
+        else:
+            if S.s == 0 and not own and two:
+                J = c - S.own
+                for rb in range(nb + 1):
+                    if (xm >> rb) & 1:
+                        acc[rb] += X[(J, rb)]
+                tp += Zx[J]
+            # staging: block rb in the slot of the dead block (c, c-rb)
+            stage = {rb: np.zeros((BT, BT)) for rb in range(nb + 1) if (nzc >> rb) & 1}
+            q0, q1 = int(d["chunk_ptr"][c]), int(d["chunk_ptr"][c + 1])
+            for q in range(q0, q1):
+                prod = []
+                for t in range(int(d["mem_ptr"][q]), int(d["mem_ptr"][q + 1])):
+                    m, j0, j1, _ = (int(v) for v in d["mem"][t])
+                    prod.append(member_products(dim, xyz, (j0, j1), aed[m][0], aed[m][1]))
+                for e in range(int(d["ent_ptr"][q]), int(d["ent_ptr"][q + 1])):
+                    x, y = int(d["ent"][e][0]), int(d["ent"][e][1])
+                    pos, cnt = x & 1023, x >> 10
+                    rb, r, k = _unpack_pos(pos)
+                    assert rb in stage, "entry in a block the mask calls zero"
+                    v = stage[rb][r, k]
+                    if cnt == 1:
+                        v = v + _term(dim, prod, y)
+                    else:
+                        for t in range(cnt):
+                            v = v + _term(dim, prod, int(d["pack"][y + t]))
+                    stage[rb][r, k] = v
+                    S.kvals[e] = v
+            for r in range(BT):
+                if d["rowdof"][c * BT + r] < 0:
+                    stage[0][r, r] = 1.0
+            P = {rb: stage[rb] - acc[rb] for rb in stage}
+            fr = np.array([force[d["rowdof"][c * BT + r]] if d["rowdof"][c * BT + r] >= 0 else 0.0 for r in range(BT)])
+            t = fr - tp
+            Pd = np.tril(P[0]) + np.tril(P[0], -1).T
+            Ld = np.linalg.cholesky(Pd)
+            Zm = np.linalg.inv(Ld).T                      # Z = L_D^{-T}
+            y = Zm.T @ t
+            S.ys.append(y)
+            blocks = {}
+            for rb in range(1, nb + 1):
+                if (nzc >> rb) & 1:
+                    Lb = P[rb] @ Zm
+                    blocks[rb] = Lb
+                    S.ring[rb * (rb - 1) // 2 + S.idx[rb]] = Lb
+            S.chunks[c] = dict(Z=Zm, y=y, blocks=blocks, lofs=int(d["lofs"][c]),
+                               size=64 + 8 + 64 * bin(nzc >> 1).count("1"))
+        for e in range(nb + 1, 1, -1):
+            S.nzprev[e] = S.nzprev[e - 1]
+        S.nzprev[1] = srcc
+        for e in range(1, nb + 2):
+            S.idx[e] = 0 if S.idx[e] + 1 == e else S.idx[e] + 1
+
+    # the two sides are independent until the separator: bottom first (its hand-over must exist), then top
+    for c in range(sides[1].tot):
+        forward_column(sides[1], c)
+    for c in range(sides[0].tot):
+        forward_column(sides[0], c)
+
+    # chunk offsets: contiguous, non-overlapping
+    spans = sorted((ch["lofs"], ch["size"]) for S in sides for ch in S.chunks.values())
+    for (o0, s0), (o1, _) in zip(spans, spans[1:]):
+        assert o0 + s0 == o1, "factor chunks overlap or leave gaps"
+    assert not spans or spans[-1][0] + spans[-1][1] == info["l_per_sys"]
+    assert max((s for _, s in spans), default=0) == info["chunk_max"]
+
+    u_dof = np.zeros(n_dof)
+    us = [dict(), dict()]
+
+    def back(S, cols):
+        d = S.d
+        for c in cols:
+            ch = S.chunks[c]
+            t = np.zeros(BT)
+            for rb, Lb in ch["blocks"].items():
+                t += Lb.T @ us[S.s][c + rb]
+            u = ch["Z"] @ (ch["y"] - t)
+            us[S.s][c] = u
+            for r in range(BT):
+                dof = d["rowdof"][c * BT + r]
+                if dof >= 0:
+                    u_dof[dof] = u[r]
+
+    T = sides[0]
+    back(T, range(T.tot - 1, T.own - 1, -1))
+    if two:
+        Bt = sides[1]
+        for c in range(Bt.own, Bt.tot):
+            us[1][c] = us[0][T.own + (nS - 1 - (c - Bt.own))][::-1]
+        back(Bt, range(Bt.own - 1, -1, -1))
+    back(T, range(T.own - 1, -1, -1))
+    return u_dof, dict(sides=sides, X=X)
