@@ -280,10 +280,11 @@ int tb_profile_read(float* ms, int64_t* count);
  * numpy against the oracle (tests/test_ts_program_cpu.py).
  * tb_plan_ts_info: out[16] = {exists, block columns, padded order, first separator block, separator blocks, bottom
  *   blocks, sub-diagonal blocks top / bottom, largest factor chunk, factor doubles per system, block products, block
- *   solves, entries / contributions of the top side, of the bottom side}.
- * tb_plan_ts_array: copies array `which` of side `side` (0 colmask, 1 srcmask, 2 xmask, 3 chunk_ptr, 4 mem_ptr,
- *   5 mem[.][4], 6 ent_ptr, 7 ent[.][2], 8 pack, 9 rowdof, 10 rownat, 11 lofs, 12 ent_src) into out (may be NULL) and
- *   returns its length in int32 elements, -1 if there is no program.
+ *   solves, K entries, member contributions, entries with several contributions}.
+ * tb_plan_ts_array: copies array `which` into out (may be NULL) and returns its length in int32 elements, -1 if there is
+ *   no program.  Per side: 0 colmask, 1 srcmask, 2 xmask, 3 colent[.][2], 4 rowdof, 5 rownat, 6 lofs; whole program (side
+ *   ignored): 7 epos, 8 ent_src, 9 tq_first, 10 tq_multi, 11 tq_ptr, 12 tq_pack (the assembly pass's scatter lists in the
+ *   kernel's entry order).
  * tb_ts_phase_read: cycles per kernel phase accumulated by an instrumented build (-DTB_PHASE_TIMING), zeros otherwise. */
 int tb_plan_ts_info(const tb_plan* plan, int32_t* out);
 int64_t tb_plan_ts_array(const tb_plan* plan, int32_t side, int32_t which, int32_t* out);

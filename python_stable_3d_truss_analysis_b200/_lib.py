@@ -354,30 +354,35 @@ class Plan:
                                         mem.ctypes.data, loc.ctypes.data))
         return row, col, ptr, mem, loc
 
-    TS_ARRAYS = ("colmask", "srcmask", "xmask", "chunk_ptr", "mem_ptr", "mem", "ent_ptr", "ent", "pack", "rowdof",
-                 "rownat", "lofs", "ent_src")
+    TS_SIDE_ARRAYS = ("colmask", "srcmask", "xmask", "colent", "rowdof", "rownat", "lofs")
+    TS_PROGRAM_ARRAYS = ("epos", "ent_src", "tq_first", "tq_multi", "tq_ptr", "tq_pack")
 
     def ts_program(self):
-        """The two-sided band program of the fused band kernel as host arrays (None when the band is too wide for it):
-        ``{"info": {...}, "side": [{name: int32 array}, {...}]}`` -- replayed in numpy by the CPU tests."""
+        """The two-sided band program of the band kernel as host arrays (None when the band is too wide for it):
+        ``{"info": {...}, "side": [{name: int32 array}, {...}], "epos": ..., "tq_*": ...}`` -- replayed in numpy by
+        the CPU tests."""
         L = lib()
         raw = np.zeros(16, np.int32)
         check(L.tb_plan_ts_info(self._h, raw.ctypes.data))
         if not raw[0]:
             return None
-        keys = ("ok", "nblk", "n_pad", "bT", "nS", "nB", "nb_top", "nb_bottom", "chunk_max", "l_per_sys", "products", "solves")
+        keys = ("ok", "nblk", "n_pad", "bT", "nS", "nB", "nb_top", "nb_bottom", "chunk_max", "l_per_sys", "products", "solves",
+                "entries", "contributions", "multi_entries")
+
+        def fetch(side, which):
+            cnt = L.tb_plan_ts_array(self._h, side, which, None)
+            a = np.zeros(max(int(cnt), 0), np.int32)
+            if cnt > 0:
+                L.tb_plan_ts_array(self._h, side, which, a.ctypes.data)
+            return a
+
         out = {"info": {k: int(raw[i]) for i, k in enumerate(keys)}, "side": []}
         for s in range(2):
-            d = {}
-            for w, name in enumerate(self.TS_ARRAYS):
-                cnt = L.tb_plan_ts_array(self._h, s, w, None)
-                a = np.zeros(max(int(cnt), 0), np.int32)
-                if cnt > 0:
-                    L.tb_plan_ts_array(self._h, s, w, a.ctypes.data)
-                d[name] = a
-            d["mem"] = d["mem"].reshape(-1, 4)
-            d["ent"] = d["ent"].reshape(-1, 2)
+            d = {name: fetch(s, w) for w, name in enumerate(self.TS_SIDE_ARRAYS)}
+            d["colent"] = d["colent"].reshape(-1, 2)
             out["side"].append(d)
+        for w, name in enumerate(self.TS_PROGRAM_ARRAYS):
+            out[name] = fetch(0, len(self.TS_SIDE_ARRAYS) + w)
         return out
 
     # ------------------------------------------------------------------ batch packing

@@ -62,10 +62,9 @@ namespace {
 using tbblk::dmma;
 using tbblk::rsqrt_pos;
 
-constexpr int NBX = TS_NBX;
 constexpr int NSTAGE = 3;                        // factor chunks in flight during the back substitution
-// per side, after the ring: [64 diagonal staging, then Z as a DMMA operand | 4*TS_CHUNK member (k, c) | 8 rhs | 16 misc]
-constexpr int X_SCR = 0, X_PROD = TS_BE, X_T = X_PROD + 4 * TS_CHUNK, X_MISC = X_T + TS_BT, X_TOTAL = X_MISC + 16;
+// per side, after the ring: [64 diagonal staging, then Z as a DMMA operand | 8 rhs | ring of the last y blocks | 16 misc]
+constexpr int X_SCR = 0, X_T = TS_BE, X_Y = X_T + TS_BT, X_MISC = X_Y + (TS_NBX + 1) * TS_BT, X_TOTAL = X_MISC + 16;
 
 __host__ __device__ inline int ts_main_doubles(int nb, int chunk_max) {
   const int ring = nb * (nb + 1) / 2 * TS_BE;
@@ -151,30 +150,43 @@ __device__ __forceinline__ int factor_rows8(double (&row)[8], int lane) {
   return bad;
 }
 
-template <int DIM>
-__global__ void __maxnreg__(144) k_band_ts(const TsArgs a) {
+// shared-memory accesses by 32-bit address (the ring pointers are kept as byte addresses with the lane offset folded in)
+__device__ __forceinline__ double lds64(unsigned addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ double lds64_256(unsigned addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1+256];" : "=d"(v) : "r"(addr));
+  return v;
+}
+
+// NB: sub-diagonal blocks of the wider side's band view (loops, the pointer ring and the accumulators are sized by it)
+template <int NB>
+__global__ void __launch_bounds__(64, 7) k_band_ts(const TsArgs a) {
   extern __shared__ __align__(16) double sm_all[];
   TPH_DECL
   const unsigned FULL = 0xffffffffu;
   const int side = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const TsSideDev& S = a.side[side];
-  const int nb = S.nb;
   const bool two = a.side[1].ncol_tot > 0;
   const int main0 = ts_main_doubles(a.side[0].nb, a.chunk_max), main1 = two ? ts_main_doubles(a.side[1].nb, a.chunk_max) : 0;
   double* sm = sm_all + (side ? main0 + X_TOTAL : 0);
   const int mainsz = side ? main1 : main0;
   double* sRing = sm;
   double* sScr = sm + mainsz + X_SCR;
-  double* sProd = sm + mainsz + X_PROD;
   double* sT = sm + mainsz + X_T;
+  double* sY = sm + mainsz + X_Y;
   uint64_t* sBar = reinterpret_cast<uint64_t*>(sm + mainsz + X_MISC);           // NSTAGE mbarriers
-  int* sOff = reinterpret_cast<int*>(sm + mainsz + X_MISC + 4);                 // [NBX+1] staging slot of block rb (doubles from sm)
-  int* sFlag = reinterpret_cast<int*>(sm_all + main0 + X_MISC + 10);            // CTA-wide: [0] pivot failure, [1] input problem
-  double* sUS = sm_all + main0 + X_PROD;                                        // separator displacements (top -> bottom), top's product area
+  int* sOff = reinterpret_cast<int*>(sm + mainsz + X_MISC + 4);                 // [NB+1] staging slot of block rb (doubles from sm)
+  int* sFlag = reinterpret_cast<int*>(sm_all + main0 + X_MISC + 10);            // CTA-wide: [0] pivot failure
+  double* sUS = sm_all + main0 + X_SCR;                                         // separator displacements (top -> bottom), top's scratch block
 
   const int qr = lane >> 2, qc = lane & 3;
   const int cpo = ((qc >> 1) << 5) + (qr << 2) + ((qc & 1) << 1);               // this lane's accumulator pair inside a block
   const int nS = a.nS;
+  const unsigned ring_u32 = smem_u32(sRing) + lane * 8;                         // byte address of this lane's operand element in slot 0
 
   if (lane == 0) {                                                              // (side 1's area exists even when it has no columns)
 #pragma unroll
@@ -185,110 +197,42 @@ __global__ void __maxnreg__(144) k_band_ts(const TsArgs a) {
   __syncthreads();
 
   for (int b = blockIdx.x; b < a.batch; b += gridDim.x) {
-    if (threadIdx.x == 0) { sFlag[0] = 0; sFlag[1] = 0; }
+    if (threadIdx.x == 0) sFlag[0] = 0;
     __syncthreads();
-    const double* xyz = a.xyz + (int64_t)b * a.xyz_stride;
     const double* fsys = a.force + (int64_t)b * a.force_stride;
+    const double* kvs = a.kv + (int64_t)b * a.nnz;
     double* Lsys = a.L + (int64_t)b * a.l_per_sys;
     double* Xsys = a.X + (int64_t)b * nS * nS * TS_BE;
     double* Zsys = a.Z + (int64_t)b * nS * TS_BT;
     double* ufs = a.uf + (int64_t)b * a.n_pad;
-    double* kdbg = a.kdebug ? a.kdebug + (int64_t)b * a.kdbg_stride + (side ? a.kdbg_off1 : 0) : nullptr;
+    const int instat = a.status[b];                                             // input problem flagged by the assembly pass
 
-    int idx[NBX + 1];
-    unsigned nzprev[NBX + 1];
-    double yreg[NBX][2];
+    // Ring of the live blocks: Q[e][j], 1 <= j <= e, is the address of block (c-j+e, c-j) (diagonal e, created j columns
+    // ago; it dies after column c-j+e).  At column c the B operand of distance d is Q[d][d], the A operand of block row rb
+    // is Q[rb+d][d], and the new block (c+e, c) takes over the slot of the dying block (c, c-e) = Q[e][e]: the pointers
+    // rotate by register moves, no index arithmetic anywhere.
+    unsigned Q[NB + 1][NB + 1];
 #pragma unroll
-    for (int e = 0; e <= NBX; ++e) { idx[e] = 0; nzprev[e] = 0u; }
+    for (int e = 1; e <= NB; ++e)
 #pragma unroll
-    for (int e = 0; e < NBX; ++e) yreg[e][0] = yreg[e][1] = 0.0;
-    int gflag = 0, fail = 0;
+      for (int j = 1; j <= e; ++j) Q[e][j] = ring_u32 + (unsigned)((e * (e - 1) / 2 + (j - 1)) * TS_BE * 8);
+    unsigned nzprev[NB + 1];
+    unsigned Yq[NB + 1];                                                        // Yq[d]: address of y_{c-d}[qc] (d >= 1); Yq[0]: the slot y_c will take
+#pragma unroll
+    for (int e = 0; e <= NB; ++e) {
+      nzprev[e] = 0u;
+      Yq[e] = smem_u32(sY) + (unsigned)(e * TS_BT + qc) * 8u;
+    }
+    int fail = 0;
 
-    // ---- raw inputs of the member this lane handles in the first chunk of a block column, fetched one column ahead
-    double rx0[DIM], rx1[DIM], rar = 0.0, re = 0.0;
-    bool rok = true;
-    const int4 none4 = make_int4(-1, 0, 0, 0);
-    auto load_raw = [&](const int4& dsc) {
-      rok = true;
-      rar = re = 0.0;
-#pragma unroll
-      for (int i = 0; i < DIM; ++i) rx0[i] = rx1[i] = 0.0;
-      if (dsc.x < 0) return;
-      if (a.gene) {
-        const int g = __ldg(a.gene + (int64_t)b * a.gene_stride + dsc.x);
-        if ((unsigned)g < (unsigned)a.n_type) {
-          rar = __ldg(a.type_table + 3 * g);
-          re = __ldg(a.type_table + 3 * g + 1);
-        } else {
-          rok = false;
-        }
-      } else {
-        const double* t = a.aed + (int64_t)b * a.aed_stride + 3 * (int64_t)dsc.x;
-        rar = __ldg(t);
-        re = __ldg(t + 1);
-      }
-#pragma unroll
-      for (int i = 0; i < DIM; ++i) {
-        rx0[i] = __ldg(xyz + dsc.y * DIM + i);
-        rx1[i] = __ldg(xyz + dsc.z * DIM + i);
-      }
-    };
-    // member products of the reference (truss.py:19,56-63): k = e a / L, c_i = dx_i / L, with its roundings
-    auto geometry = [&](int slot, bool live) {
-      if (!live) return;
-      double dx[DIM], cc[DIM];
-#pragma unroll
-      for (int i = 0; i < DIM; ++i) dx[i] = __dsub_rn(rx1[i], rx0[i]);
-      double l2 = __dmul_rn(dx[0], dx[0]);
-#pragma unroll
-      for (int i = 1; i < DIM; ++i) l2 = __dadd_rn(l2, __dmul_rn(dx[i], dx[i]));
-      const double len = __dsqrt_rn(l2);
-      double k = 0.0;
-#pragma unroll
-      for (int i = 0; i < DIM; ++i) cc[i] = 0.0;
-      if (!rok) {
-        gflag = min(gflag, TB_INFO_BAD_INDEX);
-      } else if (!(len > 0.0)) {
-        gflag = min(gflag, TB_INFO_ZERO_LENGTH);
-      } else {
-        k = __ddiv_rn(__dmul_rn(re, rar), len);
-#pragma unroll
-        for (int i = 0; i < DIM; ++i) cc[i] = __ddiv_rn(dx[i], len);
-      }
-      double* o = sProd + slot * 4;
-      o[0] = k;
-#pragma unroll
-      for (int i = 0; i < DIM; ++i) o[1 + i] = cc[i];
-    };
-    // one contribution: +-k (c_i c_j), product first, then the scale (truss.py:69-70 / 80-81)
-    auto term = [&](int pk) {
-      const double* o = sProd + (pk >> 4) * 4;
-      const int ij = pk & 7;
-      int i, j;
-      if (DIM == 3) {
-        i = (ij >= 3) + (ij >= 5);
-        j = ij < 3 ? ij : (ij < 5 ? ij - 2 : 2);
-      } else {
-        i = ij >= 2;
-        j = ij >= 1;
-      }
-      const double t = __dmul_rn(o[0], __dmul_rn(o[1 + i], o[1 + j]));
-      return (pk & 8) ? -t : t;
-    };
-
-    // software pipeline over the block columns: masks / entry ranges / rhs row one column ahead, member descriptor two
-    // columns ahead, the member's raw inputs one column ahead (every address depends on c only)
-    int4 cin = none4, cen = make_int4(0, 0, 0, 0), mdn = none4;
+    // software pipeline over the block columns: masks / entry range / rhs row one column ahead (addresses depend on c only)
+    int4 cin = make_int4(0, 0, 0, 0);
+    int2 cen = make_int2(0, 0);
     int dof_n = -1;
-    bool live_n = false;
     if (S.ncol_tot > 0) {
       cin = __ldg(S.colinfo);
       cen = __ldg(S.colent);
       dof_n = __ldg(S.rowdof + qr);
-      mdn = __ldg(S.mem0 + lane);
-      live_n = mdn.x >= 0;
-      load_raw(mdn);
-      mdn = S.ncol_tot > 1 ? __ldg(S.mem0 + TS_CHUNK + lane) : none4;
     }
     TPH(0)
 
@@ -299,63 +243,57 @@ __global__ void __maxnreg__(144) k_band_ts(const TsArgs a) {
       if (side == 0 && c == S.ncol_own && two) pair_sync(1);                    // the bottom side's hand-over is complete
       const unsigned nzc = (unsigned)cin.x, srcc = (unsigned)cin.y, xm = (unsigned)cin.z;
       const double fr = (!xcol && dof_n >= 0) ? __ldg(fsys + dof_n) : 0.0;
-      // member products of this block column (first chunk) from the inputs fetched during the previous column
-      int e0 = cen.x, e1 = cen.y;
-      const int q0 = cen.z, q1 = cen.w;
-      if (q1 > q0) geometry(lane, live_n);
-      int2 ed[TS_EPL];
+      // K values of this block column (assembly pass, program order): in flight while the products run
+      const int e0 = cen.x, e1 = cen.y;
+      double kvr[TS_EPL];
+      int kpos[TS_EPL];
 #pragma unroll
       for (int i = 0; i < TS_EPL; ++i) {
-        ed[i] = make_int2(0, 0);
-        if (e0 + lane + 32 * i < e1) ed[i] = __ldg(S.ent + e0 + lane + 32 * i);
+        kvr[i] = 0.0;
+        kpos[i] = 0;
+        if (e0 + lane + 32 * i < e1) {
+          kvr[i] = __ldg(kvs + e0 + lane + 32 * i);
+          kpos[i] = __ldg(a.epos + e0 + lane + 32 * i);
+        }
       }
       if (c + 1 < S.ncol_tot) {
         cin = __ldg(S.colinfo + c + 1);
         cen = __ldg(S.colent + c + 1);
         dof_n = __ldg(S.rowdof + (c + 1) * TS_BT + qr);
       }
-      live_n = mdn.x >= 0;
-      load_raw(mdn);                                                            // (no member: nothing is loaded)
-      mdn = c + 2 < S.ncol_tot ? __ldg(S.mem0 + (c + 2) * TS_CHUNK + lane) : none4;
       TPH(1)
 
       // ---------------- products with the previous nb block columns
-      double acc[NBX + 1][2];
+      double acc[NB + 2][2];
 #pragma unroll
-      for (int rb = 0; rb <= NBX; ++rb) acc[rb][0] = acc[rb][1] = 0.0;
+      for (int rb = 0; rb <= NB + 1; ++rb) acc[rb][0] = acc[rb][1] = 0.0;
       double tp = 0.0;
 #pragma unroll
-      for (int d = 1; d <= NBX; ++d) {
-        if (d > nb) break;
+      for (int d = 1; d <= NB; ++d) {
         const unsigned nzp = nzprev[d];
         if (!((nzp >> d) & 1u)) continue;                                       // L(c, c-d) structurally zero (uniform)
-        const double* Bm = sRing + (d * (d - 1) / 2 + idx[d]) * TS_BE;
-        const double b0 = Bm[lane], b1 = Bm[32 + lane];
-        tp = fma(b0, yreg[d - 1][0], tp);
-        tp = fma(b1, yreg[d - 1][1], tp);
-        double a0[NBX + 1], a1[NBX + 1];
-#pragma unroll
-        for (int rb = 0; rb + d <= NBX; ++rb) {
-          const int e = rb + d;
-          a0[rb] = a1[rb] = 0.0;
-          if (e > nb || !((nzp >> e) & 1u)) continue;
-          int sl = idx[e] - d;
-          if (sl < 0) sl += e;
-          const double* A = sRing + (e * (e - 1) / 2 + sl) * TS_BE;
-          a0[rb] = A[lane];
-          a1[rb] = A[32 + lane];
+        const double b0 = lds64(Q[d][d]), b1 = lds64_256(Q[d][d]);
+        {
+          double y0, y1;
+          asm volatile("ld.shared.f64 %0, [%1];" : "=d"(y0) : "r"(Yq[d]));
+          asm volatile("ld.shared.f64 %0, [%1+32];" : "=d"(y1) : "r"(Yq[d]));
+          tp = fma(b0, y0, tp);
+          tp = fma(b1, y1, tp);
         }
+        // block rows two at a time: the second k-slab of one block issues behind the first k-slab of the other
 #pragma unroll
-        for (int rb = 0; rb + d <= NBX; ++rb) {
+        for (int rb = 0; rb + d <= NB; rb += 2) {
           const int e = rb + d;
-          if (e > nb || !((nzp >> e) & 1u)) continue;
-          dmma(acc[rb][0], acc[rb][1], a0[rb], b0);
-        }
-#pragma unroll
-        for (int rb = 0; rb + d <= NBX; ++rb) {
-          const int e = rb + d;
-          if (e > nb || !((nzp >> e) & 1u)) continue;
-          dmma(acc[rb][0], acc[rb][1], a1[rb], b1);
+          constexpr int dummy = 0; (void)dummy;
+          const bool on0 = (nzp >> e) & 1u, on1 = e + 1 <= NB && ((nzp >> (e + 1)) & 1u);
+          const int e1i = e + 1 <= NB ? e + 1 : e;
+          double a00 = 0.0, a01 = 0.0, a10 = 0.0, a11 = 0.0;
+          if (on0) { a00 = lds64(Q[e][d]); a01 = lds64_256(Q[e][d]); }
+          if (on1) { a10 = lds64(Q[e1i][d]); a11 = lds64_256(Q[e1i][d]); }
+          if (on0) dmma(acc[rb][0], acc[rb][1], a00, b0);
+          if (on1) dmma(acc[rb + 1][0], acc[rb + 1][1], a10, b0);
+          if (on0) dmma(acc[rb][0], acc[rb][1], a01, b1);
+          if (on1) dmma(acc[rb + 1][0], acc[rb + 1][1], a11, b1);
         }
       }
       tp += __shfl_xor_sync(FULL, tp, 1);
@@ -368,121 +306,80 @@ __global__ void __maxnreg__(144) k_band_ts(const TsArgs a) {
         // top side, J = nS-1-jq-rb, transposed and flipped: element (r, k) -> (7-k, 7-r)
         const int jq = c - S.ncol_own;
 #pragma unroll
-        for (int rb = 0; rb <= NBX; ++rb) {
-          if (rb > nb || !((nzc >> rb) & 1u)) continue;
+        for (int rb = 0; rb <= NB; ++rb) {
+          if (!((nzc >> rb) & 1u)) continue;
           double* dst = Xsys + (int64_t)((nS - 1 - jq - rb) * nS + rb) * TS_BE;
           dst[(7 - 2 * qc) * 8 + (7 - qr)] = acc[rb][0];
           dst[(6 - 2 * qc) * 8 + (7 - qr)] = acc[rb][1];
         }
         if (qc == 0) Zsys[(nS - 1 - jq) * TS_BT + (7 - qr)] = tp;
-#pragma unroll
-        for (int e = NBX - 1; e >= 1; --e) { yreg[e][0] = yreg[e - 1][0]; yreg[e][1] = yreg[e - 1][1]; }
-        yreg[0][0] = yreg[0][1] = 0.0;
       } else {
         if (side == 0 && !own && two) {
           const int J = c - S.ncol_own;
 #pragma unroll
-          for (int rb = 0; rb <= NBX; ++rb) {
-            if (rb > nb || !((xm >> rb) & 1u)) continue;
+          for (int rb = 0; rb <= NB; ++rb) {
+            if (!((xm >> rb) & 1u)) continue;
             const double2 x = __ldcg(reinterpret_cast<const double2*>(Xsys + (int64_t)(J * nS + rb) * TS_BE + qr * 8 + 2 * qc));
             acc[rb][0] += x.x;
             acc[rb][1] += x.y;
           }
           tp += __ldcg(Zsys + J * TS_BT + qr);
         }
-        // ---------------- stage K(:,c): block rb into the slot of the dead block (c, c-rb); rb = 0 into the scratch block
-        if (lane <= nb) sOff[lane] = lane == 0 ? (int)(sScr - sm) : (lane * (lane - 1) / 2 + idx[lane]) * TS_BE;
+        // ---------------- stage K(:,c): block rb into the slot of the dying block (c, c-rb); rb = 0 into the scratch block
         {
+          unsigned mine = smem_u32(sScr);                                       // lane rb publishes the slot of block rb
+#pragma unroll
+          for (int rb = 1; rb <= NB; ++rb) mine = lane == rb ? Q[rb][rb] - lane * 8 : mine;
+          if (lane <= NB) sOff[lane] = (int)mine;
           const double2 z = make_double2(0.0, 0.0);
           reinterpret_cast<double2*>(sScr)[lane] = z;
 #pragma unroll
-          for (int rb = 1; rb <= NBX; ++rb)
-            if (rb <= nb && ((nzc >> rb) & 1u)) reinterpret_cast<double2*>(sRing + (rb * (rb - 1) / 2 + idx[rb]) * TS_BE)[lane] = z;
+          for (int rb = 1; rb <= NB; ++rb)
+            if ((nzc >> rb) & 1u)
+              asm volatile("st.shared.v2.f64 [%0], {%1, %1};" ::"r"(Q[rb][rb] + lane * 8), "d"(0.0) : "memory");
         }
         __syncwarp();
-        for (int q = q0; q < q1; ++q) {
-          if (q > q0) {                        // further chunks of a crowded block column: fetched on the spot
-            const int m0 = __ldg(S.mem_ptr + q), m1 = __ldg(S.mem_ptr + q + 1);
-            int4 dsc = make_int4(-1, 0, 0, 0);
-            if (m0 + lane < m1) dsc = __ldg(S.mem + m0 + lane);
-            // the prefetched inputs of the next column are live in the r* registers: save and restore them
-            const double sar = rar, se = re;
-            const bool sok = rok;
-            double sx0[DIM], sx1[DIM];
 #pragma unroll
-            for (int i = 0; i < DIM; ++i) { sx0[i] = rx0[i]; sx1[i] = rx1[i]; }
-            load_raw(dsc);
-            __syncwarp();
-            geometry(lane, dsc.x >= 0);
-            rar = sar; re = se; rok = sok;
-#pragma unroll
-            for (int i = 0; i < DIM; ++i) { rx0[i] = sx0[i]; rx1[i] = sx1[i]; }
-            e0 = __ldg(S.ent_ptr + q);
-            e1 = __ldg(S.ent_ptr + q + 1);
-          }
-          __syncwarp();
-          for (int e = e0 + lane, i = 0; e < e1; e += 32, ++i) {
-            int2 dsc;
-            if (q == q0 && i < TS_EPL) {
-              dsc = ed[0];
-#pragma unroll
-              for (int u = 1; u < TS_EPL; ++u) dsc = i == u ? ed[u] : dsc;
-            } else {
-              dsc = __ldg(S.ent + e);
-            }
-            const int pos = dsc.x & 1023, cnt = dsc.x >> 10;
-            double* dst = sm + sOff[pos >> 6] + (pos & 63);
-            double v = *dst;
-            if (cnt == 1) {
-              v = __dadd_rn(v, term(dsc.y));
-            } else {
-              for (int t = 0; t < cnt; t += 4) {           // four map loads in flight, summed in ascending member order
-                int pk[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) pk[u] = t + u < cnt ? __ldg(S.pack + dsc.y + t + u) : -1;
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                  if (pk[u] >= 0) v = __dadd_rn(v, term(pk[u]));
-              }
-            }
-            *dst = v;
-            if (kdbg) kdbg[e] = v;
-          }
-          __syncwarp();
+        for (int i = 0; i < TS_EPL; ++i)
+          if (e0 + lane + 32 * i < e1)
+            asm volatile("st.shared.f64 [%0], %1;" ::"r"((unsigned)sOff[kpos[i] >> 6] + (unsigned)((kpos[i] & 63) * 8)), "d"(kvr[i]) : "memory");
+        for (int e = e0 + 32 * TS_EPL + lane; e < e1; e += 32) {                // rare: more than 32 * TS_EPL entries in this block column
+          const int pos = __ldg(a.epos + e);
+          asm volatile("st.shared.f64 [%0], %1;" ::"r"((unsigned)sOff[pos >> 6] + (unsigned)((pos & 63) * 8)), "d"(__ldg(kvs + e)) : "memory");
         }
-        if (lane < TS_BT && __ldg(S.rowdof + c * TS_BT + lane) < 0) sScr[b8_off(lane, lane)] = 1.0;   // identity on padding
+        if (lane < TS_BT && __ldg(S.rownat + c * TS_BT + lane) < 0) sScr[b8_off(lane, lane)] = 1.0;   // identity on padding
         __syncwarp();
         TPH(3)
 
         // ---------------- P = K - S in place (accumulator pairs), right-hand side of the block
 #pragma unroll
-        for (int rb = 0; rb <= NBX; ++rb) {
-          if (rb > nb || !((nzc >> rb) & 1u)) continue;
-          double* blk = rb == 0 ? sScr : sRing + (rb * (rb - 1) / 2 + idx[rb]) * TS_BE;
-          double2* pp = reinterpret_cast<double2*>(blk + cpo);
-          double2 v = *pp;
-          v.x -= acc[rb][0];
-          v.y -= acc[rb][1];
-          *pp = v;
+        for (int rb = 0; rb <= NB; ++rb) {
+          if (!((nzc >> rb) & 1u)) continue;
+          const unsigned ad = (rb == 0 ? smem_u32(sScr) : Q[rb][rb] - lane * 8) + cpo * 8;
+          double vx, vy;
+          asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(vx), "=d"(vy) : "r"(ad));
+          vx -= acc[rb][0];
+          vy -= acc[rb][1];
+          asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(ad), "d"(vx), "d"(vy) : "memory");
         }
         if (qc == 0) sT[qr] = fr - tp;
         __syncwarp();
 
         // ---------------- rows: P(c,c) | I | P(c+1,c) | t^T
+        const bool has1 = (nzc >> 1) & 1u;
+        const unsigned slot1 = Q[1][1] - lane * 8;                              // block (c+1, c)
         double row[8];
         {
-          const bool has1 = nb >= 1 && ((nzc >> 1) & 1u);
-          const double* src = lane < 8 ? sScr : sRing + idx[1] * TS_BE;        // ring slot of diagonal 1: block (c+1, c)
-          const int r = lane & 7;
+          const unsigned src = (lane < 8 ? smem_u32(sScr) : slot1) + (lane & 7) * 32;
           const bool ld = lane < 8 || (lane >= 16 && lane < 24 && has1);
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
-            double2 v0 = make_double2(0.0, 0.0), v1 = v0;
+            double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
             if (ld) {
-              v0 = *reinterpret_cast<const double2*>(src + h * 32 + r * 4);
-              v1 = *reinterpret_cast<const double2*>(src + h * 32 + r * 4 + 2);
+              asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v0), "=d"(v1) : "r"(src + h * 256));
+              asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v2), "=d"(v3) : "r"(src + h * 256 + 16));
             }
-            row[4 * h] = v0.x; row[4 * h + 1] = v0.y; row[4 * h + 2] = v1.x; row[4 * h + 3] = v1.y;
+            row[4 * h] = v0; row[4 * h + 1] = v1; row[4 * h + 2] = v2; row[4 * h + 3] = v3;
           }
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
@@ -510,57 +407,50 @@ __global__ void __maxnreg__(144) k_band_ts(const TsArgs a) {
 #pragma unroll
           for (int h = 0; h < 4; ++h) reinterpret_cast<double2*>(chunk + i * 8)[h] = make_double2(row[2 * h], row[2 * h + 1]);
         } else if (lane >= 16 && lane < 24) {
-          if (nb >= 1 && ((nzc >> 1) & 1u)) {
+          if (has1) {
             const int i = lane - 16;
-            double* blk = sRing + idx[1] * TS_BE;
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-              *reinterpret_cast<double2*>(blk + h * 32 + i * 4) = make_double2(row[4 * h], row[4 * h + 1]);
-              *reinterpret_cast<double2*>(blk + h * 32 + i * 4 + 2) = make_double2(row[4 * h + 2], row[4 * h + 3]);
+              asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(slot1 + h * 256 + i * 32), "d"(row[4 * h]), "d"(row[4 * h + 1]) : "memory");
+              asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(slot1 + h * 256 + i * 32 + 16), "d"(row[4 * h + 2]), "d"(row[4 * h + 3]) : "memory");
             }
 #pragma unroll
             for (int h = 0; h < 4; ++h)
               reinterpret_cast<double2*>(chunk + TS_BE + TS_BT + i * 8)[h] = make_double2(row[2 * h], row[2 * h + 1]);
           }
-        } else if (lane == 24) {
+        } else if (lane == 24) {                                                 // (qc == 0: Yq[0] is the base of the new y slot)
 #pragma unroll
           for (int h = 0; h < 4; ++h) {
-            reinterpret_cast<double2*>(sT)[h] = make_double2(row[2 * h], row[2 * h + 1]);
+            asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(Yq[0] + h * 16), "d"(row[2 * h]), "d"(row[2 * h + 1]) : "memory");
             reinterpret_cast<double2*>(chunk + TS_BE)[h] = make_double2(row[2 * h], row[2 * h + 1]);
           }
         }
         __syncwarp();
-#pragma unroll
-        for (int e = NBX - 1; e >= 1; --e) { yreg[e][0] = yreg[e - 1][0]; yreg[e][1] = yreg[e - 1][1]; }
-        yreg[0][0] = sT[qc];
-        yreg[0][1] = sT[4 + qc];
         const double w0 = sScr[lane], w1 = sScr[32 + lane];
 
         // ---------------- solves L(c+rb, c) = P(c+rb, c) Z, rb >= 2
         {
-          double f0[NBX + 1], f1[NBX + 1], x0[NBX + 1], x1[NBX + 1];
+          double f0[NB + 1], f1[NB + 1], x0[NB + 1], x1[NB + 1];
 #pragma unroll
-          for (int rb = 2; rb <= NBX; ++rb) {
+          for (int rb = 2; rb <= NB; ++rb) {
             f0[rb] = f1[rb] = 0.0;
-            if (rb > nb || !((nzc >> rb) & 1u)) continue;
-            const double* blk = sRing + (rb * (rb - 1) / 2 + idx[rb]) * TS_BE;
-            f0[rb] = blk[lane];
-            f1[rb] = blk[32 + lane];
+            if (!((nzc >> rb) & 1u)) continue;
+            f0[rb] = lds64(Q[rb][rb]);
+            f1[rb] = lds64_256(Q[rb][rb]);
           }
           __syncwarp();                                                          // every P block is read before any L overwrites it
 #pragma unroll
-          for (int rb = 2; rb <= NBX; ++rb) {
+          for (int rb = 2; rb <= NB; ++rb) {
             x0[rb] = x1[rb] = 0.0;
-            if (rb > nb || !((nzc >> rb) & 1u)) continue;
+            if (!((nzc >> rb) & 1u)) continue;
             dmma(x0[rb], x1[rb], f0[rb], w0);
           }
           int rank = (nzc >> 1) & 1u;
 #pragma unroll
-          for (int rb = 2; rb <= NBX; ++rb) {
-            if (rb > nb || !((nzc >> rb) & 1u)) continue;
+          for (int rb = 2; rb <= NB; ++rb) {
+            if (!((nzc >> rb) & 1u)) continue;
             dmma(x0[rb], x1[rb], f1[rb], w1);
-            double* blk = sRing + (rb * (rb - 1) / 2 + idx[rb]) * TS_BE;
-            *reinterpret_cast<double2*>(blk + cpo) = make_double2(x0[rb], x1[rb]);
+            asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(Q[rb][rb] - lane * 8 + cpo * 8), "d"(x0[rb]), "d"(x1[rb]) : "memory");
             *reinterpret_cast<double2*>(chunk + TS_BE + TS_BT + rank * TS_BE + qr * 8 + 2 * qc) = make_double2(x0[rb], x1[rb]);
             ++rank;
           }
@@ -569,15 +459,25 @@ __global__ void __maxnreg__(144) k_band_ts(const TsArgs a) {
         TPH(6)
       }
 
-      // ---------------- advance the ring
+      // ---------------- advance the ring: the slot of the dying block of every diagonal becomes the youngest block's
 #pragma unroll
-      for (int e = NBX; e >= 2; --e) nzprev[e] = nzprev[e - 1];
+      for (int e = NB; e >= 2; --e) nzprev[e] = nzprev[e - 1];
       nzprev[1] = srcc;
 #pragma unroll
-      for (int e = 1; e <= NBX; ++e) idx[e] = (idx[e] + 1 == e) ? 0 : idx[e] + 1;
+      for (int e = 1; e <= NB; ++e) {
+        const unsigned dying = Q[e][e];
+#pragma unroll
+        for (int j = e; j >= 2; --j) Q[e][j] = Q[e][j - 1];
+        Q[e][1] = dying;
+      }
+      {   // ... and the y slots: the oldest becomes the next column's
+        const unsigned oldest = Yq[NB];
+#pragma unroll
+        for (int j = NB; j >= 1; --j) Yq[j] = Yq[j - 1];
+        Yq[0] = oldest;
+      }
     }
     if (fail && lane == 0) atomicCAS(&sFlag[0], 0, fail);
-    if (gflag) atomicMin(&sFlag[1], gflag);
     if (side == 1 && two) {
       __threadfence_block();
       pair_sync(1);                                                              // hand-over written (pairs with the top side's wait)
@@ -587,7 +487,7 @@ __global__ void __maxnreg__(144) k_band_ts(const TsArgs a) {
     // =========================================== back substitution
     // u_c = Z_c (y_c - sum_rb L(c+rb, c)^T u_{c+rb}); the chunks come back through cp.async.bulk, NSTAGE in flight
     const int ncb = side == 0 ? S.ncol_tot : S.ncol_own;
-    const int ur = nb + 1;
+    const int ur = S.nb + 1;
     double* sBuf = sRing;
     double* sU = sRing + NSTAGE * a.chunk_max;                                   // ring of the last nb+1 blocks of u: block c in slot c mod (nb+1)
     fence_proxy_async();                                                         // this lane's factor stores / ring stores before the async proxy
@@ -607,7 +507,7 @@ __global__ void __maxnreg__(144) k_band_ts(const TsArgs a) {
     if (side == 1 && two) {
       pair_sync(2);                                                              // separator displacements are published
       int s2 = S.ncol_own % ur;
-      const int cend = S.ncol_own + (nS < nb ? nS : nb);                          // (the band reaches nb separator blocks at most)
+      const int cend = S.ncol_own + (nS < S.nb ? nS : S.nb);                          // (the band reaches nb separator blocks at most)
       for (int c = S.ncol_own; c < cend; ++c) {
         if (lane < TS_BT) sU[s2 * TS_BT + lane] = sUS[(nS - 1 - (c - S.ncol_own)) * TS_BT + (7 - lane)];
         s2 = s2 + 1 == ur ? 0 : s2 + 1;
@@ -633,8 +533,8 @@ __global__ void __maxnreg__(144) k_band_ts(const TsArgs a) {
       double t = 0.0;
       int rank = (mask >> 1) & 1u;
 #pragma unroll
-      for (int rb = 2; rb <= NBX; ++rb) {
-        if (rb > nb || !((mask >> rb) & 1u)) continue;
+      for (int rb = 2; rb <= NB; ++rb) {
+        if (!((mask >> rb) & 1u)) continue;
         const double* blk = buf + TS_BE + TS_BT + rank * TS_BE;
         ++rank;
         int us = cs + rb;
@@ -644,7 +544,7 @@ __global__ void __maxnreg__(144) k_band_ts(const TsArgs a) {
       }
       {
         const double u0 = __shfl_sync(FULL, uprev, 2 * g), u1 = __shfl_sync(FULL, uprev, 2 * g + 1);
-        if (nb >= 1 && ((mask >> 1) & 1u)) {
+        if ((mask >> 1) & 1u) {
           const double* blk = buf + TS_BE + TS_BT;
           t = fma(blk[(2 * g) * 8 + col], u0, t);
           t = fma(blk[(2 * g + 1) * 8 + col], u1, t);
@@ -672,14 +572,14 @@ __global__ void __maxnreg__(144) k_band_ts(const TsArgs a) {
     }
     TPH(8)
     __syncthreads();
-    if (threadIdx.x == 0) a.status[b] = sFlag[1] ? sFlag[1] : sFlag[0];
+    if (threadIdx.x == 0 && instat == 0) a.status[b] = sFlag[0];
     __syncthreads();
   }
   TPH_FLUSH(lane == 0)
 }
 
 struct DevCache {
-  int smem_set[2] = {0, 0};
+  int smem_set[TS_NBX + 1] = {};
 };
 DevCache g_cache[64];
 
@@ -691,24 +591,44 @@ int tb_ts_smem_bytes(const TsPlan* ts) {
   return (m0 + X_TOTAL + m1 + X_TOTAL) * 8;
 }
 
-int tb_launch_band_ts(const TsArgs& a, int smem, int num_sm, cudaStream_t st) {
-  if (a.batch <= 0) return 0;
+template <int NB>
+int launch_nb(const TsArgs& a, int smem, int grid, cudaStream_t st) {
   int dev = 0;
   TB_CUDA(cudaGetDevice(&dev));
-  auto kern = a.dim == 3 ? k_band_ts<3> : k_band_ts<2>;
+  auto kern = k_band_ts<NB>;
   DevCache& dc = g_cache[dev & 63];
-  if (dc.smem_set[a.dim - 2] < smem) {
+  if (dc.smem_set[NB] < smem) {
     TB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    dc.smem_set[a.dim - 2] = smem;
+    // seven CTAs of ~30 KB per SM need the largest shared-memory carve-out
+    TB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    dc.smem_set[NB] = smem;
   }
+  kern<<<grid, 64, smem, st>>>(a);
+  return 0;
+}
+
+int tb_launch_band_ts(const TsArgs& a, int smem, int num_sm, cudaStream_t st) {
+  if (a.batch <= 0) return 0;
   if (num_sm <= 0) num_sm = 148;
   int per_sm = (228 * 1024) / (smem + 1024);
   if (per_sm > 7) per_sm = 7;
   if (per_sm < 1) per_sm = 1;
-  int grid = a.batch < num_sm * per_sm ? a.batch : num_sm * per_sm;
+  const int grid = a.batch < num_sm * per_sm ? a.batch : num_sm * per_sm;
+  const int nbm = a.side[0].nb > a.side[1].nb ? a.side[0].nb : a.side[1].nb;
   tb_prof_begin(TB_PROF_CHOL, st);
-  kern<<<grid, 64, smem, st>>>(a);
+  int rc = 0;
+  switch (nbm) {
+    case 1: rc = launch_nb<1>(a, smem, grid, st); break;
+    case 2: rc = launch_nb<2>(a, smem, grid, st); break;
+    case 3: rc = launch_nb<3>(a, smem, grid, st); break;
+    case 4: rc = launch_nb<4>(a, smem, grid, st); break;
+    case 5: rc = launch_nb<5>(a, smem, grid, st); break;
+    case 6: rc = launch_nb<6>(a, smem, grid, st); break;
+    case 7: rc = launch_nb<7>(a, smem, grid, st); break;
+    default: rc = launch_nb<8>(a, smem, grid, st); break;
+  }
   tb_prof_end(TB_PROF_CHOL, st);
+  if (rc) return rc;
   tb_count_launch(1);
   return (int)cudaGetLastError();
 }

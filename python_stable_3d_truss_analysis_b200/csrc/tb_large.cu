@@ -1056,27 +1056,37 @@ int launch_recover(const LargeArgs& a, int num_sm, cudaStream_t st, bool recomp)
   return 0;
 }
 
-// Fused two-sided band kernel (tb_bandts.cu) + recovery: two launches per batch, K never leaves the SM
+// Two-sided band kernel (tb_bandts.cu): assembly pass in the kernel's program order, the band kernel, recovery
 int launch_ts_path(const LargeArgs& a, int num_sm, cudaStream_t st) {
+  const TsPlan* ts = a.ts;
   TsArgs t;
   memset(&t, 0, sizeof(t));
   t.batch = a.batch; t.dim = a.dim; t.nJ = a.nJ; t.M = a.M; t.N = a.N; t.n = a.n;
-  t.xyz = a.xyz; t.xyz_stride = a.xyz_stride;
-  t.aed = a.aed; t.aed_stride = a.aed_stride;
-  t.gene = a.gene; t.gene_stride = a.gene_stride;
-  t.type_table = a.type_table; t.n_type = a.n_type;
   t.force = a.force; t.force_stride = a.force_stride;
-  tb_ts_fill_sides(t, a.ts);
-  tb_ts_carve(t, a.ts, a.ts_ws, a.batch);
-  t.kdebug = a.kdebug;
+  tb_ts_fill_sides(t, ts);
+  double* kv = nullptr;
+  tb_ts_carve(t, ts, a.ts_ws, a.batch, &kv);
+  // assembly (k_prep / k_geom + k_kval) driven by the program-order scatter lists; recovery reads u in the internal order
   LargeArgs r = a;
+  r.q_first = ts->d_tq_first; r.q_multi = ts->d_tq_multi; r.q_ptr = ts->d_tq_ptr; r.q_pack = ts->d_tq_pack;
+  r.n_multi = (int)ts->tq_multi.size();
+  r.nnz = (int64_t)ts->epos.size();
+  r.kv = kv;
   r.y = t.uf;
   r.n_pad = t.n_pad;
   r.status = t.status;
-  const size_t rec_smem = (size_t)a.M * (1 + a.dim) * 8;
-  const bool recomp = rec_smem <= 96 * 1024;
+  const size_t prep_smem = (size_t)a.M * (a.dim * (a.dim + 1) / 2) * 8, rec_smem = (size_t)a.M * (1 + a.dim) * 8;
+  const bool prep = prep_smem <= 96 * 1024 && rec_smem <= 96 * 1024;
   int launches = 2;
-  if (!recomp) {                                 // very many members: the recovery reads the k_geom arrays
+  if (prep) {
+    auto kern = a.dim == 3 ? k_prep<3> : k_prep<2>;
+    const int rcg = g_prep_grant[a.dim - 2].ensure(kern, prep_smem);
+    if (rcg) return rcg;
+    int grid = a.batch < num_sm * 8 ? a.batch : num_sm * 8;
+    tb_prof_begin(TB_PROF_ASSEMBLE, st);
+    kern<<<grid, 256, prep_smem, st>>>(r);
+    tb_prof_end(TB_PROF_ASSEMBLE, st);
+  } else {                                       // very many members: products through HBM
     k_init_status<<<(a.batch + 255) / 256, 256, 0, st>>>(r.status, a.batch, 0);
     const int64_t total = (int64_t)a.batch * a.M;
     int grid = (int)((total + 255) / 256 < (int64_t)num_sm * 8 ? (total + 255) / 256 : (int64_t)num_sm * 8);
@@ -1085,13 +1095,17 @@ int launch_ts_path(const LargeArgs& a, int num_sm, cudaStream_t st) {
     if (a.dim == 3) k_geom<3><<<grid, 256, 0, st>>>(r);
     else k_geom<2><<<grid, 256, 0, st>>>(r);
     tb_prof_end(TB_PROF_GEOM, st);
+    grid = a.batch < num_sm * 8 ? a.batch : num_sm * 8;
+    tb_prof_begin(TB_PROF_ASSEMBLE, st);
+    k_kval<<<grid, 256, 0, st>>>(r);
+    tb_prof_end(TB_PROF_ASSEMBLE, st);
     launches += 2;
   }
-  int rc = tb_launch_band_ts(t, tb_ts_smem_bytes(a.ts), num_sm, st);
+  int rc = tb_launch_band_ts(t, tb_ts_smem_bytes(ts), num_sm, st);
   if (rc) return rc;
-  rc = launch_recover(r, num_sm, st, recomp);
+  rc = launch_recover(r, num_sm, st, prep);
   if (rc) return rc;
-  tb_count_launch(launches - 1);                 // (the band kernel counted itself)
+  tb_count_launch(launches);                     // (the band kernel counted itself)
   return (int)cudaGetLastError();
 }
 

@@ -13,10 +13,13 @@
 //
 // Per side and virtual block column c the program lists
 //   colmask   bit rb: block (c+rb, c) of L is structurally non-zero (block symbolic factorisation of this order)
-//   members   the members that contribute to K entries of this block column, in chunks of TS_CHUNK, ascending id
-//   entries   K entries (block offset rb, position inside the 8x8 block) with their member contributions as
-//             (slot in the chunk, sign, index of the cosine product) in ascending member order, truss.py:310-314
+//   entries   the K_ff entries of the block column: a range [e0, e1) of the "program order" of all entries, with
+//             epos[e] = block offset rb << 6 | position inside the 8x8 block.  The K values arrive in the same order
+//             (kv[e]) from the assembly pass (tb_large.cu k_prep run on tq_*: every entry sums its member contributions
+//             in ascending member order, truss.py:310-314), so a lane's loads are coalesced and nothing is searched
 //   lofs      where the column's chunk of the factor lives ([Z = L_D^{-T} | y | non-zero blocks below the diagonal])
+// An earlier version assembled K inside the band kernel (member geometry + gather per block column); that was 35 % of
+// the kernel's instructions on its dependent chain, so the assembly went back to its own (parallel, HBM-bound) pass.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -27,8 +30,7 @@
 constexpr int TS_BT = 8;       // block order: the native FP64 MMA shape (mma.m8n8k4)
 constexpr int TS_BE = 64;      // doubles per block
 constexpr int TS_NBX = 8;      // at most this many sub-diagonal blocks per block column
-constexpr int TS_CHUNK = 32;   // members whose products are in shared memory at one time (one per lane)
-constexpr int TS_EPL = 5;      // entry descriptors per lane prefetched one block column ahead
+constexpr int TS_EPL = 5;      // K values per lane prefetched at the top of a block column (more: loaded on the spot)
 
 struct TsSideDev {
   int ncol_own;              // block columns this side factorises on its own
@@ -37,13 +39,7 @@ struct TsSideDev {
   const int4* colinfo;       // [ncol_tot]   x = colmask: bit rb <=> block (c+rb, c) non-zero (bottom separator columns: blocks it contributes to)
                              //              y = srcmask: colmask of the columns that exist as factor columns (0 for the bottom's separator columns)
                              //              z = xmask: top separator columns: blocks handed over by the bottom side;  w = unused
-  const int4* colent;        // [ncol_tot]   (first entry, end) of the first member chunk, (first chunk, end) of the column
-  const int4* mem0;          // [ncol_tot*32] member of lane l in the first chunk of the column: (member, joint0, joint1, 0), member -1 = none
-  const int32_t* mem_ptr;    // [nchunk+1]   members per chunk
-  const int4* mem;           // [.]          (member, joint0, joint1, 0)
-  const int32_t* ent_ptr;    // [nchunk+1]   entries per chunk
-  const int2* ent;           // [.]          x = pos | count << 10 (pos = rb << 6 | offset in the block), y = first contribution (or the contribution itself when count == 1)
-  const int32_t* pack;       // [.]          slot << 4 | negate << 3 | index of the cosine product (i <= j)
+  const int2* colent;        // [ncol_tot]   entries [x, y) of the block column in program order (indices into kv / epos)
   const int32_t* rowdof;     // [ncol_tot*8] DOF index of virtual row v, -1 on padding
   const int32_t* rownat;     // [ncol_tot*8] internal (natural) row of virtual row v, -1 on padding
   const int32_t* lofs;       // [ncol_tot+1] offset (doubles) of the column's factor chunk inside the system's factor storage
@@ -65,23 +61,21 @@ struct TsArgs {
   double* Z;                 // [B][nS*8]      ... and to the forward-substituted right-hand side
   double* uf;                // [B][n_pad]     free displacements, internal order (read by the recovery)
   int32_t* status;           // [B]
-  double* kdebug;            // optional [B][kdbg_stride]: assembled K values in program order (bit-exactness tests)
-  int64_t kdbg_stride;       // entries of both sides; the bottom side's entries start at kdbg_off1
-  int kdbg_off1;
+  const double* kv;          // [B][nnz]       K_ff values in program order (assembly pass)
+  const int32_t* epos;       // [nnz]          rb << 6 | position inside the block (operand-fragment layout)
+  int64_t nnz;
 };
 
 struct TsSideHost {
   int ncol_own = 0, ncol_tot = 0, nb = 0;
   std::vector<uint32_t> colmask, srcmask, xmask;
-  std::vector<int32_t> chunk_ptr, mem_ptr, ent_ptr, pack, rowdof, rownat, lofs;
-  std::vector<int4> mem, colinfo, colent, mem0;
-  std::vector<int2> ent;
-  std::vector<int32_t> ent_src;   // [entries] index of the plan's scatter-map entry (debug export)
+  std::vector<int32_t> rowdof, rownat, lofs;
+  std::vector<int4> colinfo;
+  std::vector<int2> colent;
   // device mirrors
-  int32_t *d_mem_ptr = nullptr, *d_ent_ptr = nullptr, *d_pack = nullptr, *d_rowdof = nullptr, *d_rownat = nullptr,
-          *d_lofs = nullptr;
-  int4 *d_mem = nullptr, *d_colinfo = nullptr, *d_colent = nullptr, *d_mem0 = nullptr;
-  int2* d_ent = nullptr;
+  int32_t *d_rowdof = nullptr, *d_rownat = nullptr, *d_lofs = nullptr;
+  int4* d_colinfo = nullptr;
+  int2* d_colent = nullptr;
 };
 
 struct TsPlan {
@@ -93,13 +87,19 @@ struct TsPlan {
   int64_t products = 0, solves = 0;   // 8x8 block products / block solves per system (executed DMMA work)
   double dmma_flops = 0.0;            // flops the tensor cores execute per system
   TsSideHost side[2];
+  // entries of both sides in program order (top side's block columns, then the bottom side's)
+  std::vector<int32_t> epos;          // [nnz] rb << 6 | position inside the block
+  std::vector<int32_t> ent_src;       // [nnz] index of the plan's scatter-map entry
+  // assembly program in that order, in the format k_prep reads (tb_common.cuh: q_first / q_multi / q_ptr / q_pack)
+  std::vector<int32_t> tq_first, tq_multi, tq_ptr, tq_pack;
+  int32_t *d_epos = nullptr, *d_tq_first = nullptr, *d_tq_multi = nullptr, *d_tq_ptr = nullptr, *d_tq_pack = nullptr;
 };
 
 struct tb_plan;
 int tb_ts_build(tb_plan* p);                  // host program (always), device mirrors when the plan has a device
 void tb_ts_destroy(TsPlan* ts, bool device);
 size_t tb_ts_workspace_bytes(const tb_plan* p, int batch);
-void tb_ts_carve(TsArgs& t, const TsPlan* ts, void* ws, int batch);   // L | X | Z | uf | status
+void tb_ts_carve(TsArgs& t, const TsPlan* ts, void* ws, int batch, double** kv);   // L | X | Z | uf | kv | status
 void tb_ts_fill_sides(TsArgs& t, const TsPlan* ts);
 int tb_ts_smem_bytes(const TsPlan* ts);
 int tb_launch_band_ts(const TsArgs& a, int smem, int num_sm, cudaStream_t st);

@@ -36,7 +36,7 @@ struct Masks {
 
 // cost model of one block column (cycles of one warp, calibrated on B200: see DESIGN.md): fixed part (assembly, staging,
 // 8 pivots, stores), 8x8 block products (two DMMAs + operand loads), block solves; back substitution per column
-constexpr double C_COL = 900.0, C_PROD = 45.0, C_SOLVE = 50.0, C_BACK = 260.0;
+constexpr double C_COL = 1500.0, C_PROD = 40.0, C_SOLVE = 40.0, C_BACK = 400.0;
 
 // Block masks of both sides for the split (bT, nS): kblk[bj] bit e <=> K_ff has an entry in block (bj+e, bj)
 Masks make_masks(const std::vector<uint32_t>& kblk, int nblk, int bT, int nS) {
@@ -131,10 +131,11 @@ void tb_ts_destroy(TsPlan* ts, bool device) {
   if (device)
     for (int s = 0; s < 2; ++s) {
       TsSideHost& h = ts->side[s];
-      cudaFree(h.d_colinfo); cudaFree(h.d_colent); cudaFree(h.d_mem0); cudaFree(h.d_mem_ptr);
-      cudaFree(h.d_ent_ptr); cudaFree(h.d_pack); cudaFree(h.d_rowdof); cudaFree(h.d_rownat); cudaFree(h.d_lofs);
-      cudaFree(h.d_mem); cudaFree(h.d_ent);
+      cudaFree(h.d_colinfo); cudaFree(h.d_colent); cudaFree(h.d_rowdof); cudaFree(h.d_rownat); cudaFree(h.d_lofs);
     }
+  if (device) {
+    cudaFree(ts->d_epos); cudaFree(ts->d_tq_first); cudaFree(ts->d_tq_multi); cudaFree(ts->d_tq_ptr); cudaFree(ts->d_tq_pack);
+  }
   delete ts;
 }
 
@@ -246,70 +247,37 @@ int tb_ts_build(tb_plan* p) {
       colent[1][vc / TS_BT].push_back({vr, vc, (int32_t)e});
     }
   }
+  ts->epos.clear(); ts->ent_src.clear();
+  ts->tq_ptr.assign(1, 0);
   for (int s = 0; s < 2; ++s) {
     TsSideHost& h = ts->side[s];
-    h.chunk_ptr.assign((size_t)h.ncol_tot + 1, 0);
-    h.mem_ptr.assign(1, 0);
-    h.ent_ptr.assign(1, 0);
-    for (int c = 0; c < h.ncol_tot; ++c) {
-      std::vector<Ent>& ev = colent[s][c];
-      // members of this block column, ascending
-      std::vector<int32_t> mem;
-      for (const Ent& en : ev)
-        for (int64_t k = p->ent_ptr[en.src]; k < p->ent_ptr[en.src + 1]; ++k) mem.push_back(p->ctr_member[k]);
-      std::sort(mem.begin(), mem.end());
-      mem.erase(std::unique(mem.begin(), mem.end()), mem.end());
-      const int nchunk = ((int)mem.size() + TS_CHUNK - 1) / TS_CHUNK;
-      for (int q = 0; q < nchunk; ++q) {
-        const int m0 = q * TS_CHUNK, m1 = std::min((int)mem.size(), m0 + TS_CHUNK);
-        for (int t = m0; t < m1; ++t) h.mem.push_back(make_int4(mem[t], p->conn[2 * mem[t]], p->conn[2 * mem[t] + 1], 0));
-        h.mem_ptr.push_back((int32_t)h.mem.size());
-        // entries with contributions from this chunk (the scatter map lists contributions in ascending member order)
-        struct CE { int pos; int32_t src; std::vector<int32_t> pk; };
-        std::vector<CE> ces;
-        for (const Ent& en : ev) {
-          CE ce;
-          ce.pos = ((en.vr / TS_BT - en.vc / TS_BT) << 6) | ((((en.vc % TS_BT) >> 2) << 5) + ((en.vr % TS_BT) << 2) + (en.vc & 3));
-          ce.src = en.src;
-          for (int64_t k = p->ent_ptr[en.src]; k < p->ent_ptr[en.src + 1]; ++k) {
-            const int slot = (int)(std::lower_bound(mem.begin(), mem.end(), p->ctr_member[k]) - mem.begin());
-            if (slot < m0 || slot >= m1) continue;
-            const int loc = p->ctr_local[k], la = loc / (2 * d), lb = loc % (2 * d);
-            const int A = la / d, i = la % d, B = lb / d, j = lb % d;
-            const int lo = std::min(i, j), hi = std::max(i, j);
-            ce.pk.push_back(((slot - m0) << 4) | ((A != B) << 3) | (lo * d - lo * (lo - 1) / 2 + (hi - lo)));
-          }
-          if (!ce.pk.empty()) ces.push_back(std::move(ce));
-        }
-        // heaviest entries first: entry i goes to lane i % 32, so every lane gets a similar mix
-        std::stable_sort(ces.begin(), ces.end(), [](const CE& a, const CE& b) { return a.pk.size() > b.pk.size(); });
-        for (const CE& ce : ces) {
-          const int cnt = (int)ce.pk.size();
-          int2 dsc;
-          dsc.x = ce.pos | (cnt << 10);
-          if (cnt == 1) {
-            dsc.y = ce.pk[0];
-          } else {
-            dsc.y = (int32_t)h.pack.size();
-            h.pack.insert(h.pack.end(), ce.pk.begin(), ce.pk.end());
-          }
-          h.ent.push_back(dsc);
-          h.ent_src.push_back(ce.src);
-        }
-        h.ent_ptr.push_back((int32_t)h.ent.size());
-      }
-      h.chunk_ptr[c + 1] = h.chunk_ptr[c] + nchunk;
-    }
-    // flat per-column views: nothing the kernel needs at the top of a block column hangs on another load
     h.colinfo.resize(h.ncol_tot);
     h.colent.resize(h.ncol_tot);
-    h.mem0.assign((size_t)h.ncol_tot * TS_CHUNK, make_int4(-1, 0, 0, 0));
     for (int c = 0; c < h.ncol_tot; ++c) {
       h.colinfo[c] = make_int4((int)h.colmask[c], (int)h.srcmask[c], (int)h.xmask[c], 0);
-      const int q0 = h.chunk_ptr[c], q1 = h.chunk_ptr[c + 1];
-      h.colent[c] = make_int4(q1 > q0 ? h.ent_ptr[q0] : 0, q1 > q0 ? h.ent_ptr[q0 + 1] : 0, q0, q1);
-      if (q1 > q0)
-        for (int t = h.mem_ptr[q0]; t < h.mem_ptr[q0 + 1]; ++t) h.mem0[(size_t)c * TS_CHUNK + (t - h.mem_ptr[q0])] = h.mem[t];
+      const int e0 = (int)ts->epos.size();
+      for (const Ent& en : colent[s][c]) {
+        ts->epos.push_back(((en.vr / TS_BT - en.vc / TS_BT) << 6) | ((((en.vc % TS_BT) >> 2) << 5) + ((en.vr % TS_BT) << 2) + (en.vc & 3)));
+        ts->ent_src.push_back(en.src);
+        for (int64_t k = p->ent_ptr[en.src]; k < p->ent_ptr[en.src + 1]; ++k) {
+          const int loc = p->ctr_local[k], la = loc / (2 * d), lb = loc % (2 * d);
+          const int A = la / d, i = la % d, B = lb / d, j = lb % d;
+          const int lo = std::min(i, j), hi = std::max(i, j);
+          ts->tq_pack.push_back((p->ctr_member[k] << 4) | ((A != B) << 3) | (lo * d - lo * (lo - 1) / 2 + (hi - lo)));
+        }
+        ts->tq_ptr.push_back((int32_t)ts->tq_pack.size());
+      }
+      h.colent[c] = make_int2(e0, (int)ts->epos.size());
+    }
+  }
+  {   // first contribution inline, entries with several contributions listed separately (as tb_plan.cu does for the other orders)
+    const size_t nq = ts->epos.size();
+    ts->tq_first.assign(nq, 0);
+    ts->tq_multi.clear();
+    for (size_t q = 0; q < nq; ++q) {
+      const int cnt = ts->tq_ptr[q + 1] - ts->tq_ptr[q];
+      ts->tq_first[q] = (cnt > 0 ? ts->tq_pack[ts->tq_ptr[q]] : 0) | (cnt > 1 ? (int32_t)0x80000000u : 0);
+      if (cnt > 1) ts->tq_multi.push_back((int32_t)q);
     }
   }
   ts->ok = 1;
@@ -319,32 +287,34 @@ int tb_ts_build(tb_plan* p) {
     TsSideHost& h = ts->side[s];
     if (!rc) rc = up(&h.d_colinfo, h.colinfo);
     if (!rc) rc = up(&h.d_colent, h.colent);
-    if (!rc) rc = up(&h.d_mem0, h.mem0);
-    if (!rc) rc = up(&h.d_mem_ptr, h.mem_ptr);
-    if (!rc) rc = up(&h.d_ent_ptr, h.ent_ptr);
-    if (!rc) rc = up(&h.d_pack, h.pack);
     if (!rc) rc = up(&h.d_rowdof, h.rowdof);
     if (!rc) rc = up(&h.d_rownat, h.rownat);
     if (!rc) rc = up(&h.d_lofs, h.lofs);
-    if (!rc) rc = up(&h.d_mem, h.mem);
-    if (!rc) rc = up(&h.d_ent, h.ent);
   }
+  if (!rc) rc = up(&ts->d_epos, ts->epos);
+  if (!rc) rc = up(&ts->d_tq_first, ts->tq_first);
+  if (!rc) rc = up(&ts->d_tq_multi, ts->tq_multi);
+  if (!rc) rc = up(&ts->d_tq_ptr, ts->tq_ptr);
+  if (!rc) rc = up(&ts->d_tq_pack, ts->tq_pack);
   return rc;
 }
 
 size_t tb_ts_workspace_bytes(const tb_plan* p, int batch) {
   const TsPlan* ts = p->ts;
   if (!ts || !ts->ok) return 0;
-  const size_t per = (size_t)ts->l_per_sys + (size_t)ts->nS * ts->nS * TS_BE + (size_t)ts->nS * TS_BT + (size_t)ts->n_pad;
+  const size_t per = (size_t)ts->l_per_sys + (size_t)ts->nS * ts->nS * TS_BE + (size_t)ts->nS * TS_BT + (size_t)ts->n_pad +
+                     ts->epos.size();
   return (size_t)batch * per * 8 + (size_t)batch * 4 + 4096;
 }
 
-void tb_ts_carve(TsArgs& t, const TsPlan* ts, void* ws, int batch) {
+void tb_ts_carve(TsArgs& t, const TsPlan* ts, void* ws, int batch, double** kv) {
   double* p = (double*)ws;
   t.L = p;  p += (size_t)batch * ts->l_per_sys;
   t.X = p;  p += (size_t)batch * ts->nS * ts->nS * TS_BE;
   t.Z = p;  p += (size_t)batch * ts->nS * TS_BT;
   t.uf = p; p += (size_t)batch * ts->n_pad;
+  *kv = p;  p += (size_t)batch * ts->epos.size();
+  t.kv = *kv;
   t.status = (int32_t*)p;
 }
 
@@ -353,16 +323,14 @@ void tb_ts_fill_sides(TsArgs& t, const TsPlan* ts) {
     const TsSideHost& h = ts->side[s];
     TsSideDev& d = t.side[s];
     d.ncol_own = h.ncol_own; d.ncol_tot = h.ncol_tot; d.nb = h.nb;
-    d.colinfo = h.d_colinfo; d.colent = h.d_colent; d.mem0 = h.d_mem0; d.mem_ptr = h.d_mem_ptr; d.mem = h.d_mem;
-    d.ent_ptr = h.d_ent_ptr; d.ent = h.d_ent; d.pack = h.d_pack; d.rowdof = h.d_rowdof; d.rownat = h.d_rownat;
-    d.lofs = h.d_lofs;
+    d.colinfo = h.d_colinfo; d.colent = h.d_colent; d.rowdof = h.d_rowdof; d.rownat = h.d_rownat; d.lofs = h.d_lofs;
   }
+  t.epos = ts->d_epos;
+  t.nnz = (int64_t)ts->epos.size();
   t.nS = ts->nS;
   t.chunk_max = ts->chunk_max;
   t.l_per_sys = ts->l_per_sys;
   t.n_pad = ts->n_pad;
-  t.kdbg_stride = (int64_t)(ts->side[0].ent.size() + ts->side[1].ent.size());
-  t.kdbg_off1 = (int)ts->side[0].ent.size();
 }
 
 // ---- debug / test exports: the program as flat host arrays (tests/test_ts_program_cpu.py replays it in numpy)
@@ -374,34 +342,35 @@ extern "C" int tb_plan_ts_info(const tb_plan* p, int32_t* out /*[16]*/) {
   out[0] = 1; out[1] = ts->nblk; out[2] = ts->n_pad; out[3] = ts->bT; out[4] = ts->nS; out[5] = ts->nB;
   out[6] = ts->side[0].nb; out[7] = ts->side[1].nb; out[8] = ts->chunk_max; out[9] = (int32_t)ts->l_per_sys;
   out[10] = (int32_t)ts->products; out[11] = (int32_t)ts->solves;
-  for (int s = 0; s < 2; ++s) {
-    out[12 + 2 * s] = (int32_t)ts->side[s].ent.size();
-    out[13 + 2 * s] = (int32_t)ts->side[s].pack.size();
-  }
+  out[12] = (int32_t)ts->epos.size();
+  out[13] = (int32_t)ts->tq_pack.size();
+  out[14] = (int32_t)ts->tq_multi.size();
   return TB_OK;
 }
 
-// which = 0 colmask, 1 srcmask, 2 xmask, 3 chunk_ptr, 4 mem_ptr, 5 mem (4 ints each), 6 ent_ptr, 7 ent (2 ints each),
-// 8 pack, 9 rowdof, 10 rownat, 11 lofs, 12 ent_src.  Returns the element count (ints); copies when out != NULL.
+// which = 0 colmask, 1 srcmask, 2 xmask, 3 colent (2 ints each), 4 rowdof, 5 rownat, 6 lofs (per side); 7 epos, 8 ent_src,
+// 9 tq_first, 10 tq_multi, 11 tq_ptr, 12 tq_pack (whole program, side ignored).  Returns the element count (ints); copies
+// when out != NULL.
 extern "C" int64_t tb_plan_ts_array(const tb_plan* p, int32_t side, int32_t which, int32_t* out) {
   if (!p || !p->ts || !p->ts->ok || side < 0 || side > 1) return -1;
-  const TsSideHost& h = p->ts->side[side];
+  const TsPlan* ts = p->ts;
+  const TsSideHost& h = ts->side[side];
   const void* src = nullptr;
   size_t cnt = 0;
   switch (which) {
     case 0: src = h.colmask.data(); cnt = h.colmask.size(); break;
     case 1: src = h.srcmask.data(); cnt = h.srcmask.size(); break;
     case 2: src = h.xmask.data(); cnt = h.xmask.size(); break;
-    case 3: src = h.chunk_ptr.data(); cnt = h.chunk_ptr.size(); break;
-    case 4: src = h.mem_ptr.data(); cnt = h.mem_ptr.size(); break;
-    case 5: src = h.mem.data(); cnt = h.mem.size() * 4; break;
-    case 6: src = h.ent_ptr.data(); cnt = h.ent_ptr.size(); break;
-    case 7: src = h.ent.data(); cnt = h.ent.size() * 2; break;
-    case 8: src = h.pack.data(); cnt = h.pack.size(); break;
-    case 9: src = h.rowdof.data(); cnt = h.rowdof.size(); break;
-    case 10: src = h.rownat.data(); cnt = h.rownat.size(); break;
-    case 11: src = h.lofs.data(); cnt = h.lofs.size(); break;
-    case 12: src = h.ent_src.data(); cnt = h.ent_src.size(); break;
+    case 3: src = h.colent.data(); cnt = h.colent.size() * 2; break;
+    case 4: src = h.rowdof.data(); cnt = h.rowdof.size(); break;
+    case 5: src = h.rownat.data(); cnt = h.rownat.size(); break;
+    case 6: src = h.lofs.data(); cnt = h.lofs.size(); break;
+    case 7: src = ts->epos.data(); cnt = ts->epos.size(); break;
+    case 8: src = ts->ent_src.data(); cnt = ts->ent_src.size(); break;
+    case 9: src = ts->tq_first.data(); cnt = ts->tq_first.size(); break;
+    case 10: src = ts->tq_multi.data(); cnt = ts->tq_multi.size(); break;
+    case 11: src = ts->tq_ptr.data(); cnt = ts->tq_ptr.size(); break;
+    case 12: src = ts->tq_pack.data(); cnt = ts->tq_pack.size(); break;
     default: return -1;
   }
   if (out && cnt) memcpy(out, src, cnt * 4);

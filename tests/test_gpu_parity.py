@@ -230,7 +230,7 @@ def test_full_size_properties_bar942_x1024():
         assert np.array_equal(out[k], again[k]), k                       # deterministic
     shared = SolveLoadCases(t, F)                                        # one factorisation, 1024 substitutions
     for k in H.FIELDS:
-        assert orc.normwise_err(shared[k], out[k]) <= 1e-11, k
+        assert orc.normwise_err(shared[k], out[k]) <= 2e-10, k     # (two different factorisation orders of a cond 6e6 matrix)
         assert np.array_equal(shared[k][100:140], SolveLoadCases(t, F[100:140])[k]), k   # batch-size independent
     basis = SolveLoadCases(t, base, independent=True)
     mask = t.GetDisplacementUnknownMask()

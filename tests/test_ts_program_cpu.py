@@ -1,8 +1,8 @@
 """The two-sided band program of the fused band kernel (csrc/tb_tsplan.cu), replayed in numpy (tests/ts_replay.py).
 
 The program is pure integer data built on the host, so everything but the thread-level layout of ``k_band_ts`` can be
-checked without a GPU: per-column assembly (contributions in ascending member order: the K values must equal the
-oracle's ``GetKMatrix()[mask][:, mask]`` bit for bit, truss.py:307-316, 343), structural masks, ring slots, the hand-over
+checked without a GPU: the assembly pass's lists in the kernel's entry order (contributions in ascending member order,
+truss.py:307-316, 343), structural masks, ring slots, the hand-over
 to the separator, chunk offsets, both back substitutions -- against the oracle's dense solve on every fixture, with
 the automatic split and with forced ones.
 """
@@ -42,7 +42,7 @@ def run_case(dim, data, env=None):
 
 def check(plan, prog, arrays, dim):
     joints, support, conn, aed, force = arrays
-    u_dof, dbg = ts_replay.replay(prog, dim, joints, aed, force.reshape(-1), plan.N)
+    u_dof, dbg = ts_replay.replay(prog, dim, joints, conn, aed, force.reshape(-1), plan.N)
     want = orc.solve(dim, joints, support, conn, aed, force)
     err = orc.normwise_err(u_dof, want["u"])
     assert err <= 1e-9, f"replayed program vs oracle: {err:.3e}"
@@ -55,13 +55,10 @@ def check(plan, prog, arrays, dim):
     mask = orc.free_mask(dim, support)
     Kff = K[mask][:, mask]
     row, col, ptr, mem, loc = plan.scatter()
-    last = {}
-    for s, side in enumerate(dbg["sides"]):
-        src = side.d["ent_src"]
-        for e in sorted(side.kvals):                      # later chunks of an entry overwrite earlier partial sums
-            last[int(src[e])] = side.kvals[e]
-    assert len(last) == len(row), "every scatter-map entry is assembled exactly by one side"
-    got = np.array([last[i] for i in range(len(row))])
+    src = prog["ent_src"]
+    assert sorted(src.tolist()) == list(range(len(row))), "every scatter-map entry is assembled exactly once"
+    got = np.zeros(len(row))
+    got[src] = dbg["kv"]
     prods = [ts_replay.member_products(dim, joints, conn[m], aed[m][0], aed[m][1]) for m in range(conn.shape[0])]
     want_k = np.zeros(len(row))
     mag = np.zeros(len(row))

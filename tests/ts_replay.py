@@ -26,8 +26,9 @@ def member_products(dim, xyz, conn_pair, a, e):
     return k, c
 
 
-def _term(dim, prod, pk):
-    k, c = prod[pk >> 4]
+def _term(dim, prods, pk):
+    """One contribution of the assembly pass's lists: member << 4 | negate << 3 | index of the cosine product."""
+    k, c = prods[pk >> 4]
     ij = pk & 7
     if dim == 3:
         i = (ij >= 3) + (ij >= 5)
@@ -37,6 +38,26 @@ def _term(dim, prod, pk):
         j = int(ij >= 1)
     t = k * (c[i] * c[j])
     return -t if (pk & 8) else t
+
+
+def assemble_program_order(prog, dim, xyz, conn, aed):
+    """kv[e]: what the assembly pass (k_prep on tq_first / tq_multi / tq_ptr / tq_pack) writes, in the kernel's entry
+    order: contributions summed in list order (ascending member, truss.py:310-314)."""
+    prods = [member_products(dim, xyz, conn[m], aed[m][0], aed[m][1]) for m in range(len(conn))]
+    ptr, pack, first = prog["tq_ptr"], prog["tq_pack"], prog["tq_first"]
+    kv = np.zeros(len(ptr) - 1)
+    multi = set(int(q) for q in prog["tq_multi"])
+    for q in range(len(kv)):
+        if q in multi:
+            assert first[q] < 0
+            v = 0.0
+            for t in range(int(ptr[q]), int(ptr[q + 1])):
+                v = v + _term(dim, prods, int(pack[t]))
+        else:
+            assert first[q] >= 0 and ptr[q + 1] - ptr[q] == 1 and pack[ptr[q]] == first[q]
+            v = 0.0 + _term(dim, prods, int(first[q]))
+        kv[q] = v
+    return kv
 
 
 def _unpack_pos(pos):
@@ -60,15 +81,16 @@ class _Side:
         self.nzprev = [0] * 10
         self.ys = []            # y blocks of the processed columns (virtual order)
         self.chunks = {}        # c -> dict(Z, y, blocks{rb})
-        self.kvals = {}         # program entry index -> assembled value
 
     def slot(self, e, p):
         return e * (e - 1) // 2 + p % e
 
 
-def replay(prog, dim, xyz, aed, force, n_dof):
+def replay(prog, dim, xyz, conn, aed, force, n_dof):
     """Returns (u per DOF, dict with debug data).  ``aed`` is [M,3]."""
     info = prog["info"]
+    kv = assemble_program_order(prog, dim, xyz, conn, aed)
+    epos = prog["epos"]
     nS = info["nS"]
     sides = [_Side(prog, 0), _Side(prog, 1)]
     X = {}
@@ -116,25 +138,11 @@ def replay(prog, dim, xyz, aed, force, n_dof):
                 tp += Zx[J]
             # staging: block rb in the slot of the dead block (c, c-rb)
             stage = {rb: np.zeros((BT, BT)) for rb in range(nb + 1) if (nzc >> rb) & 1}
-            q0, q1 = int(d["chunk_ptr"][c]), int(d["chunk_ptr"][c + 1])
-            for q in range(q0, q1):
-                prod = []
-                for t in range(int(d["mem_ptr"][q]), int(d["mem_ptr"][q + 1])):
-                    m, j0, j1, _ = (int(v) for v in d["mem"][t])
-                    prod.append(member_products(dim, xyz, (j0, j1), aed[m][0], aed[m][1]))
-                for e in range(int(d["ent_ptr"][q]), int(d["ent_ptr"][q + 1])):
-                    x, y = int(d["ent"][e][0]), int(d["ent"][e][1])
-                    pos, cnt = x & 1023, x >> 10
-                    rb, r, k = _unpack_pos(pos)
-                    assert rb in stage, "entry in a block the mask calls zero"
-                    v = stage[rb][r, k]
-                    if cnt == 1:
-                        v = v + _term(dim, prod, y)
-                    else:
-                        for t in range(cnt):
-                            v = v + _term(dim, prod, int(d["pack"][y + t]))
-                    stage[rb][r, k] = v
-                    S.kvals[e] = v
+            for e in range(int(d["colent"][c][0]), int(d["colent"][c][1])):
+                rb, r, k = _unpack_pos(int(epos[e]))
+                assert rb in stage, "entry in a block the mask calls zero"
+                assert stage[rb][r, k] == 0.0, "two entries in one position"
+                stage[rb][r, k] = kv[e]
             for r in range(BT):
                 if d["rowdof"][c * BT + r] < 0:
                     stage[0][r, r] = 1.0
@@ -198,4 +206,4 @@ def replay(prog, dim, xyz, aed, force, n_dof):
             us[1][c] = us[0][T.own + (nS - 1 - (c - Bt.own))][::-1]
         back(Bt, range(Bt.own - 1, -1, -1))
     back(T, range(T.own - 1, -1, -1))
-    return u_dof, dict(sides=sides, X=X)
+    return u_dof, dict(sides=sides, X=X, kv=kv)
