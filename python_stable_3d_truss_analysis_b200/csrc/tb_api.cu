@@ -143,6 +143,8 @@ int run_plan_range(tb_plan* p, const tb_batch_in* in, const tb_batch_out* out, c
   a.shared_k = shared_k;
   if (p->path == 2 && p->ts && p->ts->ok) {      // fused two-sided band kernel: its slice follows the 16x16 pipeline's
     a.ts = p->ts;
+    a.ts_b0 = 0;
+    a.ts_total = nb;
     a.ts_ws = (char*)ws + ((tb_large_workspace_bytes(nb, p->dim, p->M, p->n_pad, a.nnz, p->path, p->nb16, p->NB) + 255) & ~(size_t)255);
   }
   return tb_launch_large(a, p->num_sm, st, p->path);

@@ -62,18 +62,9 @@ namespace {
 using tbblk::dmma;
 using tbblk::rsqrt_pos;
 
-constexpr int NSTAGE = 3;                        // factor chunks in flight during the back substitution
-// per side, after the ring: [64 diagonal staging, then Z as a DMMA operand | 8 rhs | ring of the last y blocks | 16 misc]
-constexpr int X_SCR = 0, X_T = TS_BE, X_Y = X_T + TS_BT, X_MISC = X_Y + (TS_NBX + 1) * TS_BT, X_TOTAL = X_MISC + 16;
-
-__host__ __device__ inline int ts_main_doubles(int nb, int chunk_max) {
-  const int ring = nb * (nb + 1) / 2 * TS_BE;
-  const int back = NSTAGE * chunk_max + (nb + 1) * TS_BT;
-  return ring > back ? ring : back;
-}
-
-// element (r, k) of an 8x8 block in operand-fragment layout: slab k / 4 holds [row 8][k 4]
-__device__ __forceinline__ int b8_off(int r, int k) { return ((k >> 2) << 5) + (r << 2) + (k & 3); }
+constexpr int NSTAGE = TS_NSTAGE;
+constexpr int X_SCR = TS_X_SCR, X_T = TS_X_T, X_Y = TS_X_Y, X_MISC = TS_X_MISC, X_TOTAL = TS_X_TOTAL;
+__device__ __forceinline__ int b8_off(int r, int k) { return ts_b8_off(r, k); }
 
 // 1/d for a normal positive d: hardware seed (relative error ~2^-20) and one cubic step, three dependent FP64 operations
 __device__ __forceinline__ double rcp_pos(double d) {
@@ -168,8 +159,10 @@ __global__ void __launch_bounds__(64, 7) k_band_ts(const TsArgs a) {
   extern __shared__ __align__(16) double sm_all[];
   TPH_DECL
   const unsigned FULL = 0xffffffffu;
-  const int side = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // (the warp index through a shuffle: the compiler then knows that everything derived from it is warp-uniform)
+  const int side = __shfl_sync(FULL, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const TsSideDev& S = a.side[side];
+  const int ncol_own = S.ncol_own, ncol_tot = S.ncol_tot, nbs = S.nb;
   const bool two = a.side[1].ncol_tot > 0;
   const int main0 = ts_main_doubles(a.side[0].nb, a.chunk_max), main1 = two ? ts_main_doubles(a.side[1].nb, a.chunk_max) : 0;
   double* sm = sm_all + (side ? main0 + X_TOTAL : 0);
@@ -179,14 +172,15 @@ __global__ void __launch_bounds__(64, 7) k_band_ts(const TsArgs a) {
   double* sT = sm + mainsz + X_T;
   double* sY = sm + mainsz + X_Y;
   uint64_t* sBar = reinterpret_cast<uint64_t*>(sm + mainsz + X_MISC);           // NSTAGE mbarriers
-  int* sOff = reinterpret_cast<int*>(sm + mainsz + X_MISC + 4);                 // [NB+1] staging slot of block rb (doubles from sm)
   int* sFlag = reinterpret_cast<int*>(sm_all + main0 + X_MISC + 10);            // CTA-wide: [0] pivot failure
   double* sUS = sm_all + main0 + X_SCR;                                         // separator displacements (top -> bottom), top's scratch block
 
   const int qr = lane >> 2, qc = lane & 3;
   const int cpo = ((qc >> 1) << 5) + (qr << 2) + ((qc & 1) << 1);               // this lane's accumulator pair inside a block
   const int nS = a.nS;
-  const unsigned ring_u32 = smem_u32(sRing) + lane * 8;                         // byte address of this lane's operand element in slot 0
+  const unsigned sm_u32 = smem_u32(sm);
+  const unsigned ring_u32 = sm_u32 + lane * 8;                                  // byte address of this lane's operand element in slot 0
+  const unsigned scr_u32 = smem_u32(sScr);
 
   if (lane == 0) {                                                              // (side 1's area exists even when it has no columns)
 #pragma unroll
@@ -200,7 +194,6 @@ __global__ void __launch_bounds__(64, 7) k_band_ts(const TsArgs a) {
     if (threadIdx.x == 0) sFlag[0] = 0;
     __syncthreads();
     const double* fsys = a.force + (int64_t)b * a.force_stride;
-    const double* kvs = a.kv + (int64_t)b * a.nnz;
     double* Lsys = a.L + (int64_t)b * a.l_per_sys;
     double* Xsys = a.X + (int64_t)b * nS * nS * TS_BE;
     double* Zsys = a.Z + (int64_t)b * nS * TS_BT;
@@ -210,7 +203,7 @@ __global__ void __launch_bounds__(64, 7) k_band_ts(const TsArgs a) {
     // Ring of the live blocks: Q[e][j], 1 <= j <= e, is the address of block (c-j+e, c-j) (diagonal e, created j columns
     // ago; it dies after column c-j+e).  At column c the B operand of distance d is Q[d][d], the A operand of block row rb
     // is Q[rb+d][d], and the new block (c+e, c) takes over the slot of the dying block (c, c-e) = Q[e][e]: the pointers
-    // rotate by register moves, no index arithmetic anywhere.
+    // rotate by register moves, no index arithmetic anywhere (and the slot sequence is ts_ring_slot, known to the plan).
     unsigned Q[NB + 1][NB + 1];
 #pragma unroll
     for (int e = 1; e <= NB; ++e)
@@ -225,41 +218,48 @@ __global__ void __launch_bounds__(64, 7) k_band_ts(const TsArgs a) {
     }
     int fail = 0;
 
-    // software pipeline over the block columns: masks / entry range / rhs row one column ahead (addresses depend on c only)
-    int4 cin = make_int4(0, 0, 0, 0);
-    int2 cen = make_int2(0, 0);
+    // running pointers into the program: one record per block column, the rhs rows, the K values and their positions
+    const int4* recp = S.colrec;
+    const int32_t* dofp = S.rowdof + qr;
+    const double* kvp = a.kv + (int64_t)b * a.nnz + S.ent0 + lane;
+    const int32_t* epp = a.epos + S.ent0 + lane;
+    int4 recn = make_int4(0, 0, 0, 0);
     int dof_n = -1;
-    if (S.ncol_tot > 0) {
-      cin = __ldg(S.colinfo);
-      cen = __ldg(S.colent);
-      dof_n = __ldg(S.rowdof + qr);
+    if (ncol_tot > 0) {
+      recn = __ldg(recp);
+      dof_n = __ldg(dofp);
     }
     TPH(0)
 
     // =========================================== factorisation + forward substitution
-    for (int c = 0; c < S.ncol_tot; ++c) {
-      const bool own = c < S.ncol_own;
+    for (int c = 0; c < ncol_tot; ++c) {
+      const bool own = c < ncol_own;
       const bool xcol = side == 1 && !own;                                      // bottom side, separator column: products only
-      if (side == 0 && c == S.ncol_own && two) pair_sync(1);                    // the bottom side's hand-over is complete
-      const unsigned nzc = (unsigned)cin.x, srcc = (unsigned)cin.y, xm = (unsigned)cin.z;
-      const double fr = (!xcol && dof_n >= 0) ? __ldg(fsys + dof_n) : 0.0;
+      if (side == 0 && c == ncol_own && two) pair_sync(1);                      // the bottom side's hand-over is complete
+      const unsigned nzc = (unsigned)recn.x & 511u, srcc = ((unsigned)recn.x >> 9) & 511u, xm = ((unsigned)recn.x >> 18) & 511u;
+      const int ecnt = recn.y, lof = recn.z;
+      const int dof_c = dof_n;
+      const double fr = (!xcol && dof_c >= 0) ? __ldg(fsys + dof_c) : 0.0;
       // K values of this block column (assembly pass, program order): in flight while the products run
-      const int e0 = cen.x, e1 = cen.y;
       double kvr[TS_EPL];
       int kpos[TS_EPL];
 #pragma unroll
       for (int i = 0; i < TS_EPL; ++i) {
         kvr[i] = 0.0;
         kpos[i] = 0;
-        if (e0 + lane + 32 * i < e1) {
-          kvr[i] = __ldg(kvs + e0 + lane + 32 * i);
-          kpos[i] = __ldg(a.epos + e0 + lane + 32 * i);
+        if (lane + 32 * i < ecnt) {
+          kvr[i] = __ldg(kvp + 32 * i);
+          kpos[i] = __ldg(epp + 32 * i);
         }
       }
-      if (c + 1 < S.ncol_tot) {
-        cin = __ldg(S.colinfo + c + 1);
-        cen = __ldg(S.colent + c + 1);
-        dof_n = __ldg(S.rowdof + (c + 1) * TS_BT + qr);
+      const double* kvx = kvp + 32 * TS_EPL;                                    // (entries beyond the prefetched ones: rare)
+      const int32_t* epx = epp + 32 * TS_EPL;
+      kvp += ecnt;
+      epp += ecnt;
+      if (c + 1 < ncol_tot) {
+        recn = __ldg(++recp);
+        dofp += TS_BT;
+        dof_n = __ldg(dofp);
       }
       TPH(1)
 
@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(64, 7) k_band_ts(const TsArgs a) {
       for (int d = 1; d <= NB; ++d) {
         const unsigned nzp = nzprev[d];
         if (!((nzp >> d) & 1u)) continue;                                       // L(c, c-d) structurally zero (uniform)
-        const double b0 = lds64(Q[d][d]), b1 = lds64_256(Q[d][d]);
+        double b0 = lds64(Q[d][d]), b1 = lds64_256(Q[d][d]);
         {
           double y0, y1;
           asm volatile("ld.shared.f64 %0, [%1];" : "=d"(y0) : "r"(Yq[d]));
@@ -280,6 +280,8 @@ __global__ void __launch_bounds__(64, 7) k_band_ts(const TsArgs a) {
           tp = fma(b0, y0, tp);
           tp = fma(b1, y1, tp);
         }
+        b0 = -b0;                                                              // the accumulators collect -S: P = K - S needs no pass of its own
+        b1 = -b1;
         // block rows two at a time: the second k-slab of one block issues behind the first k-slab of the other
 #pragma unroll
         for (int rb = 0; rb + d <= NB; rb += 2) {
@@ -304,66 +306,55 @@ __global__ void __launch_bounds__(64, 7) k_band_ts(const TsArgs a) {
       if (xcol) {
         // ---------------- hand-over of the bottom side: block (c+rb, c) here is separator block (row J+rb, column J) of the
         // top side, J = nS-1-jq-rb, transposed and flipped: element (r, k) -> (7-k, 7-r)
-        const int jq = c - S.ncol_own;
+        const int jq = c - ncol_own;
 #pragma unroll
         for (int rb = 0; rb <= NB; ++rb) {
           if (!((nzc >> rb) & 1u)) continue;
           double* dst = Xsys + (int64_t)((nS - 1 - jq - rb) * nS + rb) * TS_BE;
-          dst[(7 - 2 * qc) * 8 + (7 - qr)] = acc[rb][0];
-          dst[(6 - 2 * qc) * 8 + (7 - qr)] = acc[rb][1];
+          dst[(7 - 2 * qc) * 8 + (7 - qr)] = -acc[rb][0];
+          dst[(6 - 2 * qc) * 8 + (7 - qr)] = -acc[rb][1];
         }
         if (qc == 0) Zsys[(nS - 1 - jq) * TS_BT + (7 - qr)] = tp;
       } else {
         if (side == 0 && !own && two) {
-          const int J = c - S.ncol_own;
+          const int J = c - ncol_own;
 #pragma unroll
           for (int rb = 0; rb <= NB; ++rb) {
             if (!((xm >> rb) & 1u)) continue;
             const double2 x = __ldcg(reinterpret_cast<const double2*>(Xsys + (int64_t)(J * nS + rb) * TS_BE + qr * 8 + 2 * qc));
-            acc[rb][0] += x.x;
-            acc[rb][1] += x.y;
+            acc[rb][0] -= x.x;
+            acc[rb][1] -= x.y;
           }
           tp += __ldcg(Zsys + J * TS_BT + qr);
         }
-        // ---------------- stage K(:,c): block rb into the slot of the dying block (c, c-rb); rb = 0 into the scratch block
-        {
-          unsigned mine = smem_u32(sScr);                                       // lane rb publishes the slot of block rb
-#pragma unroll
-          for (int rb = 1; rb <= NB; ++rb) mine = lane == rb ? Q[rb][rb] - lane * 8 : mine;
-          if (lane <= NB) sOff[lane] = (int)mine;
-          const double2 z = make_double2(0.0, 0.0);
-          reinterpret_cast<double2*>(sScr)[lane] = z;
-#pragma unroll
-          for (int rb = 1; rb <= NB; ++rb)
-            if ((nzc >> rb) & 1u)
-              asm volatile("st.shared.v2.f64 [%0], {%1, %1};" ::"r"(Q[rb][rb] + lane * 8), "d"(0.0) : "memory");
-        }
-        __syncwarp();
-#pragma unroll
-        for (int i = 0; i < TS_EPL; ++i)
-          if (e0 + lane + 32 * i < e1)
-            asm volatile("st.shared.f64 [%0], %1;" ::"r"((unsigned)sOff[kpos[i] >> 6] + (unsigned)((kpos[i] & 63) * 8)), "d"(kvr[i]) : "memory");
-        for (int e = e0 + 32 * TS_EPL + lane; e < e1; e += 32) {                // rare: more than 32 * TS_EPL entries in this block column
-          const int pos = __ldg(a.epos + e);
-          asm volatile("st.shared.f64 [%0], %1;" ::"r"((unsigned)sOff[pos >> 6] + (unsigned)((pos & 63) * 8)), "d"(__ldg(kvs + e)) : "memory");
-        }
-        if (lane < TS_BT && __ldg(S.rownat + c * TS_BT + lane) < 0) sScr[b8_off(lane, lane)] = 1.0;   // identity on padding
-        __syncwarp();
-        TPH(3)
-
-        // ---------------- P = K - S in place (accumulator pairs), right-hand side of the block
+        // ---------------- P = K - S: -S into the staging slots (block rb: slot of the dying block (c, c-rb); rb = 0: scratch),
+        // then every K value is added at its position (resolved by the plan: byte offset from this side's base)
 #pragma unroll
         for (int rb = 0; rb <= NB; ++rb) {
           if (!((nzc >> rb) & 1u)) continue;
-          const unsigned ad = (rb == 0 ? smem_u32(sScr) : Q[rb][rb] - lane * 8) + cpo * 8;
-          double vx, vy;
-          asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(vx), "=d"(vy) : "r"(ad));
-          vx -= acc[rb][0];
-          vy -= acc[rb][1];
-          asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(ad), "d"(vx), "d"(vy) : "memory");
+          const unsigned ad = (rb == 0 ? scr_u32 : Q[rb][rb] - lane * 8) + cpo * 8;
+          asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(ad), "d"(acc[rb][0]), "d"(acc[rb][1]) : "memory");
         }
         if (qc == 0) sT[qr] = fr - tp;
         __syncwarp();
+#pragma unroll
+        for (int i = 0; i < TS_EPL; ++i)
+          if (lane + 32 * i < ecnt) {
+            double v;
+            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(sm_u32 + (unsigned)kpos[i]));
+            v += kvr[i];
+            asm volatile("st.shared.f64 [%0], %1;" ::"r"(sm_u32 + (unsigned)kpos[i]), "d"(v) : "memory");
+          }
+        for (int e = 32 * TS_EPL + lane; e < ecnt; e += 32) {                   // rare: more than 32 * TS_EPL entries in this block column
+          const unsigned ad = sm_u32 + (unsigned)__ldg(epx + (e - 32 * TS_EPL - lane));
+          double v;
+          asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(ad));
+          v += __ldg(kvx + (e - 32 * TS_EPL - lane));
+          asm volatile("st.shared.f64 [%0], %1;" ::"r"(ad), "d"(v) : "memory");
+        }
+        if (qc == 0 && dof_c < 0) sScr[b8_off(qr, qr)] = 1.0;                   // identity on padding (no entries there)
+        __syncwarp();
+        TPH(3)
 
         // ---------------- rows: P(c,c) | I | P(c+1,c) | t^T
         const bool has1 = (nzc >> 1) & 1u;
@@ -399,7 +390,7 @@ __global__ void __launch_bounds__(64, 7) k_band_ts(const TsArgs a) {
         TPH(5)
 
         // ---------------- Z (as the solves' operand, and to HBM), L(c+1,c) into the ring and to HBM, y_c
-        double* chunk = Lsys + __ldg(S.lofs + c);
+        double* chunk = Lsys + lof;
         if (lane >= 8 && lane < 16) {
           const int i = lane - 8;
 #pragma unroll
@@ -486,17 +477,16 @@ __global__ void __launch_bounds__(64, 7) k_band_ts(const TsArgs a) {
 
     // =========================================== back substitution
     // u_c = Z_c (y_c - sum_rb L(c+rb, c)^T u_{c+rb}); the chunks come back through cp.async.bulk, NSTAGE in flight
-    const int ncb = side == 0 ? S.ncol_tot : S.ncol_own;
-    const int ur = S.nb + 1;
+    const int ncb = side == 0 ? ncol_tot : ncol_own;
+    const int ur = nbs + 1;
     double* sBuf = sRing;
     double* sU = sRing + NSTAGE * a.chunk_max;                                   // ring of the last nb+1 blocks of u: block c in slot c mod (nb+1)
     fence_proxy_async();                                                         // this lane's factor stores / ring stores before the async proxy
     __syncwarp();
     auto issue = [&](int c, int stage) {
-      const int o0 = __ldg(S.lofs + c), o1 = __ldg(S.lofs + c + 1);
-      const unsigned bytes = (unsigned)(o1 - o0) * 8u;
-      mbar_expect_tx(&sBar[stage], bytes);
-      bulk_g2s(sBuf + stage * a.chunk_max, Lsys + o0, bytes, &sBar[stage]);
+      const int4 rc = __ldg(S.colrec + c);
+      mbar_expect_tx(&sBar[stage], (unsigned)rc.w);
+      bulk_g2s(sBuf + stage * a.chunk_max, Lsys + rc.z, (unsigned)rc.w, &sBar[stage]);
     };
     if (lane == 0)
       for (int i = 0; i < NSTAGE; ++i)
@@ -507,7 +497,7 @@ __global__ void __launch_bounds__(64, 7) k_band_ts(const TsArgs a) {
     if (side == 1 && two) {
       pair_sync(2);                                                              // separator displacements are published
       int s2 = S.ncol_own % ur;
-      const int cend = S.ncol_own + (nS < S.nb ? nS : S.nb);                          // (the band reaches nb separator blocks at most)
+      const int cend = ncol_own + (nS < nbs ? nS : nbs);                          // (the band reaches nb separator blocks at most)
       for (int c = S.ncol_own; c < cend; ++c) {
         if (lane < TS_BT) sU[s2 * TS_BT + lane] = sUS[(nS - 1 - (c - S.ncol_own)) * TS_BT + (7 - lane)];
         s2 = s2 + 1 == ur ? 0 : s2 + 1;
@@ -515,14 +505,14 @@ __global__ void __launch_bounds__(64, 7) k_band_ts(const TsArgs a) {
       __syncwarp();
       uprev = sU[(S.ncol_own % ur) * TS_BT + col];
     }
-    unsigned maskn = ncb > 0 ? (unsigned)__ldg(&S.colinfo[ncb - 1].x) : 0u;
+    unsigned maskn = ncb > 0 ? ((unsigned)__ldg(&S.colrec[ncb - 1].x) & 511u) : 0u;
     int natn = ncb > 0 ? __ldg(S.rownat + (ncb - 1) * TS_BT + col) : -1;
     int stage = 0;
     for (int c = ncb - 1; c >= 0; --c) {
       const unsigned mask = maskn;
       const int nat = natn;
       if (c > 0) {
-        maskn = (unsigned)__ldg(&S.colinfo[c - 1].x);
+        maskn = ((unsigned)__ldg(&S.colrec[c - 1].x) & 511u);
         natn = __ldg(S.rownat + (c - 1) * TS_BT + col);
       }
       mbar_wait(&sBar[stage], (phase >> stage) & 1u);

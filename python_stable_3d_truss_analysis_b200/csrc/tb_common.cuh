@@ -203,6 +203,7 @@ struct LargeArgs {
   // two-sided fused band kernel (tb_bandts.cu): program + its slice of the workspace; null = the 16x16 band kernels
   const TsPlan* ts;
   void* ts_ws;
+  int ts_b0, ts_total;   // this call covers systems [ts_b0, ts_b0 + batch) of a workspace carved for ts_total systems
   double* kdebug;   // optional debug export of the assembled K values (tb_debug_assemble)
 };
 

@@ -1065,7 +1065,7 @@ int launch_ts_path(const LargeArgs& a, int num_sm, cudaStream_t st) {
   t.force = a.force; t.force_stride = a.force_stride;
   tb_ts_fill_sides(t, ts);
   double* kv = nullptr;
-  tb_ts_carve(t, ts, a.ts_ws, a.batch, &kv);
+  tb_ts_carve(t, ts, a.ts_ws, a.ts_total, a.ts_b0, &kv);
   // assembly (k_prep / k_geom + k_kval) driven by the program-order scatter lists; recovery reads u in the internal order
   LargeArgs r = a;
   r.q_first = ts->d_tq_first; r.q_multi = ts->d_tq_multi; r.q_ptr = ts->d_tq_ptr; r.q_pack = ts->d_tq_pack;
@@ -1115,7 +1115,7 @@ int tb_launch_large(const LargeArgs& a, int num_sm, cudaStream_t st, int path) {
   if (a.batch <= 0) return 0;
   if (num_sm <= 0) num_sm = 148;
   static const bool ts_legacy = [] { const char* s = getenv("TB_BAND_LEGACY"); return s && s[0] == '1'; }();
-  if (path == 2 && a.ts && a.ts_ws && !a.shared_k && !ts_legacy) return launch_ts_path(a, num_sm, st);
+  const bool use_ts = path == 2 && a.ts && a.ts_ws && !a.shared_k && !ts_legacy;
   // TB_UNFUSED_ASSEMBLY=1 keeps the separate HBM-bound assembly kernel (A/B measurements, tiled path only)
   static const bool fused_env = [] { const char* s = getenv("TB_UNFUSED_ASSEMBLY"); return !(s && s[0] == '1'); }();
   const bool fused = fused_env || path == 2;
@@ -1128,8 +1128,9 @@ int tb_launch_large(const LargeArgs& a, int num_sm, cudaStream_t st, int path) {
   // recovery runs under the second half's factorisation.  Both halves use the two-warp band kernel (eight systems per
   // SM), so together they occupy the SMs like the unsplit batch.  Not under per-kernel profiling (one stream there).
   static const bool split_env = [] { const char* s = getenv("TB_LARGE_SPLIT"); return !(s && s[0] == '0'); }();
-  if (split_env && !a.no_split && !tb_prof_on() && path == 2 && prep && !a.shared_k && a.NB <= 5 &&
-      a.batch > num_sm * 6 && a.batch <= num_sm * 8) {
+  // (the two-sided kernel holds seven systems per SM: the halves of a batch of up to 7 x SMs run side by side)
+  if (split_env && !a.no_split && !tb_prof_on() && path == 2 && prep && !a.shared_k &&
+      (use_ts ? a.batch > num_sm * 4 && a.batch <= num_sm * 7 : a.NB <= 5 && a.batch > num_sm * 6 && a.batch <= num_sm * 8)) {
     static std::mutex split_mu;                // the second stream and its events are shared by every plan of the process:
     std::lock_guard<std::mutex> split_lock(split_mu);   // fork .. join is enqueued as one unit
     static cudaStream_t aux = nullptr;
@@ -1147,6 +1148,7 @@ int tb_launch_large(const LargeArgs& a, int num_sm, cudaStream_t st, int path) {
       h.batch = nb;
       h.no_split = 1;
       h.band_warps = 2;
+      h.ts_b0 = a.ts_b0 + b0;
       h.xyz = a.xyz + (int64_t)b0 * a.xyz_stride;
       if (a.aed) h.aed = a.aed + (int64_t)b0 * a.aed_stride;
       if (a.gene) h.gene = a.gene + (int64_t)b0 * a.gene_stride;
@@ -1181,6 +1183,7 @@ int tb_launch_large(const LargeArgs& a, int num_sm, cudaStream_t st, int path) {
     TB_CUDA(cudaStreamWaitEvent(st, ev_join, 0));
     return (int)cudaGetLastError();
   }
+  if (use_ts) return launch_ts_path(a, num_sm, st);
   if (!prep) k_init_status<<<(a.batch + 255) / 256, 256, 0, st>>>(a.status, a.batch, 0);   // k_prep clears its own
   // load cases of one truss (shared_k): assembly and factorisation run for system 0 only
   const bool shared = a.shared_k && path == 2 && prep && a.batch > 1;

@@ -36,13 +36,15 @@ struct TsSideDev {
   int ncol_own;              // block columns this side factorises on its own
   int ncol_tot;              // + separator columns (top: factorised after the hand-over; bottom: products only)
   int nb;                    // sub-diagonal blocks of this side's band view
-  const int4* colinfo;       // [ncol_tot]   x = colmask: bit rb <=> block (c+rb, c) non-zero (bottom separator columns: blocks it contributes to)
-                             //              y = srcmask: colmask of the columns that exist as factor columns (0 for the bottom's separator columns)
-                             //              z = xmask: top separator columns: blocks handed over by the bottom side;  w = unused
-  const int2* colent;        // [ncol_tot]   entries [x, y) of the block column in program order (indices into kv / epos)
+  int ent0;                  // first entry of this side in program order (its block columns follow each other in kv / epos)
+  const int4* colrec;        // [ncol_tot]   one record per block column, all the kernel reads at the top of a column:
+                             //              x = colmask | srcmask << 9 | xmask << 18
+                             //                  colmask: bit rb <=> block (c+rb, c) non-zero (bottom separator columns: blocks it contributes to)
+                             //                  srcmask: colmask of the columns that exist as factor columns (0 for the bottom's separator columns)
+                             //                  xmask:   top separator columns: blocks handed over by the bottom side
+                             //              y = number of K entries, z = offset (doubles) of the factor chunk, w = its size in bytes
   const int32_t* rowdof;     // [ncol_tot*8] DOF index of virtual row v, -1 on padding
   const int32_t* rownat;     // [ncol_tot*8] internal (natural) row of virtual row v, -1 on padding
-  const int32_t* lofs;       // [ncol_tot+1] offset (doubles) of the column's factor chunk inside the system's factor storage
 };
 
 struct TsArgs {
@@ -62,7 +64,7 @@ struct TsArgs {
   double* uf;                // [B][n_pad]     free displacements, internal order (read by the recovery)
   int32_t* status;           // [B]
   const double* kv;          // [B][nnz]       K_ff values in program order (assembly pass)
-  const int32_t* epos;       // [nnz]          rb << 6 | position inside the block (operand-fragment layout)
+  const int32_t* epos;       // [nnz]          byte offset of the entry's staging position from the side's shared-memory base
   int64_t nnz;
 };
 
@@ -70,12 +72,11 @@ struct TsSideHost {
   int ncol_own = 0, ncol_tot = 0, nb = 0;
   std::vector<uint32_t> colmask, srcmask, xmask;
   std::vector<int32_t> rowdof, rownat, lofs;
-  std::vector<int4> colinfo;
-  std::vector<int2> colent;
+  std::vector<int4> colrec;
+  std::vector<int2> colent;       // entries [x, y) per block column (program order)
   // device mirrors
-  int32_t *d_rowdof = nullptr, *d_rownat = nullptr, *d_lofs = nullptr;
-  int4* d_colinfo = nullptr;
-  int2* d_colent = nullptr;
+  int32_t *d_rowdof = nullptr, *d_rownat = nullptr;
+  int4* d_colrec = nullptr;
 };
 
 struct TsPlan {
@@ -88,18 +89,35 @@ struct TsPlan {
   double dmma_flops = 0.0;            // flops the tensor cores execute per system
   TsSideHost side[2];
   // entries of both sides in program order (top side's block columns, then the bottom side's)
-  std::vector<int32_t> epos;          // [nnz] rb << 6 | position inside the block
+  std::vector<int32_t> epos;          // [nnz] staging position: byte offset from the side's shared-memory base (ts_stage_offset)
   std::vector<int32_t> ent_src;       // [nnz] index of the plan's scatter-map entry
   // assembly program in that order, in the format k_prep reads (tb_common.cuh: q_first / q_multi / q_ptr / q_pack)
   std::vector<int32_t> tq_first, tq_multi, tq_ptr, tq_pack;
   int32_t *d_epos = nullptr, *d_tq_first = nullptr, *d_tq_multi = nullptr, *d_tq_ptr = nullptr, *d_tq_pack = nullptr;
 };
 
+// ---- shared-memory layout of one side (doubles): [main: ring of live blocks, later the back substitution's chunk buffers
+// and u ring | 64 diagonal-block staging, then Z as a DMMA operand | 8 rhs | ring of the last y blocks | 16 misc]
+constexpr int TS_NSTAGE = 3;                     // factor chunks in flight during the back substitution
+constexpr int TS_X_SCR = 0, TS_X_T = TS_BE, TS_X_Y = TS_X_T + TS_BT, TS_X_MISC = TS_X_Y + (TS_NBX + 1) * TS_BT,
+              TS_X_TOTAL = TS_X_MISC + 16;
+__host__ __device__ inline int ts_main_doubles(int nb, int chunk_max) {
+  const int ring = nb * (nb + 1) / 2 * TS_BE;
+  const int back = TS_NSTAGE * chunk_max + (nb + 1) * TS_BT;
+  return ring > back ? ring : back;
+}
+// Ring slot the new block (c+rb, c) of diagonal rb takes at block column c: the kernel's pointer ring starts with slot
+// rb(rb-1)/2 + j - 1 for the block created j columns ago and always reuses the slot of the dying block, which makes the
+// slot a function of c alone -- so the plan can resolve every K entry's staging address.
+__host__ __device__ inline int ts_ring_slot(int rb, int c) { return rb * (rb - 1) / 2 + (rb - 1 - c % rb); }
+// element (r, k) of an 8x8 block in operand-fragment layout: slab k / 4 holds [row 8][k 4]
+__host__ __device__ inline int ts_b8_off(int r, int k) { return ((k >> 2) << 5) + (r << 2) + (k & 3); }
+
 struct tb_plan;
 int tb_ts_build(tb_plan* p);                  // host program (always), device mirrors when the plan has a device
 void tb_ts_destroy(TsPlan* ts, bool device);
 size_t tb_ts_workspace_bytes(const tb_plan* p, int batch);
-void tb_ts_carve(TsArgs& t, const TsPlan* ts, void* ws, int batch, double** kv);   // L | X | Z | uf | kv | status
+void tb_ts_carve(TsArgs& t, const TsPlan* ts, void* ws, int total, int b0, double** kv);   // L | X | Z | uf | kv | status, for systems b0.. of a workspace of `total`
 void tb_ts_fill_sides(TsArgs& t, const TsPlan* ts);
 int tb_ts_smem_bytes(const TsPlan* ts);
 int tb_launch_band_ts(const TsArgs& a, int smem, int num_sm, cudaStream_t st);

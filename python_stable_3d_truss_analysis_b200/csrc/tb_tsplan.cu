@@ -30,13 +30,21 @@ struct Masks {
   bool valid = false;
   int nb[2] = {0, 0};
   std::vector<uint32_t> col[2], src[2], xm[2];
-  double t_own[2] = {0, 0}, t_sep = 0, t_x = 0;
+  double t_own[2] = {0, 0}, t_sep = 0, t_x = 0;      // forward time of the own columns, the separator columns, the hand-over
+  double b_own[2] = {0, 0}, b_sep = 0;                // back substitution
+  // end of the slower side: the top side runs T, S forward and S, T backward; the bottom side B forward, then (once the
+  // separator displacements exist) B backward
+  double total() const {
+    const double top_end = t_own[0] + t_sep + b_sep + b_own[0];
+    const double bot_end = std::max(t_own[1] + t_x, t_own[0] + t_sep + b_sep) + b_own[1];
+    return std::max(top_end, bot_end);
+  }
   int64_t products = 0, solves = 0;
 };
 
-// cost model of one block column (cycles of one warp, calibrated on B200: see DESIGN.md): fixed part (assembly, staging,
-// 8 pivots, stores), 8x8 block products (two DMMAs + operand loads), block solves; back substitution per column
-constexpr double C_COL = 1500.0, C_PROD = 40.0, C_SOLVE = 40.0, C_BACK = 400.0;
+// cost model of one block column (cycles of one warp with seven systems per SM, from the kernel's phase counters on B200):
+// fixed part (staging, 8 pivots, stores), 8x8 block products (two DMMAs + operand loads), block solves; back substitution
+constexpr double C_COL = 9700.0, C_PROD = 215.0, C_SOLVE = 300.0, C_BACK = 3100.0;
 
 // Block masks of both sides for the split (bT, nS): kblk[bj] bit e <=> K_ff has an entry in block (bj+e, bj)
 Masks make_masks(const std::vector<uint32_t>& kblk, int nblk, int bT, int nS) {
@@ -110,13 +118,15 @@ Masks make_masks(const std::vector<uint32_t>& kblk, int nblk, int bT, int nS) {
     for (int c = 0; c < tot; ++c) {
       const int sol = std::max(0, popc(m.col[s][c] >> 2));
       if (c < own) {
-        m.t_own[s] += C_COL + C_PROD * prod[c] + C_SOLVE * sol + C_BACK;
+        m.t_own[s] += C_COL + C_PROD * prod[c] + C_SOLVE * sol;
+        m.b_own[s] += C_BACK;
         m.solves += popc(m.col[s][c] >> 2);
       } else if (s == 0) {
-        m.t_sep += C_COL + C_PROD * prod[c] + C_SOLVE * sol + C_BACK;
+        m.t_sep += C_COL + C_PROD * prod[c] + C_SOLVE * sol;
+        m.b_sep += C_BACK;
         m.solves += popc(m.col[s][c] >> 2);
       } else {
-        m.t_x += 150.0 + C_PROD * prod[c];
+        m.t_x += 0.15 * C_COL + C_PROD * prod[c];
       }
     }
   }
@@ -131,7 +141,7 @@ void tb_ts_destroy(TsPlan* ts, bool device) {
   if (device)
     for (int s = 0; s < 2; ++s) {
       TsSideHost& h = ts->side[s];
-      cudaFree(h.d_colinfo); cudaFree(h.d_colent); cudaFree(h.d_rowdof); cudaFree(h.d_rownat); cudaFree(h.d_lofs);
+      cudaFree(h.d_colrec); cudaFree(h.d_rowdof); cudaFree(h.d_rownat);
     }
   if (device) {
     cudaFree(ts->d_epos); cudaFree(ts->d_tq_first); cudaFree(ts->d_tq_multi); cudaFree(ts->d_tq_ptr); cudaFree(ts->d_tq_pack);
@@ -165,7 +175,7 @@ int tb_ts_build(tb_plan* p) {
   Masks best = make_masks(kblk, nblk, nblk, 0);
   if (!best.valid) return 0;
   int best_bT = nblk, best_nS = 0;
-  const double t_one = best.t_own[0];
+  const double t_one = best.total();
   double best_t = t_one;
   const char* env1 = getenv("TB_TS_ONE_SIDED");
   const bool allow_two = !(env1 && env1[0] == '1');
@@ -181,7 +191,7 @@ int tb_ts_build(tb_plan* p) {
       if (nS < 1 || nS > TS_NBX || bT + nS >= nblk) continue;
       Masks m = make_masks(kblk, nblk, bT, nS);
       if (!m.valid) continue;
-      const double t = std::max(m.t_own[0], m.t_own[1] + m.t_x) + m.t_sep;
+      const double t = m.total();
       if (t < (force_bT >= 0 ? 1e300 : 0.9 * t_one) && (t < best_t || best_nS == 0)) {
         best = m; best_bT = bT; best_nS = nS; best_t = t;
       }
@@ -251,13 +261,15 @@ int tb_ts_build(tb_plan* p) {
   ts->tq_ptr.assign(1, 0);
   for (int s = 0; s < 2; ++s) {
     TsSideHost& h = ts->side[s];
-    h.colinfo.resize(h.ncol_tot);
+    h.colrec.resize(h.ncol_tot);
     h.colent.resize(h.ncol_tot);
+    const int mainsz = ts_main_doubles(h.nb, ts->chunk_max);
     for (int c = 0; c < h.ncol_tot; ++c) {
-      h.colinfo[c] = make_int4((int)h.colmask[c], (int)h.srcmask[c], (int)h.xmask[c], 0);
       const int e0 = (int)ts->epos.size();
       for (const Ent& en : colent[s][c]) {
-        ts->epos.push_back(((en.vr / TS_BT - en.vc / TS_BT) << 6) | ((((en.vc % TS_BT) >> 2) << 5) + ((en.vr % TS_BT) << 2) + (en.vc & 3)));
+        const int rb = en.vr / TS_BT - en.vc / TS_BT;
+        const int slot_off = rb == 0 ? mainsz + TS_X_SCR : ts_ring_slot(rb, c) * TS_BE;
+        ts->epos.push_back((slot_off + ts_b8_off(en.vr % TS_BT, en.vc % TS_BT)) * 8);
         ts->ent_src.push_back(en.src);
         for (int64_t k = p->ent_ptr[en.src]; k < p->ent_ptr[en.src + 1]; ++k) {
           const int loc = p->ctr_local[k], la = loc / (2 * d), lb = loc % (2 * d);
@@ -268,6 +280,9 @@ int tb_ts_build(tb_plan* p) {
         ts->tq_ptr.push_back((int32_t)ts->tq_pack.size());
       }
       h.colent[c] = make_int2(e0, (int)ts->epos.size());
+      const bool has_chunk = c < (s == 0 ? h.ncol_tot : h.ncol_own);
+      h.colrec[c] = make_int4((int)(h.colmask[c] | (h.srcmask[c] << 9) | (h.xmask[c] << 18)), (int)ts->epos.size() - e0, h.lofs[c],
+                              has_chunk ? (h.lofs[c + 1] - h.lofs[c]) * 8 : 0);
     }
   }
   {   // first contribution inline, entries with several contributions listed separately (as tb_plan.cu does for the other orders)
@@ -285,11 +300,9 @@ int tb_ts_build(tb_plan* p) {
   int rc = 0;
   for (int s = 0; s < 2 && !rc; ++s) {
     TsSideHost& h = ts->side[s];
-    if (!rc) rc = up(&h.d_colinfo, h.colinfo);
-    if (!rc) rc = up(&h.d_colent, h.colent);
+    if (!rc) rc = up(&h.d_colrec, h.colrec);
     if (!rc) rc = up(&h.d_rowdof, h.rowdof);
     if (!rc) rc = up(&h.d_rownat, h.rownat);
-    if (!rc) rc = up(&h.d_lofs, h.lofs);
   }
   if (!rc) rc = up(&ts->d_epos, ts->epos);
   if (!rc) rc = up(&ts->d_tq_first, ts->tq_first);
@@ -307,15 +320,15 @@ size_t tb_ts_workspace_bytes(const tb_plan* p, int batch) {
   return (size_t)batch * per * 8 + (size_t)batch * 4 + 4096;
 }
 
-void tb_ts_carve(TsArgs& t, const TsPlan* ts, void* ws, int batch, double** kv) {
+void tb_ts_carve(TsArgs& t, const TsPlan* ts, void* ws, int total, int b0, double** kv) {
   double* p = (double*)ws;
-  t.L = p;  p += (size_t)batch * ts->l_per_sys;
-  t.X = p;  p += (size_t)batch * ts->nS * ts->nS * TS_BE;
-  t.Z = p;  p += (size_t)batch * ts->nS * TS_BT;
-  t.uf = p; p += (size_t)batch * ts->n_pad;
-  *kv = p;  p += (size_t)batch * ts->epos.size();
+  t.L = p + (size_t)b0 * ts->l_per_sys;               p += (size_t)total * ts->l_per_sys;
+  t.X = p + (size_t)b0 * ts->nS * ts->nS * TS_BE;     p += (size_t)total * ts->nS * ts->nS * TS_BE;
+  t.Z = p + (size_t)b0 * ts->nS * TS_BT;              p += (size_t)total * ts->nS * TS_BT;
+  t.uf = p + (size_t)b0 * ts->n_pad;                  p += (size_t)total * ts->n_pad;
+  *kv = p + (size_t)b0 * ts->epos.size();             p += (size_t)total * ts->epos.size();
   t.kv = *kv;
-  t.status = (int32_t*)p;
+  t.status = (int32_t*)p + b0;
 }
 
 void tb_ts_fill_sides(TsArgs& t, const TsPlan* ts) {
@@ -323,7 +336,8 @@ void tb_ts_fill_sides(TsArgs& t, const TsPlan* ts) {
     const TsSideHost& h = ts->side[s];
     TsSideDev& d = t.side[s];
     d.ncol_own = h.ncol_own; d.ncol_tot = h.ncol_tot; d.nb = h.nb;
-    d.colinfo = h.d_colinfo; d.colent = h.d_colent; d.rowdof = h.d_rowdof; d.rownat = h.d_rownat; d.lofs = h.d_lofs;
+    d.colrec = h.d_colrec; d.rowdof = h.d_rowdof; d.rownat = h.d_rownat;
+    d.ent0 = h.colent.empty() ? 0 : h.colent[0].x;
   }
   t.epos = ts->d_epos;
   t.nnz = (int64_t)ts->epos.size();

@@ -60,8 +60,28 @@ def assemble_program_order(prog, dim, xyz, conn, aed):
     return kv
 
 
-def _unpack_pos(pos):
-    rb, off = pos >> 6, pos & 63
+NSTAGE = 3
+
+
+def main_doubles(nb, chunk_max):
+    """csrc/tb_ts.cuh ts_main_doubles: ring of live blocks, reused by the back substitution's chunk buffers + u ring."""
+    return max(nb * (nb + 1) // 2 * 64, NSTAGE * chunk_max + (nb + 1) * BT)
+
+
+def _unpack_pos(epos, c, mainsz):
+    """Staging position (byte offset from the side's shared-memory base, resolved by the plan) -> (rb, row, col); checks
+    that a ring position is the slot the kernel's pointer ring hands to block (c+rb, c) (csrc/tb_ts.cuh ts_ring_slot)."""
+    assert epos % 8 == 0
+    off8 = epos // 8
+    if off8 >= mainsz:
+        rb, off = 0, off8 - mainsz
+        assert off < 64
+    else:
+        slot, off = divmod(off8, 64)
+        rb = 1
+        while rb * (rb + 1) // 2 <= slot:
+            rb += 1
+        assert slot == rb * (rb - 1) // 2 + (rb - 1 - c % rb), "entry staged in a slot the ring does not give to this block"
     k = ((off >> 5) << 2) | (off & 3)
     r = (off >> 2) & 7
     return rb, r, k
@@ -139,7 +159,7 @@ def replay(prog, dim, xyz, conn, aed, force, n_dof):
             # staging: block rb in the slot of the dead block (c, c-rb)
             stage = {rb: np.zeros((BT, BT)) for rb in range(nb + 1) if (nzc >> rb) & 1}
             for e in range(int(d["colent"][c][0]), int(d["colent"][c][1])):
-                rb, r, k = _unpack_pos(int(epos[e]))
+                rb, r, k = _unpack_pos(int(epos[e]), c, main_doubles(S.nb, info["chunk_max"]))
                 assert rb in stage, "entry in a block the mask calls zero"
                 assert stage[rb][r, k] == 0.0, "two entries in one position"
                 stage[rb][r, k] = kv[e]
