@@ -366,6 +366,24 @@ def run_gpu(args):
     d2h = int(sum(v.nbytes for v in h_out.values()))
     clocks = sampler.stop() if rank == 0 else None
 
+    # ---- the other GPU configurations of BASELINE.json (3: GA population, 4: ragged cube-7 batch, 5: cube 12^3), every rank
+    configs = {}
+    if not args.headline_only:
+        import bench_configs
+        peak_dmma0, _ = _lib.fp64_peak(1, 8192)
+        peak_dfma0, _ = _lib.fp64_peak(0, 8192)
+        try:
+            hbm0 = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0)
+        except Exception:
+            hbm0 = 6650.0
+        del flush
+        torch.cuda.empty_cache()
+        flush2 = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        configs = bench_configs.run_configs(torch, dist, rank, world, dev, max(3, min(args.steps, 10)), flush2,
+                                            {"dmma": peak_dmma0, "dfma": peak_dfma0, "hbm": hbm0},
+                                            which=tuple(args.configs.split(",")))
+        del flush2
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -378,17 +396,22 @@ def run_gpu(args):
     peak_dmma, _ = _lib.fp64_peak(1, 8192)
     peak_dfma, _ = _lib.fp64_peak(0, 8192)
     path = plan.path
-    kname = {0: "k_dense16", 1: "k_chol", 2: "k_band2"}[path]   # B = 1024 < 2368: the two-warp band kernel (tb_band.cu: launch_band)
+    ts_prog = plan.ts_program() if path == 2 and os.environ.get("TB_BAND_LEGACY") != "1" else None
+    kname = {0: "k_dense16", 1: "k_chol", 2: "k_band_ts" if ts_prog else "k_band2"}[path]
     chol_ms, chol_n = prof["small"] if path == 0 else prof["chol"]
     dense_flops = n ** 3 / 3.0 + n ** 2 / 2.0 + n / 6.0 + 2.0 * n * n               # potrf + two triangular solves
     dense_mode = os.environ.get("TB_DENSE_TILES") == "1" and path == 1
     flops_per_system = dense_flops if dense_mode else float(plan.info.envelope_flops)
     per_launch_s = chol_ms / max(chol_n, 1) * 1e-3
     achieved = B * flops_per_system / per_launch_s / 1e12
-    traffic = None
+    # DRAM traffic of that kernel per launch: an ncu capture (dram__bytes_read.sum + dram__bytes_write.sum) recorded under
+    # profiles/ together with the code revision it was taken at; null when there is none for this kernel
+    traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(f"{kname}_dram_bytes_per_launch")
+        tj = json.load(open(tpath))
+        traffic = tj.get(f"{kname}_dram_bytes_per_launch")
+        traffic_src = tj.get(f"{kname}_source")
     kernels = {k: {"ms_per_step": v[0] / args.steps, "launches": v[1]} for k, v in prof.items() if v[1]}
     peaks = {}
     try:
@@ -417,12 +440,21 @@ def run_gpu(args):
                            "bytes_per_launch": byts, "ms_per_launch": ms_k / cnt}
 
     cpu = cpu_port_throughput(6)
+    line_extra = {}
+    if ts_prog:
+        ti = ts_prog["info"]
+        executed = 1024.0 * (ti["products"] + ti["solves"])          # two DMMA m8n8k4 (512 flop) per 8x8 block product / solve
+        line_extra = {"executed_dmma_flops_per_system": executed, "executed_over_envelope": executed / flops_per_system,
+                      "split": {"top_blocks": ti["bT"], "separator_blocks": ti["nS"], "bottom_blocks": ti["nB"],
+                                "chain_block_columns": max(ti["bT"], ti["nB"]) + ti["nS"], "block_columns": ti["nblk"]}}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "batch_per_gpu": B, "n_free": n, "n_member": M, "mode": "independent K per system",
-                   "pipeline": {0: "fused shared-memory kernel", 1: "tiled 64x64 block-sparse Cholesky", 2: "block-band Cholesky (16x16 blocks)"}[path],
+                   "pipeline": {0: "fused shared-memory kernel", 1: "tiled 64x64 block-sparse Cholesky",
+                                2: "two-sided block-band Cholesky (8x8 DMMA blocks, top-down and bottom-up warps meeting at a separator)" if ts_prog
+                                else "block-band Cholesky (16x16 blocks)"}[path],
                    "l2": "explicit 256 MB flush (> 126 MB L2) between timed steps, outside the events",
                    "launch": "CUDA graph replay of the step" if graph is not None else "plain stream launches",
                    "multi_gpu": "contiguous block partition of the batch; " + gather_mode},
@@ -432,17 +464,18 @@ def run_gpu(args):
         "clocks": clocks,
         "roofline": {"kernel": kname + " (block Cholesky + forward/back substitution)", "bound": "tensor",
                      "achieved": achieved, "peak": peak_dmma, "unit": "TFLOP/s", "frac": achieved / peak_dmma,
-                     "traffic": traffic, "flops_per_system": flops_per_system,
+                     "traffic": traffic, "traffic_source": traffic_src, "flops_per_system": flops_per_system,
                      "flops_model": "dense potrf (SURVEY 8d)" if dense_mode else "envelope Cholesky + two triangular solves (plan.envelope_flops)",
                      "dense_potrf_equivalent_tflops": B * dense_flops / per_launch_s / 1e12,
                      "peak_source": "FP64 DMMA m8n8k4 microbenchmark (tb_fp64_peak) measured in this run; "
                                     "MEASURED_PEAKS.json has no FP64 entry", "peak_dfma": peak_dfma,
-                     "share_of_step": chol_ms / prof_ms},
+                     "share_of_step": chol_ms / prof_ms, **line_extra},
         "roofline_hbm_view": roof_hbm,
         "roofline_stages": stages,
         "kernels": kernels,
         "cpu_baseline": cpu,
         "shared_k": shared,
+        "configs": configs,
         "wall_s_timed_region": wall,
     }
     sys.stdout.flush()
@@ -457,6 +490,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--configs", default="3,4,5", help="which of the other BASELINE.json configurations to measure as well")
     ap.add_argument("--headline-only", action="store_true",
                     help="skip the shared-factor extra (profiler runs: the launch list then holds the headline step only)")
     args = ap.parse_args()
