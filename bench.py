@@ -203,32 +203,57 @@ def run_gpu(args):
     # failed rendezvous) falls back to a separate NCCL gather of the local flat buffer.
     per_rank = B * (2 * N + M)
     gathered, symm, gather_mode = None, None, "single GPU"
-    if world > 1 and os.environ.get("TB_BENCH_GATHER", "peer") == "peer":
+    mode = os.environ.get("TB_BENCH_GATHER", "pipelined")
+    pipelined = False
+    if world > 1 and mode in ("peer", "pipelined"):
         try:
-            from python_stable_3d_truss_analysis_b200.parallel import PeerGather
-            symm = PeerGather(per_rank, torch.float64, dev, dst=0)
-            flat = symm.local                                   # my slice of rank 0's buffer
+            from python_stable_3d_truss_analysis_b200.parallel import PeerGather, PipelinedPeerGather
+            if mode == "pipelined":
+                symm = PipelinedPeerGather(per_rank, torch.float64, dev, dst=0)
+                pipelined = True
+                flat = symm.bufs[0]
+                gather_mode = ("results of step i are pushed into rank 0's buffer (peer-mapped symmetric memory over NVLink) by a copy "
+                               "stream while step i+1 computes into a second buffer; one signal barrier after the last step")
+            else:
+                symm = PeerGather(per_rank, torch.float64, dev, dst=0)
+                flat = symm.local                               # my slice of rank 0's buffer
+                gather_mode = "k_recover stores straight into rank 0's buffer (peer-mapped symmetric memory over NVLink), one signal barrier"
             gathered = symm.slices
-            gather_mode = "k_recover stores straight into rank 0's buffer (peer-mapped symmetric memory over NVLink), one signal barrier"
         except Exception as exc:   # noqa: BLE001
             print(f"bench.py: symmetric-memory rendezvous failed ({exc!r}); using the NCCL gather", file=sys.stderr)
-            symm = None
+            symm, pipelined = None, False
     if symm is None:
         flat = torch.empty(per_rank, dtype=torch.float64, device=dev)
         if world > 1:
             gathered = [torch.empty_like(flat) for _ in range(world)] if rank == 0 else None
             gather_mode = "NCCL gather of u/ext/axial to rank 0 inside the step"
-    out = {"u": flat[:B * N].view(B, N), "ext": flat[B * N:2 * B * N].view(B, N), "axial": flat[2 * B * N:].view(B, M),
-           "weight": torch.empty(B, dtype=torch.float64, device=dev), "info": torch.empty(B, dtype=torch.int32, device=dev)}
+    def views(fl):
+        return {"u": fl[:B * N].view(B, N), "ext": fl[B * N:2 * B * N].view(B, N), "axial": fl[2 * B * N:].view(B, M)}
+
+    w_info = {"weight": torch.empty(B, dtype=torch.float64, device=dev), "info": torch.empty(B, dtype=torch.int32, device=dev)}
+    out = {**views(flat), **w_info}
+    outs2 = [{**views(bf), **w_info} for bf in symm.bufs] if pipelined else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
     stream = torch.cuda.current_stream()
+    step_no = [0]
 
     def step(st=None):
+        if pipelined:                          # compute into buffer i & 1; the copy stream ships it while the next step runs
+            i = step_no[0]
+            step_no[0] += 1
+            symm.acquire(i, stream)
+            plan.solve_device(B, d_xyz, d_F, aed=d_aed, out=outs2[i & 1], stream=stream)
+            symm.submit(i, stream)
+            return
         plan.solve_device(B, d_xyz, d_F, aed=d_aed, out=out, stream=stream if st is None else st)
         if symm is not None:
             symm.barrier()                     # every rank's results have landed in rank 0's buffer
         elif world > 1:
             dist.gather(flat, gathered, dst=0)
+
+    def drain():
+        if pipelined:
+            symm.drain(stream)
 
     def barrier():
         if world > 1:
@@ -237,8 +262,11 @@ def run_gpu(args):
 
     for _ in range(max(3, args.warmup)):
         step()
+    drain()
     barrier()
     assert not bool(out["info"].any().item()), "a system failed to factorise"
+    if pipelined:
+        out = outs2[(step_no[0] - 1) & 1]      # the buffer the last step computed into (parity gate below)
 
     # ---- multi-GPU: what rank 0 received from the last rank equals what it computes itself for those load cases
     if world > 1 and rank == 0:
@@ -294,6 +322,10 @@ def run_gpu(args):
         else:
             step()
         e1.record(stream)
+    ev_drain = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+    ev_drain[0].record(stream)
+    drain()                                    # pipelined gather: the last copies + the signal barrier are part of the timed region
+    ev_drain[1].record(stream)
     barrier()
     wall = time.perf_counter() - wall0
     launches = launches_per_step * args.steps
@@ -306,11 +338,12 @@ def run_gpu(args):
         e0.record(stream)
         step()
         e1.record(stream)
+    drain()
     barrier()
     prof = _lib.profile_read()
     _lib.profile_enable(False)
     prof_ms = sum(e0.elapsed_time(e1) for e0, e1 in evp)
-    dev_ms = sum(e0.elapsed_time(e1) for e0, e1 in ev)
+    dev_ms = sum(e0.elapsed_time(e1) for e0, e1 in ev) + ev_drain[0].elapsed_time(ev_drain[1])
     t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -104,6 +104,59 @@ class PeerGather:
         self._hdl.barrier()
 
 
+class PipelinedPeerGather(PeerGather):
+    """PeerGather with the transfer taken off the critical path: every rank computes into one of TWO local result buffers
+    and a copy stream pushes the finished one into its slice of rank ``dst``'s buffer (peer-mapped symmetric memory, NVLink /
+    NVSwitch) while the next step is already computing into the other.  With eight GPUs the 7 x 20 MB that converge on rank
+    ``dst``'s NVLink ingress every step (0.15-0.2 ms at the measured 770 GB/s) then ride under the next step's
+    factorisation instead of stalling the recovery kernel's stores.
+
+        buf = pg.acquire(i, stream)      # result buffer of step i (waits, on `stream`, until step i-2's copy has left it)
+        ... enqueue the solve of step i into views of buf on `stream` ...
+        pg.submit(i, stream)             # copy stream: wait for the solve, push buf to rank dst
+        pg.drain(stream)                 # after the last step: `stream` waits for the outstanding copies, then the barrier
+
+    Rank ``dst`` computes straight into its own slice (nothing to copy)."""
+
+    def __init__(self, per_rank_elems: int, dtype=None, device=None, dst: int = 0, group=None):
+        import torch
+
+        super().__init__(per_rank_elems, dtype, device, dst, group)
+        dtype = torch.float64 if dtype is None else dtype
+        self.is_dst = self.rank == dst
+        self.bufs = [self.local, self.local] if self.is_dst else [torch.empty(self.per_rank, dtype=dtype, device=device) for _ in range(2)]
+        self.copy_stream = torch.cuda.Stream(device=device)
+        self.ev_solved = [torch.cuda.Event() for _ in range(2)]
+        self.ev_copied = [torch.cuda.Event() for _ in range(2)]
+        self._pending = [False, False]
+
+    def acquire(self, i: int, stream):
+        k = i & 1
+        if self._pending[k]:
+            stream.wait_event(self.ev_copied[k])
+        return self.bufs[k]
+
+    def submit(self, i: int, stream):
+        import torch
+
+        k = i & 1
+        if self.is_dst:
+            return
+        self.ev_solved[k].record(stream)
+        self.copy_stream.wait_event(self.ev_solved[k])
+        with torch.cuda.stream(self.copy_stream):
+            self.local.copy_(self.bufs[k], non_blocking=True)
+        self.ev_copied[k].record(self.copy_stream)
+        self._pending[k] = True
+
+    def drain(self, stream):
+        for k in range(2):
+            if self._pending[k]:
+                stream.wait_event(self.ev_copied[k])
+                self._pending[k] = False
+        self.barrier()
+
+
 def gather_results(local: dict, n_total: int, dst: int = 0):
     """Gather a dict of row-sharded arrays (u, ext, axial, weight, info, fitness, flags ...) to rank ``dst``."""
     out = {k: gather_rows(v, n_total, dst) for k, v in sorted(local.items()) if v is not None}
