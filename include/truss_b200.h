@@ -30,6 +30,15 @@
  *     synchronise; "_host" entry points take host pointers and perform the H2D copies,
  *     the solve, and the D2H copies themselves (they synchronise before returning)
  *   - the caller owns every in/out buffer; a plan owns only its maps and workspace
+ *   - devices: a plan belongs to the CUDA device that was current when it was created; every solve checks that this
+ *     device is current (TB_ERR_WRONG_DEVICE otherwise).  Kernel attributes, helper streams and staging arenas are kept
+ *     per device, so one process may hold plans on several GPUs.
+ *   - threads: a plan owns ONE workspace, so calls on the same plan are serialised (a mutex inside the plan) and
+ *     ordered across streams (the library records an event after the last kernel of a call and makes a call on a
+ *     different stream wait for it) -- two threads / two streams may use one plan, they just do not overlap; use one
+ *     plan per thread or stream for concurrency.  The *_host entry points are additionally serialised per process
+ *     (they share the helper streams and staging arenas).  A call captured into a CUDA graph must stay on one stream.
+ *     On an error return no copy or kernel of the failed call is still in flight against the caller's buffers.
  */
 #ifndef TRUSS_B200_H
 #define TRUSS_B200_H
@@ -53,6 +62,7 @@ extern "C" {
 #define TB_ERR_TOO_LARGE (-6)  /* system too large for the selected path / workspace */
 #define TB_ERR_NO_DEVICE (-7)  /* no CUDA device: there is NO CPU fallback */
 #define TB_ERR_ALLOC (-8)
+#define TB_ERR_WRONG_DEVICE (-9) /* the plan was created on another CUDA device than the current one */
 
 /* per-system status codes in info[] */
 #define TB_INFO_OK 0
@@ -257,6 +267,10 @@ int tb_pinned_free(void* ptr);
 
 /* Largest system (free DOFs are bounded by d*nJ) the fused shared-memory kernel accepts. */
 int tb_small_path_limits(int32_t* max_dof, int32_t* max_member);
+/* 1 when a truss of n_joint joints and n_member members (every DOF possibly free, as in a ragged batch) fits the shared
+ * memory of the fused kernels -- the test tb_solve_ragged applies to (max_joint, max_member); the size limits above are
+ * necessary, not sufficient (many members on few joints run out of shared memory first). */
+int tb_small_path_fits(int32_t dim, int32_t n_joint, int32_t n_member);
 
 /* FP64 pipe microbenchmarks used as roofline denominators (MEASURED_PEAKS.json has no FP64
  * entry): which = 0 DFMA (vector), 1 DMMA m8n8k4 (tensor).  Returns TFLOP/s in *tflops. */
@@ -284,8 +298,12 @@ int tb_profile_read(float* ms, int64_t* count);
  * tb_plan_ts_array: copies array `which` into out (may be NULL) and returns its length in int32 elements, -1 if there is
  *   no program.  Per side: 0 colmask, 1 srcmask, 2 xmask, 3 colent[.][2], 4 rowdof, 5 rownat, 6 lofs; whole program (side
  *   ignored): 7 epos, 8 ent_src, 9 tq_first, 10 tq_multi, 11 tq_ptr, 12 tq_pack (the assembly pass's scatter lists in the
- *   kernel's entry order).
+ *   kernel's entry order); 13 colrec[.][8] (per side: the records the kernel reads per block column).
  * tb_ts_phase_read: cycles per kernel phase accumulated by an instrumented build (-DTB_PHASE_TIMING), zeros otherwise. */
+/* tb_debug_assemble_host: runs the assembly pass alone on host inputs (explicit member properties) and returns the K_ff
+ *   values the DEVICE computed, kv_out[B][nnz_lower] in the entry order of tb_plan_get_scatter -- the gate
+ *   "device-assembled K_ff == GetKMatrix()[mask][:, mask]" (truss.py:307-316, 343) of the GPU tests. */
+int tb_debug_assemble_host(tb_plan* plan, const tb_batch_in* in, double* kv_out);
 int tb_plan_ts_info(const tb_plan* plan, int32_t* out);
 int64_t tb_plan_ts_array(const tb_plan* plan, int32_t side, int32_t which, int32_t* out);
 int tb_ts_phase_read(unsigned long long* out);

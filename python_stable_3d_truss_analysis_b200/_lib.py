@@ -150,7 +150,7 @@ class TbRaggedIn(C.Structure):
 EXPORTS = ["tb_plan_create", "tb_plan_destroy", "tb_plan_query", "tb_plan_set_path", "tb_plan_get_maps",
            "tb_plan_get_scatter", "tb_solve", "tb_solve_host", "tb_solve_loadcases", "tb_solve_loadcases_host", "tb_fitness", "tb_fitness_host", "tb_solve_ragged",
            "tb_solve_ragged_host", "tb_ga_init", "tb_ga_step", "tb_augment_ragged", "tb_pinned_alloc", "tb_pinned_free", "tb_small_path_limits", "tb_fp64_peak", "tb_rsqrt_probe", "tb_profile_enable", "tb_profile_read",
-           "tb_launch_count", "tb_strerror", "tb_version", "tb_plan_ts_info", "tb_plan_ts_array", "tb_ts_phase_read"]
+           "tb_launch_count", "tb_strerror", "tb_version", "tb_small_path_fits", "tb_debug_assemble_host", "tb_plan_ts_info", "tb_plan_ts_array", "tb_ts_phase_read"]
 
 _lib = None
 
@@ -192,6 +192,7 @@ def lib():
     L.tb_profile_enable.argtypes = [i32]
     L.tb_profile_read.argtypes = [vp, vp]
     L.tb_launch_count.restype = i64
+    L.tb_debug_assemble_host.argtypes = [vp, C.POINTER(TbBatchIn), vp]
     L.tb_plan_ts_info.argtypes = [vp, vp]
     L.tb_plan_ts_array.argtypes = [vp, i32, i32, vp]
     L.tb_plan_ts_array.restype = i64
@@ -354,6 +355,14 @@ class Plan:
                                         mem.ctypes.data, loc.ctypes.data))
         return row, col, ptr, mem, loc
 
+    def assemble_host(self, B, xyz, aed):
+        """Debug: the K_ff values the device assembles, [B, nnz_lower] in the entry order of ``scatter()``."""
+        keep = []
+        bi = self._batch_in(B, xyz, aed, None, None, np.zeros(self.N), keep)
+        kv = np.empty((B, int(self.info.nnz_lower)), np.float64)
+        check(lib().tb_debug_assemble_host(self._h, C.byref(bi), kv.ctypes.data))
+        return kv
+
     TS_SIDE_ARRAYS = ("colmask", "srcmask", "xmask", "colent", "rowdof", "rownat", "lofs")
     TS_PROGRAM_ARRAYS = ("epos", "ent_src", "tq_first", "tq_multi", "tq_ptr", "tq_pack")
 
@@ -380,6 +389,7 @@ class Plan:
         for s in range(2):
             d = {name: fetch(s, w) for w, name in enumerate(self.TS_SIDE_ARRAYS)}
             d["colent"] = d["colent"].reshape(-1, 2)
+            d["colrec"] = fetch(s, 13).reshape(-1, 8)
             out["side"].append(d)
         for w, name in enumerate(self.TS_PROGRAM_ARRAYS):
             out[name] = fetch(0, len(self.TS_SIDE_ARRAYS) + w)
@@ -481,6 +491,11 @@ class Plan:
 
 
 # --------------------------------------------------------------------------- ragged batches
+def small_path_fits(dim: int, n_joint: int, n_member: int) -> bool:
+    """Does a truss of this size fit the fused shared-memory kernels (the test tb_solve_ragged applies)?"""
+    return bool(lib().tb_small_path_fits(int(dim), int(n_joint), int(n_member)))
+
+
 def small_path_limits():
     a, b = C.c_int32(), C.c_int32()
     lib().tb_small_path_limits(C.byref(a), C.byref(b))

@@ -110,8 +110,8 @@ def SolveBatch(trusses, raise_on_error=True):
     for i, p in enumerate(packs):
         groups.setdefault(signature(p), []).append(i)
 
-    max_dof, max_mem = _lib.small_path_limits()
-    fits_small = all(p[0].shape[0] * dim <= max_dof and p[2].shape[0] <= max_mem and p[0].shape[0] <= 80 for p in packs)
+    # one ragged batch needs the LARGEST truss of the batch to fit the fused kernels' shared memory
+    fits_small = _lib.small_path_fits(dim, max(p[0].shape[0] for p in packs), max(p[2].shape[0] for p in packs))
     if len(groups) > 1 and fits_small:
         _, jo, mo, xyz, sup, conn, aed, force = pack_ragged(trusses)
         out = _lib.solve_ragged_host(dim, jo, mo, xyz, sup, conn, aed, force, want=("u", "ext", "axial"))

@@ -171,8 +171,52 @@ int ensure_ws(tb_plan* p, size_t need, cudaStream_t st) {
   return TB_OK;
 }
 
+// The plan belongs to the device it was created on (its maps and workspace live there)
+int check_device(const tb_plan* p) {
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess) return TB_ERR_NO_DEVICE;
+  return dev == p->device ? TB_OK : TB_ERR_WRONG_DEVICE;
+}
+
+// Workspace ordering across streams: the previous call's kernels may still be running on another stream
+int ws_acquire(tb_plan* p, cudaStream_t st) {
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cap) != cudaSuccess) (void)cudaGetLastError();
+  if (cap != cudaStreamCaptureStatusNone) return TB_OK;          // a captured step is single-stream by contract
+  if (p->ws_used && p->ws_stream != st && p->ws_event) TB_CUDA(cudaStreamWaitEvent(st, p->ws_event, 0));
+  return TB_OK;
+}
+int ws_release(tb_plan* p, cudaStream_t st) {
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cap) != cudaSuccess) (void)cudaGetLastError();
+  if (cap != cudaStreamCaptureStatusNone) return TB_OK;
+  if (!p->ws_event) TB_CUDA(cudaEventCreateWithFlags(&p->ws_event, cudaEventDisableTiming));
+  TB_CUDA(cudaEventRecord(p->ws_event, st));
+  p->ws_stream = st;
+  p->ws_used = true;
+  return TB_OK;
+}
+
+int run_plan_unlocked(tb_plan* p, const tb_batch_in* in, const tb_batch_out* out, const tb_fit_out* fit, double allow_s,
+                      double allow_d, cudaStream_t st, int shared_k);
+
+// Device entry points: one call at a time per plan (the plan owns ONE workspace), ordered across streams by an event
 int run_plan(tb_plan* p, const tb_batch_in* in, const tb_batch_out* out, const tb_fit_out* fit, double allow_s,
              double allow_d, cudaStream_t st, int shared_k = 0) {
+  int rc = check_device(p);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lock(p->mu);
+  if (p->path != 0) {
+    rc = ws_acquire(p, st);
+    if (rc) return rc;
+  }
+  rc = run_plan_unlocked(p, in, out, fit, allow_s, allow_d, st, shared_k);
+  if (!rc && p->path != 0) rc = ws_release(p, st);
+  return rc;
+}
+
+int run_plan_unlocked(tb_plan* p, const tb_batch_in* in, const tb_batch_out* out, const tb_fit_out* fit, double allow_s,
+                      double allow_d, cudaStream_t st, int shared_k) {
   static const tb_batch_out none = {nullptr, nullptr, nullptr, nullptr, nullptr};
   if (!out) out = &none;
   if (p->path == 0) {
@@ -225,31 +269,70 @@ Tp* take(char*& cur, size_t count) {
   return p;
 }
 
-cudaStream_t host_stream() {
-  static cudaStream_t st = [] {
-    cudaStream_t s = nullptr;
-    cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
-    return s;
-  }();
-  return st;
-}
-
+// Helper streams and events of the *_host entry points: one set per device (streams and events belong to the device that
+// was current when they were created), made on first use under the pipe mutex.
 constexpr int TB_HOST_STREAMS = 8;
-cudaStream_t* host_streams() {
-  static cudaStream_t sts[TB_HOST_STREAMS];
-  static bool init = [] {
-    for (int i = 0; i < TB_HOST_STREAMS; ++i) cudaStreamCreateWithFlags(&sts[i], cudaStreamNonBlocking);
-    return true;
-  }();
-  (void)init;
-  return sts;
+constexpr int TB_MAX_DEVICES = 64;
+struct HostPipe {
+  bool ready = false;
+  cudaStream_t comp = nullptr;
+  cudaStream_t copy[TB_HOST_STREAMS] = {};
+  cudaEvent_t ev_in[TB_HOST_STREAMS] = {}, ev_out[TB_HOST_STREAMS] = {};
+};
+HostPipe g_pipes[TB_MAX_DEVICES];
+std::mutex g_pipe_mu;                          // one *_host call at a time per process (the pipes and arenas are shared)
+
+HostPipe* host_pipe() {                        // call with g_pipe_mu held
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  HostPipe& hp = g_pipes[dev & (TB_MAX_DEVICES - 1)];
+  if (!hp.ready) {
+    if (cudaStreamCreateWithFlags(&hp.comp, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    for (int i = 0; i < TB_HOST_STREAMS; ++i) {
+      if (cudaStreamCreateWithFlags(&hp.copy[i], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+      if (cudaEventCreateWithFlags(&hp.ev_in[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+      if (cudaEventCreateWithFlags(&hp.ev_out[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    }
+    hp.ready = true;
+  }
+  return &hp;
+}
+void host_pipe_drain(HostPipe* hp) {           // after an error: nothing of the call may still touch the caller's buffers
+  if (!hp) return;
+  cudaStreamSynchronize(hp->comp);
+  for (int i = 0; i < TB_HOST_STREAMS; ++i) cudaStreamSynchronize(hp->copy[i]);
+  (void)cudaGetLastError();
 }
 int stride_ok(int64_t stride, int64_t row) { return stride == 0 || stride == row; }
 
+int run_plan_host_locked(tb_plan* p, const tb_batch_in* in, const tb_batch_out* out, const tb_fit_out* fit, double allow_s,
+                         double allow_d, int shared_k, HostPipe* hp);
+
+// Host entry points: serialised per process (g_pipe_mu: helper streams, events) and per plan (p->mu: staging arena,
+// workspace); on an error the helper streams are drained before the code is returned.
 int run_plan_host(tb_plan* p, const tb_batch_in* in, const tb_batch_out* out, const tb_fit_out* fit, double allow_s,
                   double allow_d, int shared_k = 0) {
   int rc = check_batch_in(p, in);
   if (rc) return rc;
+  rc = check_device(p);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> pipe_lock(g_pipe_mu);
+  std::lock_guard<std::mutex> plan_lock(p->mu);
+  HostPipe* hp = host_pipe();
+  if (!hp) return TB_ERR_ALLOC;
+  if (p->path != 0) {
+    rc = ws_acquire(p, hp->comp);
+    if (rc) return rc;
+  }
+  rc = run_plan_host_locked(p, in, out, fit, allow_s, allow_d, shared_k, hp);
+  if (rc) host_pipe_drain(hp);
+  else if (p->path != 0) rc = ws_release(p, hp->comp);
+  return rc;
+}
+
+int run_plan_host_locked(tb_plan* p, const tb_batch_in* in, const tb_batch_out* out, const tb_fit_out* fit, double allow_s,
+                         double allow_d, int shared_k, HostPipe* hp) {
+  int rc = 0;
   const int B = in->batch;
   if (B == 0) return TB_OK;
   const int64_t rowJ = (int64_t)p->nJ * p->dim, rowM3 = (int64_t)p->M * 3, rowM = p->M, rowN = p->N;
@@ -273,7 +356,7 @@ int run_plan_host(tb_plan* p, const tb_batch_in* in, const tb_batch_out* out, co
   rc = arena_reserve(&p->stage_dev, &p->stage_dev_bytes, need + 4096);
   if (rc) return rc;
 
-  cudaStream_t st = host_stream();
+  cudaStream_t st = hp->comp;
   char* cur = (char*)p->stage_dev;
   tb_batch_in din = *in;
   double* dxyz = take<double>(cur, nxyz);
@@ -337,19 +420,10 @@ int run_plan_host(tb_plan* p, const tb_batch_in* in, const tb_batch_out* out, co
     rc = ensure_ws(p, per_sys * (size_t)csz + 4096, st);       // chunks run one after the other: one workspace slice
     if (rc) return rc;
   }
-  static std::mutex pipe_mu;                   // the copy streams and events below are shared by every plan of the process
-  std::lock_guard<std::mutex> pipe_lock(pipe_mu);
   cudaStream_t comp = st;                      // compute stream
-  cudaStream_t* cps = host_streams();          // copy streams, one per chunk
-  static cudaEvent_t ev_in[TB_HOST_STREAMS], ev_out[TB_HOST_STREAMS];
-  static bool ev_init = [] {
-    for (int k = 0; k < TB_HOST_STREAMS; ++k) {
-      cudaEventCreateWithFlags(&ev_in[k], cudaEventDisableTiming);
-      cudaEventCreateWithFlags(&ev_out[k], cudaEventDisableTiming);
-    }
-    return true;
-  }();
-  (void)ev_init;
+  cudaStream_t* cps = hp->copy;                // copy streams, one per chunk
+  cudaEvent_t* ev_in = hp->ev_in;
+  cudaEvent_t* ev_out = hp->ev_out;
   const bool sx = in->joint_stride == 0, sf = in->force_stride == 0;
   const bool sm_ = in->member_aed ? in->member_stride == 0 : in->gene_stride == 0;
   // shared inputs first, on the compute stream
@@ -380,7 +454,7 @@ int run_plan_host(tb_plan* p, const tb_batch_in* in, const tb_batch_out* out, co
     cudaStream_t sj = nch == 1 ? comp : cps[j];
     if (nch > 1) TB_CUDA(cudaStreamWaitEvent(comp, ev_in[j], 0));
     if (nch == 1 && p->path != 0) {
-      rc = run_plan(p, &din, &dout, fit ? &dfit : nullptr, allow_s, allow_d, comp, shared_k);   // handles the workspace cap itself
+      rc = run_plan_unlocked(p, &din, &dout, fit ? &dfit : nullptr, allow_s, allow_d, comp, shared_k);   // handles the workspace cap itself
     } else {
       rc = run_plan_range(p, &din, &dout, fit ? &dfit : nullptr, allow_s, allow_d, comp, b0, nb, p->ws, shared_k);
     }
@@ -413,9 +487,7 @@ int check_ragged(const tb_ragged_in* in) {
   if (in->batch == 0) return TB_OK;
   if (!in->joint_off || !in->member_off || !in->joint_xyz || !in->support || !in->conn || !in->member_aed || !in->force)
     return TB_ERR_NULL;
-  if (in->max_joint * in->dim > TB_SMALL_MAX_DOF || in->max_member > TB_SMALL_MAX_MEMBER ||
-      in->max_joint > TB_SMALL_MAX_JOINT)
-    return TB_ERR_TOO_LARGE;
+  if (!tb_small_fits(in->dim, in->max_joint, in->max_member, in->max_joint * in->dim)) return TB_ERR_TOO_LARGE;
   return TB_OK;
 }
 
@@ -441,9 +513,9 @@ int run_ragged(const tb_ragged_in* in, const tb_batch_out* out, cudaStream_t st)
   return tb_launch_small(a, in->dim, st);
 }
 
-void* g_rag_dev = nullptr;
-size_t g_rag_dev_bytes = 0;
-std::mutex g_rag_mu;
+// staging arena of the ragged host entry point: one per device (device memory), used under g_pipe_mu
+void* g_rag_dev[TB_MAX_DEVICES] = {};
+size_t g_rag_dev_bytes[TB_MAX_DEVICES] = {};
 
 }  // namespace
 
@@ -524,16 +596,23 @@ extern "C" int tb_solve_ragged_host(const tb_ragged_in* in, const tb_batch_out* 
     if (nj > in->max_joint || nm > in->max_member) return TB_ERR_TOO_LARGE;
   }
   const size_t SJ = (size_t)in->joint_off[B], SM = (size_t)in->member_off[B];
-  std::lock_guard<std::mutex> lock(g_rag_mu);
+  std::lock_guard<std::mutex> lock(g_pipe_mu);
+  HostPipe* hp = host_pipe();
+  if (!hp) return TB_ERR_ALLOC;
+  int dev = 0;
+  TB_CUDA(cudaGetDevice(&dev));
+  void*& rag_dev = g_rag_dev[dev & (TB_MAX_DEVICES - 1)];
+  size_t& rag_bytes = g_rag_dev_bytes[dev & (TB_MAX_DEVICES - 1)];
+  auto body = [&]() -> int {
   size_t need = 0;
   auto add = [&](size_t bytes) { need += Arena::al(bytes); };
   add((B + 1) * 8); add((B + 1) * 8); add(SJ * d * 8); add(SJ); add(SM * 8); add(SM * 24); add(SJ * d * 8);
   add(out->u ? SJ * d * 8 : 0); add(out->ext ? SJ * d * 8 : 0); add(out->axial ? SM * 8 : 0);
   add(out->weight ? (size_t)B * 8 : 0); add((size_t)B * 4);
-  rc = arena_reserve(&g_rag_dev, &g_rag_dev_bytes, need + 4096);
+  int rc = arena_reserve(&rag_dev, &rag_bytes, need + 4096);
   if (rc) return rc;
-  cudaStream_t st = host_stream();
-  char* cur = (char*)g_rag_dev;
+  cudaStream_t st = hp->comp;
+  char* cur = (char*)rag_dev;
   tb_ragged_in din = *in;
   int64_t* djo = take<int64_t>(cur, B + 1);
   int64_t* dmo = take<int64_t>(cur, B + 1);
@@ -565,6 +644,78 @@ extern "C" int tb_solve_ragged_host(const tb_ragged_in* in, const tb_batch_out* 
   if (out->weight) TB_CUDA(cudaMemcpyAsync(out->weight, dout.weight, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
   if (out->info) TB_CUDA(cudaMemcpyAsync(out->info, dout.info, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
   TB_CUDA(cudaStreamSynchronize(st));
+  return TB_OK;
+  };
+  rc = body();
+  if (rc) host_pipe_drain(hp);                 // nothing of a failed call may still be copying into the caller's buffers
+  return rc;
+}
+
+// Debug export: the K_ff values the device assembles (the band path's program-order lists when the plan has the two-sided
+// program, else the tile-order lists), returned in the order of tb_plan_get_scatter.  Host pointers; uniform batch.
+extern "C" int tb_debug_assemble_host(tb_plan* p, const tb_batch_in* in, double* kv_out) {
+  int rc = check_batch_in(p, in);
+  if (rc) return rc;
+  if (!kv_out) return TB_ERR_NULL;
+  rc = check_device(p);
+  if (rc) return rc;
+  const int B = in->batch;
+  if (B == 0) return TB_OK;
+  if (!in->member_aed) return TB_ERR_NULL;                       // (explicit member properties only)
+  const size_t nnz = p->ent_row.size();
+  const bool ts = p->ts && p->ts->ok;
+  const int64_t rowJ = (int64_t)p->nJ * p->dim, rowM3 = (int64_t)p->M * 3;
+  if (!stride_ok(in->joint_stride, rowJ) || !stride_ok(in->member_stride, rowM3)) return TB_ERR_SIZE;
+  std::lock_guard<std::mutex> pipe_lock(g_pipe_mu);
+  std::lock_guard<std::mutex> plan_lock(p->mu);
+  HostPipe* hp = host_pipe();
+  if (!hp) return TB_ERR_ALLOC;
+  cudaStream_t st = hp->comp;
+  const size_t nxyz = (size_t)(in->joint_stride == 0 ? rowJ : rowJ * B), naed = (size_t)(in->member_stride == 0 ? rowM3 : rowM3 * B);
+  const int nv = p->dim * (p->dim + 1) / 2;
+  double *dxyz = nullptr, *daed = nullptr, *dkv = nullptr, *dscr = nullptr;
+  int32_t* dstat = nullptr;
+  std::vector<double> host((size_t)B * nnz);
+  auto body = [&]() -> int {
+    TB_CUDA(cudaMalloc(&dxyz, nxyz * 8));
+    TB_CUDA(cudaMalloc(&daed, naed * 8));
+    TB_CUDA(cudaMalloc(&dkv, (size_t)B * nnz * 8));
+    TB_CUDA(cudaMalloc(&dscr, (size_t)B * p->M * (2 + p->dim + nv) * 8));     // k_geom arrays (only used for very many members)
+    TB_CUDA(cudaMalloc(&dstat, (size_t)B * 4));
+    TB_CUDA(cudaMemcpyAsync(dxyz, in->joint_xyz, nxyz * 8, cudaMemcpyHostToDevice, st));
+    TB_CUDA(cudaMemcpyAsync(daed, in->member_aed, naed * 8, cudaMemcpyHostToDevice, st));
+    LargeArgs a;
+    memset(&a, 0, sizeof(a));
+    a.batch = B; a.dim = p->dim; a.nJ = p->nJ; a.M = p->M; a.N = p->N; a.n = p->n;
+    a.xyz = dxyz; a.xyz_stride = in->joint_stride;
+    a.aed = daed; a.aed_stride = in->member_stride;
+    a.conn = p->d_conn;
+    a.nnz = (int64_t)nnz;
+    a.q_first = ts ? p->ts->d_tq_first : p->d_q_first;
+    a.q_multi = ts ? p->ts->d_tq_multi : p->d_q_multi;
+    a.q_ptr = ts ? p->ts->d_tq_ptr : p->d_q_ptr;
+    a.q_pack = ts ? p->ts->d_tq_pack : p->d_q_pack;
+    a.n_multi = (int)(ts ? p->ts->tq_multi.size() : p->q_multi.size());
+    a.kv = dkv;
+    a.status = dstat;
+    double* q = dscr;
+    a.mk = q; q += (size_t)B * p->M;
+    a.mc = q; q += (size_t)B * p->M * p->dim;
+    a.mw = q; q += (size_t)B * p->M;
+    a.mkc = q;
+    int r2 = tb_launch_assemble_only(a, p->num_sm, st);
+    if (r2) return r2;
+    TB_CUDA(cudaMemcpyAsync(host.data(), dkv, (size_t)B * nnz * 8, cudaMemcpyDeviceToHost, st));
+    TB_CUDA(cudaStreamSynchronize(st));
+    return TB_OK;
+  };
+  rc = body();
+  if (rc) host_pipe_drain(hp);
+  cudaFree(dxyz); cudaFree(daed); cudaFree(dkv); cudaFree(dscr); cudaFree(dstat);
+  if (rc) return rc;
+  const std::vector<int32_t>& src = ts ? p->ts->ent_src : p->tile_ent;      // device order -> scatter-map entry
+  for (int b = 0; b < B; ++b)
+    for (size_t q2 = 0; q2 < nnz; ++q2) kv_out[(size_t)b * nnz + src[q2]] = host[(size_t)b * nnz + q2];
   return TB_OK;
 }
 

@@ -32,6 +32,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "tb_common.cuh"
 #include "tb_blocks.cuh"
 #include "tb_ts.cuh"
@@ -59,7 +61,10 @@ extern "C" int tb_ts_phase_read(unsigned long long* out) {
 
 namespace {
 
-using tbblk::dmma;
+// (not volatile: the scheduler may sink an MMA below later shared-memory loads, so operand loads run ahead of the tensor pipe)
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
 using tbblk::rsqrt_pos;
 
 constexpr int NSTAGE = TS_NSTAGE;
@@ -152,6 +157,45 @@ __device__ __forceinline__ double lds64_256(unsigned addr) {
   asm volatile("ld.shared.f64 %0, [%1+256];" : "=d"(v) : "r"(addr));
   return v;
 }
+// Operand loads of the products: not volatile, so that the scheduler can issue them well ahead of the MMAs.  Safe there:
+// nothing writes the ring between the previous column's last __syncwarp() and the stores of this column's staging, and
+// those stores take the accumulators these loads feed (a data dependence keeps every load in front of them).
+__device__ __forceinline__ double lds64_nv(unsigned addr) {
+  double v;
+  asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ double lds64_256_nv(unsigned addr) {
+  double v;
+  asm("ld.shared.f64 %0, [%1+256];" : "=d"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ double lds64_32_nv(unsigned addr) {
+  double v;
+  asm("ld.shared.f64 %0, [%1+32];" : "=d"(v) : "r"(addr));
+  return v;
+}
+
+// The block products of a column as one flat list: pair i -> (distance d, block row rb), d = 1..NB, rb = 0..NB-d
+template <int NB>
+__host__ __device__ constexpr int pair_d(int i) {
+  int d = 1;
+  while (i >= NB - d + 1) { i -= NB - d + 1; ++d; }
+  return d;
+}
+template <int NB>
+__host__ __device__ constexpr int pair_rb(int i) {
+  int d = 1;
+  while (i >= NB - d + 1) { i -= NB - d + 1; ++d; }
+  return i;
+}
+template <int I, int N, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+  if constexpr (I < N) {
+    f(std::integral_constant<int, I>{});
+    static_for<I + 1, N>(f);
+  }
+}
 
 // NB: sub-diagonal blocks of the wider side's band view (loops, the pointer ring and the accumulators are sized by it)
 template <int NB>
@@ -209,13 +253,9 @@ __global__ void __launch_bounds__(64, 7) k_band_ts(const TsArgs a) {
     for (int e = 1; e <= NB; ++e)
 #pragma unroll
       for (int j = 1; j <= e; ++j) Q[e][j] = ring_u32 + (unsigned)((e * (e - 1) / 2 + (j - 1)) * TS_BE * 8);
-    unsigned nzprev[NB + 1];
     unsigned Yq[NB + 1];                                                        // Yq[d]: address of y_{c-d}[qc] (d >= 1); Yq[0]: the slot y_c will take
 #pragma unroll
-    for (int e = 0; e <= NB; ++e) {
-      nzprev[e] = 0u;
-      Yq[e] = smem_u32(sY) + (unsigned)(e * TS_BT + qc) * 8u;
-    }
+    for (int e = 0; e <= NB; ++e) Yq[e] = smem_u32(sY) + (unsigned)(e * TS_BT + qc) * 8u;
     int fail = 0;
 
     // running pointers into the program: one record per block column, the rhs rows, the K values and their positions
@@ -223,10 +263,11 @@ __global__ void __launch_bounds__(64, 7) k_band_ts(const TsArgs a) {
     const int32_t* dofp = S.rowdof + qr;
     const double* kvp = a.kv + (int64_t)b * a.nnz + S.ent0 + lane;
     const int32_t* epp = a.epos + S.ent0 + lane;
-    int4 recn = make_int4(0, 0, 0, 0);
+    int4 recn = make_int4(0, 0, 0, 0), recm = make_int4(0, 0, 0, 0);
     int dof_n = -1;
     if (ncol_tot > 0) {
       recn = __ldg(recp);
+      recm = __ldg(recp + 1);
       dof_n = __ldg(dofp);
     }
     TPH(0)
@@ -236,8 +277,9 @@ __global__ void __launch_bounds__(64, 7) k_band_ts(const TsArgs a) {
       const bool own = c < ncol_own;
       const bool xcol = side == 1 && !own;                                      // bottom side, separator column: products only
       if (side == 0 && c == ncol_own && two) pair_sync(1);                      // the bottom side's hand-over is complete
-      const unsigned nzc = (unsigned)recn.x & 511u, srcc = ((unsigned)recn.x >> 9) & 511u, xm = ((unsigned)recn.x >> 18) & 511u;
+      const unsigned nzc = (unsigned)recn.x & 511u, xm = ((unsigned)recn.x >> 18) & 511u;
       const int ecnt = recn.y, lof = recn.z;
+      const unsigned long long pmask = (unsigned)recm.x | ((unsigned long long)(unsigned)recm.y << 32);   // live block products
       const int dof_c = dof_n;
       const double fr = (!xcol && dof_c >= 0) ? __ldg(fsys + dof_c) : 0.0;
       // K values of this block column (assembly pass, program order): in flight while the products run
@@ -257,7 +299,9 @@ __global__ void __launch_bounds__(64, 7) k_band_ts(const TsArgs a) {
       kvp += ecnt;
       epp += ecnt;
       if (c + 1 < ncol_tot) {
-        recn = __ldg(++recp);
+        recp += 2;
+        recn = __ldg(recp);
+        recm = __ldg(recp + 1);
         dofp += TS_BT;
         dof_n = __ldg(dofp);
       }
@@ -268,34 +312,37 @@ __global__ void __launch_bounds__(64, 7) k_band_ts(const TsArgs a) {
 #pragma unroll
       for (int rb = 0; rb <= NB + 1; ++rb) acc[rb][0] = acc[rb][1] = 0.0;
       double tp = 0.0;
+      // (a flat, fully predicated software pipeline over all NB(NB+1)/2 products was tried: 8 % faster for a lone system,
+      // 3-5 % slower with seven systems per SM -- the dead products' predicated-off instructions still take issue slots)
+      {
+        int base = 0;                                                           // flat index of (d, rb = 0)
 #pragma unroll
-      for (int d = 1; d <= NB; ++d) {
-        const unsigned nzp = nzprev[d];
-        if (!((nzp >> d) & 1u)) continue;                                       // L(c, c-d) structurally zero (uniform)
-        double b0 = lds64(Q[d][d]), b1 = lds64_256(Q[d][d]);
-        {
-          double y0, y1;
-          asm volatile("ld.shared.f64 %0, [%1];" : "=d"(y0) : "r"(Yq[d]));
-          asm volatile("ld.shared.f64 %0, [%1+32];" : "=d"(y1) : "r"(Yq[d]));
-          tp = fma(b0, y0, tp);
-          tp = fma(b1, y1, tp);
-        }
-        b0 = -b0;                                                              // the accumulators collect -S: P = K - S needs no pass of its own
-        b1 = -b1;
-        // block rows two at a time: the second k-slab of one block issues behind the first k-slab of the other
+        for (int d = 1; d <= NB; ++d) {
+          const unsigned bits = (unsigned)(pmask >> base);                      // bit rb: product (d, rb) is live
+          base += NB - d + 1;
+          if (!(bits & 1u)) continue;                                           // L(c, c-d) structurally zero (uniform)
+          double b0 = lds64_nv(Q[d][d]), b1 = lds64_256_nv(Q[d][d]);
+          {
+            const double y0 = lds64_nv(Yq[d]), y1 = lds64_32_nv(Yq[d]);
+            tp = fma(b0, y0, tp);
+            tp = fma(b1, y1, tp);
+          }
+          b0 = -b0;                                                            // the accumulators collect -S: P = K - S needs no pass of its own
+          b1 = -b1;
+          // block rows two at a time: the second k-slab of one block issues behind the first k-slab of the other
 #pragma unroll
-        for (int rb = 0; rb + d <= NB; rb += 2) {
-          const int e = rb + d;
-          constexpr int dummy = 0; (void)dummy;
-          const bool on0 = (nzp >> e) & 1u, on1 = e + 1 <= NB && ((nzp >> (e + 1)) & 1u);
-          const int e1i = e + 1 <= NB ? e + 1 : e;
-          double a00 = 0.0, a01 = 0.0, a10 = 0.0, a11 = 0.0;
-          if (on0) { a00 = lds64(Q[e][d]); a01 = lds64_256(Q[e][d]); }
-          if (on1) { a10 = lds64(Q[e1i][d]); a11 = lds64_256(Q[e1i][d]); }
-          if (on0) dmma(acc[rb][0], acc[rb][1], a00, b0);
-          if (on1) dmma(acc[rb + 1][0], acc[rb + 1][1], a10, b0);
-          if (on0) dmma(acc[rb][0], acc[rb][1], a01, b1);
-          if (on1) dmma(acc[rb + 1][0], acc[rb + 1][1], a11, b1);
+          for (int rb = 0; rb + d <= NB; rb += 2) {
+            const int e = rb + d;
+            const bool on0 = (bits >> rb) & 1u, on1 = e + 1 <= NB && ((bits >> (rb + 1)) & 1u);
+            const int e1i = e + 1 <= NB ? e + 1 : e;
+            double a00 = 0.0, a01 = 0.0, a10 = 0.0, a11 = 0.0;
+            if (on0) { a00 = lds64_nv(Q[e][d]); a01 = lds64_256_nv(Q[e][d]); }
+            if (on1) { a10 = lds64_nv(Q[e1i][d]); a11 = lds64_256_nv(Q[e1i][d]); }
+            if (on0) dmma(acc[rb][0], acc[rb][1], a00, b0);
+            if (on1) dmma(acc[rb + 1][0], acc[rb + 1][1], a10, b0);
+            if (on0) dmma(acc[rb][0], acc[rb][1], a01, b1);
+            if (on1) dmma(acc[rb + 1][0], acc[rb + 1][1], a11, b1);
+          }
         }
       }
       tp += __shfl_xor_sync(FULL, tp, 1);
@@ -452,9 +499,6 @@ __global__ void __launch_bounds__(64, 7) k_band_ts(const TsArgs a) {
 
       // ---------------- advance the ring: the slot of the dying block of every diagonal becomes the youngest block's
 #pragma unroll
-      for (int e = NB; e >= 2; --e) nzprev[e] = nzprev[e - 1];
-      nzprev[1] = srcc;
-#pragma unroll
       for (int e = 1; e <= NB; ++e) {
         const unsigned dying = Q[e][e];
 #pragma unroll
@@ -478,13 +522,12 @@ __global__ void __launch_bounds__(64, 7) k_band_ts(const TsArgs a) {
     // =========================================== back substitution
     // u_c = Z_c (y_c - sum_rb L(c+rb, c)^T u_{c+rb}); the chunks come back through cp.async.bulk, NSTAGE in flight
     const int ncb = side == 0 ? ncol_tot : ncol_own;
-    const int ur = nbs + 1;
     double* sBuf = sRing;
     double* sU = sRing + NSTAGE * a.chunk_max;                                   // ring of the last nb+1 blocks of u: block c in slot c mod (nb+1)
     fence_proxy_async();                                                         // this lane's factor stores / ring stores before the async proxy
     __syncwarp();
     auto issue = [&](int c, int stage) {
-      const int4 rc = __ldg(S.colrec + c);
+      const int4 rc = __ldg(S.colrec + 2 * c);
       mbar_expect_tx(&sBar[stage], (unsigned)rc.w);
       bulk_g2s(sBuf + stage * a.chunk_max, Lsys + rc.z, (unsigned)rc.w, &sBar[stage]);
     };
@@ -493,72 +536,96 @@ __global__ void __launch_bounds__(64, 7) k_band_ts(const TsArgs a) {
         if (ncb - 1 - i >= 0) issue(ncb - 1 - i, i);
     const int g = lane >> 3, col = lane & 7;
     double uprev = 0.0;
-    int cs = ncb > 0 ? (ncb - 1) % ur : 0;                                       // ring slot of block c
+    // the last nb+1 blocks of u live in a ring addressed by rotating pointers: Uq[d] = address of u_{c+d}[2g] (d >= 1),
+    // Uq[0] = the slot u_c takes (all with this lane's 2g offset folded in)
+    const unsigned su_u32 = smem_u32(sU);
+    unsigned Uq[NB + 1];
+#pragma unroll
+    for (int e = 0; e <= NB; ++e) Uq[e] = su_u32 + (unsigned)(e * TS_BT + 2 * g) * 8u;
     if (side == 1 && two) {
       pair_sync(2);                                                              // separator displacements are published
-      int s2 = S.ncol_own % ur;
-      const int cend = ncol_own + (nS < nbs ? nS : nbs);                          // (the band reaches nb separator blocks at most)
-      for (int c = S.ncol_own; c < cend; ++c) {
-        if (lane < TS_BT) sU[s2 * TS_BT + lane] = sUS[(nS - 1 - (c - S.ncol_own)) * TS_BT + (7 - lane)];
-        s2 = s2 + 1 == ur ? 0 : s2 + 1;
+      // virtual separator column ncol_own + j is u_{c+1+j} of the first back-substituted column c = ncol_own - 1: slot Uq[1+j]
+      const int cnt = nS < nbs ? nS : nbs;                                       // (the band reaches nb separator blocks at most)
+      if (lane < TS_BT) {
+#pragma unroll
+        for (int j = 0; j < NB; ++j)
+          if (j < cnt) {
+            const double v = sUS[(nS - 1 - j) * TS_BT + (7 - lane)];
+            asm volatile("st.shared.f64 [%0], %1;" ::"r"(Uq[1 + j] - (unsigned)(2 * g) * 8u + (unsigned)lane * 8u), "d"(v) : "memory");
+          }
       }
       __syncwarp();
-      uprev = sU[(S.ncol_own % ur) * TS_BT + col];
+      asm volatile("ld.shared.f64 %0, [%1];" : "=d"(uprev) : "r"(Uq[1] - (unsigned)(2 * g) * 8u + (unsigned)col * 8u));
     }
-    unsigned maskn = ncb > 0 ? ((unsigned)__ldg(&S.colrec[ncb - 1].x) & 511u) : 0u;
+    unsigned maskn = ncb > 0 ? ((unsigned)__ldg(&S.colrec[2 * (ncb - 1)].x) & 511u) : 0u;
     int natn = ncb > 0 ? __ldg(S.rownat + (ncb - 1) * TS_BT + col) : -1;
     int stage = 0;
+    const unsigned buf0 = smem_u32(sBuf);
+    const unsigned lane_l = (unsigned)((2 * g) * 8 + col) * 8u, lane_z = (unsigned)(col * 8 + 2 * g) * 8u;
     for (int c = ncb - 1; c >= 0; --c) {
       const unsigned mask = maskn;
       const int nat = natn;
       if (c > 0) {
-        maskn = ((unsigned)__ldg(&S.colrec[c - 1].x) & 511u);
+        maskn = ((unsigned)__ldg(&S.colrec[2 * (c - 1)].x) & 511u);
         natn = __ldg(S.rownat + (c - 1) * TS_BT + col);
       }
       mbar_wait(&sBar[stage], (phase >> stage) & 1u);
       phase ^= 1u << stage;
-      const double* buf = sBuf + stage * a.chunk_max;
+      const unsigned bufa = buf0 + (unsigned)(stage * a.chunk_max) * 8u;
       // t[col] = sum_rb sum_r L(c+rb,c)[r][col] u_{c+rb}[r]; this lane: r = 2g, 2g+1.  The blocks further away first (their u is
       // in the ring), the neighbour last (its u has just been produced and comes by shuffle)
-      double t = 0.0;
-      int rank = (mask >> 1) & 1u;
+      double t = 0.0, t2 = 0.0;
+      unsigned la = bufa + (unsigned)(TS_BE + TS_BT) * 8u + lane_l + (((mask >> 1) & 1u) ? (unsigned)TS_BE * 8u : 0u);
 #pragma unroll
       for (int rb = 2; rb <= NB; ++rb) {
         if (!((mask >> rb) & 1u)) continue;
-        const double* blk = buf + TS_BE + TS_BT + rank * TS_BE;
-        ++rank;
-        int us = cs + rb;
-        if (us >= ur) us -= ur;
-        t = fma(blk[(2 * g) * 8 + col], sU[us * TS_BT + 2 * g], t);
-        t = fma(blk[(2 * g + 1) * 8 + col], sU[us * TS_BT + 2 * g + 1], t);
+        double l0, l1, u0, u1;
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(l0) : "r"(la));
+        asm volatile("ld.shared.f64 %0, [%1+64];" : "=d"(l1) : "r"(la));
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(u0) : "r"(Uq[rb]));
+        asm volatile("ld.shared.f64 %0, [%1+8];" : "=d"(u1) : "r"(Uq[rb]));
+        la += (unsigned)TS_BE * 8u;
+        if (rb & 1) { t = fma(l0, u0, t); t = fma(l1, u1, t); }
+        else { t2 = fma(l0, u0, t2); t2 = fma(l1, u1, t2); }
       }
+      double yc, z0, z1, l10 = 0.0, l11 = 0.0;
+      asm volatile("ld.shared.f64 %0, [%1];" : "=d"(yc) : "r"(bufa + (unsigned)(TS_BE + col) * 8u));
+      asm volatile("ld.shared.f64 %0, [%1];" : "=d"(z0) : "r"(bufa + lane_z));
+      asm volatile("ld.shared.f64 %0, [%1+8];" : "=d"(z1) : "r"(bufa + lane_z));
+      if ((mask >> 1) & 1u) {
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(l10) : "r"(bufa + (unsigned)(TS_BE + TS_BT) * 8u + lane_l));
+        asm volatile("ld.shared.f64 %0, [%1+64];" : "=d"(l11) : "r"(bufa + (unsigned)(TS_BE + TS_BT) * 8u + lane_l));
+      }
+      t += t2;
       {
         const double u0 = __shfl_sync(FULL, uprev, 2 * g), u1 = __shfl_sync(FULL, uprev, 2 * g + 1);
-        if ((mask >> 1) & 1u) {
-          const double* blk = buf + TS_BE + TS_BT;
-          t = fma(blk[(2 * g) * 8 + col], u0, t);
-          t = fma(blk[(2 * g + 1) * 8 + col], u1, t);
-        }
+        t = fma(l10, u0, t);
+        t = fma(l11, u1, t);
       }
       t += __shfl_xor_sync(FULL, t, 8);
       t += __shfl_xor_sync(FULL, t, 16);
-      const double rr = buf[TS_BE + col] - t;
+      const double rr = yc - t;
       const double r0 = __shfl_sync(FULL, rr, 2 * g), r1 = __shfl_sync(FULL, rr, 2 * g + 1);
-      double u = buf[col * 8 + 2 * g] * r0;
-      u = fma(buf[col * 8 + 2 * g + 1], r1, u);
+      double u = z0 * r0;
+      u = fma(z1, r1, u);
       u += __shfl_xor_sync(FULL, u, 8);
       u += __shfl_xor_sync(FULL, u, 16);
       uprev = u;
       if (g == 0) {
-        sU[cs * TS_BT + col] = u;
+        asm volatile("st.shared.f64 [%0], %1;" ::"r"(Uq[0] + (unsigned)col * 8u), "d"(u) : "memory");   // (g == 0: no 2g offset in Uq)
         if (nat >= 0) ufs[nat] = u;
-        if (side == 0 && c >= S.ncol_own) sUS[(c - S.ncol_own) * TS_BT + col] = u;
+        if (side == 0 && c >= ncol_own) sUS[(c - ncol_own) * TS_BT + col] = u;
       }
       __syncwarp();
       if (lane == 0 && c - NSTAGE >= 0) issue(c - NSTAGE, stage);
-      if (side == 0 && two && c == S.ncol_own) pair_sync(2);
+      if (side == 0 && two && c == ncol_own) pair_sync(2);
       stage = stage + 1 == NSTAGE ? 0 : stage + 1;
-      cs = cs == 0 ? ur - 1 : cs - 1;
+      {   // u_c becomes u_{(c-1)+1}: rotate the ring pointers, the oldest slot is the next column's
+        const unsigned oldest = Uq[NB];
+#pragma unroll
+        for (int j = NB; j >= 1; --j) Uq[j] = Uq[j - 1];
+        Uq[0] = oldest;
+      }
     }
     TPH(8)
     __syncthreads();

@@ -5,6 +5,7 @@
 #include <stdint.h>
 
 #include <atomic>
+#include <mutex>
 #include <vector>
 
 #include "truss_b200.h"
@@ -132,9 +133,15 @@ struct tb_plan {
   // two-sided band program of the fused band kernel (tb_tsplan.cu); ts->ok == 0 when the band is too wide for it
   TsPlan* ts = nullptr;
 
-  // grow-only device workspace of the blocked path
+  // grow-only device workspace of the blocked path.  One workspace per plan: `mu` serialises the calls that enqueue work
+  // on it (and the growth of the arenas), `ws_event` orders its use across streams (recorded after the last kernel of a
+  // call; a call on another stream waits for it first).  See the threading contract in truss_b200.h.
   void* ws = nullptr;
   size_t ws_bytes = 0;
+  std::mutex mu;
+  cudaEvent_t ws_event = nullptr;
+  cudaStream_t ws_stream = nullptr;   // stream of the last call that used the workspace
+  bool ws_used = false;
   // grow-only staging for the *_host entry points
   void* stage_dev = nullptr;
   size_t stage_dev_bytes = 0;
@@ -212,10 +219,14 @@ int tb_launch_small(const SmallArgs& a, int dim, cudaStream_t st);
 int tb_small_smem_bytes(int dim, int nJ, int M, int max_n, int* threads);
 int tb_launch_dense16(const SmallArgs& a, int dim, cudaStream_t st);   // -1: does not fit, use the CTA-per-truss kernel
 int tb_dense16_smem_bytes(int dim, int nJ, int M, int max_n);
+// does a system of this size fit one of the two fused shared-memory kernels?  (sizes alone are not enough: many members on
+// few joints exhaust the per-warp / per-CTA shared memory long before the DOF limit)
+bool tb_small_fits(int dim, int nJ, int M, int max_n);
 int tb_launch_large(const LargeArgs& a, int num_sm, cudaStream_t st, int path);
 size_t tb_large_workspace_bytes(int batch, int dim, int M, int n_pad, int64_t nnz, int path, int nb16, int NB);
 void tb_large_carve(LargeArgs& a, void* ws, int path);
 int tb_launch_band_chol(const LargeArgs& a, int num_sm, cudaStream_t st);
+int tb_launch_assemble_only(const LargeArgs& a, int num_sm, cudaStream_t st);   // member products + K_ff values (a.kv) through a.q_*
 int tb_launch_band_subst(const LargeArgs& a, int num_sm, cudaStream_t st);   // load cases against the factor of system 0
 int tb_band_smem_bytes(int NB);
 

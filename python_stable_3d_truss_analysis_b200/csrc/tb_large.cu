@@ -1111,6 +1111,31 @@ int launch_ts_path(const LargeArgs& a, int num_sm, cudaStream_t st) {
 
 }  // namespace
 
+// The assembly pass alone (debug export of the device-assembled K_ff values): k_prep, or k_geom + k_kval when the member
+// products do not fit shared memory, driven by whatever scatter lists a.q_* point at; writes a.kv[B][a.nnz].
+int tb_launch_assemble_only(const LargeArgs& a, int num_sm, cudaStream_t st) {
+  if (a.batch <= 0) return 0;
+  if (num_sm <= 0) num_sm = 148;
+  const size_t prep_smem = (size_t)a.M * (a.dim * (a.dim + 1) / 2) * 8;
+  const int grid = a.batch < num_sm * 8 ? a.batch : num_sm * 8;
+  if (prep_smem <= 96 * 1024) {
+    auto kern = a.dim == 3 ? k_prep<3> : k_prep<2>;
+    const int rcg = g_prep_grant[a.dim - 2].ensure(kern, prep_smem);
+    if (rcg) return rcg;
+    kern<<<grid, 256, prep_smem, st>>>(a);
+  } else {
+    k_init_status<<<(a.batch + 255) / 256, 256, 0, st>>>(a.status, a.batch, 0);
+    const int64_t total = (int64_t)a.batch * a.M;
+    int g2 = (int)((total + 255) / 256 < (int64_t)num_sm * 8 ? (total + 255) / 256 : (int64_t)num_sm * 8);
+    if (g2 < 1) g2 = 1;
+    if (a.dim == 3) k_geom<3><<<g2, 256, 0, st>>>(a);
+    else k_geom<2><<<g2, 256, 0, st>>>(a);
+    k_kval<<<grid, 256, 0, st>>>(a);
+  }
+  tb_count_launch(1);
+  return (int)cudaGetLastError();
+}
+
 int tb_launch_large(const LargeArgs& a, int num_sm, cudaStream_t st, int path) {
   if (a.batch <= 0) return 0;
   if (num_sm <= 0) num_sm = 148;

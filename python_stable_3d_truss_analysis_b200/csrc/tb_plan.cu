@@ -275,7 +275,7 @@ extern "C" int tb_plan_create(const tb_topology* topo, tb_plan** plan_out) {
   const std::vector<int32_t>& icol = p->int_col;
 
   // ---- path + tile grouping of entries for the blocked path
-  p->path = (p->N <= TB_SMALL_MAX_DOF && p->M <= TB_SMALL_MAX_MEMBER && p->nJ <= TB_SMALL_MAX_JOINT) ? 0 : 1;
+  p->path = tb_small_fits(d, p->nJ, p->M, p->n) ? 0 : 1;     // (the shared-memory budgets of the fused kernels, not just the sizes)
   // (a narrow band promotes path 1 to the band path 2 once the band view is known, below)
   p->n_pad = std::max(TB_TILE, (p->n + TB_TILE - 1) / TB_TILE * TB_TILE);
   p->nt = p->n_pad / TB_TILE;
@@ -535,6 +535,7 @@ extern "C" void tb_plan_destroy(tb_plan* p) {
   cudaFree(p->d_prod_k);
   cudaFree(p->d_inc_ptr);
   cudaFree(p->d_inc_mem);
+  if (p->ws_event) cudaEventDestroy(p->ws_event);
   cudaFree(p->ws);
   cudaFree(p->stage_dev);
   if (p->stage_pinned) cudaFreeHost(p->stage_pinned);
@@ -573,8 +574,7 @@ extern "C" int tb_plan_set_path(tb_plan* p, int32_t path) {
   if (!p) return TB_ERR_NULL;
   if (path < 0 || path > 2) return TB_ERR_SIZE;
   if (path == 2 && p->NB > TB_BAND_MAX_NB) return TB_ERR_TOO_LARGE;
-  if (path == 0 && !(p->N <= TB_SMALL_MAX_DOF && p->M <= TB_SMALL_MAX_MEMBER && p->nJ <= TB_SMALL_MAX_JOINT))
-    return TB_ERR_TOO_LARGE;
+  if (path == 0 && !tb_small_fits(p->dim, p->nJ, p->M, p->n)) return TB_ERR_TOO_LARGE;
   p->path = path;
   return TB_OK;
 }
@@ -599,6 +599,11 @@ extern "C" int tb_plan_get_scatter(const tb_plan* p, int32_t* row, int32_t* col,
   return TB_OK;
 }
 
+extern "C" int tb_small_path_fits(int32_t dim, int32_t n_joint, int32_t n_member) {
+  if (dim != 2 && dim != 3) return 0;
+  return tb_small_fits(dim, n_joint, n_member, n_joint * dim) ? 1 : 0;       // (ragged batches size by d * nJ: every DOF free)
+}
+
 extern "C" int tb_small_path_limits(int32_t* max_dof, int32_t* max_member) {
   if (max_dof) *max_dof = TB_SMALL_MAX_DOF;
   if (max_member) *max_member = TB_SMALL_MAX_MEMBER;
@@ -619,6 +624,7 @@ extern "C" const char* tb_strerror(int code) {
     case TB_ERR_TOO_LARGE: return "system too large for the selected path";
     case TB_ERR_NO_DEVICE: return "no CUDA device (this library has no CPU fallback)";
     case TB_ERR_ALLOC: return "allocation failed";
+    case TB_ERR_WRONG_DEVICE: return "the plan belongs to another CUDA device than the current one";
     default: break;
   }
   if (code > 0) return cudaGetErrorString((cudaError_t)code);

@@ -394,6 +394,15 @@ int tb_small_smem_bytes(int dim, int nJ, int M, int max_n, int* threads) {
   return (int)bytes;
 }
 
+bool tb_small_fits(int dim, int nJ, int M, int max_n) {
+  if (nJ * dim > TB_SMALL_MAX_DOF || M > TB_SMALL_MAX_MEMBER || nJ > TB_SMALL_MAX_JOINT) return false;
+  const int nbm = max_n > 0 ? (max_n + 15) / 16 : 1;
+  if (nbm <= 10 && tb_dense16_smem_bytes(dim, nJ, M, max_n) <= 110 * 1024) return true;      // k_dense16: one warp per truss
+  int threads = 0;
+  const int smem = tb_small_smem_bytes(dim, nJ, M, max_n, &threads);                         // k_small: one CTA per truss
+  return threads <= SMALL_MAX_THREADS && smem <= 227 * 1024;
+}
+
 int tb_launch_small(const SmallArgs& a, int dim, cudaStream_t st) {
   if (a.batch <= 0) return 0;
   // warp-per-system kernel (tb_dense16.cu) first; this CTA-per-truss kernel takes what does not fit its budget

@@ -37,12 +37,14 @@ struct TsSideDev {
   int ncol_tot;              // + separator columns (top: factorised after the hand-over; bottom: products only)
   int nb;                    // sub-diagonal blocks of this side's band view
   int ent0;                  // first entry of this side in program order (its block columns follow each other in kv / epos)
-  const int4* colrec;        // [ncol_tot]   one record per block column, all the kernel reads at the top of a column:
+  const int4* colrec;        // [2*ncol_tot] two int4 per block column, all the kernel reads at the top of a column:
                              //              x = colmask | srcmask << 9 | xmask << 18
                              //                  colmask: bit rb <=> block (c+rb, c) non-zero (bottom separator columns: blocks it contributes to)
                              //                  srcmask: colmask of the columns that exist as factor columns (0 for the bottom's separator columns)
                              //                  xmask:   top separator columns: blocks handed over by the bottom side
                              //              y = number of K entries, z = offset (doubles) of the factor chunk, w = its size in bytes
+                             //              second int4: x, y = bit i <=> block product i of the column is structurally non-zero, i the
+                             //              flat index of (distance d, block row rb) for NB = max(nb of both sides): d = 1..NB, rb = 0..NB-d
   const int32_t* rowdof;     // [ncol_tot*8] DOF index of virtual row v, -1 on padding
   const int32_t* rownat;     // [ncol_tot*8] internal (natural) row of virtual row v, -1 on padding
 };
@@ -103,7 +105,7 @@ constexpr int TS_X_SCR = 0, TS_X_T = TS_BE, TS_X_Y = TS_X_T + TS_BT, TS_X_MISC =
               TS_X_TOTAL = TS_X_MISC + 16;
 __host__ __device__ inline int ts_main_doubles(int nb, int chunk_max) {
   const int ring = nb * (nb + 1) / 2 * TS_BE;
-  const int back = TS_NSTAGE * chunk_max + (nb + 1) * TS_BT;
+  const int back = TS_NSTAGE * chunk_max + (TS_NBX + 1) * TS_BT;   // (the u ring rotates through TS_NBX + 1 slots whatever nb is)
   return ring > back ? ring : back;
 }
 // Ring slot the new block (c+rb, c) of diagonal rb takes at block column c: the kernel's pointer ring starts with slot

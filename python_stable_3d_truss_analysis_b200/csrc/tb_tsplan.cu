@@ -261,8 +261,9 @@ int tb_ts_build(tb_plan* p) {
   ts->tq_ptr.assign(1, 0);
   for (int s = 0; s < 2; ++s) {
     TsSideHost& h = ts->side[s];
-    h.colrec.resize(h.ncol_tot);
+    h.colrec.resize(2 * (size_t)h.ncol_tot);
     h.colent.resize(h.ncol_tot);
+    const int NBK = std::max(ts->side[0].nb, ts->side[1].nb);   // the kernel instantiation (its flat product list)
     const int mainsz = ts_main_doubles(h.nb, ts->chunk_max);
     for (int c = 0; c < h.ncol_tot; ++c) {
       const int e0 = (int)ts->epos.size();
@@ -281,8 +282,18 @@ int tb_ts_build(tb_plan* p) {
       }
       h.colent[c] = make_int2(e0, (int)ts->epos.size());
       const bool has_chunk = c < (s == 0 ? h.ncol_tot : h.ncol_own);
-      h.colrec[c] = make_int4((int)(h.colmask[c] | (h.srcmask[c] << 9) | (h.xmask[c] << 18)), (int)ts->epos.size() - e0, h.lofs[c],
-                              has_chunk ? (h.lofs[c + 1] - h.lofs[c]) * 8 : 0);
+      h.colrec[2 * c] = make_int4((int)(h.colmask[c] | (h.srcmask[c] << 9) | (h.xmask[c] << 18)), (int)ts->epos.size() - e0, h.lofs[c],
+                                  has_chunk ? (h.lofs[c + 1] - h.lofs[c]) * 8 : 0);
+      // block products of this column: L(c+rb, c-d) L(c, c-d)^T needs both blocks of column c-d
+      uint64_t pm = 0;
+      int idx = 0;
+      for (int dd = 1; dd <= NBK; ++dd)
+        for (int rb = 0; rb + dd <= NBK; ++rb, ++idx) {
+          if (c - dd < 0) continue;
+          const uint32_t sm = h.srcmask[c - dd];
+          if (((sm >> dd) & 1u) && ((sm >> (rb + dd)) & 1u)) pm |= (uint64_t)1 << idx;
+        }
+      h.colrec[2 * c + 1] = make_int4((int)(uint32_t)pm, (int)(uint32_t)(pm >> 32), 0, 0);
     }
   }
   {   // first contribution inline, entries with several contributions listed separately (as tb_plan.cu does for the other orders)
@@ -363,7 +374,7 @@ extern "C" int tb_plan_ts_info(const tb_plan* p, int32_t* out /*[16]*/) {
 }
 
 // which = 0 colmask, 1 srcmask, 2 xmask, 3 colent (2 ints each), 4 rowdof, 5 rownat, 6 lofs (per side); 7 epos, 8 ent_src,
-// 9 tq_first, 10 tq_multi, 11 tq_ptr, 12 tq_pack (whole program, side ignored).  Returns the element count (ints); copies
+// 9 tq_first, 10 tq_multi, 11 tq_ptr, 12 tq_pack (whole program, side ignored); 13 colrec (8 ints per block column, per side).  Returns the element count (ints); copies
 // when out != NULL.
 extern "C" int64_t tb_plan_ts_array(const tb_plan* p, int32_t side, int32_t which, int32_t* out) {
   if (!p || !p->ts || !p->ts->ok || side < 0 || side > 1) return -1;
@@ -385,6 +396,7 @@ extern "C" int64_t tb_plan_ts_array(const tb_plan* p, int32_t side, int32_t whic
     case 10: src = ts->tq_multi.data(); cnt = ts->tq_multi.size(); break;
     case 11: src = ts->tq_ptr.data(); cnt = ts->tq_ptr.size(); break;
     case 12: src = ts->tq_pack.data(); cnt = ts->tq_pack.size(); break;
+    case 13: src = h.colrec.data(); cnt = h.colrec.size() * 4; break;
     default: return -1;
   }
   if (out && cnt) memcpy(out, src, cnt * 4);

@@ -160,3 +160,28 @@ def test_ga_and_augment_argument_errors_without_a_device():
     assert L.tb_augment_ragged(None, 4, None, None, None, C.byref(prm), None, None, None, None, None, None) == -1
     if not _has_cuda():
         assert L.tb_ga_init(C.byref(ok), None, dummy.ctypes.data, None) == _lib.TB_ERR_NO_DEVICE
+
+
+def test_fused_path_is_chosen_by_shared_memory_not_by_size_alone():
+    """53 joints / 600 members (N = 159 <= 160, M <= 1024) passes the size limits of the fused kernels but
+    needs more shared memory than either of them has: the plan must route it to a blocked pipeline, and a ragged batch
+    holding such a truss must be refused up front instead of failing at launch time."""
+    rng = np.random.default_rng(3)
+    nj, m = 53, 600
+    pairs = set()
+    while len(pairs) < m:
+        a, b = rng.integers(0, nj, 2)
+        if a != b:
+            pairs.add((int(min(a, b)), int(max(a, b))))
+    conn = np.array(sorted(pairs), np.int32)
+    support = np.zeros(nj, np.uint8)
+    support[:1] = orc.PIN                              # n = 156 free DOFs
+    plan = _lib.Plan(3, conn, support)
+    assert plan.info.path in (1, 2), "a truss that does not fit the fused kernels' shared memory was routed to them"
+    with pytest.raises(_lib.TrussLibError) as ei:
+        plan.set_path(0)
+    assert ei.value.code == _lib.TB_ERR_TOO_LARGE
+    assert not _lib.small_path_fits(3, nj, m)
+    assert _lib.small_path_fits(3, 32, 119)            # the cube-7 trusses of the generator
+    # 2-D: 80 joints, 400 members
+    assert not _lib.small_path_fits(2, 80, 400) or _lib.Plan(2, conn[conn.max(axis=1) < 80][:400], np.r_[np.ones(2, np.uint8), np.zeros(78, np.uint8)]).info.path == 0

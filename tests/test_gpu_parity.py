@@ -506,3 +506,106 @@ def test_blocked_paths_report_failures_per_system(path):
     N = t.nJoint * 3
     res = SolveLoadCases(t, np.ones((4, N)), raise_on_error=False)
     assert np.all(res["info"] > 0) and not np.any(res["u"])
+
+
+def _k_reference_with_device_squares(dim, joints, conn, aed, row, col, ptr, mem, loc):
+    """GetKMatrix()[mask][:, mask] entries (truss.py:307-316, 343) with the squares of the cosines taken as products: the
+    reference's ``l ** 2.`` goes through libm pow, which is an ulp off the product now and then (no GPU reproduces libm)."""
+    from tests import ts_replay
+    prods = [ts_replay.member_products(dim, joints, conn[m], aed[m][0], aed[m][1]) for m in range(conn.shape[0])]
+    out = np.zeros(len(row))
+    for i in range(len(row)):
+        v = 0.0
+        for q in range(ptr[i], ptr[i + 1]):
+            a, b = divmod(int(loc[q]), 2 * dim)
+            k, c = prods[mem[q]]
+            t = k * (c[a % dim] * c[b % dim])
+            v = v + (-t if (a // dim) != (b // dim) else t)
+        out[i] = v
+    return out
+
+
+@pytest.mark.parametrize("name,dim,data,gold", [c for c in H.shipped_cases() if c[0].split("_")[0] in ("bar-6", "bar-10", "bar-72", "bar-942")],
+                         ids=lambda v: v if isinstance(v, str) else None)
+def test_device_assembled_K_is_bit_exact(name, dim, data, gold):
+    """SURVEY section 7 step-2 gate: the K_ff values the DEVICE assembles (its own roundings of length, EA/L, cosines, the
+    products and the ascending-member sums) equal the reference's reduced stiffness matrix bit for bit."""
+    joints, support, conn, aed, force = orc.arrays_from_json(data, dim)
+    for path in (2, 1):
+        plan = _lib.Plan(dim, conn, support)
+        try:
+            plan.set_path(path)
+        except _lib.TrussLibError:
+            continue
+        kv = plan.assemble_host(2, joints, aed)
+        row, col, ptr, mem, loc = plan.scatter()
+        want = _k_reference_with_device_squares(dim, joints, conn, aed, row, col, ptr, mem, loc)
+        assert np.array_equal(kv[0], want) and np.array_equal(kv[1], want), (name, path)
+        K = orc.assemble_K(dim, joints, conn, aed)
+        mask = orc.free_mask(dim, support)
+        ref = K[mask][:, mask][row, col]
+        mism = np.count_nonzero(kv[0] != ref)
+        # the oracle itself (CPython's compensated sum() in the length, pow for the squares) may sit an ulp away
+        assert mism <= 0.02 * len(ref) + 2 and np.all(np.abs(kv[0] - ref) <= 1e-12 * np.abs(ref).max()), (name, path, mism)
+
+
+def test_two_streams_and_two_threads_share_one_plan():
+    """ADVICE r1: a plan owns one workspace; calls from two streams / two threads must serialise, not corrupt each other."""
+    import threading
+    import torch
+    name, dim, data, gold = next(c for c in H.shipped_cases() if c[0].startswith("bar-942"))
+    t = Truss(dim).LoadFromJSON(data=data)
+    xyz, sup, conn, aed, force = t._pack()
+    plan = t._get_plan()
+    dev = torch.device("cuda:0")
+    td = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+    B = 64
+    rng = np.random.default_rng(7)
+    Fs = [rng.uniform(-10, 10, size=(B, plan.N)) for _ in range(2)]
+    dx, da = td(xyz), td(aed)
+    dF = [td(F) for F in Fs]
+    outs = [{k: torch.empty(B, plan.N if k in ("u", "ext") else plan.M, dtype=torch.float64, device=dev) for k in ("u", "ext", "axial")}
+            for _ in range(2)]
+    for o in outs:
+        o["weight"] = torch.empty(B, dtype=torch.float64, device=dev)
+        o["info"] = torch.empty(B, dtype=torch.int32, device=dev)
+    ref = [plan.solve_host(B, xyz, F, aed=aed) for F in Fs]
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+
+    def work(i):
+        for _ in range(20):
+            plan.solve_device(B, dx, dF[i], aed=da, out=outs[i], stream=streams[i])
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    for x in th:
+        x.start()
+    for x in th:
+        x.join()
+    torch.cuda.synchronize()
+    for i in range(2):
+        for k in ("u", "ext", "axial"):
+            assert np.array_equal(outs[i][k].cpu().numpy(), ref[i][k]), (i, k)
+
+
+def test_one_process_two_devices():
+    """VERDICT r1 #8: kernel attributes / helper streams are per device; a plan refuses to run on a device it was not made on."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    name, dim, data, gold = next(c for c in H.shipped_cases() if c[0].startswith("bar-942"))
+    res = []
+    for d in (0, 1):
+        torch.cuda.set_device(d)
+        t = Truss(dim).LoadFromJSON(data=data)
+        t.Solve()
+        H.assert_close(dense(t), gold, what=f"device {d}")
+        res.append(t._dense["u"].copy())
+        if d == 1:
+            plan1 = t._get_plan()
+    assert np.array_equal(res[0], res[1])
+    torch.cuda.set_device(0)
+    xyz, sup, conn, aed, force = t._pack()
+    with pytest.raises(_lib.TrussLibError) as ei:
+        plan1.solve_host(1, xyz, force, aed=aed)
+    assert ei.value.code == -9
+    torch.cuda.set_device(0)

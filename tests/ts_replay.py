@@ -65,7 +65,7 @@ NSTAGE = 3
 
 def main_doubles(nb, chunk_max):
     """csrc/tb_ts.cuh ts_main_doubles: ring of live blocks, reused by the back substitution's chunk buffers + u ring."""
-    return max(nb * (nb + 1) // 2 * 64, NSTAGE * chunk_max + (nb + 1) * BT)
+    return max(nb * (nb + 1) // 2 * 64, NSTAGE * chunk_max + 9 * BT)
 
 
 def _unpack_pos(epos, c, mainsz):
@@ -116,6 +116,7 @@ def replay(prog, dim, xyz, conn, aed, force, n_dof):
     X = {}
     Zx = np.zeros((max(nS, 1), BT))
     two = sides[1].tot > 0
+    NBK = max(info["nb_top"], info["nb_bottom"])
 
     def forward_column(S, c):
         d = S.d
@@ -125,6 +126,19 @@ def replay(prog, dim, xyz, conn, aed, force, n_dof):
         nzc, srcc, xm = int(d["colmask"][c]), int(d["srcmask"][c]), int(d["xmask"][c])
         acc = {rb: np.zeros((BT, BT)) for rb in range(nb + 1)}
         tp = np.zeros(BT)
+        # the kernel takes the liveness of every block product from the column record (bit = flat index of (d, rb) for NB =
+        # the wider side's band): it must be exactly "both blocks of column c-d exist"
+        rec = d["colrec"][c]
+        assert int(rec[0]) == (nzc | (srcc << 9) | (xm << 18)) and int(rec[1]) == int(d["colent"][c][1] - d["colent"][c][0])
+        pmask = (int(rec[4]) & 0xffffffff) | ((int(rec[5]) & 0xffffffff) << 32)
+        idx, want = 0, 0
+        for dd in range(1, NBK + 1):
+            for rb in range(0, NBK - dd + 1):
+                nzp = S.nzprev[dd] if dd <= nb else 0
+                if (nzp >> dd) & 1 and (nzp >> (rb + dd)) & 1:
+                    want |= 1 << idx
+                idx += 1
+        assert pmask == want, "product mask of the column record disagrees with the block structure"
         for dd in range(1, nb + 1):
             nzp = S.nzprev[dd]
             if not (nzp >> dd) & 1:
