@@ -36,6 +36,10 @@ BATCH_PER_GPU = 1024
 METRIC = "FP64 trusses solved/sec (batched Truss.Solve)"
 UNIT = "trusses/s"
 WORKLOAD = "bar-942 (n=696 free DOF, 942 members) x 1024 independent load-case solves per GPU, FP64"
+# the workload description both arms print (the driver compares the two lines' `config`): nothing arm-specific in here
+CONFIG = {"workload": WORKLOAD, "batch_per_gpu": BATCH_PER_GPU, "n_free": 696, "n_member": 942, "mode": "independent K per system",
+          "timing": "GPU arm: device time per step (CUDA events), explicit 256 MB L2 flush (> 126 MB L2) between timed steps, "
+                    "outside the events; CPU arm: wall clock of a bounded sample of the same load cases on all host cores"}
 
 
 def load_cases(n_case: int, seed: int = 0):
@@ -88,7 +92,7 @@ def cpu_port_throughput(n_solve_per_core: int = 6):
         t0 = time.perf_counter()
         pool.map(_cpu_worker, jobs)
         dt = time.perf_counter() - t0
-    return {"value": cores * per / dt, "unit": UNIT, "cores": cores, "kind": "port",
+    return {"value": cores * per / dt, "unit": UNIT, "cores": cores, "kind": "port", "sample_solves": cores * per,
             "sample": f"{cores * per} of the 1024 bar-942 load cases, {cores} processes x {per} solves, "
                       f"OPENBLAS_NUM_THREADS=1 (oracle/truss_oracle.py: solve)",
             "serial_value": serial, "serial_sample": f"{n_serial} solves on one core, OpenBLAS default threads"}
@@ -107,11 +111,15 @@ def run_reference(args):
         vals.append(base["value"])
     v = float(np.mean(vals))
     base["value"] = v
+    # a "step" of this arm is the bounded sample (cores x 6 solves): ms_per_step is its measured wall time; the time the
+    # full 1024 x n_gpus batch would take at this rate is reported beside it, never instead of it
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * BATCH_PER_GPU * args.gpus / v, "higher_is_better": True,
+            "warmup": args.warmup, "ms_per_step": 1e3 * base["sample_solves"] / v, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH_PER_GPU,
-                       "note": "reference algorithm (oracle port) on the host cores; each step is a bounded sample"},
+            "config": dict(CONFIG),
+            "reference_run": {"what": "reference algorithm (oracle port: per-member Python loops + LAPACK dgesv) on the host cores",
+                              "solves_per_step": base["sample_solves"],
+                              "extrapolated_ms_for_the_full_batch": 1e3 * BATCH_PER_GPU * args.gpus / v},
             "cpu_baseline": base,
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -343,6 +351,32 @@ def run_gpu(args):
     prof = _lib.profile_read()
     _lib.profile_enable(False)
     prof_ms = sum(e0.elapsed_time(e1) for e0, e1 in evp)
+    # ---- sustained rate: back-to-back steps for --sustain-s seconds (no flush: a step cycles 350 MB of factor / K workspace
+    # through the 126 MB L2 on its own), one event pair around the whole run, clocks sampled during it
+    sustained = None
+    if args.sustain_s > 0:
+        n_sus = max(50, int(args.sustain_s / max(1e-6, (sum(e0.elapsed_time(e1) for e0, e1 in ev) / args.steps) * 1e-3)))
+        sus_sampler = ClockSampler(local)
+        if rank == 0:
+            sus_sampler.start()
+        barrier()
+        es0, es1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        es0.record(stream)
+        for _ in range(n_sus):
+            if graph is not None:
+                graph.replay()
+            else:
+                step()
+        drain()
+        es1.record(stream)
+        barrier()
+        ts_ = torch.tensor([es0.elapsed_time(es1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ts_, op=dist.ReduceOp.MAX)
+        sus_clocks = sus_sampler.stop() if rank == 0 else None
+        sustained = {"value": B * world * n_sus / (float(ts_.item()) * 1e-3), "unit": UNIT, "seconds": float(ts_.item()) * 1e-3,
+                     "steps": n_sus, "ms_per_step": float(ts_.item()) / n_sus, "clocks": sus_clocks,
+                     "what": "back-to-back steps without the L2 flush, one CUDA-event pair around the run, max over ranks"}
     dev_ms = sum(e0.elapsed_time(e1) for e0, e1 in ev) + ev_drain[0].elapsed_time(ev_drain[1])
     t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -484,13 +518,12 @@ def run_gpu(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "batch_per_gpu": B, "n_free": n, "n_member": M, "mode": "independent K per system",
-                   "pipeline": {0: "fused shared-memory kernel", 1: "tiled 64x64 block-sparse Cholesky",
-                                2: "two-sided block-band Cholesky (8x8 DMMA blocks, top-down and bottom-up warps meeting at a separator)" if ts_prog
-                                else "block-band Cholesky (16x16 blocks)"}[path],
-                   "l2": "explicit 256 MB flush (> 126 MB L2) between timed steps, outside the events",
-                   "launch": "CUDA graph replay of the step" if graph is not None else "plain stream launches",
-                   "multi_gpu": "contiguous block partition of the batch; " + gather_mode},
+        "config": dict(CONFIG),
+        "run": {"pipeline": {0: "fused shared-memory kernel", 1: "tiled 64x64 block-sparse Cholesky",
+                             2: "two-sided block-band Cholesky (8x8 DMMA blocks, top-down and bottom-up warps meeting at a separator)" if ts_prog
+                             else "block-band Cholesky (16x16 blocks)"}[path],
+                "launch": "CUDA graph replay of the step" if graph is not None else "plain stream launches",
+                "multi_gpu": "contiguous block partition of the batch; " + gather_mode},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "tb_solve_host (C ABI) with pinned host buffers", "steps": e2e_steps},
         "gpu_launches": int(launches),
@@ -507,6 +540,7 @@ def run_gpu(args):
         "roofline_stages": stages,
         "kernels": kernels,
         "cpu_baseline": cpu,
+        "sustained": sustained,
         "shared_k": shared,
         "configs": configs,
         "wall_s_timed_region": wall,
@@ -523,6 +557,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--sustain-s", type=float, default=2.0, help="seconds of back-to-back steps for the sustained figure (0: skip)")
     ap.add_argument("--configs", default="3,4,5", help="which of the other BASELINE.json configurations to measure as well")
     ap.add_argument("--headline-only", action="store_true",
                     help="skip the shared-factor extra (profiler runs: the launch list then holds the headline step only)")

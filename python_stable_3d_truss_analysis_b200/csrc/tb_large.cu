@@ -1153,9 +1153,9 @@ int tb_launch_large(const LargeArgs& a, int num_sm, cudaStream_t st, int path) {
   // recovery runs under the second half's factorisation.  Both halves use the two-warp band kernel (eight systems per
   // SM), so together they occupy the SMs like the unsplit batch.  Not under per-kernel profiling (one stream there).
   static const bool split_env = [] { const char* s = getenv("TB_LARGE_SPLIT"); return !(s && s[0] == '0'); }();
-  // (the two-sided kernel holds seven systems per SM: the halves of a batch of up to 7 x SMs run side by side)
-  if (split_env && !a.no_split && !tb_prof_on() && path == 2 && prep && !a.shared_k &&
-      (use_ts ? a.batch > num_sm * 4 && a.batch <= num_sm * 7 : a.NB <= 5 && a.batch > num_sm * 6 && a.batch <= num_sm * 8)) {
+  // (not for the two-sided kernel: its halves start together once both assemblies are done, nothing overlaps -- measured)
+  if (split_env && !a.no_split && !tb_prof_on() && path == 2 && prep && !a.shared_k && !use_ts && a.NB <= 5 &&
+      a.batch > num_sm * 6 && a.batch <= num_sm * 8) {
     static std::mutex split_mu;                // the second stream and its events are shared by every plan of the process:
     std::lock_guard<std::mutex> split_lock(split_mu);   // fork .. join is enqueued as one unit
     static cudaStream_t aux = nullptr;
