@@ -389,7 +389,7 @@ class Plan:
         for s in range(2):
             d = {name: fetch(s, w) for w, name in enumerate(self.TS_SIDE_ARRAYS)}
             d["colent"] = d["colent"].reshape(-1, 2)
-            d["colrec"] = fetch(s, 13).reshape(-1, 8)
+            d["colrec"] = fetch(s, 13).reshape(-1, 4)
             out["side"].append(d)
         for w, name in enumerate(self.TS_PROGRAM_ARRAYS):
             out[name] = fetch(0, len(self.TS_SIDE_ARRAYS) + w)

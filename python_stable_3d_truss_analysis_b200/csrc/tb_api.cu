@@ -662,8 +662,9 @@ extern "C" int tb_debug_assemble_host(tb_plan* p, const tb_batch_in* in, double*
   const int B = in->batch;
   if (B == 0) return TB_OK;
   if (!in->member_aed) return TB_ERR_NULL;                       // (explicit member properties only)
-  const size_t nnz = p->ent_row.size();
   const bool ts = p->ts && p->ts->ok;
+  const size_t nnz_map = p->ent_row.size();                      // scatter-map entries (the output's order)
+  const size_t nnz = ts ? p->ts->epos.size() : nnz_map;          // device order: the band program's schedule has holes
   const int64_t rowJ = (int64_t)p->nJ * p->dim, rowM3 = (int64_t)p->M * 3;
   if (!stride_ok(in->joint_stride, rowJ) || !stride_ok(in->member_stride, rowM3)) return TB_ERR_SIZE;
   std::lock_guard<std::mutex> pipe_lock(g_pipe_mu);
@@ -715,7 +716,8 @@ extern "C" int tb_debug_assemble_host(tb_plan* p, const tb_batch_in* in, double*
   if (rc) return rc;
   const std::vector<int32_t>& src = ts ? p->ts->ent_src : p->tile_ent;      // device order -> scatter-map entry
   for (int b = 0; b < B; ++b)
-    for (size_t q2 = 0; q2 < nnz; ++q2) kv_out[(size_t)b * nnz + src[q2]] = host[(size_t)b * nnz + q2];
+    for (size_t q2 = 0; q2 < nnz; ++q2)
+      if (src[q2] >= 0) kv_out[(size_t)b * nnz_map + src[q2]] = host[(size_t)b * nnz + q2];
   return TB_OK;
 }
 

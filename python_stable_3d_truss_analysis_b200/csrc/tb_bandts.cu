@@ -152,22 +152,12 @@ __device__ __forceinline__ double lds64(unsigned addr) {
   asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
   return v;
 }
-__device__ __forceinline__ double lds64_256(unsigned addr) {
-  double v;
-  asm volatile("ld.shared.f64 %0, [%1+256];" : "=d"(v) : "r"(addr));
-  return v;
-}
 // Operand loads of the products: not volatile, so that the scheduler can issue them well ahead of the MMAs.  Safe there:
 // nothing writes the ring between the previous column's last __syncwarp() and the stores of this column's staging, and
 // those stores take the accumulators these loads feed (a data dependence keeps every load in front of them).
 __device__ __forceinline__ double lds64_nv(unsigned addr) {
   double v;
   asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ double lds64_256_nv(unsigned addr) {
-  double v;
-  asm("ld.shared.f64 %0, [%1+256];" : "=d"(v) : "r"(addr));
   return v;
 }
 __device__ __forceinline__ double lds64_32_nv(unsigned addr) {
@@ -220,7 +210,8 @@ __global__ void __launch_bounds__(64, 7) k_band_ts(const TsArgs a) {
   double* sUS = sm_all + main0 + X_SCR;                                         // separator displacements (top -> bottom), top's scratch block
 
   const int qr = lane >> 2, qc = lane & 3;
-  const int cpo = ((qc >> 1) << 5) + (qr << 2) + ((qc & 1) << 1);               // this lane's accumulator pair inside a block
+  const int cpo = ((qc >> 1) << 5) + ((qr ^ (qc & 2)) << 2) + ((qc & 1) << 1);  // this lane's accumulator pair inside a block (ts_b8_off)
+  const unsigned sl1 = (lane & 8) ? 192u : 320u;                                // from this lane's operand element in slab 0 to the one in slab 1 (rows r ^ 2)
   const int nS = a.nS;
   const unsigned sm_u32 = smem_u32(sm);
   const unsigned ring_u32 = sm_u32 + lane * 8;                                  // byte address of this lane's operand element in slot 0
@@ -263,11 +254,10 @@ __global__ void __launch_bounds__(64, 7) k_band_ts(const TsArgs a) {
     const int32_t* dofp = S.rowdof + qr;
     const double* kvp = a.kv + (int64_t)b * a.nnz + S.ent0 + lane;
     const int32_t* epp = a.epos + S.ent0 + lane;
-    int4 recn = make_int4(0, 0, 0, 0), recm = make_int4(0, 0, 0, 0);
+    int4 recn = make_int4(0, 0, 0, 0);
     int dof_n = -1;
     if (ncol_tot > 0) {
       recn = __ldg(recp);
-      recm = __ldg(recp + 1);
       dof_n = __ldg(dofp);
     }
     TPH(0)
@@ -277,9 +267,9 @@ __global__ void __launch_bounds__(64, 7) k_band_ts(const TsArgs a) {
       const bool own = c < ncol_own;
       const bool xcol = side == 1 && !own;                                      // bottom side, separator column: products only
       if (side == 0 && c == ncol_own && two) pair_sync(1);                      // the bottom side's hand-over is complete
-      const unsigned nzc = (unsigned)recn.x & 511u, xm = ((unsigned)recn.x >> 18) & 511u;
-      const int ecnt = recn.y, lof = recn.z;
-      const unsigned long long pmask = (unsigned)recm.x | ((unsigned long long)(unsigned)recm.y << 32);   // live block products
+      const unsigned nzc = (unsigned)recn.x & 511u, xm = ((unsigned)recn.x >> 9) & 511u;
+      const int ecnt = (int)((unsigned)recn.x >> 18), lof = recn.y;
+      const unsigned long long pmask = (unsigned)recn.z | ((unsigned long long)(unsigned)recn.w << 32);   // live block products
       const int dof_c = dof_n;
       const double fr = (!xcol && dof_c >= 0) ? __ldg(fsys + dof_c) : 0.0;
       // K values of this block column (assembly pass, program order): in flight while the products run
@@ -288,7 +278,7 @@ __global__ void __launch_bounds__(64, 7) k_band_ts(const TsArgs a) {
 #pragma unroll
       for (int i = 0; i < TS_EPL; ++i) {
         kvr[i] = 0.0;
-        kpos[i] = 0;
+        kpos[i] = -1;
         if (lane + 32 * i < ecnt) {
           kvr[i] = __ldg(kvp + 32 * i);
           kpos[i] = __ldg(epp + 32 * i);
@@ -299,9 +289,8 @@ __global__ void __launch_bounds__(64, 7) k_band_ts(const TsArgs a) {
       kvp += ecnt;
       epp += ecnt;
       if (c + 1 < ncol_tot) {
-        recp += 2;
+        recp += 1;
         recn = __ldg(recp);
-        recm = __ldg(recp + 1);
         dofp += TS_BT;
         dof_n = __ldg(dofp);
       }
@@ -321,7 +310,7 @@ __global__ void __launch_bounds__(64, 7) k_band_ts(const TsArgs a) {
           const unsigned bits = (unsigned)(pmask >> base);                      // bit rb: product (d, rb) is live
           base += NB - d + 1;
           if (!(bits & 1u)) continue;                                           // L(c, c-d) structurally zero (uniform)
-          double b0 = lds64_nv(Q[d][d]), b1 = lds64_256_nv(Q[d][d]);
+          double b0 = lds64_nv(Q[d][d]), b1 = lds64_nv(Q[d][d] + sl1);
           {
             const double y0 = lds64_nv(Yq[d]), y1 = lds64_32_nv(Yq[d]);
             tp = fma(b0, y0, tp);
@@ -336,8 +325,8 @@ __global__ void __launch_bounds__(64, 7) k_band_ts(const TsArgs a) {
             const bool on0 = (bits >> rb) & 1u, on1 = e + 1 <= NB && ((bits >> (rb + 1)) & 1u);
             const int e1i = e + 1 <= NB ? e + 1 : e;
             double a00 = 0.0, a01 = 0.0, a10 = 0.0, a11 = 0.0;
-            if (on0) { a00 = lds64_nv(Q[e][d]); a01 = lds64_256_nv(Q[e][d]); }
-            if (on1) { a10 = lds64_nv(Q[e1i][d]); a11 = lds64_256_nv(Q[e1i][d]); }
+            if (on0) { a00 = lds64_nv(Q[e][d]); a01 = lds64_nv(Q[e][d] + sl1); }
+            if (on1) { a10 = lds64_nv(Q[e1i][d]); a11 = lds64_nv(Q[e1i][d] + sl1); }
             if (on0) dmma(acc[rb][0], acc[rb][1], a00, b0);
             if (on1) dmma(acc[rb + 1][0], acc[rb + 1][1], a10, b0);
             if (on0) dmma(acc[rb][0], acc[rb][1], a01, b1);
@@ -384,16 +373,21 @@ __global__ void __launch_bounds__(64, 7) k_band_ts(const TsArgs a) {
         }
         if (qc == 0) sT[qr] = fr - tp;
         __syncwarp();
+        {   // (the positions of a block column are distinct: all loads, then all stores)
+          double pv[TS_EPL];
 #pragma unroll
-        for (int i = 0; i < TS_EPL; ++i)
-          if (lane + 32 * i < ecnt) {
-            double v;
-            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(sm_u32 + (unsigned)kpos[i]));
-            v += kvr[i];
-            asm volatile("st.shared.f64 [%0], %1;" ::"r"(sm_u32 + (unsigned)kpos[i]), "d"(v) : "memory");
+          for (int i = 0; i < TS_EPL; ++i) {
+            pv[i] = 0.0;
+            if (kpos[i] >= 0) asm volatile("ld.shared.f64 %0, [%1];" : "=d"(pv[i]) : "r"(sm_u32 + (unsigned)kpos[i]));
           }
+#pragma unroll
+          for (int i = 0; i < TS_EPL; ++i)
+            if (kpos[i] >= 0) asm volatile("st.shared.f64 [%0], %1;" ::"r"(sm_u32 + (unsigned)kpos[i]), "d"(pv[i] + kvr[i]) : "memory");
+        }
         for (int e = 32 * TS_EPL + lane; e < ecnt; e += 32) {                   // rare: more than 32 * TS_EPL entries in this block column
-          const unsigned ad = sm_u32 + (unsigned)__ldg(epx + (e - 32 * TS_EPL - lane));
+          const int kp = __ldg(epx + (e - 32 * TS_EPL - lane));
+          if (kp < 0) continue;
+          const unsigned ad = sm_u32 + (unsigned)kp;
           double v;
           asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(ad));
           v += __ldg(kvx + (e - 32 * TS_EPL - lane));
@@ -408,14 +402,15 @@ __global__ void __launch_bounds__(64, 7) k_band_ts(const TsArgs a) {
         const unsigned slot1 = Q[1][1] - lane * 8;                              // block (c+1, c)
         double row[8];
         {
-          const unsigned src = (lane < 8 ? smem_u32(sScr) : slot1) + (lane & 7) * 32;
+          const unsigned blk = lane < 8 ? smem_u32(sScr) : slot1;
           const bool ld = lane < 8 || (lane >= 16 && lane < 24 && has1);
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
+            const unsigned src = blk + h * 256 + (((lane & 7) ^ (2 * h)) << 5);   // row (lane & 7), columns 4h .. 4h+3
             double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
             if (ld) {
-              asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v0), "=d"(v1) : "r"(src + h * 256));
-              asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v2), "=d"(v3) : "r"(src + h * 256 + 16));
+              asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v0), "=d"(v1) : "r"(src));
+              asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v2), "=d"(v3) : "r"(src + 16));
             }
             row[4 * h] = v0; row[4 * h + 1] = v1; row[4 * h + 2] = v2; row[4 * h + 3] = v3;
           }
@@ -443,14 +438,14 @@ __global__ void __launch_bounds__(64, 7) k_band_ts(const TsArgs a) {
 #pragma unroll
           for (int k = 0; k < 8; ++k) sScr[b8_off(k, i)] = row[k];             // W[k][i] = Z[i][k]
 #pragma unroll
-          for (int h = 0; h < 4; ++h) reinterpret_cast<double2*>(chunk + i * 8)[h] = make_double2(row[2 * h], row[2 * h + 1]);
+          for (int k = 0; k < 8; ++k) chunk[k * 8 + i] = row[k];                 // the chunk holds Z^T (the back substitution's lanes read it without bank conflicts)
         } else if (lane >= 16 && lane < 24) {
           if (has1) {
             const int i = lane - 16;
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-              asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(slot1 + h * 256 + i * 32), "d"(row[4 * h]), "d"(row[4 * h + 1]) : "memory");
-              asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(slot1 + h * 256 + i * 32 + 16), "d"(row[4 * h + 2]), "d"(row[4 * h + 3]) : "memory");
+              asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(slot1 + h * 256 + ((i ^ (2 * h)) << 5)), "d"(row[4 * h]), "d"(row[4 * h + 1]) : "memory");
+              asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(slot1 + h * 256 + ((i ^ (2 * h)) << 5) + 16), "d"(row[4 * h + 2]), "d"(row[4 * h + 3]) : "memory");
             }
 #pragma unroll
             for (int h = 0; h < 4; ++h)
@@ -464,7 +459,7 @@ __global__ void __launch_bounds__(64, 7) k_band_ts(const TsArgs a) {
           }
         }
         __syncwarp();
-        const double w0 = sScr[lane], w1 = sScr[32 + lane];
+        const double w0 = sScr[lane], w1 = sScr[32 + (lane ^ 8)];
 
         // ---------------- solves L(c+rb, c) = P(c+rb, c) Z, rb >= 2
         {
@@ -474,7 +469,7 @@ __global__ void __launch_bounds__(64, 7) k_band_ts(const TsArgs a) {
             f0[rb] = f1[rb] = 0.0;
             if (!((nzc >> rb) & 1u)) continue;
             f0[rb] = lds64(Q[rb][rb]);
-            f1[rb] = lds64_256(Q[rb][rb]);
+            f1[rb] = lds64(Q[rb][rb] + sl1);
           }
           __syncwarp();                                                          // every P block is read before any L overwrites it
 #pragma unroll
@@ -527,9 +522,10 @@ __global__ void __launch_bounds__(64, 7) k_band_ts(const TsArgs a) {
     fence_proxy_async();                                                         // this lane's factor stores / ring stores before the async proxy
     __syncwarp();
     auto issue = [&](int c, int stage) {
-      const int4 rc = __ldg(S.colrec + 2 * c);
-      mbar_expect_tx(&sBar[stage], (unsigned)rc.w);
-      bulk_g2s(sBuf + stage * a.chunk_max, Lsys + rc.z, (unsigned)rc.w, &sBar[stage]);
+      const int4 rc = __ldg(S.colrec + c);
+      const unsigned bytes = (unsigned)(TS_BE + TS_BT + TS_BE * __popc(((unsigned)rc.x >> 1) & 255u)) * 8u;
+      mbar_expect_tx(&sBar[stage], bytes);
+      bulk_g2s(sBuf + stage * a.chunk_max, Lsys + rc.y, bytes, &sBar[stage]);
     };
     if (lane == 0)
       for (int i = 0; i < NSTAGE; ++i)
@@ -557,16 +553,16 @@ __global__ void __launch_bounds__(64, 7) k_band_ts(const TsArgs a) {
       __syncwarp();
       asm volatile("ld.shared.f64 %0, [%1];" : "=d"(uprev) : "r"(Uq[1] - (unsigned)(2 * g) * 8u + (unsigned)col * 8u));
     }
-    unsigned maskn = ncb > 0 ? ((unsigned)__ldg(&S.colrec[2 * (ncb - 1)].x) & 511u) : 0u;
+    unsigned maskn = ncb > 0 ? ((unsigned)__ldg(&S.colrec[ncb - 1].x) & 511u) : 0u;
     int natn = ncb > 0 ? __ldg(S.rownat + (ncb - 1) * TS_BT + col) : -1;
     int stage = 0;
     const unsigned buf0 = smem_u32(sBuf);
-    const unsigned lane_l = (unsigned)((2 * g) * 8 + col) * 8u, lane_z = (unsigned)(col * 8 + 2 * g) * 8u;
+    const unsigned lane_l = (unsigned)((2 * g) * 8 + col) * 8u, lane_z = lane_l;      // L[2g][col], L[2g+1][col]; Z^T[2g][col], Z^T[2g+1][col]
     for (int c = ncb - 1; c >= 0; --c) {
       const unsigned mask = maskn;
       const int nat = natn;
       if (c > 0) {
-        maskn = ((unsigned)__ldg(&S.colrec[2 * (c - 1)].x) & 511u);
+        maskn = ((unsigned)__ldg(&S.colrec[c - 1].x) & 511u);
         natn = __ldg(S.rownat + (c - 1) * TS_BT + col);
       }
       mbar_wait(&sBar[stage], (phase >> stage) & 1u);
@@ -591,7 +587,7 @@ __global__ void __launch_bounds__(64, 7) k_band_ts(const TsArgs a) {
       double yc, z0, z1, l10 = 0.0, l11 = 0.0;
       asm volatile("ld.shared.f64 %0, [%1];" : "=d"(yc) : "r"(bufa + (unsigned)(TS_BE + col) * 8u));
       asm volatile("ld.shared.f64 %0, [%1];" : "=d"(z0) : "r"(bufa + lane_z));
-      asm volatile("ld.shared.f64 %0, [%1+8];" : "=d"(z1) : "r"(bufa + lane_z));
+      asm volatile("ld.shared.f64 %0, [%1+64];" : "=d"(z1) : "r"(bufa + lane_z));
       if ((mask >> 1) & 1u) {
         asm volatile("ld.shared.f64 %0, [%1];" : "=d"(l10) : "r"(bufa + (unsigned)(TS_BE + TS_BT) * 8u + lane_l));
         asm volatile("ld.shared.f64 %0, [%1+64];" : "=d"(l11) : "r"(bufa + (unsigned)(TS_BE + TS_BT) * 8u + lane_l));

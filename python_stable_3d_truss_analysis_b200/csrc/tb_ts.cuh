@@ -30,6 +30,8 @@
 constexpr int TS_BT = 8;       // block order: the native FP64 MMA shape (mma.m8n8k4)
 constexpr int TS_BE = 64;      // doubles per block
 constexpr int TS_NBX = 8;      // at most this many sub-diagonal blocks per block column
+constexpr int32_t TB_Q_DUMMY = (int32_t)0x80000000u;   // tq_first of a hole in the entry schedule: negative (the assembly pass's
+                                                         // first loop skips it) and absent from tq_multi (so does the second)
 constexpr int TS_EPL = 5;      // K values per lane prefetched at the top of a block column (more: loaded on the spot)
 
 struct TsSideDev {
@@ -37,14 +39,13 @@ struct TsSideDev {
   int ncol_tot;              // + separator columns (top: factorised after the hand-over; bottom: products only)
   int nb;                    // sub-diagonal blocks of this side's band view
   int ent0;                  // first entry of this side in program order (its block columns follow each other in kv / epos)
-  const int4* colrec;        // [2*ncol_tot] two int4 per block column, all the kernel reads at the top of a column:
-                             //              x = colmask | srcmask << 9 | xmask << 18
+  const int4* colrec;        // [ncol_tot] one int4 per block column, all the kernel reads at the top of a column:
+                             //              x = colmask | xmask << 9 | (number of K entries) << 18
                              //                  colmask: bit rb <=> block (c+rb, c) non-zero (bottom separator columns: blocks it contributes to)
-                             //                  srcmask: colmask of the columns that exist as factor columns (0 for the bottom's separator columns)
                              //                  xmask:   top separator columns: blocks handed over by the bottom side
-                             //              y = number of K entries, z = offset (doubles) of the factor chunk, w = its size in bytes
-                             //              second int4: x, y = bit i <=> block product i of the column is structurally non-zero, i the
-                             //              flat index of (distance d, block row rb) for NB = max(nb of both sides): d = 1..NB, rb = 0..NB-d
+                             //              y = offset (doubles) of the factor chunk [Z^T | y | blocks]; its size follows from colmask
+                             //              z, w = bit i <=> block product i of the column is structurally non-zero, i the flat index of
+                             //              (distance d, block row rb) for NB = max(nb of both sides): d = 1..NB, rb = 0..NB-d
   const int32_t* rowdof;     // [ncol_tot*8] DOF index of virtual row v, -1 on padding
   const int32_t* rownat;     // [ncol_tot*8] internal (natural) row of virtual row v, -1 on padding
 };
@@ -112,8 +113,10 @@ __host__ __device__ inline int ts_main_doubles(int nb, int chunk_max) {
 // rb(rb-1)/2 + j - 1 for the block created j columns ago and always reuses the slot of the dying block, which makes the
 // slot a function of c alone -- so the plan can resolve every K entry's staging address.
 __host__ __device__ inline int ts_ring_slot(int rb, int c) { return rb * (rb - 1) / 2 + (rb - 1 - c % rb); }
-// element (r, k) of an 8x8 block in operand-fragment layout: slab k / 4 holds [row 8][k 4]
-__host__ __device__ inline int ts_b8_off(int r, int k) { return ((k >> 2) << 5) + (r << 2) + (k & 3); }
+// element (r, k) of an 8x8 block in operand-fragment layout: slab k / 4 holds [row 8][k 4]; the rows of slab 1 are
+// permuted (r ^ 2) so that a warp's 16-byte stores of accumulator pairs (lane (qr, qc) -> elements (qr, 2qc), (qr, 2qc+1))
+// fall into eight different 16-byte bank groups per quarter warp: slab 0 takes bytes [0, 64) of every 128, slab 1 [64, 128)
+__host__ __device__ inline int ts_b8_off(int r, int k) { return ((k >> 2) << 5) + ((r ^ ((k >> 2) << 1)) << 2) + (k & 3); }
 
 struct tb_plan;
 int tb_ts_build(tb_plan* p);                  // host program (always), device mirrors when the plan has a device

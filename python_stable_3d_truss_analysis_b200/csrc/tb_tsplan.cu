@@ -261,29 +261,76 @@ int tb_ts_build(tb_plan* p) {
   ts->tq_ptr.assign(1, 0);
   for (int s = 0; s < 2; ++s) {
     TsSideHost& h = ts->side[s];
-    h.colrec.resize(2 * (size_t)h.ncol_tot);
+    h.colrec.resize((size_t)h.ncol_tot);
     h.colent.resize(h.ncol_tot);
     const int NBK = std::max(ts->side[0].nb, ts->side[1].nb);   // the kernel instantiation (its flat product list)
     const int mainsz = ts_main_doubles(h.nb, ts->chunk_max);
     for (int c = 0; c < h.ncol_tot; ++c) {
       const int e0 = (int)ts->epos.size();
-      for (const Ent& en : colent[s][c]) {
+      // Entry order inside the block column: the kernel adds entry e0 + 32 i + lane in round i with one 8-byte shared-memory
+      // read-modify-write per lane, which the hardware serves per half warp.  Entries are dealt out so that the 16 lanes of
+      // a half warp hit different 8-byte bank pairs (address / 8 mod 16) wherever the bucket sizes allow it; holes are dummy
+      // entries (epos -1, no contributions, never read).
+      std::vector<int32_t> pos(colent[s][c].size());
+      std::vector<std::vector<int>> bucket(16);
+      for (size_t i = 0; i < colent[s][c].size(); ++i) {
+        const Ent& en = colent[s][c][i];
         const int rb = en.vr / TS_BT - en.vc / TS_BT;
         const int slot_off = rb == 0 ? mainsz + TS_X_SCR : ts_ring_slot(rb, c) * TS_BE;
-        ts->epos.push_back((slot_off + ts_b8_off(en.vr % TS_BT, en.vc % TS_BT)) * 8);
-        ts->ent_src.push_back(en.src);
-        for (int64_t k = p->ent_ptr[en.src]; k < p->ent_ptr[en.src + 1]; ++k) {
-          const int loc = p->ctr_local[k], la = loc / (2 * d), lb = loc % (2 * d);
-          const int A = la / d, i = la % d, B = lb / d, j = lb % d;
-          const int lo = std::min(i, j), hi = std::max(i, j);
-          ts->tq_pack.push_back((p->ctr_member[k] << 4) | ((A != B) << 3) | (lo * d - lo * (lo - 1) / 2 + (hi - lo)));
+        pos[i] = (slot_off + ts_b8_off(en.vr % TS_BT, en.vc % TS_BT)) * 8;
+        bucket[(pos[i] >> 3) & 15].push_back((int)i);
+      }
+      // the fewest rounds the entries need; inside them, every bucket is spread over the half-rounds as evenly as possible
+      // (largest buckets first, each entry to the half-round holding the fewest entries of its bucket, then the fewest at all)
+      size_t halves = 2 * ((colent[s][c].size() + 31) / 32);
+      std::vector<std::vector<int>> half(halves);
+      // Measured on B200 (bar-942 x 1024): the bank-aware order takes 3 us off the band kernel (0.256 -> 0.253 ms) and adds
+      // 18 us to the assembly pass (0.064 -> 0.082 ms: its shared-memory reads of the member products lose the locality of
+      // the scatter map's order), so the scatter map's order is the default; TB_TS_BANK_ORDER=1 selects the other one.
+      static const bool bank_order = getenv("TB_TS_BANK_ORDER") && getenv("TB_TS_BANK_ORDER")[0] == '1';
+      if (!bank_order) {
+        for (size_t i = 0; i < colent[s][c].size(); ++i) half[i / 16].push_back((int)i);
+      } else {
+        std::vector<int> order(16);
+        std::iota(order.begin(), order.end(), 0);
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return bucket[a].size() > bucket[b].size(); });
+        std::vector<int> mult(halves);
+        for (int k : order) {
+          std::fill(mult.begin(), mult.end(), 0);
+          for (int i : bucket[k]) {
+            size_t bestp = halves;
+            for (size_t hr = 0; hr < halves; ++hr) {
+              if (half[hr].size() >= 16) continue;
+              if (bestp == halves || mult[hr] < mult[bestp] || (mult[hr] == mult[bestp] && half[hr].size() < half[bestp].size())) bestp = hr;
+            }
+            half[bestp].push_back(i);
+            mult[bestp]++;
+          }
         }
-        ts->tq_ptr.push_back((int32_t)ts->tq_pack.size());
+      }
+      for (size_t hr = 0; hr < halves; ++hr)
+        for (int k = 0; k < 16; ++k) {
+          const int i = k < (int)half[hr].size() ? half[hr][k] : -1;
+          if (i < 0) {
+            ts->epos.push_back(-1);
+            ts->ent_src.push_back(-1);
+          } else {
+            const Ent& en = colent[s][c][i];
+            ts->epos.push_back(pos[i]);
+            ts->ent_src.push_back(en.src);
+            for (int64_t k2 = p->ent_ptr[en.src]; k2 < p->ent_ptr[en.src + 1]; ++k2) {
+              const int loc = p->ctr_local[k2], la = loc / (2 * d), lb = loc % (2 * d);
+              const int A = la / d, i2 = la % d, B = lb / d, j2 = lb % d;
+              const int lo = std::min(i2, j2), hi = std::max(i2, j2);
+              ts->tq_pack.push_back((p->ctr_member[k2] << 4) | ((A != B) << 3) | (lo * d - lo * (lo - 1) / 2 + (hi - lo)));
+            }
+          }
+          ts->tq_ptr.push_back((int32_t)ts->tq_pack.size());
+        }
+      while (!ts->epos.empty() && (int)ts->epos.size() > e0 && ts->epos.back() < 0) {   // trailing holes of the last half-round
+        ts->epos.pop_back(); ts->ent_src.pop_back(); ts->tq_ptr.pop_back();
       }
       h.colent[c] = make_int2(e0, (int)ts->epos.size());
-      const bool has_chunk = c < (s == 0 ? h.ncol_tot : h.ncol_own);
-      h.colrec[2 * c] = make_int4((int)(h.colmask[c] | (h.srcmask[c] << 9) | (h.xmask[c] << 18)), (int)ts->epos.size() - e0, h.lofs[c],
-                                  has_chunk ? (h.lofs[c + 1] - h.lofs[c]) * 8 : 0);
       // block products of this column: L(c+rb, c-d) L(c, c-d)^T needs both blocks of column c-d
       uint64_t pm = 0;
       int idx = 0;
@@ -293,7 +340,8 @@ int tb_ts_build(tb_plan* p) {
           const uint32_t sm = h.srcmask[c - dd];
           if (((sm >> dd) & 1u) && ((sm >> (rb + dd)) & 1u)) pm |= (uint64_t)1 << idx;
         }
-      h.colrec[2 * c + 1] = make_int4((int)(uint32_t)pm, (int)(uint32_t)(pm >> 32), 0, 0);
+      h.colrec[c] = make_int4((int)(h.colmask[c] | (h.xmask[c] << 9) | ((uint32_t)((int)ts->epos.size() - e0) << 18)), h.lofs[c],
+                              (int)(uint32_t)pm, (int)(uint32_t)(pm >> 32));
     }
   }
   {   // first contribution inline, entries with several contributions listed separately (as tb_plan.cu does for the other orders)
@@ -302,7 +350,7 @@ int tb_ts_build(tb_plan* p) {
     ts->tq_multi.clear();
     for (size_t q = 0; q < nq; ++q) {
       const int cnt = ts->tq_ptr[q + 1] - ts->tq_ptr[q];
-      ts->tq_first[q] = (cnt > 0 ? ts->tq_pack[ts->tq_ptr[q]] : 0) | (cnt > 1 ? (int32_t)0x80000000u : 0);
+      ts->tq_first[q] = cnt > 0 ? (ts->tq_pack[ts->tq_ptr[q]] | (cnt > 1 ? (int32_t)0x80000000u : 0)) : TB_Q_DUMMY;
       if (cnt > 1) ts->tq_multi.push_back((int32_t)q);
     }
   }
@@ -374,7 +422,7 @@ extern "C" int tb_plan_ts_info(const tb_plan* p, int32_t* out /*[16]*/) {
 }
 
 // which = 0 colmask, 1 srcmask, 2 xmask, 3 colent (2 ints each), 4 rowdof, 5 rownat, 6 lofs (per side); 7 epos, 8 ent_src,
-// 9 tq_first, 10 tq_multi, 11 tq_ptr, 12 tq_pack (whole program, side ignored); 13 colrec (8 ints per block column, per side).  Returns the element count (ints); copies
+// 9 tq_first, 10 tq_multi, 11 tq_ptr, 12 tq_pack (whole program, side ignored); 13 colrec (4 ints per block column, per side).  Returns the element count (ints); copies
 // when out != NULL.
 extern "C" int64_t tb_plan_ts_array(const tb_plan* p, int32_t side, int32_t which, int32_t* out) {
   if (!p || !p->ts || !p->ts->ok || side < 0 || side > 1) return -1;

@@ -56,9 +56,10 @@ def check(plan, prog, arrays, dim):
     Kff = K[mask][:, mask]
     row, col, ptr, mem, loc = plan.scatter()
     src = prog["ent_src"]
-    assert sorted(src.tolist()) == list(range(len(row))), "every scatter-map entry is assembled exactly once"
+    live = src >= 0                     # (holes of the entry schedule carry -1)
+    assert sorted(src[live].tolist()) == list(range(len(row))), "every scatter-map entry is assembled exactly once"
     got = np.zeros(len(row))
-    got[src] = dbg["kv"]
+    got[src[live]] = dbg["kv"][live]
     prods = [ts_replay.member_products(dim, joints, conn[m], aed[m][0], aed[m][1]) for m in range(conn.shape[0])]
     want_k = np.zeros(len(row))
     mag = np.zeros(len(row))

@@ -48,6 +48,9 @@ def assemble_program_order(prog, dim, xyz, conn, aed):
     kv = np.zeros(len(ptr) - 1)
     multi = set(int(q) for q in prog["tq_multi"])
     for q in range(len(kv)):
+        if ptr[q + 1] == ptr[q]:          # hole of the bank-conflict-free entry schedule: skipped by both loops of the pass
+            assert first[q] == -2**31 and q not in multi
+            continue
         if q in multi:
             assert first[q] < 0
             v = 0.0
@@ -83,7 +86,7 @@ def _unpack_pos(epos, c, mainsz):
             rb += 1
         assert slot == rb * (rb - 1) // 2 + (rb - 1 - c % rb), "entry staged in a slot the ring does not give to this block"
     k = ((off >> 5) << 2) | (off & 3)
-    r = (off >> 2) & 7
+    r = ((off >> 2) & 7) ^ ((off >> 5) << 1)      # rows of the second k-slab are stored permuted (csrc/tb_ts.cuh ts_b8_off)
     return rb, r, k
 
 
@@ -129,8 +132,9 @@ def replay(prog, dim, xyz, conn, aed, force, n_dof):
         # the kernel takes the liveness of every block product from the column record (bit = flat index of (d, rb) for NB =
         # the wider side's band): it must be exactly "both blocks of column c-d exist"
         rec = d["colrec"][c]
-        assert int(rec[0]) == (nzc | (srcc << 9) | (xm << 18)) and int(rec[1]) == int(d["colent"][c][1] - d["colent"][c][0])
-        pmask = (int(rec[4]) & 0xffffffff) | ((int(rec[5]) & 0xffffffff) << 32)
+        assert (int(rec[0]) & 0xffffffff) == (nzc | (xm << 9) | (int(d["colent"][c][1] - d["colent"][c][0]) << 18))
+        assert int(rec[1]) == int(d["lofs"][c])
+        pmask = (int(rec[2]) & 0xffffffff) | ((int(rec[3]) & 0xffffffff) << 32)
         idx, want = 0, 0
         for dd in range(1, NBK + 1):
             for rb in range(0, NBK - dd + 1):
@@ -172,7 +176,13 @@ def replay(prog, dim, xyz, conn, aed, force, n_dof):
                 tp += Zx[J]
             # staging: block rb in the slot of the dead block (c, c-rb)
             stage = {rb: np.zeros((BT, BT)) for rb in range(nb + 1) if (nzc >> rb) & 1}
-            for e in range(int(d["colent"][c][0]), int(d["colent"][c][1])):
+            e_lo, e_hi = int(d["colent"][c][0]), int(d["colent"][c][1])
+            nlive = int(np.sum(epos[e_lo:e_hi] >= 0))
+            assert e_hi - e_lo <= 32 * ((nlive + 31) // 32), "the entry schedule takes more rounds than the entries need"
+            for e in range(e_lo, e_hi):
+                if epos[e] < 0:
+                    assert prog["ent_src"][e] < 0
+                    continue
                 rb, r, k = _unpack_pos(int(epos[e]), c, main_doubles(S.nb, info["chunk_max"]))
                 assert rb in stage, "entry in a block the mask calls zero"
                 assert stage[rb][r, k] == 0.0, "two entries in one position"
