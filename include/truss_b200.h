@@ -174,6 +174,17 @@ typedef struct {
 int tb_solve(tb_plan* plan, const tb_batch_in* in, const tb_batch_out* out, void* cuda_stream);
 int tb_solve_host(tb_plan* plan, const tb_batch_in* in, const tb_batch_out* out);
 
+/* Pipelined form of tb_solve_host for callers that stream batches (a load-case sweep, the dataset generator's solve
+ * site generate.py:354-357 called batch after batch): the call enqueues the batch -- host-to-device copies, kernels,
+ * device-to-host copies, each on its own stream -- and returns at once with a ticket; tb_host_wait(plan, ticket) blocks
+ * until that call's results are in its `out` buffers.  Consecutive calls use three staging areas in turn, so the
+ * copies of one batch overlap the kernels of its neighbours (PCIe is full duplex).  At most three calls are in flight per
+ * plan (one uploading, one computing, one downloading): a fourth submission first waits for the oldest one.  `in` / `out` buffers must stay valid (and should be
+ * page-locked, tb_pinned_alloc) until the ticket has been waited for; tickets complete in submission order.  The
+ * blocking *_host calls and tb_plan_destroy first wait for every pipelined call of the plan. */
+int tb_solve_host_async(tb_plan* plan, const tb_batch_in* in, const tb_batch_out* out, uint64_t* ticket);
+int tb_host_wait(tb_plan* plan, uint64_t ticket);
+
 /* B load cases of ONE truss: `for f in F: truss.SetForces(f); truss.Solve()` (truss.py:329-364 called B times on
  * the same joints and members).  joint_stride and member_stride (or gene_stride) must be 0; only `force` varies.
  * On the band path the stiffness matrix is assembled and factorised ONCE and every load case runs the two triangular

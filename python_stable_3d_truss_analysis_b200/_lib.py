@@ -148,7 +148,7 @@ class TbRaggedIn(C.Structure):
 
 
 EXPORTS = ["tb_plan_create", "tb_plan_destroy", "tb_plan_query", "tb_plan_set_path", "tb_plan_get_maps",
-           "tb_plan_get_scatter", "tb_solve", "tb_solve_host", "tb_solve_loadcases", "tb_solve_loadcases_host", "tb_fitness", "tb_fitness_host", "tb_solve_ragged",
+           "tb_plan_get_scatter", "tb_solve", "tb_solve_host", "tb_solve_host_async", "tb_host_wait", "tb_solve_loadcases", "tb_solve_loadcases_host", "tb_fitness", "tb_fitness_host", "tb_solve_ragged",
            "tb_solve_ragged_host", "tb_ga_init", "tb_ga_step", "tb_augment_ragged", "tb_pinned_alloc", "tb_pinned_free", "tb_small_path_limits", "tb_fp64_peak", "tb_rsqrt_probe", "tb_profile_enable", "tb_profile_read",
            "tb_launch_count", "tb_strerror", "tb_version", "tb_small_path_fits", "tb_debug_assemble_host", "tb_plan_ts_info", "tb_plan_ts_array", "tb_ts_phase_read"]
 
@@ -175,6 +175,8 @@ def lib():
     L.tb_plan_get_scatter.argtypes = [vp, vp, vp, vp, vp, vp]
     L.tb_solve.argtypes = [vp, C.POINTER(TbBatchIn), C.POINTER(TbBatchOut), vp]
     L.tb_solve_host.argtypes = [vp, C.POINTER(TbBatchIn), C.POINTER(TbBatchOut)]
+    L.tb_solve_host_async.argtypes = [vp, C.POINTER(TbBatchIn), C.POINTER(TbBatchOut), C.POINTER(C.c_uint64)]
+    L.tb_host_wait.argtypes = [vp, C.c_uint64]
     L.tb_solve_loadcases.argtypes = [vp, C.POINTER(TbBatchIn), C.POINTER(TbBatchOut), vp]
     L.tb_solve_loadcases_host.argtypes = [vp, C.POINTER(TbBatchIn), C.POINTER(TbBatchOut)]
     L.tb_fitness.argtypes = [vp, C.POINTER(TbBatchIn), dbl, dbl, C.POINTER(TbFitOut), C.POINTER(TbBatchOut), vp]
@@ -228,30 +230,29 @@ def _np(a, dtype, shape=None):
     return a
 
 
+class _PinnedOwner:
+    """Frees a page-locked allocation when the last view of it is gone."""
+
+    def __init__(self, addr):
+        self.addr = addr
+
+    def __del__(self):
+        try:
+            lib().tb_pinned_free(self.addr)
+        except Exception:
+            pass
+
+
 def pinned_empty(shape, dtype=np.float64):
-    """numpy array backed by page-locked memory from the library (freed with the array)."""
+    """numpy array backed by page-locked memory from the library.  The allocation is owned by the ctypes buffer at the
+    bottom of the array's ``base`` chain, so it is freed when the array and every view of it have been collected."""
     dtype = np.dtype(dtype)
     n = int(np.prod(shape)) * dtype.itemsize
     p = C.c_void_p()
     check(lib().tb_pinned_alloc(C.byref(p), max(n, 1)))
     buf = (C.c_char * max(n, 1)).from_address(p.value)
-    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
-
-    class _Owner:
-        def __init__(self, addr):
-            self.addr = addr
-
-        def __del__(self):
-            try:
-                lib().tb_pinned_free(self.addr)
-            except Exception:
-                pass
-
-    _PINNED_OWNERS[p.value] = _Owner(p.value)
-    return arr
-
-
-_PINNED_OWNERS = {}
+    buf._owner = _PinnedOwner(p.value)
+    return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
 
 
 def fp64_peak(which: int, iters: int = 4096):
@@ -441,6 +442,34 @@ class Plan:
         fn = lib().tb_solve_loadcases_host if shared_factor else lib().tb_solve_host
         check(fn(self._h, C.byref(bi), C.byref(bo)))
         return out
+
+    def solve_host_async(self, B, xyz, force, aed=None, gene=None, type_table=None, want=("u", "ext", "axial", "weight"),
+                         out=None):
+        """Pipelined tb_solve_host (tb_solve_host_async): enqueues the batch and returns ``(ticket, out)`` at once;
+        ``host_wait(ticket)`` blocks until ``out`` holds the results.  Three calls may be in flight per plan.  Buffers should
+        be page-locked (``pinned_empty``) and must not be touched before the wait."""
+        keep = []
+        bi = self._batch_in(B, xyz, aed, gene, type_table, force, keep)
+        out = {} if out is None else out
+        shp = {"u": (B, self.N), "ext": (B, self.N), "axial": (B, self.M), "weight": (B,)}
+        for k in want:
+            if k not in out:
+                out[k] = pinned_empty(shp[k], np.float64)
+        if "info" not in out:
+            out["info"] = pinned_empty((B,), np.int32)
+        bo = TbBatchOut(_ptr(out.get("u")), _ptr(out.get("ext")), _ptr(out.get("axial")), _ptr(out.get("weight")),
+                        _ptr(out["info"]))
+        ticket = C.c_uint64(0)
+        check(lib().tb_solve_host_async(self._h, C.byref(bi), C.byref(bo), C.byref(ticket)))
+        self._async_keep = getattr(self, "_async_keep", {})
+        self._async_keep[ticket.value] = (keep, out, xyz, force, aed, gene, type_table)   # inputs stay alive until the wait
+        return ticket.value, out
+
+    def host_wait(self, ticket):
+        check(lib().tb_host_wait(self._h, C.c_uint64(int(ticket))))
+        keep = getattr(self, "_async_keep", {})
+        for t in [t for t in keep if t <= ticket]:
+            del keep[t]
 
     def fitness_host(self, B, xyz, force, gene, type_table, allow_stress, allow_displace, aed=None, full=False,
                      out=None):

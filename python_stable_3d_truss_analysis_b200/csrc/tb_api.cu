@@ -276,6 +276,7 @@ constexpr int TB_MAX_DEVICES = 64;
 struct HostPipe {
   bool ready = false;
   cudaStream_t comp = nullptr;
+  cudaStream_t ain = nullptr, aout = nullptr;  // H2D / D2H streams of the pipelined calls (tb_solve_host_async)
   cudaStream_t copy[TB_HOST_STREAMS] = {};
   cudaEvent_t ev_in[TB_HOST_STREAMS] = {}, ev_out[TB_HOST_STREAMS] = {};
 };
@@ -288,6 +289,8 @@ HostPipe* host_pipe() {                        // call with g_pipe_mu held
   HostPipe& hp = g_pipes[dev & (TB_MAX_DEVICES - 1)];
   if (!hp.ready) {
     if (cudaStreamCreateWithFlags(&hp.comp, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaStreamCreateWithFlags(&hp.ain, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaStreamCreateWithFlags(&hp.aout, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
     for (int i = 0; i < TB_HOST_STREAMS; ++i) {
       if (cudaStreamCreateWithFlags(&hp.copy[i], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
       if (cudaEventCreateWithFlags(&hp.ev_in[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
@@ -300,13 +303,24 @@ HostPipe* host_pipe() {                        // call with g_pipe_mu held
 void host_pipe_drain(HostPipe* hp) {           // after an error: nothing of the call may still touch the caller's buffers
   if (!hp) return;
   cudaStreamSynchronize(hp->comp);
+  cudaStreamSynchronize(hp->ain);
+  cudaStreamSynchronize(hp->aout);
   for (int i = 0; i < TB_HOST_STREAMS; ++i) cudaStreamSynchronize(hp->copy[i]);
   (void)cudaGetLastError();
 }
 int stride_ok(int64_t stride, int64_t row) { return stride == 0 || stride == row; }
 
 int run_plan_host_locked(tb_plan* p, const tb_batch_in* in, const tb_batch_out* out, const tb_fit_out* fit, double allow_s,
-                         double allow_d, int shared_k, HostPipe* hp);
+                         double allow_d, int shared_k, HostPipe* hp, int async_slot = -1);
+
+// every pipelined call of this plan has completed (its results are in the caller's buffers)
+int async_drain(tb_plan* p) {
+  while (p->async_completed < p->async_submitted) {
+    TB_CUDA(cudaEventSynchronize(p->async_done[p->async_completed % TB_ASYNC_SLOTS]));
+    p->async_completed++;
+  }
+  return TB_OK;
+}
 
 // Host entry points: serialised per process (g_pipe_mu: helper streams, events) and per plan (p->mu: staging arena,
 // workspace); on an error the helper streams are drained before the code is returned.
@@ -320,6 +334,8 @@ int run_plan_host(tb_plan* p, const tb_batch_in* in, const tb_batch_out* out, co
   std::lock_guard<std::mutex> plan_lock(p->mu);
   HostPipe* hp = host_pipe();
   if (!hp) return TB_ERR_ALLOC;
+  rc = async_drain(p);                          // (the blocking calls share the compute stream and the workspace with the pipelined ones)
+  if (rc) return rc;
   if (p->path != 0) {
     rc = ws_acquire(p, hp->comp);
     if (rc) return rc;
@@ -330,9 +346,46 @@ int run_plan_host(tb_plan* p, const tb_batch_in* in, const tb_batch_out* out, co
   return rc;
 }
 
+// Pipelined host call: enqueue H2D (stream ain) -> kernels (comp) -> D2H (aout) and return; consecutive calls use the
+// async staging arenas in turn, so the copies of one call overlap the kernels of its neighbours.  At most TB_ASYNC_SLOTS
+// calls are in flight (one uploading, one computing, one downloading): a further submission first waits for the oldest.
+int run_plan_host_async(tb_plan* p, const tb_batch_in* in, const tb_batch_out* out, uint64_t* ticket) {
+  int rc = check_batch_in(p, in);
+  if (rc) return rc;
+  rc = check_device(p);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> pipe_lock(g_pipe_mu);
+  std::lock_guard<std::mutex> plan_lock(p->mu);
+  HostPipe* hp = host_pipe();
+  if (!hp) return TB_ERR_ALLOC;
+  const int slot = (int)(p->async_submitted % TB_ASYNC_SLOTS);
+  if (p->async_submitted - p->async_completed >= (uint64_t)TB_ASYNC_SLOTS) {      // the slot's previous call
+    TB_CUDA(cudaEventSynchronize(p->async_done[p->async_completed % TB_ASYNC_SLOTS]));
+    p->async_completed++;
+  }
+  for (cudaEvent_t* e : {&p->async_in[slot], &p->async_k[slot], &p->async_done[slot]})
+    if (!*e) TB_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+  if (p->path != 0) {
+    rc = ws_acquire(p, hp->comp);
+    if (rc) return rc;
+  }
+  rc = in->batch == 0 ? TB_OK : run_plan_host_locked(p, in, out, nullptr, 0.0, 0.0, 0, hp, slot);
+  if (rc) {
+    host_pipe_drain(hp);
+    p->async_completed = p->async_submitted;
+    return rc;
+  }
+  if (p->path != 0) rc = ws_release(p, hp->comp);
+  TB_CUDA(cudaEventRecord(p->async_done[slot], hp->aout));
+  if (ticket) *ticket = p->async_submitted;
+  p->async_submitted++;
+  return rc;
+}
+
 int run_plan_host_locked(tb_plan* p, const tb_batch_in* in, const tb_batch_out* out, const tb_fit_out* fit, double allow_s,
-                         double allow_d, int shared_k, HostPipe* hp) {
+                         double allow_d, int shared_k, HostPipe* hp, int async_slot) {
   int rc = 0;
+  const bool async = async_slot >= 0;
   const int B = in->batch;
   if (B == 0) return TB_OK;
   const int64_t rowJ = (int64_t)p->nJ * p->dim, rowM3 = (int64_t)p->M * 3, rowM = p->M, rowN = p->N;
@@ -353,11 +406,13 @@ int run_plan_host_locked(tb_plan* p, const tb_batch_in* in, const tb_batch_out* 
   add(out->u ? (size_t)B * rowN * 8 : 0); add(out->ext ? (size_t)B * rowN * 8 : 0);
   add(out->axial ? (size_t)B * rowM * 8 : 0); add(out->weight ? (size_t)B * 8 : 0);
   add((size_t)B * 4); add(fit ? (size_t)B * 8 : 0); add(fit ? (size_t)B * 2 : 0);
-  rc = arena_reserve(&p->stage_dev, &p->stage_dev_bytes, need + 4096);
+  void** arena = async ? &p->stage_async[async_slot] : &p->stage_dev;
+  size_t* arena_bytes = async ? &p->stage_async_bytes[async_slot] : &p->stage_dev_bytes;
+  rc = arena_reserve(arena, arena_bytes, need + 4096);
   if (rc) return rc;
 
   cudaStream_t st = hp->comp;
-  char* cur = (char*)p->stage_dev;
+  char* cur = (char*)*arena;
   tb_batch_in din = *in;
   double* dxyz = take<double>(cur, nxyz);
   double* df = take<double>(cur, nf);
@@ -409,6 +464,7 @@ int run_plan_host_locked(tb_plan* p, const tb_batch_in* in, const tb_batch_out* 
     // with little to copy back (fitness only, weights only) one launch over the whole batch is faster
     const size_t d2h_bytes = ((out->u ? rowN : 0) + (out->ext ? rowN : 0) + (out->axial ? rowM : 0)) * (size_t)B * 8;
     if (want == 0 && p->path != 0 && d2h_bytes < ((size_t)4 << 20)) nch = 1;
+    if (async) nch = 1;                        // a pipelined call is one chunk: its neighbours hide its copies
   }
   // chunk boundaries: equal parts (a 3:1 split, to shrink the D2H of the last chunk that nothing hides, measured slower:
   // 0.89 ms against 0.82 ms for 1024 bar-942 systems -- the larger first wave costs more than the copy saves)
@@ -422,23 +478,25 @@ int run_plan_host_locked(tb_plan* p, const tb_batch_in* in, const tb_batch_out* 
   }
   cudaStream_t comp = st;                      // compute stream
   cudaStream_t* cps = hp->copy;                // copy streams, one per chunk
+  cudaStream_t cin = async ? hp->ain : comp;   // where a one-chunk call's inputs / results travel
+  cudaStream_t cout = async ? hp->aout : comp;
   cudaEvent_t* ev_in = hp->ev_in;
   cudaEvent_t* ev_out = hp->ev_out;
   const bool sx = in->joint_stride == 0, sf = in->force_stride == 0;
   const bool sm_ = in->member_aed ? in->member_stride == 0 : in->gene_stride == 0;
   // shared inputs first, on the compute stream
-  if (sx) TB_CUDA(cudaMemcpyAsync(dxyz, in->joint_xyz, nxyz * 8, cudaMemcpyHostToDevice, comp));
-  if (sf) TB_CUDA(cudaMemcpyAsync(df, in->force, nf * 8, cudaMemcpyHostToDevice, comp));
+  if (sx) TB_CUDA(cudaMemcpyAsync(dxyz, in->joint_xyz, nxyz * 8, cudaMemcpyHostToDevice, cin));
+  if (sf) TB_CUDA(cudaMemcpyAsync(df, in->force, nf * 8, cudaMemcpyHostToDevice, cin));
   if (in->member_aed) {
-    if (sm_) TB_CUDA(cudaMemcpyAsync(daed, in->member_aed, naed * 8, cudaMemcpyHostToDevice, comp));
+    if (sm_) TB_CUDA(cudaMemcpyAsync(daed, in->member_aed, naed * 8, cudaMemcpyHostToDevice, cin));
   } else {
-    if (sm_) TB_CUDA(cudaMemcpyAsync(dgene, in->gene, ngene * 4, cudaMemcpyHostToDevice, comp));
-    TB_CUDA(cudaMemcpyAsync(dtab, in->type_table, ntab * 8, cudaMemcpyHostToDevice, comp));
+    if (sm_) TB_CUDA(cudaMemcpyAsync(dgene, in->gene, ngene * 4, cudaMemcpyHostToDevice, cin));
+    TB_CUDA(cudaMemcpyAsync(dtab, in->type_table, ntab * 8, cudaMemcpyHostToDevice, cin));
   }
   for (int j = 0; j < nch; ++j) {              // every chunk's inputs are queued at once, each on its copy stream
     const int b0 = cb[j], nb = cb[j + 1] - cb[j];
     if (nb <= 0) continue;
-    cudaStream_t sj = nch == 1 ? comp : cps[j];
+    cudaStream_t sj = nch == 1 ? cin : cps[j];
     if (!sx) TB_CUDA(cudaMemcpyAsync(dxyz + (size_t)b0 * rowJ, in->joint_xyz + (size_t)b0 * rowJ, (size_t)nb * rowJ * 8, cudaMemcpyHostToDevice, sj));
     if (!sf) TB_CUDA(cudaMemcpyAsync(df + (size_t)b0 * rowN, in->force + (size_t)b0 * rowN, (size_t)nb * rowN * 8, cudaMemcpyHostToDevice, sj));
     if (in->member_aed) {
@@ -448,10 +506,14 @@ int run_plan_host_locked(tb_plan* p, const tb_batch_in* in, const tb_batch_out* 
     }
     if (nch > 1) TB_CUDA(cudaEventRecord(ev_in[j], sj));
   }
+  if (async) {
+    TB_CUDA(cudaEventRecord(p->async_in[async_slot], cin));
+    TB_CUDA(cudaStreamWaitEvent(comp, p->async_in[async_slot], 0));
+  }
   for (int j = 0; j < nch; ++j) {
     const int b0 = cb[j], nb = cb[j + 1] - cb[j];
     if (nb <= 0) continue;
-    cudaStream_t sj = nch == 1 ? comp : cps[j];
+    cudaStream_t sj = nch == 1 ? cout : cps[j];
     if (nch > 1) TB_CUDA(cudaStreamWaitEvent(comp, ev_in[j], 0));
     if (nch == 1 && p->path != 0) {
       rc = run_plan_unlocked(p, &din, &dout, fit ? &dfit : nullptr, allow_s, allow_d, comp, shared_k);   // handles the workspace cap itself
@@ -462,6 +524,10 @@ int run_plan_host_locked(tb_plan* p, const tb_batch_in* in, const tb_batch_out* 
     if (nch > 1) {
       TB_CUDA(cudaEventRecord(ev_out[j], comp));
       TB_CUDA(cudaStreamWaitEvent(sj, ev_out[j], 0));
+    }
+    if (async) {
+      TB_CUDA(cudaEventRecord(p->async_k[async_slot], comp));
+      TB_CUDA(cudaStreamWaitEvent(cout, p->async_k[async_slot], 0));
     }
     if (out->u) TB_CUDA(cudaMemcpyAsync(out->u + (size_t)b0 * rowN, dout.u + (size_t)b0 * rowN, (size_t)nb * rowN * 8, cudaMemcpyDeviceToHost, sj));
     if (out->ext) TB_CUDA(cudaMemcpyAsync(out->ext + (size_t)b0 * rowN, dout.ext + (size_t)b0 * rowN, (size_t)nb * rowN * 8, cudaMemcpyDeviceToHost, sj));
@@ -474,6 +540,7 @@ int run_plan_host_locked(tb_plan* p, const tb_batch_in* in, const tb_batch_out* 
       if (fit->info) TB_CUDA(cudaMemcpyAsync(fit->info + b0, dinfo + b0, (size_t)nb * 4, cudaMemcpyDeviceToHost, sj));
     }
   }
+  if (async) return TB_OK;                     // completion: the event the caller records on `cout`
   TB_CUDA(cudaStreamSynchronize(comp));
   if (nch > 1)
     for (int j = 0; j < nch; ++j) TB_CUDA(cudaStreamSynchronize(cps[j]));
@@ -528,6 +595,21 @@ extern "C" int tb_solve(tb_plan* plan, const tb_batch_in* in, const tb_batch_out
 
 extern "C" int tb_solve_host(tb_plan* plan, const tb_batch_in* in, const tb_batch_out* out) {
   return run_plan_host(plan, in, out, nullptr, 0.0, 0.0);
+}
+
+extern "C" int tb_solve_host_async(tb_plan* plan, const tb_batch_in* in, const tb_batch_out* out, uint64_t* ticket) {
+  return run_plan_host_async(plan, in, out, ticket);
+}
+
+extern "C" int tb_host_wait(tb_plan* plan, uint64_t ticket) {
+  if (!plan) return TB_ERR_NULL;
+  std::lock_guard<std::mutex> plan_lock(plan->mu);
+  if (ticket >= plan->async_submitted) return TB_ERR_SIZE;
+  while (plan->async_completed <= ticket) {
+    TB_CUDA(cudaEventSynchronize(plan->async_done[plan->async_completed % TB_ASYNC_SLOTS]));
+    plan->async_completed++;
+  }
+  return TB_OK;
 }
 
 namespace {

@@ -48,6 +48,9 @@ void tb_prof_end(int slot, cudaStream_t st);
 // ---------------------------------------------------------------------------------------------
 // Plan: host-built integer maps for one topology (truss.py:307-326), mirrored on the device.
 // ---------------------------------------------------------------------------------------------
+// calls of tb_solve_host_async in flight per plan: one uploading, one computing, one downloading
+constexpr int TB_ASYNC_SLOTS = 3;
+
 struct tb_plan {
   int dim = 0, nJ = 0, M = 0, N = 0, n = 0, s = 0;
   int n_resist = 0, stable = 0, path = 0, n_pad = 0, nt = 0;
@@ -147,6 +150,12 @@ struct tb_plan {
   size_t stage_dev_bytes = 0;
   void* stage_pinned = nullptr;
   size_t stage_pinned_bytes = 0;
+  // pipelined host calls (tb_solve_host_async): TB_ASYNC_SLOTS more staging arenas used in turn by consecutive calls,
+  // the events that chain a call's copies and kernels, and the ticket counters (submitted / known to be complete)
+  void* stage_async[TB_ASYNC_SLOTS] = {};
+  size_t stage_async_bytes[TB_ASYNC_SLOTS] = {};
+  cudaEvent_t async_in[TB_ASYNC_SLOTS] = {}, async_k[TB_ASYNC_SLOTS] = {}, async_done[TB_ASYNC_SLOTS] = {};
+  uint64_t async_submitted = 0, async_completed = 0;
 };
 
 // ---------------------------------------------------------------------------------------------

@@ -538,6 +538,13 @@ extern "C" void tb_plan_destroy(tb_plan* p) {
   if (p->ws_event) cudaEventDestroy(p->ws_event);
   cudaFree(p->ws);
   cudaFree(p->stage_dev);
+  for (int i = 0; i < TB_ASYNC_SLOTS; ++i) {
+    if (p->async_done[i]) cudaEventSynchronize(p->async_done[i]);     // (a pipelined call may still be in flight)
+    cudaFree(p->stage_async[i]);
+    if (p->async_in[i]) cudaEventDestroy(p->async_in[i]);
+    if (p->async_k[i]) cudaEventDestroy(p->async_k[i]);
+    if (p->async_done[i]) cudaEventDestroy(p->async_done[i]);
+  }
   if (p->stage_pinned) cudaFreeHost(p->stage_pinned);
   delete p;
 }

@@ -609,3 +609,39 @@ def test_one_process_two_devices():
         plan1.solve_host(1, xyz, force, aed=aed)
     assert ei.value.code == -9
     torch.cuda.set_device(0)
+
+
+@pytest.mark.gpu
+def test_pipelined_host_calls_match_blocking_calls():
+    """tb_solve_host_async / tb_host_wait: five batches streamed with two in flight give the bits of tb_solve_host,
+    tickets complete in order, a blocking call in between drains the pipeline, and a bad ticket is refused."""
+    name, dim, data, _ = next(c for c in H.shipped_cases() if c[0].startswith("bar-942"))
+    t = Truss(dim).LoadFromJSON(data=data)
+    xyz, sup, conn, aed, force = t._pack()
+    plan = t._get_plan()
+    rng = np.random.default_rng(5)
+    B = 37
+    Fs = [rng.uniform(-10, 10, size=(B, plan.N)) for _ in range(5)]
+    want = [plan.solve_host(B, xyz, F, aed=aed) for F in Fs]
+    pinned = []
+    for F in Fs:
+        h = _lib.pinned_empty(F.shape)
+        h[...] = F
+        pinned.append(h)
+    outs, tickets = [], []
+    for i, F in enumerate(pinned):
+        tk, out = plan.solve_host_async(B, xyz, F, aed=aed)
+        tickets.append(tk)
+        outs.append(out)
+        if i >= 1:
+            plan.host_wait(tickets[i - 1])
+            for k in ("u", "ext", "axial", "weight"):
+                assert np.array_equal(outs[i - 1][k], want[i - 1][k]), (i - 1, k)
+    assert tickets == sorted(tickets) and len(set(tickets)) == len(tickets)
+    again = plan.solve_host(B, xyz, Fs[0], aed=aed)          # a blocking call first waits for everything in flight
+    for k in ("u", "ext", "axial", "weight"):
+        assert np.array_equal(outs[-1][k], want[-1][k]), k
+        assert np.array_equal(again[k], want[0][k]), k
+    plan.host_wait(tickets[-1])                               # already complete: returns at once
+    with pytest.raises(_lib.TrussLibError):
+        plan.host_wait(tickets[-1] + 7)
