@@ -20,6 +20,8 @@
 // its row.  Systems too large for this kernel's shared-memory budget fall back to tb_small.cu's CTA-per-truss kernel.
 #include <math.h>
 
+#include <mutex>
+
 #include "tb_common.cuh"
 #include "tb_blocks.cuh"
 
@@ -605,28 +607,43 @@ int tb_launch_dense16(const SmallArgs& a, int dim, cudaStream_t st) {
   const int nbm = a.max_n > 0 ? (a.max_n + 15) / 16 : 1;
   if (nbm > 10) return -1;
   const int per = d16_layout(dim, a.nJ, a.M, nbm).total * 8;
-  const int budget = 110 * 1024;               // at least two CTAs per SM
-  int nwarp = budget / per;
-  if (nwarp < 1) return -1;
-  if (nwarp > 4) nwarp = 4;
-  const int smem = per * nwarp;
+  if (per > 110 * 1024) return -1;             // fewer than two systems per SM: the CTA-per-truss kernel takes it (tb_small_fits)
   auto kern = (dim == 3) ? k_dense16<3> : k_dense16<2>;
-  // attribute / occupancy queries are cached per (instantiation, shared-memory size, warps): they cost more than the launch
-  static int c_smem[2] = {-1, -1}, c_nwarp[2] = {0, 0}, c_per_sm[2] = {0, 0}, c_sms = 0;
-  const int ci = dim - 2;
-  if (c_smem[ci] != smem || c_nwarp[ci] != nwarp) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return (int)e;
-    int dev = 0, q = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&c_sms, cudaDevAttrMultiProcessorCount, dev);
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, kern, 32 * nwarp, smem);
-    if (e != cudaSuccess) return (int)e;
-    c_per_sm[ci] = q < 1 ? 1 : q;
-    c_smem[ci] = smem;
-    c_nwarp[ci] = nwarp;
+  // Warps per CTA: whatever puts the most warps (= systems in flight) on an SM.  The kernel is latency-bound per warp, so
+  // throughput follows the resident warps; shared memory per system decides (bar-72: 19.6 KB per warp -> 11 one-warp CTAs
+  // per SM against 8 warps with four-warp CTAs).  Attribute / occupancy queries are cached per device, instantiation and
+  // per-system size: they cost more than the launch.
+  struct Choice { int per = -1, nwarp = 0, per_sm = 0, sms = 0; };
+  static Choice cache[64][2];
+  static std::mutex cache_mu;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return (int)cudaGetLastError();
+  Choice ch;
+  {
+    std::lock_guard<std::mutex> lock(cache_mu);
+    Choice& c = cache[dev & 63][dim - 2];
+    if (c.per != per) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (e != cudaSuccess) return (int)e;
+      e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      if (e != cudaSuccess) return (int)e;
+      Choice best;
+      for (int nw = 4; nw >= 1; --nw) {
+        if ((size_t)per * nw > (size_t)227 * 1024) continue;
+        int q = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, kern, 32 * nw, (size_t)per * nw);
+        if (e != cudaSuccess) return (int)e;
+        if (q * nw > best.per_sm * best.nwarp) { best.nwarp = nw; best.per_sm = q; }
+      }
+      if (best.nwarp == 0) return -1;
+      cudaDeviceGetAttribute(&best.sms, cudaDevAttrMultiProcessorCount, dev);
+      best.per = per;
+      c = best;
+    }
+    ch = c;
   }
-  const int per_sm = c_per_sm[ci], sms = c_sms;
+  const int nwarp = ch.nwarp, smem = per * nwarp;
+  const int per_sm = ch.per_sm, sms = ch.sms;
   long long grid = (long long)sms * per_sm;    // persistent: a multiple of the SM count
   const long long need = (a.batch + nwarp - 1) / nwarp;
   if (grid > need) grid = need;
