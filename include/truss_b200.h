@@ -63,6 +63,7 @@ extern "C" {
 #define TB_ERR_NO_DEVICE (-7)  /* no CUDA device: there is NO CPU fallback */
 #define TB_ERR_ALLOC (-8)
 #define TB_ERR_WRONG_DEVICE (-9) /* the plan was created on another CUDA device than the current one */
+#define TB_ERR_JSON (-10)      /* a document is not a truss JSON file of the reference's format (truss.py:401-421) */
 
 /* per-system status codes in info[] */
 #define TB_INFO_OK 0
@@ -271,6 +272,26 @@ typedef struct {
 int tb_augment_ragged(const tb_ragged_in* pool, int32_t n_out, const int32_t* src, const int64_t* out_joint_off,
                       const int64_t* out_member_off, const tb_augment_params* params, double* out_xyz,
                       uint8_t* out_support, int32_t* out_conn, double* out_aed, double* out_force, void* cuda_stream);
+
+/* ---- Bulk JSON loader (slientruss3d/truss.py:401-421 Truss.LoadFromJSON) ------------------
+ * Parses n documents of the reference's JSON format ({"joint": [[[x,y,z],"PIN"],...], "force": [[id,[fx,fy,fz]],...],
+ * "member": [[[j0,j1],[a,e,density]],...]} and, for output files, the sparse "displace" / "external" / "internal" lists
+ * and "weight") straight into the packed arrays of tb_ragged_in -- no per-truss objects -- on `threads` host threads
+ * (<= 0: all cores).  Host code only: works without a GPU.  Two passes: tb_json_scan counts the joints and members of
+ * every document (the caller turns the counts into the [n+1] prefix sums joint_off / member_off and allocates), then
+ * tb_json_fill writes document i's slices.  texts[i] must be NUL-terminated (lens[i] excludes the terminator).  Semantics
+ * follow the reference: numbers become the doubles json.load produces, a zero load vector is ignored and a later entry
+ * of the same joint replaces an earlier one (truss.py:177-182), results missing from the sparse lists are zeros
+ * (truss.py:344-361 dropped them under the 1e-10 filter).  err[i] (may be NULL) receives the status of document i:
+ * TB_ERR_JSON malformed / missing keys, TB_ERR_INDEX joint or member id out of range, TB_ERR_SUPPORT unknown support
+ * name; the return value is TB_OK or TB_ERR_JSON when any document failed.  u / ext / axial / weight are only written
+ * when is_output != 0 (weight may be NULL; it is NaN for documents without the key). */
+int tb_json_scan(int32_t n, const char* const* texts, const int64_t* lens, int64_t* n_joint, int64_t* n_member,
+                 int32_t* err, int32_t threads);
+int tb_json_fill(int32_t n, const char* const* texts, const int64_t* lens, int32_t dim, int32_t is_output,
+                 const int64_t* joint_off, const int64_t* member_off, double* xyz, uint8_t* support, double* force,
+                 int32_t* conn, double* aed, double* u, double* ext, double* axial, double* weight, int32_t* err,
+                 int32_t threads);
 
 /* Page-locked host buffers for callers of the *_host entry points (full-speed H2D/D2H). */
 int tb_pinned_alloc(void** ptr, size_t bytes);

@@ -18,7 +18,7 @@ CSRC = os.path.join(_HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 LIB_PATH = os.environ.get("TB_LIB_PATH") or os.path.join(CSRC, "libtruss_b200.so")   # TB_LIB_PATH: instrumented builds (tools/)
 SOURCES = ["tb_plan.cu", "tb_tsplan.cu", "tb_small.cu", "tb_dense16.cu", "tb_large.cu", "tb_band.cu", "tb_bandts.cu", "tb_api.cu", "tb_peak.cu",
-           "tb_ga.cu", "tb_augment.cu"]
+           "tb_ga.cu", "tb_augment.cu", "tb_json.cu"]
 
 TB_ERR_NO_DEVICE = -7
 TB_ERR_TOO_LARGE = -6
@@ -149,7 +149,7 @@ class TbRaggedIn(C.Structure):
 
 EXPORTS = ["tb_plan_create", "tb_plan_destroy", "tb_plan_query", "tb_plan_set_path", "tb_plan_get_maps",
            "tb_plan_get_scatter", "tb_solve", "tb_solve_host", "tb_solve_host_async", "tb_host_wait", "tb_solve_loadcases", "tb_solve_loadcases_host", "tb_fitness", "tb_fitness_host", "tb_solve_ragged",
-           "tb_solve_ragged_host", "tb_ga_init", "tb_ga_step", "tb_augment_ragged", "tb_pinned_alloc", "tb_pinned_free", "tb_small_path_limits", "tb_fp64_peak", "tb_rsqrt_probe", "tb_profile_enable", "tb_profile_read",
+           "tb_solve_ragged_host", "tb_ga_init", "tb_ga_step", "tb_augment_ragged", "tb_json_scan", "tb_json_fill", "tb_pinned_alloc", "tb_pinned_free", "tb_small_path_limits", "tb_fp64_peak", "tb_rsqrt_probe", "tb_profile_enable", "tb_profile_read",
            "tb_launch_count", "tb_strerror", "tb_version", "tb_small_path_fits", "tb_debug_assemble_host", "tb_plan_ts_info", "tb_plan_ts_array", "tb_ts_phase_read"]
 
 _lib = None
@@ -189,6 +189,8 @@ def lib():
     L.tb_fp64_peak.argtypes = [i32, i32, C.POINTER(dbl), C.POINTER(C.c_float)]
     L.tb_rsqrt_probe.argtypes = [i32, C.POINTER(dbl)]
     L.tb_augment_ragged.argtypes = [C.POINTER(TbRaggedIn), i32, vp, vp, vp, C.POINTER(TbAugmentParams), vp, vp, vp, vp, vp, vp]
+    L.tb_json_scan.argtypes = [i32, vp, vp, vp, vp, vp, i32]
+    L.tb_json_fill.argtypes = [i32, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32]
     L.tb_ga_init.argtypes = [C.POINTER(TbGaParams), vp, vp, vp]
     L.tb_ga_step.argtypes = [C.POINTER(TbGaParams), C.c_uint64, vp, vp, vp, vp, vp, vp, vp]
     L.tb_profile_enable.argtypes = [i32]
@@ -203,6 +205,10 @@ def lib():
     L.tb_strerror.restype = C.c_char_p
     _lib = L
     return L
+
+
+def strerror(rc: int) -> str:
+    return lib().tb_strerror(int(rc)).decode()
 
 
 def check(rc: int):
@@ -241,6 +247,40 @@ class _PinnedOwner:
             lib().tb_pinned_free(self.addr)
         except Exception:
             pass
+
+
+def json_load_packed(texts, dim, is_output=False, threads=0):
+    """Parse JSON documents of the reference's format (bytes objects) straight into packed arrays through the native
+    loader (tb_json_scan / tb_json_fill, csrc/tb_json.cu).  Returns ``(arrays, err)``: the dict of packed arrays
+    (joint_off, member_off, xyz, support, conn, aed, force [+ u, ext, axial, weight]) and the per-document status codes;
+    raises TrussLibError on argument errors only (a malformed document is reported through ``err``)."""
+    n = len(texts)
+    bufs = [t if isinstance(t, bytes) else bytes(t) for t in texts]          # (bytes objects are NUL-terminated in memory)
+    ptrs = (C.c_char_p * max(n, 1))(*bufs)
+    lens = np.array([len(b) for b in bufs], np.int64)
+    nj, nm, err = np.zeros(n, np.int64), np.zeros(n, np.int64), np.zeros(n, np.int32)
+    L = lib()
+    rc = L.tb_json_scan(n, ptrs, _ptr(lens), _ptr(nj), _ptr(nm), _ptr(err), int(threads))
+    if rc not in (0, -10):
+        check(rc)
+    nj[err != 0] = 0
+    nm[err != 0] = 0
+    jo, mo = np.zeros(n + 1, np.int64), np.zeros(n + 1, np.int64)
+    jo[1:], mo[1:] = np.cumsum(nj), np.cumsum(nm)
+    SJ, SM = int(jo[-1]), int(mo[-1])
+    a = {"joint_off": jo, "member_off": mo, "xyz": np.empty(SJ * dim), "support": np.empty(SJ, np.uint8),
+         "conn": np.empty(2 * SM, np.int32), "aed": np.empty(3 * SM), "force": np.empty(SJ * dim)}
+    if is_output:
+        a.update(u=np.empty(SJ * dim), ext=np.empty(SJ * dim), axial=np.empty(SM), weight=np.empty(n))
+    # documents that failed the scan keep empty slices; the fill pass reports them again
+    err2 = np.zeros(n, np.int32)
+    rc = L.tb_json_fill(n, ptrs, _ptr(lens), int(dim), int(bool(is_output)), _ptr(jo), _ptr(mo), _ptr(a["xyz"]),
+                        _ptr(a["support"]), _ptr(a["force"]), _ptr(a["conn"]), _ptr(a["aed"]), _ptr(a.get("u")),
+                        _ptr(a.get("ext")), _ptr(a.get("axial")), _ptr(a.get("weight")), _ptr(err2), int(threads))
+    if rc not in (0, -10):
+        check(rc)
+    err = np.where(err != 0, err, err2)
+    return a, err
 
 
 def pinned_empty(shape, dtype=np.float64):

@@ -8,6 +8,7 @@ hand the whole batch to the CUDA library in one call:
   ``SolveLoadCases(truss, forces)``          one truss, many dense load vectors (same K, many f)
   ``SolveMemberTypes(truss, genes, types)``  one truss, many member-type assignments (GA population)
   ``FitnessBatch(...)``                      GA.GetFitness for a population (ga.py:139-149)
+  ``SolveWithFixedMemberType(trusses, t)``   the graph-data converter's double solve (data.py:17-44, 108-114)
 
 All of them return dense numpy arrays (``u [B,N]``, ``ext [B,N]``, ``axial [B,M]``, ``weight [B]``,
 ``info [B]``); ``SolveBatch`` also stores the results back into the Truss objects.
@@ -17,7 +18,7 @@ from __future__ import annotations
 import numpy as np
 
 from . import _lib
-from .truss import Truss, raise_for_info
+from .truss import ZERO_EPS, Truss, make_plan, raise_for_info
 from .type import MemberType
 
 
@@ -82,6 +83,64 @@ def pack_ragged(trusses):
         cat(4, np.float64)
 
 
+_PLAN_CACHE = {}
+
+
+def _cached_plan(dim, conn, support):
+    """Plans of the last few topologies seen by the batched calls (a plan costs a host pass over the scatter map and a
+    few uploads; repeated batches of one topology should not pay it again)."""
+    key = (dim, conn.shape[0], support.tobytes(), conn.tobytes())
+    plan = _PLAN_CACHE.pop(key, None)
+    if plan is None:
+        plan = make_plan(dim, conn, support)
+    _PLAN_CACHE[key] = plan                     # (re-inserted: most recently used last)
+    while len(_PLAN_CACHE) > 8:
+        _PLAN_CACHE.pop(next(iter(_PLAN_CACHE)))
+    return plan
+
+
+def _solve_packs(dim, packs):
+    """Dense results of a list of packed trusses ((xyz, support, conn, aed, force) each): same topology everywhere -> one
+    plan and a uniform batch per topology group; otherwise, if every truss fits the fused shared-memory kernel, one ragged
+    batch (the generator's case).  Returns (u, ext, axial) as lists of per-truss arrays and the info codes."""
+    n = len(packs)
+    info = np.zeros(n, np.int32)
+    u, ext, axial = [None] * n, [None] * n, [None] * n
+
+    def signature(p):
+        return (p[0].shape[0], p[2].shape[0], p[1].tobytes(), p[2].tobytes())
+
+    groups = {}
+    for i, p in enumerate(packs):
+        groups.setdefault(signature(p), []).append(i)
+
+    # one ragged batch needs the LARGEST truss of the batch to fit the fused kernels' shared memory
+    fits_small = _lib.small_path_fits(dim, max(p[0].shape[0] for p in packs), max(p[2].shape[0] for p in packs))
+    if len(groups) > 1 and fits_small:
+        joint_off = np.zeros(n + 1, np.int64)
+        member_off = np.zeros(n + 1, np.int64)
+        joint_off[1:] = np.cumsum([p[0].shape[0] for p in packs])
+        member_off[1:] = np.cumsum([p[2].shape[0] for p in packs])
+        cat = lambda i, dt: np.concatenate([np.asarray(p[i]).reshape(-1) for p in packs]).astype(dt)  # noqa: E731
+        out = _lib.solve_ragged_host(dim, joint_off, member_off, cat(0, np.float64), cat(1, np.uint8), cat(2, np.int32),
+                                     cat(3, np.float64), cat(4, np.float64), want=("u", "ext", "axial"))
+        for i in range(n):
+            info[i] = out["info"][i]
+            u[i] = out["u"][joint_off[i] * dim:joint_off[i + 1] * dim]
+            ext[i] = out["ext"][joint_off[i] * dim:joint_off[i + 1] * dim]
+            axial[i] = out["axial"][member_off[i]:member_off[i + 1]]
+    else:
+        for idx in groups.values():
+            p0 = packs[idx[0]]
+            plan = _cached_plan(dim, p0[2], p0[1])
+            out = plan.solve_host(len(idx), np.stack([packs[i][0] for i in idx]), np.stack([packs[i][4] for i in idx]),
+                                  aed=np.stack([packs[i][3] for i in idx]), want=("u", "ext", "axial"))
+            for k, i in enumerate(idx):
+                info[i] = out["info"][k]
+                u[i], ext[i], axial[i] = out["u"][k], out["ext"][k], out["axial"][k]
+    return u, ext, axial, info
+
+
 def SolveBatch(trusses, raise_on_error=True):
     """Solve a list of Truss objects in one call and store the results into them.
 
@@ -94,41 +153,52 @@ def SolveBatch(trusses, raise_on_error=True):
     dim = trusses[0].dim
     if any(t.dim != dim for t in trusses):
         raise ValueError("all trusses of a batch must have the same dimension")
-    packs = [t._pack() for t in trusses]
-    info = np.zeros(len(trusses), np.int32)
-
-    def store(idx, u, ext, axial, inf):
-        for k, i in enumerate(idx):
-            info[i] = inf[k]
-            if inf[k] == 0:
-                trusses[i]._set_dense_results(u[k], ext[k], axial[k])
-
-    def signature(p):
-        return (p[0].shape[0], p[2].shape[0], p[1].tobytes(), p[2].tobytes())
-
-    groups = {}
-    for i, p in enumerate(packs):
-        groups.setdefault(signature(p), []).append(i)
-
-    # one ragged batch needs the LARGEST truss of the batch to fit the fused kernels' shared memory
-    fits_small = _lib.small_path_fits(dim, max(p[0].shape[0] for p in packs), max(p[2].shape[0] for p in packs))
-    if len(groups) > 1 and fits_small:
-        _, jo, mo, xyz, sup, conn, aed, force = pack_ragged(trusses)
-        out = _lib.solve_ragged_host(dim, jo, mo, xyz, sup, conn, aed, force, want=("u", "ext", "axial"))
-        for i in range(len(trusses)):
-            info[i] = out["info"][i]
-            if info[i] == 0:
-                trusses[i]._set_dense_results(out["u"][jo[i] * dim:jo[i + 1] * dim], out["ext"][jo[i] * dim:jo[i + 1] * dim],
-                                              out["axial"][mo[i]:mo[i + 1]])
-    else:
-        for idx in groups.values():
-            t0, p0 = trusses[idx[0]], packs[idx[0]]
-            plan = t0._get_plan(p0[1], p0[2])
-            B = len(idx)
-            xyz = np.stack([packs[i][0] for i in idx])
-            aed = np.stack([packs[i][3] for i in idx])
-            force = np.stack([packs[i][4] for i in idx])
-            out = plan.solve_host(B, xyz, force, aed=aed, want=("u", "ext", "axial"))
-            store(idx, out["u"], out["ext"], out["axial"], out["info"])
+    u, ext, axial, info = _solve_packs(dim, [t._pack() for t in trusses])
+    for i, t in enumerate(trusses):
+        if info[i] == 0:
+            t._set_dense_results(u[i], ext[i], axial[i])
     _check_infos(info, raise_on_error)
     return info
+
+
+def SolveWithFixedMemberType(trusses, fixedMemberType=MemberType(1., 1e7, 0.1), raise_on_error=True, dense=False):
+    """The double solve of the reference's graph-data converter for a whole list of trusses in two batched calls.
+
+    ``TrussHeteroDataCreator.FromTruss`` / ``FromJSON`` (data.py:17-44) solve the truss as it is and then, in
+    ``__GetFixedInternalAndDisplace`` (data.py:108-114), copy it, set EVERY member to ``fixedMemberType`` and solve again
+    to get reference stresses and displacements that do not depend on the member sizing.  Here the trusses that are not
+    solved yet go through ``SolveBatch`` and the fixed-type variants through a second batch that reuses the same packed
+    arrays with the member properties replaced -- no Truss copies.
+
+    Returns a list of ``(fixedInternals, fixedDisplaces)`` per truss, the reference's dicts
+    (``GetInternalStresses()`` = force / area over the members with |force| >= 1e-10, ``GetDisplacements()`` over the
+    joints with a non-zero displacement); with ``dense=True`` a dict of arrays instead:
+    ``stress`` list of [M], ``u`` list of [N], ``info`` [B]."""
+    trusses = list(trusses)
+    if not trusses:
+        return {"stress": [], "u": [], "info": np.zeros(0, np.int32)} if dense else []
+    dim = trusses[0].dim
+    todo = [t for t in trusses if not t.isSolved]
+    if todo:
+        SolveBatch(todo, raise_on_error=raise_on_error)
+    fixed = np.asarray(fixedMemberType.Serialize() if isinstance(fixedMemberType, MemberType) else fixedMemberType,
+                       dtype=np.float64).reshape(3)
+    packs = []
+    for t in trusses:
+        xyz, support, conn, aed, force = t._pack()
+        packs.append((xyz, support, conn, np.broadcast_to(fixed, aed.shape).copy(), force))
+    u, _, axial, info = _solve_packs(dim, packs)
+    _check_infos(info, raise_on_error)
+    stress = [a / fixed[0] for a in axial]
+    if dense:
+        return {"stress": stress, "u": u, "info": info}
+    out = []
+    for i in range(len(trusses)):
+        if info[i] != 0:
+            out.append((None, None))
+            continue
+        ax, rows = axial[i], np.asarray(u[i]).reshape(-1, dim)
+        internals = {int(m): float(ax[m]) / float(fixed[0]) for m in np.nonzero(~(np.abs(ax) < ZERO_EPS))[0]}
+        displaces = {int(j): rows[j].copy() for j in np.nonzero(~(np.abs(rows) < ZERO_EPS).all(axis=1))[0]}
+        out.append((internals, displaces))
+    return out

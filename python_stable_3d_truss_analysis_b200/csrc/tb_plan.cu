@@ -632,6 +632,7 @@ extern "C" const char* tb_strerror(int code) {
     case TB_ERR_NO_DEVICE: return "no CUDA device (this library has no CPU fallback)";
     case TB_ERR_ALLOC: return "allocation failed";
     case TB_ERR_WRONG_DEVICE: return "the plan belongs to another CUDA device than the current one";
+    case TB_ERR_JSON: return "not a truss JSON document of the reference's format";
     default: break;
   }
   if (code > 0) return cudaGetErrorString((cudaError_t)code);

@@ -2,6 +2,7 @@
 (``tb_ragged_in`` / ``tb_batch_out`` layout, what ``GenerateAugmentedDataset`` and ``pack_ragged`` produce) as ONE
 binary container instead of one JSON file per truss, plus the views back into the reference's formats:
 
+* ``PackedDataset.from_json_files``   N reference JSON files -> packed arrays through the native parser (no Truss objects);
 * ``PackedDataset.save / load``       one ``.npz`` (optionally compressed) holding every array;
 * ``PackedDataset.json(i)``           truss ``i`` as the reference's JSON dict (``Truss.Serialize``, truss.py:367-395 and
                                       ``detail/combine_with_JSON.md:71-163``: sparse ``displace / external / internal`` lists
@@ -19,7 +20,7 @@ import os
 import numpy as np
 
 from .type import SupportType
-from .utils import ZERO_EPS
+from .utils import CheckDim, ZERO_EPS
 
 _ARRAYS = ("joint_off", "member_off", "xyz", "support", "conn", "aed", "force")
 _RESULTS = ("u", "ext", "axial", "weight", "info")
@@ -65,6 +66,46 @@ class PackedDataset:
             arrays["weight"] = np.array([t.weight for t in trusses])
             arrays["info"] = np.zeros(len(trusses), np.int32)
         return cls(dim, arrays, names)
+
+    @classmethod
+    def from_json_texts(cls, texts, dim, isOutputFile=False, names=None, threads=0):
+        """Pack JSON documents of the reference's format (``bytes``) without building Truss objects: the bulk form of
+        ``Truss(dim).LoadFromJSON(path, isOutputFile)`` (truss.py:401-421), parsed by the native loader
+        (csrc/tb_json.cu) on ``threads`` host threads (0: all cores).  Raises ValueError naming the first bad document."""
+        from . import _lib
+        from .utils import InvaildJointError, InvalidSupportTypeError
+        arrays, err = _lib.json_load_packed(list(texts), CheckDim(dim), isOutputFile, threads)
+        bad = np.nonzero(err)[0]
+        if bad.size:
+            i, code = int(bad[0]), int(err[bad[0]])
+            who = names[i] if names is not None else f"document {i}"
+            if code == -5:
+                raise InvalidSupportTypeError(f"[GetFromString] No such support type in {who} !")
+            if code == -4:
+                raise InvaildJointError(f"{who}: a load, member or result entry refers to a joint / member that does not exist.")
+            raise ValueError(f"{who}: not a truss JSON document ({_lib.strerror(code)})")
+        if isOutputFile:
+            arrays["info"] = np.zeros(len(err), np.int32)
+            if np.isnan(arrays["weight"]).any():           # ("weight" is optional in the files: a * L * density summed, truss.py:166-168)
+                xyz = arrays["xyz"].reshape(-1, dim)
+                conn = arrays["conn"].reshape(-1, 2).astype(np.int64)
+                owner = np.repeat(np.arange(len(err)), np.diff(arrays["member_off"]))      # truss of every member
+                base = arrays["joint_off"][:-1][owner]
+                length = np.sqrt(((xyz[base + conn[:, 1]] - xyz[base + conn[:, 0]]) ** 2).sum(axis=1))
+                aed = arrays["aed"].reshape(-1, 3)
+                w = np.bincount(owner, weights=aed[:, 0] * length * aed[:, 2], minlength=len(err))
+                arrays["weight"] = np.where(np.isnan(arrays["weight"]), w, arrays["weight"])
+        return cls(dim, arrays, names)
+
+    @classmethod
+    def from_json_files(cls, paths, dim, isOutputFile=False, threads=0):
+        """``from_json_texts`` over files; truss ``i`` is named after file ``i`` (without the extension)."""
+        paths = list(paths)
+        texts = []
+        for p in paths:
+            with open(p, "rb") as f:
+                texts.append(f.read())
+        return cls.from_json_texts(texts, dim, isOutputFile, [os.path.splitext(os.path.basename(p))[0] for p in paths], threads)
 
     # ------------------------------------------------------------------ binary container
     def save(self, path, compressed=False):

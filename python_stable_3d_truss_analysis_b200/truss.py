@@ -117,6 +117,24 @@ class Member:
         return Member(tuple(self._ends[0]), tuple(self._ends[1]), self._dim, self._type.Copy())
 
 
+def make_plan(dim, conn, support):
+    """C-ABI plan of a topology, with the reference's exceptions for what tb_plan_create refuses (type.py:37-74 support
+    codes, truss.py:252-254 joints of a member)."""
+    support = np.asarray(support)
+    if support.size and (support.min() < 0 or support.max() > SupportType.ROLLER_Z):
+        from .utils import InvalidSupportTypeError
+        raise InvalidSupportTypeError(f"[GetResistanceMask] No such {dim}D-support type !")
+    try:
+        return _lib.Plan(dim, conn, support.astype(np.uint8))
+    except _lib.TrussLibError as exc:
+        if exc.code == -5:
+            from .utils import InvalidSupportTypeError
+            raise InvalidSupportTypeError(f"[GetResistanceMask] No such {dim}D-support type !") from None
+        if exc.code == -4:
+            raise InvaildJointError("A member refers to a joint that does not exist.") from None
+        raise
+
+
 class Truss:
     def __init__(self, dim):
         self._dim = CheckDim(dim)
@@ -151,18 +169,7 @@ class Truss:
         if self._plan is None:
             if support is None:
                 _, support, conn, _, _ = self._pack()
-            if support.size and (support.min() < 0 or support.max() > SupportType.ROLLER_Z):
-                from .utils import InvalidSupportTypeError
-                raise InvalidSupportTypeError(f"[GetResistanceMask] No such {self._dim}D-support type !")
-            try:
-                self._plan = _lib.Plan(self._dim, conn, support.astype(np.uint8))
-            except _lib.TrussLibError as exc:
-                if exc.code == -5:
-                    from .utils import InvalidSupportTypeError
-                    raise InvalidSupportTypeError(f"[GetResistanceMask] No such {self._dim}D-support type !") from None
-                if exc.code == -4:
-                    raise InvaildJointError("A member refers to a joint that does not exist.") from None
-                raise
+            self._plan = make_plan(self._dim, conn, support)
         return self._plan
 
     def _set_dense_results(self, u, ext, axial):

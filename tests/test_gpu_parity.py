@@ -645,3 +645,42 @@ def test_pipelined_host_calls_match_blocking_calls():
     plan.host_wait(tickets[-1])                               # already complete: returns at once
     with pytest.raises(_lib.TrussLibError):
         plan.host_wait(tickets[-1] + 7)
+
+
+@pytest.mark.gpu
+def test_fixed_member_type_double_solve_matches_oracle():
+    """SolveWithFixedMemberType (data.py:17-44, 108-114): every truss solved as it is and again with all members of the
+    fixed type, in two batched calls -- against the oracle run on arrays with the member properties replaced, on a
+    ragged list (cube-7 trusses) and on a uniform one (copies of bar-72 with different member types)."""
+    from python_stable_3d_truss_analysis_b200.batch import SolveWithFixedMemberType
+
+    fixed = MemberType(1., 1e7, 0.1)
+    ragged = [Truss(d).LoadFromJSON(data=data) for _, d, data, _ in H.cube7_shipped()[:6]]
+    name, dim, data, _ = next(c for c in H.shipped_cases() if c[0].startswith("bar-72"))
+    uniform = []
+    for i in range(4):
+        t = Truss(dim).LoadFromJSON(data=data)
+        for m in t.GetMemberIDs():
+            t.SetMemberType(m, MemberType(1.0 + 0.25 * ((m + i) % 5), 1e7, 0.1))
+        uniform.append(t)
+    for trusses in (ragged, uniform):
+        res = SolveWithFixedMemberType(trusses, fixed)
+        den = SolveWithFixedMemberType(trusses, fixed, dense=True)
+        assert len(res) == len(trusses)
+        for i, t in enumerate(trusses):
+            assert t.isSolved
+            xyz, sup, conn, aed, force = t._pack()
+            own = orc.solve(t.dim, xyz, sup, conn, aed, force.reshape(-1, t.dim))
+            assert orc.normwise_err(t._dense["u"], own["u"]) <= 1e-9
+            aed2 = np.tile(np.array(fixed.Serialize()), (conn.shape[0], 1))
+            want = orc.solve(t.dim, xyz, sup, conn, aed2, force.reshape(-1, t.dim))
+            assert orc.normwise_err(den["u"][i], want["u"]) <= 1e-9
+            assert orc.normwise_err(den["stress"][i], want["axial"] / fixed.a) <= 1e-9
+            internals, displaces = res[i]
+            for m, s in internals.items():
+                assert abs(s - want["axial"][m] / fixed.a) <= 1e-9 * np.abs(want["axial"]).max() / fixed.a
+            big = np.nonzero(np.abs(want["axial"]) > 1e-8)[0]
+            assert set(big.tolist()) <= set(internals)
+            wu = want["u"].reshape(-1, t.dim)
+            for j, v in displaces.items():
+                assert np.abs(v - wu[j]).max() <= 1e-9 * np.abs(wu).max()
