@@ -273,6 +273,47 @@ int tb_augment_ragged(const tb_ragged_in* pool, int32_t n_out, const int32_t* sr
                       const int64_t* out_member_off, const tb_augment_params* params, double* out_xyz,
                       uint8_t* out_support, int32_t* out_conn, double* out_aed, double* out_force, void* cuda_stream);
 
+/* ---- Random cube-truss topologies on the device (slientruss3d/generate.py:152-336, :338-372)
+ * GenerateRandomCubeTrusses draws, per truss, a random walk of numCube unit cells over a grid (CubeGrid.
+ * RandomGenerateCubes), numbers the cubes' corners in first-seen order, links one or both diagonals of every face and the
+ * twelve edges (CubeTruss.LinkMember, duplicates dropped unless parallel members are allowed), scales the cells by three
+ * random lengths, pins the lowest layer, puts random loads on some of the other joints, picks a random type per member
+ * and draws again until the counting rule of Truss.isStable holds.  tb_gencube does this for n trusses at once, one
+ * thread per truss, with counter-based random numbers keyed by `seed` (reproducible from (seed, index); it does not
+ * replay Python's `random` stream -- the host generator keeps that).  Every truss is written at a fixed stride
+ * (tb_gencube_limits: max_joint, max_member, max_cube); n_joint / n_member receive the actual sizes, info 0 or
+ * TB_INFO_NOT_STABLE when max_attempts draws all failed the counting rule.  After a prefix sum of the sizes,
+ * tb_gencube_pack compacts the batch into the packed layout of tb_ragged_in, ready for tb_augment_ragged /
+ * tb_solve_ragged.  cells [n][max_cube] (cell index x + gx (y + gy z) of every cube in creation order, -1 padded),
+ * picks [n][max_cube][6] (diagonal choice per face: 0 first, 1 second, 2 both) and length [n][3] are optional exports:
+ * fed to the host classes CubeTruss / CubeGrid.CubesToTruss they must reproduce the truss exactly (the tests do this).
+ * All pointers are device pointers. */
+#define TB_GEN_MAX_CELLS 216   /* grid cells (e.g. 6 x 6 x 6) */
+#define TB_GEN_MAX_VERTS 343   /* grid corners */
+typedef struct {
+  int32_t grid[3];              /* gridRange */
+  int32_t ncube_lo, ncube_hi;   /* numCube drawn uniformly from [lo, hi] per truss (lo == hi: fixed) */
+  int32_t method;               /* GenerateMethod: 0 DFS, 1 BFS, 2 Random */
+  int32_t link_type;            /* LinkType: 0 / 1 one diagonal per face, 2 both, 3 Random */
+  int32_t add_pin;              /* isAddPinSupport */
+  int32_t allow_parallel;       /* isAllowParallel */
+  int32_t nforce_lo, nforce_hi; /* nForceRange; -1 = None (1 / every unsupported joint) */
+  int32_t n_type;               /* member types to choose from (type_table [n_type][3]) */
+  int32_t max_attempts;         /* draws per truss before giving up on the counting rule */
+  double length_lo, length_hi;  /* lengthRange */
+  double force_lo[3], force_hi[3]; /* forceRange */
+  uint64_t seed;
+} tb_gencube_params;
+
+int tb_gencube_limits(const tb_gencube_params* params, int32_t* max_joint, int32_t* max_member, int32_t* max_cube);
+int tb_gencube(const tb_gencube_params* params, int32_t n, const double* type_table, double* xyz, uint8_t* support,
+               double* force, int32_t* conn, double* aed, int32_t* n_joint, int32_t* n_member, int32_t* info,
+               int16_t* cells, uint8_t* picks, double* length, void* cuda_stream);
+int tb_gencube_pack(const tb_gencube_params* params, int32_t n, const double* xyz, const uint8_t* support,
+                    const double* force, const int32_t* conn, const double* aed, const int64_t* joint_off,
+                    const int64_t* member_off, double* out_xyz, uint8_t* out_support, double* out_force,
+                    int32_t* out_conn, double* out_aed, void* cuda_stream);
+
 /* ---- Bulk JSON loader (slientruss3d/truss.py:401-421 Truss.LoadFromJSON) ------------------
  * Parses n documents of the reference's JSON format ({"joint": [[[x,y,z],"PIN"],...], "force": [[id,[fx,fy,fz]],...],
  * "member": [[[j0,j1],[a,e,density]],...]} and, for output files, the sparse "displace" / "external" / "internal" lists

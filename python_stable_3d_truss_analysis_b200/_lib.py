@@ -18,7 +18,7 @@ CSRC = os.path.join(_HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 LIB_PATH = os.environ.get("TB_LIB_PATH") or os.path.join(CSRC, "libtruss_b200.so")   # TB_LIB_PATH: instrumented builds (tools/)
 SOURCES = ["tb_plan.cu", "tb_tsplan.cu", "tb_small.cu", "tb_dense16.cu", "tb_large.cu", "tb_band.cu", "tb_bandts.cu", "tb_api.cu", "tb_peak.cu",
-           "tb_ga.cu", "tb_augment.cu", "tb_json.cu"]
+           "tb_ga.cu", "tb_augment.cu", "tb_json.cu", "tb_gencube.cu"]
 
 TB_ERR_NO_DEVICE = -7
 TB_ERR_TOO_LARGE = -6
@@ -114,6 +114,13 @@ class TbAugmentParams(C.Structure):
                 ("max_pin_ratio", C.c_double), ("seed", C.c_uint64)]
 
 
+class TbGencubeParams(C.Structure):
+    _fields_ = [("grid", C.c_int32 * 3), ("ncube_lo", C.c_int32), ("ncube_hi", C.c_int32), ("method", C.c_int32),
+                ("link_type", C.c_int32), ("add_pin", C.c_int32), ("allow_parallel", C.c_int32), ("nforce_lo", C.c_int32),
+                ("nforce_hi", C.c_int32), ("n_type", C.c_int32), ("max_attempts", C.c_int32), ("length_lo", C.c_double),
+                ("length_hi", C.c_double), ("force_lo", C.c_double * 3), ("force_hi", C.c_double * 3), ("seed", C.c_uint64)]
+
+
 class TbGaParams(C.Structure):
     _fields_ = [("n_pop", C.c_int32), ("n_elite", C.c_int32), ("n_member", C.c_int32), ("n_type", C.c_int32),
                 ("p_crossover", C.c_double), ("p_mutate", C.c_double), ("p_origin", C.c_double), ("seed", C.c_uint64)]
@@ -149,7 +156,7 @@ class TbRaggedIn(C.Structure):
 
 EXPORTS = ["tb_plan_create", "tb_plan_destroy", "tb_plan_query", "tb_plan_set_path", "tb_plan_get_maps",
            "tb_plan_get_scatter", "tb_solve", "tb_solve_host", "tb_solve_host_async", "tb_host_wait", "tb_solve_loadcases", "tb_solve_loadcases_host", "tb_fitness", "tb_fitness_host", "tb_solve_ragged",
-           "tb_solve_ragged_host", "tb_ga_init", "tb_ga_step", "tb_augment_ragged", "tb_json_scan", "tb_json_fill", "tb_pinned_alloc", "tb_pinned_free", "tb_small_path_limits", "tb_fp64_peak", "tb_rsqrt_probe", "tb_profile_enable", "tb_profile_read",
+           "tb_solve_ragged_host", "tb_ga_init", "tb_ga_step", "tb_augment_ragged", "tb_json_scan", "tb_json_fill", "tb_gencube_limits", "tb_gencube", "tb_gencube_pack", "tb_pinned_alloc", "tb_pinned_free", "tb_small_path_limits", "tb_fp64_peak", "tb_rsqrt_probe", "tb_profile_enable", "tb_profile_read",
            "tb_launch_count", "tb_strerror", "tb_version", "tb_small_path_fits", "tb_debug_assemble_host", "tb_plan_ts_info", "tb_plan_ts_array", "tb_ts_phase_read"]
 
 _lib = None
@@ -189,6 +196,9 @@ def lib():
     L.tb_fp64_peak.argtypes = [i32, i32, C.POINTER(dbl), C.POINTER(C.c_float)]
     L.tb_rsqrt_probe.argtypes = [i32, C.POINTER(dbl)]
     L.tb_augment_ragged.argtypes = [C.POINTER(TbRaggedIn), i32, vp, vp, vp, C.POINTER(TbAugmentParams), vp, vp, vp, vp, vp, vp]
+    L.tb_gencube_limits.argtypes = [C.POINTER(TbGencubeParams), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
+    L.tb_gencube.argtypes = [C.POINTER(TbGencubeParams), i32] + [vp] * 13
+    L.tb_gencube_pack.argtypes = [C.POINTER(TbGencubeParams), i32] + [vp] * 13
     L.tb_json_scan.argtypes = [i32, vp, vp, vp, vp, vp, i32]
     L.tb_json_fill.argtypes = [i32, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32]
     L.tb_ga_init.argtypes = [C.POINTER(TbGaParams), vp, vp, vp]
@@ -633,6 +643,48 @@ def augment_and_solve_device(dim, pool, n_out, params: "TbAugmentParams", src=No
         bo = TbBatchOut(_ptr(out["u"]), _ptr(out["ext"]), _ptr(out["axial"]), _ptr(out["weight"]), _ptr(out["info"]))
         check(lib().tb_solve_ragged(C.byref(ro), C.byref(bo), st))
     out["_keep"] = d
+    return out
+
+
+def gencube_device(params: "TbGencubeParams", n, type_table, solve=True, export=False, device=None):
+    """Random cube trusses generated on the device (tb_gencube), compacted into the packed ragged layout
+    (tb_gencube_pack) and, if ``solve``, solved by tb_solve_ragged without leaving the GPU.  Returns a dict of torch CUDA
+    tensors (joint_off, member_off, xyz, support, conn, aed, force, gen_info [, u, ext, axial, weight, info]); with
+    ``export`` also the walk (``cells`` [n, max_cube], ``picks`` [n, max_cube, 6], ``length`` [n, 3]) for replay tests."""
+    import torch
+
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    mj, mm, mc = C.c_int32(), C.c_int32(), C.c_int32()
+    check(lib().tb_gencube_limits(C.byref(params), C.byref(mj), C.byref(mm), C.byref(mc)))
+    mj, mm, mc = mj.value, mm.value, mc.value
+    n = int(n)
+    tt = torch.from_numpy(np.ascontiguousarray(type_table, dtype=np.float64).reshape(-1, 3)).to(dev)
+    if tt.shape[0] != params.n_type:
+        raise ValueError("type_table must hold params.n_type rows")
+    f64, e = torch.float64, lambda *shape, dt=torch.float64: torch.empty(*shape, dtype=dt, device=dev)  # noqa: E731
+    s = {"xyz": e(n, mj, 3), "support": e(n, mj, dt=torch.uint8), "force": e(n, mj, 3), "conn": e(n, mm, 2, dt=torch.int32),
+         "aed": e(n, mm, 3), "nj": e(n, dt=torch.int32), "nm": e(n, dt=torch.int32), "info": e(n, dt=torch.int32)}
+    ex = {"cells": e(n, mc, dt=torch.int16), "picks": e(n, mc, 6, dt=torch.uint8), "length": e(n, 3)} if export else {}
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    check(lib().tb_gencube(C.byref(params), n, _ptr(tt), _ptr(s["xyz"]), _ptr(s["support"]), _ptr(s["force"]), _ptr(s["conn"]),
+                           _ptr(s["aed"]), _ptr(s["nj"]), _ptr(s["nm"]), _ptr(s["info"]), _ptr(ex.get("cells")),
+                           _ptr(ex.get("picks")), _ptr(ex.get("length")), st))
+    z = torch.zeros(1, dtype=torch.int64, device=dev)
+    jo = torch.cat([z, torch.cumsum(s["nj"].to(torch.int64), 0)])
+    mo = torch.cat([z, torch.cumsum(s["nm"].to(torch.int64), 0)])
+    SJ, SM = int(jo[-1]), int(mo[-1])
+    out = {"joint_off": jo, "member_off": mo, "xyz": e(SJ * 3), "support": e(SJ, dt=torch.uint8), "force": e(SJ * 3),
+           "conn": e(SM * 2, dt=torch.int32), "aed": e(SM * 3), "gen_info": s["info"]}
+    check(lib().tb_gencube_pack(C.byref(params), n, _ptr(s["xyz"]), _ptr(s["support"]), _ptr(s["force"]), _ptr(s["conn"]),
+                                _ptr(s["aed"]), _ptr(jo), _ptr(mo), _ptr(out["xyz"]), _ptr(out["support"]), _ptr(out["force"]),
+                                _ptr(out["conn"]), _ptr(out["aed"]), st))
+    out.update(ex)
+    if solve and n > 0:
+        out.update({"u": e(SJ * 3), "ext": e(SJ * 3), "axial": e(SM), "weight": e(n), "info": e(n, dt=torch.int32)})
+        ro = TbRaggedIn(3, n, _ptr(jo), _ptr(mo), _ptr(out["xyz"]), _ptr(out["support"]), _ptr(out["conn"]), _ptr(out["aed"]),
+                        _ptr(out["force"]), int(s["nj"].max()), int(s["nm"].max()))
+        bo = TbBatchOut(_ptr(out["u"]), _ptr(out["ext"]), _ptr(out["axial"]), _ptr(out["weight"]), _ptr(out["info"]))
+        check(lib().tb_solve_ragged(C.byref(ro), C.byref(bo), st))
     return out
 
 

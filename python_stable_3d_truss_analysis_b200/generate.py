@@ -356,3 +356,44 @@ def GenerateAugmentedDataset(pool, nOut, moveToCentroid=False, translateRange=No
     if asNumpy:
         out = {k: (v.cpu().numpy() if hasattr(v, "cpu") else v) for k, v in out.items()}
     return out
+
+
+def GenerateRandomCubeTrussesOnDevice(nTruss, gridRange=(5, 5, 5), numCubeRange=(5, 5), lengthRange=(50, 150),
+                                      forceRange=((-30000, 30000), (-30000, 30000), (-30000, 30000)), nForceRange=None,
+                                      method=GenerateMethod.Random, linkType=LinkType.Random, memberTypes=((1., 1e7, 0.1),),
+                                      isAddPinSupport=True, isAllowParallel=False, isDoStructuralAnalysis=False, seed=0,
+                                      maxAttempts=64, asNumpy=True, export=False):
+    """``GenerateRandomCubeTrusses`` as one GPU pass: ``nTruss`` random cube trusses -- the
+    random walk over the grid, joint numbering, member linking, cell lengths, pin supports, random loads and member types
+    and the stability re-draw of generate.py:152-336, 338-372 -- generated by ``tb_gencube`` (one thread per truss),
+    compacted into the packed ragged layout and, if ``isDoStructuralAnalysis``, solved by ``tb_solve_ragged`` in the same
+    pass.  ``numCubeRange`` is sampled uniformly per truss (the reference's generator loops over it with
+    ``numEachRange`` trusses per value; call this once per value with ``numCubeRange=(k, k)`` for that).
+
+    Returns the packed arrays (``joint_off``, ``member_off``, ``xyz``, ``support``, ``conn``, ``aed``, ``force``,
+    ``gen_info`` [, ``u``, ``ext``, ``axial``, ``weight``, ``info``]) -- ``dataset.PackedDataset(3, arrays)`` gives the views
+    into the reference's formats.  Random numbers are counter-based (keyed by ``seed``): reproducible, but not Python's
+    ``random`` stream -- ``GenerateRandomCubeTrusses`` above keeps that."""
+    import numpy as np
+
+    from . import _lib
+
+    prm = _lib.TbGencubeParams()
+    for i in range(3):
+        prm.grid[i] = int(gridRange[i])
+        prm.force_lo[i], prm.force_hi[i] = float(forceRange[i][0]), float(forceRange[i][1])
+    prm.ncube_lo, prm.ncube_hi = int(numCubeRange[0]), int(numCubeRange[1])
+    prm.method, prm.link_type = int(method), int(linkType)
+    prm.add_pin, prm.allow_parallel = int(bool(isAddPinSupport)), int(bool(isAllowParallel))
+    prm.nforce_lo = -1 if nForceRange is None or nForceRange[0] is None else int(nForceRange[0])
+    prm.nforce_hi = -1 if nForceRange is None or nForceRange[1] is None else int(nForceRange[1])
+    table = np.array([t.Serialize() if isinstance(t, MemberType) else list(t) for t in memberTypes], dtype=np.float64).reshape(-1, 3)
+    prm.n_type = int(table.shape[0])
+    prm.max_attempts = int(maxAttempts)
+    prm.length_lo, prm.length_hi = float(lengthRange[0]), float(lengthRange[1])
+    prm.seed = int(seed)
+    out = _lib.gencube_device(prm, nTruss, table, solve=isDoStructuralAnalysis, export=export)
+    out["dim"] = 3
+    if asNumpy:
+        out = {k: (v.cpu().numpy() if hasattr(v, "cpu") else v) for k, v in out.items()}
+    return out
