@@ -355,42 +355,71 @@ struct Frag {
   double c[2][4][2];  // [m-block][n-block][2]
 };
 
+// TMA side of the tile pipeline: one elected thread moves a stage with bulk copies (cp.async.bulk: the copy engine writes
+// shared memory and signals an mbarrier with the byte count; no thread touches the data on its way in)
+__device__ __forceinline__ unsigned ch_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ch_mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(ch_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void ch_mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(ch_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void ch_mbar_wait(uint64_t* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "CH_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra CH_DONE;\n"
+      "bra CH_WAIT;\n"
+      "CH_DONE:\n"
+      "}\n" ::"r"(ch_smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void ch_bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(ch_smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(ch_smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void ch_fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
 // acc += sum over the nk block columns k in klist of L(ti,k) * L(tj,k)^T, streamed as 64-row x 16-k chunks through a two-stage
-// cp.async pipeline.  When with_y, also accumulates rows of A times the forward solution y.
+// TMA pipeline: a chunk of a fragment-major tile is eight contiguous 1 KB pieces (one per 8-row block), so one elected
+// thread issues 8 (+8 for the second operand, +1 for y) bulk copies per stage onto the stage's mbarrier and everybody waits
+// on its phase.  `phase` (bit s: parity the next wait on stage s expects) lives across calls.  When with_y, also accumulates
+// rows of A times the forward solution y.
 __device__ __forceinline__ void gemm_stream(const double* __restrict__ Lsys, const double* __restrict__ ysys, int ti,
                                             int tj, const int32_t* __restrict__ klist, int nk, bool with_y,
-                                            double* sStage, Frag& acc, double (&accy)[2], int tid) {
+                                            double* sStage, uint64_t* sBar, unsigned& phase, Frag& acc, double (&accy)[2], int tid) {
   const int lane = tid & 31, warp = tid >> 5, wm = warp >> 1, wn = warp & 1;
   const bool same = (ti == tj);
   const int S = 4 * nk;
-  // this thread's two 16-byte pieces of a chunk: piece e2 covers doubles 2*e2, 2*e2+1 of [rb 8][slab 4][lane 32]
+  if (S == 0) return;
+  // The stage buffers alias tiles written with ordinary stores, and the tiles of L in global memory were written with
+  // ordinary stores as well: order them before the copy engine's accesses (async proxy)
+  ch_fence_proxy_async();
+  __syncthreads();
   int kt = 0;
-  auto issue = [&](int s) {
+  auto issue = [&](int s) {                      // (thread 0 only)
     const int qd = s & 3;
     if (qd == 0) kt = __ldg(klist + (s >> 2));   // stages are issued in order: one list read per block column
     double* buf = sStage + (s & 1) * STAGE_DOUBLES;
+    uint64_t* bar = sBar + (s & 1);
     const int64_t tbase = ((qd >> 1) << 11) + ((qd & 1) << 7);   // k-half offset + slab offset inside the tile
     const double* ga = Lsys + tb_tile_index(ti, kt) * TB_TILE_ELEMS + tbase;
     const double* gb = Lsys + tb_tile_index(tj, kt) * TB_TILE_ELEMS + tbase;
+    ch_mbar_expect_tx(bar, (unsigned)((same ? CHUNK : 2 * CHUNK) + (with_y ? KCH : 0)) * 8u);
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const int e = (tid + q * 256) * 2;
-      const int src = ((e >> 7) << 8) + (e & 127);               // row block stride is 8 slabs in the tile
-      cp_async16(buf + e, ga + src);
-      if (!same) cp_async16(buf + CHUNK + e, gb + src);
+    for (int rb = 0; rb < 8; ++rb) {             // row block stride is 8 slabs (256 doubles) in the tile, 4 slabs in the chunk
+      ch_bulk_g2s(buf + rb * 128, ga + rb * 256, 1024u, bar);
+      if (!same) ch_bulk_g2s(buf + CHUNK + rb * 128, gb + rb * 256, 1024u, bar);
     }
-    if (with_y && tid < KCH / 2) cp_async16(buf + 2 * CHUNK + tid * 2, ysys + kt * T + qd * KCH + tid * 2);
-    cp_async_commit();
+    if (with_y) ch_bulk_g2s(buf + 2 * CHUNK, ysys + kt * T + qd * KCH, (unsigned)KCH * 8u, bar);
   };
-  if (S > 0) issue(0);
+  if (tid == 0) issue(0);
   for (int s = 0; s < S; ++s) {
-    if (s + 1 < S) {
-      issue(s + 1);
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
-    }
-    __syncthreads();
+    if (s + 1 < S && tid == 0) issue(s + 1);     // (its buffer was released by the barrier that ended stage s - 1)
+    ch_mbar_wait(sBar + (s & 1), (phase >> (s & 1)) & 1u);
+    phase ^= 1u << (s & 1);
     const double* bufA = sStage + (s & 1) * STAGE_DOUBLES;
     const double* bufB = same ? bufA : bufA + CHUNK;
     const double* bufY = bufA + 2 * CHUNK;
@@ -440,10 +469,18 @@ __global__ void __launch_bounds__(CH_THREADS, 3) k_chol(const LargeArgs a) {
   double* sDiag16 = sRv + T;           // [16]
   double* sT16 = sDiag16 + 16;         // [32]
   int* sFlag = (int*)(sT16 + 32);
+  uint64_t* sBar = reinterpret_cast<uint64_t*>(sT16 + 34);   // two stage mbarriers of the tile pipeline
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wm = warp >> 1, wn = warp & 1;
   const int nt = a.nt;
   const int64_t ntiles = (int64_t)nt * (nt + 1) / 2;
+  if (tid == 0) {
+    ch_mbar_init(&sBar[0], 1);
+    ch_mbar_init(&sBar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  unsigned phase = 0;                  // bit s: parity the next wait on stage s expects
+  __syncthreads();
 
   for (int b = blockIdx.x; b < a.batch; b += gridDim.x) {
     double* Lsys = a.L + (int64_t)b * ntiles * TB_TILE_ELEMS;
@@ -491,7 +528,7 @@ __global__ void __launch_bounds__(CH_THREADS, 3) k_chol(const LargeArgs a) {
             }
           }
         } else {
-          gemm_stream(Lsys, ysys, j, j, kl, np, true, sStage, acc, accy, tid);
+          gemm_stream(Lsys, ysys, j, j, kl, np, true, sStage, sBar, phase, acc, accy, tid);
           resident = -1;
         }
       }
@@ -674,7 +711,7 @@ __global__ void __launch_bounds__(CH_THREADS, 3) k_chol(const LargeArgs a) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) acc.c[mb][q][0] = acc.c[mb][q][1] = 0.0;
         gemm_stream(Lsys, ysys, i, j, a.prod_k + a.prod_ptr[tij], a.prod_ptr[tij + 1] - a.prod_ptr[tij], false, sStage,
-                    acc, accy, tid);
+                    sBar, phase, acc, accy, tid);
         PH(6)
         double* Xt = Lsys + tb_tile_index(i, j) * TB_TILE_ELEMS;
         // C = A(i,j) - acc  -> shared (fragment-major)
