@@ -105,8 +105,10 @@ def config3(torch, dist, rank, world, dev, steps, flush, peaks):
     ms = _timed(torch, dist, world, step, steps, flush, dev)
     kms = _kernel_ms(_lib, lambda: plan.fitness_device(B, dx, df, dg, dt, ALLOW_S, ALLOW_D, o), torch, steps)
     # end to end: host genes in, fitness + flags out (tb_fitness_host)
-    ho = {}
-    e2e_s = _wall(torch, dist, world, lambda: plan.fitness_host(B, xyz, force, mine, tt, ALLOW_S, ALLOW_D, out=ho), max(3, steps), dev)
+    h_mine = _lib.pinned_empty(mine.shape, np.int32)         # page-locked genes in, fitness / flags out
+    h_mine[...] = mine
+    ho = {"fitness": _lib.pinned_empty((B,)), "flags": _lib.pinned_empty((B, 2), np.uint8), "info": _lib.pinned_empty((B,), np.int32)}
+    e2e_s = _wall(torch, dist, world, lambda: plan.fitness_host(B, xyz, force, h_mine, tt, ALLOW_S, ALLOW_D, out=ho), max(3, steps), dev)
     # parity: sampled genes against the oracle's GA.GetFitness (ga.py:139-149)
     worst = 0.0
     if rank == 0:
@@ -188,9 +190,17 @@ def config4(torch, dist, rank, world, dev, steps, flush, peaks):
         step()
     ms = _timed(torch, dist, world, step, steps, flush, dev)
     kms = _kernel_ms(_lib, solve, torch, steps)
+    def pin(a):                                              # page-locked copies: the host entry point copies at PCIe speed
+        h = _lib.pinned_empty(a.shape, a.dtype)
+        h[...] = a
+        return h
+    hp = [pin(np.ascontiguousarray(x)) for x in (jo_r, mo_r, xyz_r, sup_r, conn_r, aed_r, force_r)]
+    ho = {"u": _lib.pinned_empty((SJ * 3,)), "ext": _lib.pinned_empty((SJ * 3,)), "axial": _lib.pinned_empty((SM,)),
+          "weight": _lib.pinned_empty((B,)), "info": _lib.pinned_empty((B,), np.int32)}
     e2e_s = _wall(torch, dist, world,
-                  lambda: _lib.solve_ragged_host(3, jo_r, mo_r, xyz_r, sup_r, conn_r, aed_r, force_r, want=("u", "ext", "axial", "weight")),
+                  lambda: _lib.solve_ragged_host(3, *hp, want=("u", "ext", "axial", "weight"), out=ho),
                   max(3, min(steps, 5)), dev)
+    assert np.array_equal(ho["u"], out["u"].cpu().numpy()), "config 4: host and device entry points disagree"
     worst = 0.0
     info = out["info"].cpu().numpy()
     solved = int((info == 0).sum())

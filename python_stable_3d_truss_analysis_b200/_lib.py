@@ -581,8 +581,10 @@ def small_path_limits():
     return a.value, b.value
 
 
-def solve_ragged_host(dim, joint_off, member_off, xyz, support, conn, aed, force, want=("u", "ext", "axial", "weight")):
-    """B independent trusses with their own topology (generate.py:354-357), packed back to back."""
+def solve_ragged_host(dim, joint_off, member_off, xyz, support, conn, aed, force, want=("u", "ext", "axial", "weight"),
+                      out=None):
+    """B independent trusses with their own topology (generate.py:354-357), packed back to back.  ``out`` may hold
+    preallocated result arrays (page-locked ones from ``pinned_empty`` travel at full PCIe speed)."""
     joint_off = _np(joint_off, np.int64)
     member_off = _np(member_off, np.int64)
     B = joint_off.shape[0] - 1
@@ -592,10 +594,14 @@ def solve_ragged_host(dim, joint_off, member_off, xyz, support, conn, aed, force
     ri = TbRaggedIn(int(dim), int(B), joint_off.ctypes.data, member_off.ctypes.data, xyz.ctypes.data,
                     support.ctypes.data, conn.ctypes.data, aed.ctypes.data, force.ctypes.data,
                     int(np.diff(joint_off).max()) if B else 0, int(np.diff(member_off).max()) if B else 0)
-    out = {"info": np.empty(B, np.int32)}
+    out = {} if out is None else out
+    out.setdefault("info", np.empty(B, np.int32))
     shp = {"u": SJ * dim, "ext": SJ * dim, "axial": SM, "weight": B}
     for k in want:
-        out[k] = np.empty(shp[k], np.float64)
+        if k not in out:
+            out[k] = np.empty(shp[k], np.float64)
+        elif out[k].size != shp[k] or out[k].dtype != np.float64:
+            raise ValueError(f"out[{k!r}] must be a float64 array of {shp[k]} elements")
     bo = TbBatchOut(_ptr(out.get("u")), _ptr(out.get("ext")), _ptr(out.get("axial")), _ptr(out.get("weight")),
                     _ptr(out["info"]))
     check(lib().tb_solve_ragged_host(C.byref(ri), C.byref(bo)))

@@ -8,6 +8,6 @@ python - <<PY
 import json
 d=json.loads(open('gpurun_out/bench_n$N.json').read())
 print(json.dumps({k:d.get(k) for k in ('value','ms_per_step','n_gpus','e2e','kernels')}, indent=None)[:1200])
-print(d['config']['multi_gpu'])
+print(d.get('run'))
 for k,v in d.get('configs',{}).items(): print(k, {kk:v.get(kk) for kk in ('value','ms_per_step','error','multi_gpu')})
 PY
