@@ -431,38 +431,46 @@ def run_gpu(args):
     assert np.array_equal(h_out["u"], out["u"].cpu().numpy()), "host and device entry points disagree"
     # the same batches streamed through the pipelined entry point (tb_solve_host_async / tb_host_wait): three batches in
     # flight, so the copies of one batch travel under the kernels of its neighbours; every step still copies its inputs
-    # from and its results to pinned host memory inside the timed region, and the region ends when the last result is home
-    h_out2 = {k: pin(np.empty_like(v)) if v.dtype == np.float64 else torch.empty(B, dtype=torch.int32).pin_memory().numpy()
-              for k, v in h_out.items()}
-    h_out3 = {k: pin(np.empty_like(v)) if v.dtype == np.float64 else torch.empty(B, dtype=torch.int32).pin_memory().numpy()
-              for k, v in h_out.items()}
-    bufs = (h_out, h_out2, h_out3)
-    for b in bufs:
-        for v in b.values():
-            v.fill(0)
+    # from and its results to pinned host memory inside the timed region, and the region ends when the last result is home.
+    # Results come back in the compact layout (u_free [n], react [s], axial [M], weight: everything the dense u / ext /
+    # axial hold -- u is zero at supports, ext is the caller's own load vector at free DOFs, truss.py:342-351) and, for
+    # comparison, in the dense one.
+    free_idx, _, sup_idx = plan.maps()
+    want_dev = {"u_free": out["u"][:, torch.from_numpy(free_idx.astype(np.int64)).to(dev)].cpu().numpy(),
+                "react": out["ext"][:, torch.from_numpy(sup_idx.astype(np.int64)).to(dev)].cpu().numpy(),
+                "u": out["u"].cpu().numpy(), "ext": out["ext"].cpu().numpy(), "axial": out["axial"].cpu().numpy()}
+    pin_i32 = lambda n_: torch.empty(n_, dtype=torch.int32).pin_memory().numpy()  # noqa: E731
     pipe_steps = max(e2e_steps, min(4 * args.steps, 60))
-    tk = [plan.solve_host_async(B, h_xyz, h_F, aed=h_aed, out=bufs[i % 3])[0] for i in range(3)]
-    for t_ in tk:
-        plan.host_wait(t_)
-    barrier()
-    t0 = time.perf_counter()
-    inflight = []
-    for i in range(pipe_steps):
-        inflight.append(plan.solve_host_async(B, h_xyz, h_F, aed=h_aed, out=bufs[i % 3])[0])
-        if len(inflight) == 3:                  # one batch uploading, one computing, one downloading
-            plan.host_wait(inflight.pop(0))
-    for t_ in inflight:
-        plan.host_wait(t_)
-    pipe_s = time.perf_counter() - t0
-    t = torch.tensor([pipe_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = B * world * pipe_steps / float(t.item())
-    for b in bufs:
-        for k in ("u", "ext", "axial"):
-            assert np.array_equal(b[k], out[k].cpu().numpy()), "pipelined host entry point disagrees with the device entry point"
+
+    def stream_batches(layout):
+        shapes = {"u": (B, N), "ext": (B, N), "axial": (B, M), "weight": (B,), "u_free": (B, plan.n), "react": (B, plan.s)}
+        bufs = [dict({k: pin(np.zeros(shapes[k])) for k in layout}, info=pin_i32(B)) for _ in range(3)]
+        tk = [plan.solve_host_async(B, h_xyz, h_F, aed=h_aed, want=layout, out=bufs[i % 3])[0] for i in range(3)]
+        for t_ in tk:
+            plan.host_wait(t_)
+        barrier()
+        t0 = time.perf_counter()
+        inflight = []
+        for i in range(pipe_steps):
+            inflight.append(plan.solve_host_async(B, h_xyz, h_F, aed=h_aed, want=layout, out=bufs[i % 3])[0])
+            if len(inflight) == 3:                  # one batch uploading, one computing, one downloading
+                plan.host_wait(inflight.pop(0))
+        for t_ in inflight:
+            plan.host_wait(t_)
+        pipe_s = time.perf_counter() - t0
+        tt = torch.tensor([pipe_s], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        for b in bufs:
+            for k in layout:
+                if k != "weight":
+                    assert np.array_equal(b[k], want_dev[k]), f"pipelined host entry point disagrees with the device entry point ({k})"
+        return B * world * pipe_steps / float(tt.item()), int(sum(v.nbytes for v in bufs[0].values()))
+
+    e2e_dense, d2h_dense = stream_batches(("u", "ext", "axial", "weight"))
+    e2e_value, d2h_compact = stream_batches(("u_free", "react", "axial", "weight"))
     h2d = int(h_xyz.nbytes + h_aed.nbytes + h_F.nbytes)
-    d2h = int(sum(v.nbytes for v in h_out.values()))
+    d2h = d2h_compact
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- the other GPU configurations of BASELINE.json (3: GA population, 4: ragged cube-7 batch, 5: cube 12^3), every rank
@@ -557,11 +565,14 @@ def run_gpu(args):
                 "launch": "CUDA graph replay of the step" if graph is not None else "plain stream launches",
                 "multi_gpu": "contiguous block partition of the batch; " + gather_mode},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "api": "tb_solve_host_async + tb_host_wait (C ABI), pinned host buffers, three batches in flight (upload / compute / download): every step "
-                       "copies its inputs H2D and its results D2H inside the timed region",
+                "api": "tb_solve_host_async + tb_host_wait (C ABI), pinned host buffers, three batches in flight (upload / compute / "
+                       "download): every step copies its inputs H2D and its results D2H inside the timed region; results in the "
+                       "compact layout (u_free [n] | react [s] | axial [M] | weight: the non-redundant content of u / ext / axial)",
                 "steps": pipe_steps,
-                "blocking": {"value": e2e_blocking, "unit": UNIT, "steps": e2e_steps,
-                             "api": "tb_solve_host: one blocking call per step (copies of the step not overlapped with other steps)"}},
+                "dense_layout": {"value": e2e_dense, "unit": UNIT, "d2h_bytes_per_step": d2h_dense,
+                                 "api": "same pipeline, results as dense u [N] | ext [N] | axial [M] | weight"},
+                "blocking": {"value": e2e_blocking, "unit": UNIT, "steps": e2e_steps, "d2h_bytes_per_step": d2h_dense,
+                             "api": "tb_solve_host: one blocking call per step, dense layout (copies of the step not overlapped with other steps)"}},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"kernel": kname + " (block Cholesky + forward/back substitution)", "bound": "tensor",

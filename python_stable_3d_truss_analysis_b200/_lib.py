@@ -141,7 +141,7 @@ class TbBatchIn(C.Structure):
 
 class TbBatchOut(C.Structure):
     _fields_ = [("u", C.c_void_p), ("ext", C.c_void_p), ("axial", C.c_void_p), ("weight", C.c_void_p),
-                ("info", C.c_void_p)]
+                ("info", C.c_void_p), ("u_free", C.c_void_p), ("react", C.c_void_p)]
 
 
 class TbFitOut(C.Structure):
@@ -481,17 +481,30 @@ class Plan:
         keep = []
         bi = self._batch_in(B, xyz, aed, gene, type_table, force, keep)
         out = {} if out is None else out
-        shp = {"u": (B, self.N), "ext": (B, self.N), "axial": (B, self.M), "weight": (B,)}
+        shp = {"u": (B, self.N), "ext": (B, self.N), "axial": (B, self.M), "weight": (B,), "u_free": (B, self.n),
+               "react": (B, self.s)}
         for k in want:
             if k not in out:
                 out[k] = np.empty(shp[k], np.float64)
         if "info" not in out:
             out["info"] = np.empty(B, np.int32)
         bo = TbBatchOut(_ptr(out.get("u")), _ptr(out.get("ext")), _ptr(out.get("axial")), _ptr(out.get("weight")),
-                        _ptr(out["info"]))
+                        _ptr(out["info"]), _ptr(out.get("u_free")), _ptr(out.get("react")))
         fn = lib().tb_solve_loadcases_host if shared_factor else lib().tb_solve_host
         check(fn(self._h, C.byref(bi), C.byref(bo)))
         return out
+
+    def expand_compact(self, u_free, react, force):
+        """Dense ``u`` / ``ext`` ([B, N]) from the compact outputs: ``u`` is zero at supported DOFs, ``ext`` is the load
+        vector with the supported DOFs overwritten by the reactions (truss.py:342-351)."""
+        free_idx, _, sup_idx = self.maps()
+        u_free = np.asarray(u_free, dtype=np.float64).reshape(-1, self.n)
+        B = u_free.shape[0]
+        u = np.zeros((B, self.N))
+        u[:, free_idx] = u_free
+        ext = np.broadcast_to(np.asarray(force, dtype=np.float64).reshape(-1, self.N), (B, self.N)).copy()
+        ext[:, sup_idx] = np.asarray(react, dtype=np.float64).reshape(B, -1)
+        return u, ext
 
     def solve_host_async(self, B, xyz, force, aed=None, gene=None, type_table=None, want=("u", "ext", "axial", "weight"),
                          out=None):
@@ -501,14 +514,15 @@ class Plan:
         keep = []
         bi = self._batch_in(B, xyz, aed, gene, type_table, force, keep)
         out = {} if out is None else out
-        shp = {"u": (B, self.N), "ext": (B, self.N), "axial": (B, self.M), "weight": (B,)}
+        shp = {"u": (B, self.N), "ext": (B, self.N), "axial": (B, self.M), "weight": (B,), "u_free": (B, self.n),
+               "react": (B, self.s)}
         for k in want:
             if k not in out:
                 out[k] = pinned_empty(shp[k], np.float64)
         if "info" not in out:
             out["info"] = pinned_empty((B,), np.int32)
         bo = TbBatchOut(_ptr(out.get("u")), _ptr(out.get("ext")), _ptr(out.get("axial")), _ptr(out.get("weight")),
-                        _ptr(out["info"]))
+                        _ptr(out["info"]), _ptr(out.get("u_free")), _ptr(out.get("react")))
         ticket = C.c_uint64(0)
         check(lib().tb_solve_host_async(self._h, C.byref(bi), C.byref(bo), C.byref(ticket)))
         self._async_keep = getattr(self, "_async_keep", {})
@@ -548,7 +562,7 @@ class Plan:
         bi = self._batch_in(B, xyz, aed, gene, type_table, force, keep)
         st = torch.cuda.current_stream() if stream is None else stream
         bo = TbBatchOut(_ptr(out.get("u")), _ptr(out.get("ext")), _ptr(out.get("axial")), _ptr(out.get("weight")),
-                        _ptr(out.get("info")))
+                        _ptr(out.get("info")), _ptr(out.get("u_free")), _ptr(out.get("react")))
         fn = lib().tb_solve_loadcases if shared_factor else lib().tb_solve
         check(fn(self._h, C.byref(bi), C.byref(bo), C.c_void_p(st.cuda_stream)))
         return out

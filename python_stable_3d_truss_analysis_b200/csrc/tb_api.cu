@@ -39,9 +39,70 @@ int check_batch_in(const tb_plan* p, const tb_batch_in* in) {
   return TB_OK;
 }
 
+// Compact outputs (tb_batch_out.u_free / react): gathered from the dense rows of the same systems
+__global__ void __launch_bounds__(256) k_compact_out(const double* __restrict__ u, const double* __restrict__ ext,
+                                                      double* __restrict__ u_free, double* __restrict__ react,
+                                                      const int32_t* __restrict__ free_ref, const int32_t* __restrict__ sup_idx,
+                                                      int N, int n, int s, int nb) {
+  for (int b = blockIdx.x; b < nb; b += gridDim.x) {
+    if (u_free)
+      for (int r = threadIdx.x; r < n; r += 256) u_free[(int64_t)b * n + r] = u[(int64_t)b * N + free_ref[r]];
+    if (react)
+      for (int r = threadIdx.x; r < s; r += 256) react[(int64_t)b * s + r] = ext[(int64_t)b * N + sup_idx[r]];
+  }
+}
+
+// dense temporaries of a call that wants the compact outputs without the dense ones (call before the ranges are enqueued)
+int ensure_compact_tmp(tb_plan* p, const tb_batch_out* out, int batch, cudaStream_t st) {
+  if (!out) return TB_OK;
+  auto grow = [&](double** buf, size_t* cap) -> int {
+    if (*cap >= (size_t)batch) return TB_OK;
+    if (*buf) {
+      TB_CUDA(cudaStreamSynchronize(st));
+      TB_CUDA(cudaDeviceSynchronize());
+      TB_CUDA(cudaFree(*buf));
+      *buf = nullptr;
+      *cap = 0;
+    }
+    TB_CUDA(cudaMalloc((void**)buf, (size_t)batch * p->N * sizeof(double)));
+    *cap = (size_t)batch;
+    return TB_OK;
+  };
+  if (out->u_free && !out->u) {
+    const int rc = grow(&p->compact_u, &p->compact_cap_u);
+    if (rc) return rc;
+  }
+  if (out->react && !out->ext) {
+    const int rc = grow(&p->compact_ext, &p->compact_cap_ext);
+    if (rc) return rc;
+  }
+  return TB_OK;
+}
+
+int run_plan_range_dense(tb_plan* p, const tb_batch_in* in, const tb_batch_out* out, const tb_fit_out* fit, double allow_s,
+                         double allow_d, cudaStream_t st, int b0, int nb, void* ws, int shared_k);
+
 // Systems [b0, b0 + nb) of a uniform batch on stream st; the blocked pipelines use the workspace slice `ws`.
 int run_plan_range(tb_plan* p, const tb_batch_in* in, const tb_batch_out* out, const tb_fit_out* fit, double allow_s,
                    double allow_d, cudaStream_t st, int b0, int nb, void* ws, int shared_k = 0) {
+  if (!out->u_free && !out->react) return run_plan_range_dense(p, in, out, fit, allow_s, allow_d, st, b0, nb, ws, shared_k);
+  tb_batch_out eff = *out;
+  if (out->u_free && !eff.u) eff.u = p->compact_u;          // (ensure_compact_tmp sized them for the whole batch)
+  if (out->react && !eff.ext) eff.ext = p->compact_ext;
+  if ((out->u_free && !eff.u) || (out->react && !eff.ext)) return TB_ERR_ALLOC;
+  const int rc = run_plan_range_dense(p, in, &eff, fit, allow_s, allow_d, st, b0, nb, ws, shared_k);
+  if (rc) return rc;
+  const int grid = nb < 148 * 8 ? nb : 148 * 8;
+  k_compact_out<<<grid, 256, 0, st>>>(eff.u ? eff.u + (int64_t)b0 * p->N : nullptr, eff.ext ? eff.ext + (int64_t)b0 * p->N : nullptr,
+                                      out->u_free ? out->u_free + (int64_t)b0 * p->n : nullptr,
+                                      out->react ? out->react + (int64_t)b0 * p->s : nullptr, p->d_free_ref, p->d_sup_idx, p->N,
+                                      p->n, p->s, nb);
+  tb_count_launch();
+  return (int)cudaGetLastError();
+}
+
+int run_plan_range_dense(tb_plan* p, const tb_batch_in* in, const tb_batch_out* out, const tb_fit_out* fit, double allow_s,
+                         double allow_d, cudaStream_t st, int b0, int nb, void* ws, int shared_k) {
   const int fitness_mode = fit ? 1 : 0;
   int32_t* info = fit && fit->info ? fit->info : out->info;
   if (p->path == 0) {
@@ -219,6 +280,10 @@ int run_plan_unlocked(tb_plan* p, const tb_batch_in* in, const tb_batch_out* out
                       double allow_d, cudaStream_t st, int shared_k) {
   static const tb_batch_out none = {nullptr, nullptr, nullptr, nullptr, nullptr};
   if (!out) out = &none;
+  {
+    const int rc0 = ensure_compact_tmp(p, out, in->batch, st);
+    if (rc0) return rc0;
+  }
   if (p->path == 0) {
     int rc = run_plan_range(p, in, out, fit, allow_s, allow_d, st, 0, in->batch, nullptr);
     if (rc) return rc;
@@ -406,6 +471,7 @@ int run_plan_host_locked(tb_plan* p, const tb_batch_in* in, const tb_batch_out* 
   add(out->u ? (size_t)B * rowN * 8 : 0); add(out->ext ? (size_t)B * rowN * 8 : 0);
   add(out->axial ? (size_t)B * rowM * 8 : 0); add(out->weight ? (size_t)B * 8 : 0);
   add((size_t)B * 4); add(fit ? (size_t)B * 8 : 0); add(fit ? (size_t)B * 2 : 0);
+  add(out->u_free ? (size_t)B * p->n * 8 : 0); add(out->react ? (size_t)B * p->s * 8 : 0);
   void** arena = async ? &p->stage_async[async_slot] : &p->stage_dev;
   size_t* arena_bytes = async ? &p->stage_async_bytes[async_slot] : &p->stage_dev_bytes;
   rc = arena_reserve(arena, arena_bytes, need + 4096);
@@ -434,6 +500,10 @@ int run_plan_host_locked(tb_plan* p, const tb_batch_in* in, const tb_batch_out* 
   dout.axial = out->axial ? take<double>(cur, (size_t)B * rowM) : nullptr;
   dout.weight = out->weight ? take<double>(cur, (size_t)B) : nullptr;
   dout.info = take<int32_t>(cur, (size_t)B);
+  dout.u_free = out->u_free ? take<double>(cur, (size_t)B * p->n) : nullptr;
+  dout.react = out->react ? take<double>(cur, (size_t)B * p->s) : nullptr;
+  rc = ensure_compact_tmp(p, &dout, B, hp->comp);
+  if (rc) return rc;
   tb_fit_out dfit = {nullptr, nullptr, nullptr};
   if (fit) {
     dfit.fitness = take<double>(cur, (size_t)B);
@@ -462,7 +532,8 @@ int run_plan_host_locked(tb_plan* p, const tb_batch_in* in, const tb_batch_out* 
     if (p->path != 0 && per_sys * (size_t)B > ws_cap_bytes()) nch = 1;   // run_plan cuts the batch to the workspace cap itself
     // chunking a blocked path only pays through the D2H it hides (each chunk is a latency-bound wave of its own):
     // with little to copy back (fitness only, weights only) one launch over the whole batch is faster
-    const size_t d2h_bytes = ((out->u ? rowN : 0) + (out->ext ? rowN : 0) + (out->axial ? rowM : 0)) * (size_t)B * 8;
+    const size_t d2h_bytes = ((out->u ? rowN : 0) + (out->ext ? rowN : 0) + (out->axial ? rowM : 0) + (out->u_free ? p->n : 0) +
+                              (out->react ? p->s : 0)) * (size_t)B * 8;
     if (want == 0 && p->path != 0 && d2h_bytes < ((size_t)4 << 20)) nch = 1;
     if (async) nch = 1;                        // a pipelined call is one chunk: its neighbours hide its copies
   }
@@ -533,6 +604,8 @@ int run_plan_host_locked(tb_plan* p, const tb_batch_in* in, const tb_batch_out* 
     if (out->ext) TB_CUDA(cudaMemcpyAsync(out->ext + (size_t)b0 * rowN, dout.ext + (size_t)b0 * rowN, (size_t)nb * rowN * 8, cudaMemcpyDeviceToHost, sj));
     if (out->axial) TB_CUDA(cudaMemcpyAsync(out->axial + (size_t)b0 * rowM, dout.axial + (size_t)b0 * rowM, (size_t)nb * rowM * 8, cudaMemcpyDeviceToHost, sj));
     if (out->weight) TB_CUDA(cudaMemcpyAsync(out->weight + b0, dout.weight + b0, (size_t)nb * 8, cudaMemcpyDeviceToHost, sj));
+    if (out->u_free) TB_CUDA(cudaMemcpyAsync(out->u_free + (size_t)b0 * p->n, dout.u_free + (size_t)b0 * p->n, (size_t)nb * p->n * 8, cudaMemcpyDeviceToHost, sj));
+    if (out->react && p->s > 0) TB_CUDA(cudaMemcpyAsync(out->react + (size_t)b0 * p->s, dout.react + (size_t)b0 * p->s, (size_t)nb * p->s * 8, cudaMemcpyDeviceToHost, sj));
     if (out->info) TB_CUDA(cudaMemcpyAsync(out->info + b0, dinfo + b0, (size_t)nb * 4, cudaMemcpyDeviceToHost, sj));
     if (fit) {
       if (fit->fitness) TB_CUDA(cudaMemcpyAsync(fit->fitness + b0, dfit.fitness + b0, (size_t)nb * 8, cudaMemcpyDeviceToHost, sj));
@@ -658,6 +731,7 @@ extern "C" int tb_solve_ragged(const tb_ragged_in* in, const tb_batch_out* out, 
   int rc = check_ragged(in);
   if (rc) return rc;
   if (!out) return TB_ERR_NULL;
+  if (out->u_free || out->react) return TB_ERR_SIZE;        // (the compact layout needs one n and s for the whole batch)
   if (!have_device()) return TB_ERR_NO_DEVICE;
   if (in->batch == 0) return TB_OK;
   return run_ragged(in, out, (cudaStream_t)cuda_stream);
@@ -667,6 +741,7 @@ extern "C" int tb_solve_ragged_host(const tb_ragged_in* in, const tb_batch_out* 
   int rc = check_ragged(in);
   if (rc) return rc;
   if (!out) return TB_ERR_NULL;
+  if (out->u_free || out->react) return TB_ERR_SIZE;
   if (!have_device()) return TB_ERR_NO_DEVICE;
   const int B = in->batch, d = in->dim;
   if (B == 0) return TB_OK;
@@ -713,6 +788,7 @@ extern "C" int tb_solve_ragged_host(const tb_ragged_in* in, const tb_batch_out* 
   din.joint_off = djo; din.member_off = dmo; din.joint_xyz = dxyz; din.support = dsup;
   din.conn = dconn; din.member_aed = daed; din.force = df;
   tb_batch_out dout;
+  dout.u_free = dout.react = nullptr;
   dout.u = out->u ? take<double>(cur, SJ * d) : nullptr;
   dout.ext = out->ext ? take<double>(cur, SJ * d) : nullptr;
   dout.axial = out->axial ? take<double>(cur, SM) : nullptr;

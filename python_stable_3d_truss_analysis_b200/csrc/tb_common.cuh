@@ -108,6 +108,7 @@ struct tb_plan {
   int32_t* d_free_idx = nullptr;
   int32_t* d_dof2free = nullptr;
   int32_t* d_sup_idx = nullptr;
+  int32_t* d_free_ref = nullptr;   // [n] DOF index of free DOF r in the reference's order (host: free_idx): compact outputs
   int32_t* d_ent_row = nullptr;
   int32_t* d_ent_col = nullptr;
   int64_t* d_ent_ptr = nullptr;
@@ -150,6 +151,10 @@ struct tb_plan {
   size_t stage_dev_bytes = 0;
   void* stage_pinned = nullptr;
   size_t stage_pinned_bytes = 0;
+  // dense u / ext of a call that asks for the compact outputs only (grow-only, [capacity][N] each)
+  double* compact_u = nullptr;
+  double* compact_ext = nullptr;
+  size_t compact_cap_u = 0, compact_cap_ext = 0;   // systems
   // pipelined host calls (tb_solve_host_async): TB_ASYNC_SLOTS more staging arenas used in turn by consecutive calls,
   // the events that chain a call's copies and kernels, and the ticket counters (submitted / known to be complete)
   void* stage_async[TB_ASYNC_SLOTS] = {};

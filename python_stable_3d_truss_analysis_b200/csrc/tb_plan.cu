@@ -466,6 +466,7 @@ extern "C" int tb_plan_create(const tb_topology* topo, tb_plan** plan_out) {
   if (!rc) rc = upload(&p->d_free_idx, p->free_int);
   if (!rc) rc = upload(&p->d_dof2free, p->d2f_int);
   if (!rc) rc = upload(&p->d_sup_idx, p->sup_idx);
+  if (!rc) rc = upload(&p->d_free_ref, p->free_idx);
   if (!rc) rc = upload(&p->d_ent_row, p->int_row);
   if (!rc) rc = upload(&p->d_ent_col, p->int_col);
   if (!rc) rc = upload(&p->d_ent_ptr, p->ent_ptr);
@@ -511,6 +512,9 @@ extern "C" void tb_plan_destroy(tb_plan* p) {
   cudaFree(p->d_free_idx);
   cudaFree(p->d_dof2free);
   cudaFree(p->d_sup_idx);
+  cudaFree(p->d_free_ref);
+  cudaFree(p->compact_u);
+  cudaFree(p->compact_ext);
   cudaFree(p->d_ent_row);
   cudaFree(p->d_ent_col);
   cudaFree(p->d_ent_ptr);

@@ -1,6 +1,7 @@
 """Parity of the CUDA path (through the C ABI) against the reference's golden files, the
 live-reference vectors and the oracle.  Tolerance: 1e-9 norm-wise per field (north_star);
 index maps are checked bit-exact in tests/test_abi_cpu.py."""
+import ctypes as C
 import json
 
 import numpy as np
@@ -684,3 +685,53 @@ def test_fixed_member_type_double_solve_matches_oracle():
             wu = want["u"].reshape(-1, t.dim)
             for j, v in displaces.items():
                 assert np.abs(v - wu[j]).max() <= 1e-9 * np.abs(wu).max()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case,path", [("bar-72", 0), ("bar-72", 1), ("bar-942", 2), ("bar-942", 1), ("bar-10", 0)])
+def test_compact_outputs_equal_the_dense_ones(case, path):
+    """tb_batch_out.u_free / react (the compact layout: n + s + M doubles per system) against the dense outputs, bit for
+    bit, on every pipeline and through the device, blocking-host and pipelined-host entry points, with and without the
+    dense arrays in the same call; expanding them gives back u and ext (truss.py:342-351)."""
+    import torch
+    name, dim, data, _ = next(c for c in H.shipped_cases() if c[0].startswith(case))
+    t = Truss(dim).LoadFromJSON(data=data)
+    xyz, sup, conn, aed, force = t._pack()
+    plan = _lib.Plan(dim, conn, sup.astype(np.uint8))
+    plan.set_path(path)
+    free_idx, _, sup_idx = plan.maps()
+    B = 19
+    rng = np.random.default_rng(11)
+    F = force.reshape(1, -1) * rng.uniform(0.5, 2.0, size=(B, 1)) + rng.uniform(-1, 1, size=(B, plan.N))
+    dense = plan.solve_host(B, xyz, F, aed=aed)
+    assert not dense["info"].any()
+    want_u, want_r = dense["u"][:, free_idx], dense["ext"][:, sup_idx]
+    # blocking host call: compact only, and compact next to dense
+    only = plan.solve_host(B, xyz, F, aed=aed, want=("u_free", "react", "axial", "weight"))
+    both = plan.solve_host(B, xyz, F, aed=aed, want=("u", "ext", "u_free", "react", "axial"))
+    for got in (only, both):
+        assert np.array_equal(got["u_free"], want_u) and np.array_equal(got["react"], want_r)
+        assert np.array_equal(got["axial"], dense["axial"])
+    assert np.array_equal(both["u"], dense["u"]) and np.array_equal(both["ext"], dense["ext"])
+    u, ext = plan.expand_compact(only["u_free"], only["react"], F)
+    assert np.array_equal(u, dense["u"]) and np.array_equal(ext, dense["ext"])
+    # pipelined host call
+    Fp = _lib.pinned_empty(F.shape)
+    Fp[...] = F
+    tk, pout = plan.solve_host_async(B, xyz, Fp, aed=aed, want=("u_free", "react", "axial"))
+    plan.host_wait(tk)
+    assert np.array_equal(pout["u_free"], want_u) and np.array_equal(pout["react"], want_r)
+    # device entry point
+    dev = torch.device("cuda:0")
+    td = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)   # noqa: E731
+    dout = {"u_free": torch.empty(B, plan.n, dtype=torch.float64, device=dev), "react": torch.empty(B, plan.s, dtype=torch.float64, device=dev),
+            "axial": torch.empty(B, plan.M, dtype=torch.float64, device=dev), "info": torch.empty(B, dtype=torch.int32, device=dev)}
+    plan.solve_device(B, td(xyz), td(F), aed=td(aed), out=dout)
+    torch.cuda.synchronize()
+    assert np.array_equal(dout["u_free"].cpu().numpy(), want_u) and np.array_equal(dout["react"].cpu().numpy(), want_r)
+    # ragged batches have no common n / s: the compact layout is refused there
+    jo, mo = np.array([0, xyz.shape[0]], np.int64), np.array([0, conn.shape[0]], np.int64)
+    ri = _lib.TbRaggedIn(dim, 1, jo.ctypes.data, mo.ctypes.data, xyz.ctypes.data, sup.astype(np.uint8).ctypes.data, conn.ctypes.data,
+                         aed.ctypes.data, force.ctypes.data, xyz.shape[0], conn.shape[0])
+    bo = _lib.TbBatchOut(None, None, None, None, None, only["u_free"].ctypes.data, None)
+    assert _lib.lib().tb_solve_ragged_host(C.byref(ri), C.byref(bo)) == -3
