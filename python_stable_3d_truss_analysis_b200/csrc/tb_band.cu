@@ -1832,10 +1832,14 @@ template <int NB>
 int launch_subst(const LargeArgs& a, int num_sm, cudaStream_t st) {
   static const int force = [] { const char* s = getenv("TB_SUBST_TILE"); return s ? atoi(s) : 0; }();   // 1 | 8: force a kernel
   const int smem8 = (2 * (NB + 1) * BE + (NB + 1) * 128 + 128 + a.nb16 * 128) * 8;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return (int)cudaGetLastError();
+  dev &= 63;                                   // (attribute caches are per device: cudaFuncSetAttribute is a per-device setting)
   tb_prof_begin(TB_PROF_SUBST, st);
   if (force != 1 && smem8 <= 200 * 1024) {
     // tiles of eight load cases on the tensor cores; y of the whole system stays in shared memory
-    static int granted = 0;
+    static int granted_dev[64] = {};
+    int& granted = granted_dev[dev];
     if (granted < smem8) {
       cudaError_t e = cudaFuncSetAttribute(k_band_subst8<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem8);
       if (e != cudaSuccess) return (int)e;
@@ -1846,7 +1850,8 @@ int launch_subst(const LargeArgs& a, int num_sm, cudaStream_t st) {
   } else {
     constexpr int NW = 4;
     const int smem = NW * SubstCfg<NB>::DOUBLES * 8;
-    static bool set = false;
+    static bool set_dev[64] = {};
+    bool& set = set_dev[dev];
     if (!set) {
       cudaError_t e = cudaFuncSetAttribute(k_band_subst<NB, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
       if (e != cudaSuccess) return (int)e;
@@ -1867,7 +1872,10 @@ int launch_band(const LargeArgs& a, int num_sm, cudaStream_t st) {
   // shared memory (NB <= 6), two for the widest bands (NB = 7, 8: 59 / 76 KB per system)
   constexpr int NW = NB <= 6 ? 4 : 2;
   const int smem1 = NW * BandCfg<NB>::DOUBLES * 8, smem2 = (BandCfg<NB>::DOUBLES + 208) * 8, smem3 = Band3Cfg<NB>::DOUBLES * 8;
-  static int per1 = 0, per2 = 0, per3 = 0;     // attribute / occupancy queries once per instantiation (single device per process)
+  static int per_dev[64][3] = {};              // attribute / occupancy queries once per instantiation and device
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return (int)cudaGetLastError();
+  int &per1 = per_dev[dev & 63][0], &per2 = per_dev[dev & 63][1], &per3 = per_dev[dev & 63][2];
   if (per1 == 0) {
     int q1 = 0, q2 = 0, q3 = 0;
     cudaError_t e = cudaFuncSetAttribute(k_band1<NB, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1);
