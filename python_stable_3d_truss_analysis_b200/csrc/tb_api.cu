@@ -728,20 +728,20 @@ extern "C" int tb_fitness_host(tb_plan* plan, const tb_batch_in* in, double allo
 }
 
 extern "C" int tb_solve_ragged(const tb_ragged_in* in, const tb_batch_out* out, void* cuda_stream) {
+  if (out && (out->u_free || out->react)) return TB_ERR_SIZE;   // (the compact layout needs one n and s for the whole batch)
   int rc = check_ragged(in);
   if (rc) return rc;
   if (!out) return TB_ERR_NULL;
-  if (out->u_free || out->react) return TB_ERR_SIZE;        // (the compact layout needs one n and s for the whole batch)
   if (!have_device()) return TB_ERR_NO_DEVICE;
   if (in->batch == 0) return TB_OK;
   return run_ragged(in, out, (cudaStream_t)cuda_stream);
 }
 
 extern "C" int tb_solve_ragged_host(const tb_ragged_in* in, const tb_batch_out* out) {
+  if (out && (out->u_free || out->react)) return TB_ERR_SIZE;
   int rc = check_ragged(in);
   if (rc) return rc;
   if (!out) return TB_ERR_NULL;
-  if (out->u_free || out->react) return TB_ERR_SIZE;
   if (!have_device()) return TB_ERR_NO_DEVICE;
   const int B = in->batch, d = in->dim;
   if (B == 0) return TB_OK;
