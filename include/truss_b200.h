@@ -213,7 +213,8 @@ int tb_fitness_host(tb_plan* plan, const tb_batch_in* in, double allow_stress, d
  * UpdatePop rules (crossover of two distinct elites / mutation of one elite / keep pop[j] / fresh random gene,
  * ga.py:172-190).  Random numbers are counter-based (Philox4x32-10 keyed by `seed`, counter = individual, generation),
  * so a run is reproducible from (seed, generation) but does NOT replay Python's `random` stream -- the host GA class
- * keeps that property.  All pointers are device pointers; n_pop <= 16384. */
+ * keeps that property.  All pointers are device pointers.  The ranking counts, for every individual, the individuals that
+ * precede it (N^2 comparisons over a 2-D grid): no sort, no population limit. */
 typedef struct {
   int32_t n_pop, n_elite, n_member, n_type;
   double p_crossover, p_mutate, p_origin;   /* GA(pCrossover, pMutate, pOrigin); the rest re-seeds */

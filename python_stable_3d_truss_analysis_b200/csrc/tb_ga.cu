@@ -11,6 +11,8 @@
 // thread can reproduce any decision, so one thread per (individual, member) needs no communication.  The reference
 // draws from Python's Mersenne Twister in program order, which cannot be replayed in parallel; the host GA
 // (python_stable_3d_truss_analysis_b200/ga.py: GA.Evolve) stays stream-compatible with it, this path is the fast one.
+#include <mutex>
+
 #include "tb_common.cuh"
 
 namespace {
@@ -61,54 +63,50 @@ __device__ __forceinline__ uint64_t key_of(double f) {
   return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
 }
 
-// One CTA ranks the population: bitonic sort of (fitness key, index) pairs in shared memory -- the index as the second
-// key makes it the stable sort of `sorted(pop, key=fitness)` (ga.py:157).  Then the report: best individual and the
-// first feasible one in rank order (_RecordFeasible, ga.py:101-108).
-__global__ void __launch_bounds__(1024) k_ga_rank(int n_pop, int p2, const double* fitness, const uint8_t* flags, int32_t* order,
-                                                  tb_ga_report* rep) {
-  extern __shared__ __align__(16) unsigned char smraw[];
-  uint64_t* key = reinterpret_cast<uint64_t*>(smraw);
-  int32_t* idx = reinterpret_cast<int32_t*>(key + p2);
-  __shared__ int first_feasible;
-  const int tid = threadIdx.x;
-  for (int i = tid; i < p2; i += 1024) {
-    key[i] = i < n_pop ? key_of(fitness[i]) : ~0ull;
-    idx[i] = i < n_pop ? i : 0x7fffffff;
-  }
-  if (tid == 0) first_feasible = 0x7fffffff;
-  __syncthreads();
-  for (int k = 2; k <= p2; k <<= 1)
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = tid; i < p2; i += 1024) {
-        const int l = i ^ j;
-        if (l > i) {
-          const bool up = (i & k) == 0;
-          const uint64_t ka = key[i], kb = key[l];
-          const int ia = idx[i], ib = idx[l];
-          const bool gt = ka > kb || (ka == kb && ia > ib);
-          if (gt == up) {
-            key[i] = kb; key[l] = ka;
-            idx[i] = ib; idx[l] = ia;
-          }
-        }
-      }
-      __syncthreads();
+// Ranking without a sort: the rank of individual i is the number of individuals that precede it in the stable order of
+// `sorted(pop, key=fitness)` (ga.py:157), i.e. #{j : key_j < key_i or (key_j == key_i and j < i)}.  N^2 comparisons are
+// nothing for a GPU (8192^2 = 67 M), they spread over a 2-D grid (tiles of 256 individuals x slices of the comparison
+// range, partial counts added atomically), and there is no one-CTA bottleneck and no population limit.
+__global__ void __launch_bounds__(256) k_ga_rank_count(int n_pop, int slice, const double* __restrict__ fitness, int32_t* __restrict__ rank) {
+  __shared__ uint64_t sKey[256];
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  const uint64_t ki = i < n_pop ? key_of(fitness[i]) : 0ull;
+  const int j0 = blockIdx.y * slice, j1 = min(n_pop, j0 + slice);
+  int cnt = 0;
+  for (int base = j0; base < j1; base += 256) {
+    const int j = base + threadIdx.x;
+    __syncthreads();
+    sKey[threadIdx.x] = j < j1 ? key_of(fitness[j]) : ~0ull;
+    __syncthreads();
+    const int m = min(256, j1 - base);
+#pragma unroll 8
+    for (int t = 0; t < m; ++t) {
+      const uint64_t kj = sKey[t];
+      cnt += (kj < ki) || (kj == ki && base + t < i);
     }
-  for (int i = tid; i < n_pop; i += 1024) {
-    const int g = idx[i];
-    order[i] = g;
-    if (flags && flags[2 * g] && flags[2 * g + 1]) atomicMin(&first_feasible, i);
   }
-  __syncthreads();
-  if (tid == 0 && rep) {
-    const int b = idx[0];
-    rep->best_index = b;
-    rep->best_fitness = fitness[b];
-    rep->best_stress_ok = flags ? flags[2 * b] : 0;
-    rep->best_displace_ok = flags ? flags[2 * b + 1] : 0;
-    rep->feasible_index = first_feasible == 0x7fffffff ? -1 : idx[first_feasible];
-    rep->feasible_fitness = first_feasible == 0x7fffffff ? 0.0 : fitness[idx[first_feasible]];
-  }
+  if (i < n_pop && cnt) atomicAdd(&rank[i], cnt);
+}
+
+// order[rank] = individual; the first feasible individual in rank order = the smallest rank among the feasible ones
+__global__ void __launch_bounds__(256) k_ga_rank_scatter(int n_pop, const int32_t* __restrict__ rank, const uint8_t* __restrict__ flags,
+                                                          int32_t* __restrict__ order, int32_t* __restrict__ first_feasible) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= n_pop) return;
+  const int r = rank[i];
+  order[r] = i;
+  if (flags && flags[2 * i] && flags[2 * i + 1]) atomicMin(first_feasible, r);
+}
+
+// the report: best individual and the first feasible one in rank order (_RecordFeasible, ga.py:101-108)
+__global__ void k_ga_report(const double* fitness, const uint8_t* flags, const int32_t* order, const int32_t* first_feasible, tb_ga_report* rep) {
+  const int b = order[0], ff = *first_feasible;
+  rep->best_index = b;
+  rep->best_fitness = fitness[b];
+  rep->best_stress_ok = flags ? flags[2 * b] : 0;
+  rep->best_displace_ok = flags ? flags[2 * b + 1] : 0;
+  rep->feasible_index = ff >= 0x7f7f7f7f ? -1 : order[ff];
+  rep->feasible_fitness = ff >= 0x7f7f7f7f ? 0.0 : fitness[order[ff]];
 }
 
 // One thread per (individual, member).  The decisions of individual j come from Philox block (j, generation, BRANCH):
@@ -187,18 +185,44 @@ extern "C" int tb_ga_step(const tb_ga_params* p, uint64_t generation, const doub
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return TB_ERR_NO_DEVICE;
   cudaStream_t st = (cudaStream_t)cuda_stream;
-  int p2 = 1;
-  while (p2 < p->n_pop) p2 <<= 1;
-  const size_t smem = (size_t)p2 * 12;
-  if (smem > 200 * 1024) return TB_ERR_TOO_LARGE;                              // one-CTA ranking: up to 16384 individuals
-  static size_t granted = 0;
-  if (granted < smem) {
-    cudaError_t e = cudaFuncSetAttribute(k_ga_rank, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    granted = smem;
+  // scratch of the ranking: rank[n_pop] + the smallest feasible rank, one grow-only buffer per device
+  static std::mutex scratch_mu;
+  static int32_t* scratch[64] = {};
+  static size_t scratch_cap[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return (int)cudaGetLastError();
+  int32_t* rank = nullptr;
+  {
+    std::lock_guard<std::mutex> lock(scratch_mu);
+    const size_t need = (size_t)p->n_pop + 1;
+    if (scratch_cap[dev & 63] < need) {
+      if (scratch[dev & 63]) {
+        cudaDeviceSynchronize();
+        cudaFree(scratch[dev & 63]);
+        scratch[dev & 63] = nullptr;
+        scratch_cap[dev & 63] = 0;
+      }
+      cudaError_t e = cudaMalloc((void**)&scratch[dev & 63], need * sizeof(int32_t));
+      if (e != cudaSuccess) return (int)e;
+      scratch_cap[dev & 63] = need;
+    }
+    rank = scratch[dev & 63];
   }
-  k_ga_rank<<<1, 1024, smem, st>>>(p->n_pop, p2, fitness, flags, order, report);
-  int launches = 1;
+  int32_t* first_feasible = rank + p->n_pop;
+  {
+    cudaError_t e = cudaMemsetAsync(rank, 0, (size_t)p->n_pop * sizeof(int32_t), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(first_feasible, 0x7f, sizeof(int32_t), st);   // 0x7f7f7f7f: "none" (> any rank)
+    if (e != cudaSuccess) return (int)e;
+  }
+  const int tiles = (p->n_pop + 255) / 256;
+  int splits = (148 * 8 + tiles - 1) / tiles;                                    // enough CTAs to fill the GPU
+  if (splits > tiles) splits = tiles;
+  if (splits < 1) splits = 1;
+  const int slice = ((p->n_pop + splits - 1) / splits + 255) / 256 * 256;
+  k_ga_rank_count<<<dim3(tiles, (p->n_pop + slice - 1) / slice), 256, 0, st>>>(p->n_pop, slice, fitness, rank);
+  k_ga_rank_scatter<<<tiles, 256, 0, st>>>(p->n_pop, rank, flags, order, first_feasible);
+  if (report) k_ga_report<<<1, 1, 0, st>>>(fitness, flags, order, first_feasible, report);
+  int launches = report ? 3 : 2;
   if (gene_out) {                              // gene_out == NULL: ranking and report only (the final Select)
     const int64_t total = (int64_t)p->n_pop * p->n_member;
     const int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
