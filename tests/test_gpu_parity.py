@@ -735,3 +735,29 @@ def test_compact_outputs_equal_the_dense_ones(case, path):
                          aed.ctypes.data, force.ctypes.data, xyz.shape[0], conn.shape[0])
     bo = _lib.TbBatchOut(None, None, None, None, None, only["u_free"].ctypes.data, None)
     assert _lib.lib().tb_solve_ragged_host(C.byref(ri), C.byref(bo)) == -3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["bar-72", "bar-25", "bar-120", "bar-10", "bar-47"])
+def test_uniform_and_ragged_entry_points_agree_bitwise(case):
+    """The same trusses through the plan's uniform batch (tb_solve_host) and as a ragged batch (tb_solve_ragged_host):
+    the warp-per-truss kernel sums every K entry in ascending member order either way (truss.py:307-316) -> the same bits."""
+    name, dim, data, _ = next(c for c in H.shipped_cases() if c[0].startswith(case))
+    t = Truss(dim).LoadFromJSON(data=data)
+    xyz, sup, conn, aed, force = t._pack()
+    plan = _lib.Plan(dim, conn, sup.astype(np.uint8))
+    if plan.info.path != 0:
+        pytest.skip("not a small-path truss")
+    B = 5
+    rng = np.random.default_rng(2)
+    xyzb = xyz[None] + rng.normal(0, 0.01, size=(B,) + xyz.shape)
+    aedb = aed[None] * rng.uniform(0.5, 2.0, size=(B, aed.shape[0], 1))
+    F = force.reshape(1, -1) * rng.uniform(0.5, 2.0, size=(B, 1))
+    uni = plan.solve_host(B, xyzb, F, aed=aedb)
+    nJ, M = xyz.shape[0], conn.shape[0]
+    jo, mo = np.arange(B + 1, dtype=np.int64) * nJ, np.arange(B + 1, dtype=np.int64) * M
+    rag = _lib.solve_ragged_host(dim, jo, mo, xyzb.reshape(-1), np.tile(sup.astype(np.uint8), B), np.tile(conn.reshape(-1), B),
+                                 aedb.reshape(-1), F.reshape(-1))
+    assert not uni["info"].any() and not rag["info"].any()
+    for k in ("u", "ext", "axial", "weight"):
+        assert np.array_equal(np.asarray(uni[k]).reshape(-1), np.asarray(rag[k]).reshape(-1)), k
