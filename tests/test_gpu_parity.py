@@ -759,5 +759,12 @@ def test_uniform_and_ragged_entry_points_agree_bitwise(case):
     rag = _lib.solve_ragged_host(dim, jo, mo, xyzb.reshape(-1), np.tile(sup.astype(np.uint8), B), np.tile(conn.reshape(-1), B),
                                  aedb.reshape(-1), F.reshape(-1))
     assert not uni["info"].any() and not rag["info"].any()
+    # (a ragged batch sizes shared memory for d * nJ free DOFs; bar-120 then no longer fits the warp kernel and runs on the
+    # CTA-per-truss kernel, another summation order: equal to rounding there, bit for bit everywhere else)
+    same_kernel = _lib.lib().tb_small_path_fits(dim, nJ, M) and case != "bar-120"
     for k in ("u", "ext", "axial", "weight"):
-        assert np.array_equal(np.asarray(uni[k]).reshape(-1), np.asarray(rag[k]).reshape(-1)), k
+        a_, b_ = np.asarray(uni[k]).reshape(-1), np.asarray(rag[k]).reshape(-1)
+        if same_kernel:
+            assert np.array_equal(a_, b_), k
+        else:
+            assert orc.normwise_err(a_, b_) <= 1e-9, k
