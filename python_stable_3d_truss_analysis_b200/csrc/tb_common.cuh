@@ -199,6 +199,7 @@ struct LargeArgs {
   int64_t nnz;
   const uint8_t* tile_nz; const int32_t* prod_ptr; const int32_t* prod_k;
   const int32_t* q_ptr; const int32_t* q_pack; const int32_t* q_first; const int32_t* q_multi; int n_multi;
+  const int4* q_multi4;   // optional: {entry, first contribution, end, 0} per multi-contribution entry (one load instead of a pointer chase)
   int nb16, NB;
   const int32_t* b16_ptr; const int32_t* b16_pos; const int32_t* b16_nz;
   const int32_t* inc_ptr; const int32_t* inc_mem;

@@ -232,8 +232,14 @@ __global__ void __launch_bounds__(256) k_prep(const LargeArgs a) {
       }
     }
     for (int i = tid; i < a.n_multi; i += 256) {             // same-joint entries: ascending member order
-      const int q = a.q_multi[i];
-      const int p0 = a.q_ptr[q], p1 = a.q_ptr[q + 1];
+      int q, p0, p1;
+      if (a.q_multi4) {
+        const int4 mr = __ldg(a.q_multi4 + i);
+        q = mr.x; p0 = mr.y; p1 = mr.z;
+      } else {
+        q = a.q_multi[i];
+        p0 = a.q_ptr[q]; p1 = a.q_ptr[q + 1];
+      }
       double v = 0.0;
       for (int p = p0; p < p1; p += 8) {                     // eight contributions' map loads in flight, summed in order
         int pk[8];
@@ -1107,6 +1113,7 @@ int launch_ts_path(const LargeArgs& a, int num_sm, cudaStream_t st) {
   LargeArgs r = a;
   r.q_first = ts->d_tq_first; r.q_multi = ts->d_tq_multi; r.q_ptr = ts->d_tq_ptr; r.q_pack = ts->d_tq_pack;
   r.n_multi = (int)ts->tq_multi.size();
+  r.q_multi4 = ts->d_tq_multi4;
   r.nnz = (int64_t)ts->epos.size();
   r.kv = kv;
   r.y = t.uf;

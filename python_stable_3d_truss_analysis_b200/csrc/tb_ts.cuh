@@ -97,6 +97,7 @@ struct TsPlan {
   // assembly program in that order, in the format k_prep reads (tb_common.cuh: q_first / q_multi / q_ptr / q_pack)
   std::vector<int32_t> tq_first, tq_multi, tq_ptr, tq_pack;
   int32_t *d_epos = nullptr, *d_tq_first = nullptr, *d_tq_multi = nullptr, *d_tq_ptr = nullptr, *d_tq_pack = nullptr;
+  int4* d_tq_multi4 = nullptr;        // {entry, first contribution, end, 0} of the entries with several contributions
 };
 
 // ---- shared-memory layout of one side (doubles): [main: ring of live blocks, later the back substitution's chunk buffers

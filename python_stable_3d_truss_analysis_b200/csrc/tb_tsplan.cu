@@ -144,6 +144,7 @@ void tb_ts_destroy(TsPlan* ts, bool device) {
       cudaFree(h.d_colrec); cudaFree(h.d_rowdof); cudaFree(h.d_rownat);
     }
   if (device) {
+    cudaFree(ts->d_tq_multi4);
     cudaFree(ts->d_epos); cudaFree(ts->d_tq_first); cudaFree(ts->d_tq_multi); cudaFree(ts->d_tq_ptr); cudaFree(ts->d_tq_pack);
   }
   delete ts;
@@ -368,6 +369,14 @@ int tb_ts_build(tb_plan* p) {
   if (!rc) rc = up(&ts->d_tq_multi, ts->tq_multi);
   if (!rc) rc = up(&ts->d_tq_ptr, ts->tq_ptr);
   if (!rc) rc = up(&ts->d_tq_pack, ts->tq_pack);
+  if (!rc) {
+    std::vector<int4> m4(ts->tq_multi.size());
+    for (size_t i = 0; i < m4.size(); ++i) {
+      const int q = ts->tq_multi[i];
+      m4[i] = make_int4(q, ts->tq_ptr[q], ts->tq_ptr[q + 1], 0);
+    }
+    rc = up(&ts->d_tq_multi4, m4);
+  }
   return rc;
 }
 
