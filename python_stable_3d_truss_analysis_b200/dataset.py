@@ -3,6 +3,7 @@
 binary container instead of one JSON file per truss, plus the views back into the reference's formats:
 
 * ``PackedDataset.from_json_files``   N reference JSON files -> packed arrays through the native parser (no Truss objects);
+* ``PackedDataset.solve``             the whole container as one ragged GPU batch, results attached to the arrays;
 * ``PackedDataset.save / load``       one ``.npz`` (optionally compressed) holding every array;
 * ``PackedDataset.json(i)``           truss ``i`` as the reference's JSON dict (``Truss.Serialize``, truss.py:367-395 and
                                       ``detail/combine_with_JSON.md:71-163``: sparse ``displace / external / internal`` lists
@@ -106,6 +107,22 @@ class PackedDataset:
             with open(p, "rb") as f:
                 texts.append(f.read())
         return cls.from_json_texts(texts, dim, isOutputFile, [os.path.splitext(os.path.basename(p))[0] for p in paths], threads)
+
+    def solve(self, raise_on_error=False):
+        """Solve every truss of the container in one ragged GPU batch (tb_solve_ragged_host; the bulk form of the
+        generator's solve site generate.py:354-357) and attach ``u / ext / axial / weight / info`` -- no Truss objects.
+        Returns the per-truss info codes (0 solved, -1 fails the counting rule, k > 0 singular at pivot k)."""
+        from . import _lib
+        from .truss import raise_for_info
+        a = self.a
+        out = _lib.solve_ragged_host(self.dim, a["joint_off"], a["member_off"], a["xyz"], a["support"], a["conn"], a["aed"], a["force"])
+        for k in _RESULTS:
+            self.a[k] = out[k]
+        if raise_on_error:
+            bad = np.nonzero(out["info"])[0]
+            if bad.size:
+                raise_for_info(int(out["info"][bad[0]]))
+        return out["info"]
 
     # ------------------------------------------------------------------ binary container
     def save(self, path, compressed=False):

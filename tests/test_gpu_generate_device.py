@@ -111,3 +111,22 @@ def test_full_recipe_solved_on_the_device_matches_the_oracle():
     assert t.isSolved and np.array_equal(t._dense["u"], ds["u"][3 * j0:3 * j1])
     again = Truss(3).LoadFromJSON(data=pd_.json(o), isOutputFile=True)
     assert again.GetInternalForces() == t.GetInternalForces()
+
+
+def test_bulk_pipeline_json_files_to_solved_container():
+    """N reference JSON files -> packed arrays (native loader) -> one ragged GPU batch -> the shipped results, without a
+    single Truss object on the way (truss.py:401-421 + generate.py:354-357 in bulk)."""
+    import glob
+    import os
+    from python_stable_3d_truss_analysis_b200.dataset import PackedDataset
+    files = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "ref_generate", "cube-7_case_*.json")))
+    gold = PackedDataset.from_json_files(files, 3, isOutputFile=True)       # the shipped results
+    ds = PackedDataset.from_json_files(files, 3)                              # inputs only
+    assert not ds.solved
+    info = ds.solve()
+    assert not info.any() and ds.solved
+    for k in ("u", "ext", "axial"):
+        assert orc.normwise_err(ds.a[k], gold.a[k]) <= 1e-9, k
+    assert np.allclose(ds.a["weight"], gold.a["weight"], rtol=1e-12)
+    j = ds.json(3)
+    assert set(j) >= {"joint", "force", "member", "displace", "external", "internal", "weight"}
