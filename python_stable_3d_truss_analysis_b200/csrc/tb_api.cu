@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(256) k_compact_out(const double* __restrict__ 
 
 // dense temporaries of a call that wants the compact outputs without the dense ones (call before the ranges are enqueued)
 int ensure_compact_tmp(tb_plan* p, const tb_batch_out* out, int batch, cudaStream_t st) {
-  if (!out) return TB_OK;
+  if (!out || p->path != 0) return TB_OK;      // (the blocked pipelines' recovery kernel writes the compact outputs itself)
   auto grow = [&](double** buf, size_t* cap) -> int {
     if (*cap >= (size_t)batch) return TB_OK;
     if (*buf) {
@@ -86,6 +86,7 @@ int run_plan_range_dense(tb_plan* p, const tb_batch_in* in, const tb_batch_out* 
 int run_plan_range(tb_plan* p, const tb_batch_in* in, const tb_batch_out* out, const tb_fit_out* fit, double allow_s,
                    double allow_d, cudaStream_t st, int b0, int nb, void* ws, int shared_k = 0) {
   if (!out->u_free && !out->react) return run_plan_range_dense(p, in, out, fit, allow_s, allow_d, st, b0, nb, ws, shared_k);
+  if (p->path != 0) return run_plan_range_dense(p, in, out, fit, allow_s, allow_d, st, b0, nb, ws, shared_k);   // the recovery kernel writes them itself
   tb_batch_out eff = *out;
   if (out->u_free && !eff.u) eff.u = p->compact_u;          // (ensure_compact_tmp sized them for the whole batch)
   if (out->react && !eff.ext) eff.ext = p->compact_ext;
@@ -195,6 +196,9 @@ int run_plan_range_dense(tb_plan* p, const tb_batch_in* in, const tb_batch_out* 
   a.axial = out->axial ? out->axial + (int64_t)b0 * p->M : nullptr;
   a.weight = out->weight ? out->weight + b0 : nullptr;
   a.info = info ? info + b0 : nullptr;
+  a.u_free = out->u_free ? out->u_free + (int64_t)b0 * p->n : nullptr;
+  a.react = out->react ? out->react + (int64_t)b0 * p->s : nullptr;
+  a.free_ref = p->d_free_ref;
   a.fitness = fit && fit->fitness ? fit->fitness + b0 : nullptr;
   a.flags = fit && fit->flags ? fit->flags + 2 * (int64_t)b0 : nullptr;
   a.allow_stress = allow_s;

@@ -215,6 +215,8 @@ struct LargeArgs {
   int32_t* status; // [B] 0 ok / k>0 pivot / <0 input problem
   // outputs
   double* u; double* ext; double* axial; double* weight; int32_t* info;
+  double* u_free; double* react;      // compact outputs [B][n] / [B][s] (reference order), written by the recovery kernel
+  const int32_t* free_ref;            // [n] DOF index of free DOF r in the reference's order
   double* fitness; uint8_t* flags;
   double allow_stress, allow_displace;
   int fitness_mode;

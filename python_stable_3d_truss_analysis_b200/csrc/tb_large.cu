@@ -886,11 +886,17 @@ __global__ void __launch_bounds__(256) k_recover(const LargeArgs a) {
     double* u_out = a.u ? a.u + (int64_t)b * a.N : nullptr;
     double* ext_out = a.ext ? a.ext + (int64_t)b * a.N : nullptr;
     double* ax_out = a.axial ? a.axial + (int64_t)b * a.M : nullptr;
+    double* uf_out = a.u_free ? a.u_free + (int64_t)b * a.n : nullptr;
+    double* re_out = a.react ? a.react + (int64_t)b * a.s : nullptr;
     if (status != 0) {
       for (int i = tid; i < a.N; i += 256) {
         if (u_out) u_out[i] = 0.0;
         if (ext_out) ext_out[i] = 0.0;
       }
+      for (int r = tid; r < a.n; r += 256)
+        if (uf_out) uf_out[r] = 0.0;
+      for (int r = tid; r < a.s; r += 256)
+        if (re_out) re_out[r] = 0.0;
       for (int m = tid; m < a.M; m += 256)
         if (ax_out) ax_out[m] = 0.0;
       if (tid == 0) {
@@ -910,10 +916,13 @@ __global__ void __launch_bounds__(256) k_recover(const LargeArgs a) {
     double* axw = RECOMP ? sRec : a.mw + (int64_t)b * a.M;  // non-RECOMP: reuse the weight terms' slot for axial after reading them
     const double* xyz = a.xyz + b * a.xyz_stride;
     double w = 0.0, vs = 0.0, vd = 0.0;
-    for (int i = tid; i < a.N; i += 256) {
-      const int fr = a.dof2free[i];
-      if (u_out) u_out[i] = fr >= 0 ? uf[fr] : 0.0;
-    }
+    if (u_out)
+      for (int i = tid; i < a.N; i += 256) {
+        const int fr = a.dof2free[i];
+        u_out[i] = fr >= 0 ? uf[fr] : 0.0;
+      }
+    if (uf_out)                                  // compact: free DOF r of the reference's order
+      for (int r = tid; r < a.n; r += 256) uf_out[r] = uf[a.dof2free[a.free_ref[r]]];
     for (int m = tid; m < a.M; m += 256) {
       const int j0 = a.conn[2 * m], j1 = a.conn[2 * m + 1];
       double km, wm, cm[DIM];
@@ -969,24 +978,22 @@ __global__ void __launch_bounds__(256) k_recover(const LargeArgs a) {
       }
     }
     __syncthreads();  // axial forces of this system are visible to the CTA
+    auto reaction = [&](int dof) {               // row of K times u at a supported DOF, member by member (ascending)
+      const int J = dof / DIM, ax = dof - J * DIM;
+      double e = 0.0;
+      for (int p = a.inc_ptr[J]; p < a.inc_ptr[J + 1]; ++p) {
+        const int me = a.inc_mem[p], m = me >> 1;
+        const double g = (me & 1) ? mc[m * DIM + ax] : -mc[m * DIM + ax];
+        e = fma(g, axw[m], e);
+      }
+      return e;
+    };
     if (ext_out) {
       const double* f = a.force + b * a.force_stride;
-      for (int dof = tid; dof < a.N; dof += 256) {
-        double e;
-        if (a.dof2free[dof] >= 0) {
-          e = f[dof];
-        } else {
-          const int J = dof / DIM, ax = dof - J * DIM;
-          e = 0.0;
-          for (int p = a.inc_ptr[J]; p < a.inc_ptr[J + 1]; ++p) {
-            const int me = a.inc_mem[p], m = me >> 1;
-            const double g = (me & 1) ? mc[m * DIM + ax] : -mc[m * DIM + ax];
-            e = fma(g, axw[m], e);
-          }
-        }
-        ext_out[dof] = e;
-      }
+      for (int dof = tid; dof < a.N; dof += 256) ext_out[dof] = a.dof2free[dof] >= 0 ? f[dof] : reaction(dof);
     }
+    if (re_out)                                  // compact: supported DOF r of the reference's order
+      for (int r = tid; r < a.s; r += 256) re_out[r] = reaction(a.sup_idx[r]);
     if (a.fitness_mode) {
       for (int j = tid; j < a.nJ; j += 256) {
         bool any = false;
@@ -1233,6 +1240,8 @@ int tb_launch_large(const LargeArgs& a, int num_sm, cudaStream_t st, int path) {
       h.y = a.y + (int64_t)b0 * a.n_pad;
       h.status = a.status + b0;
       if (a.u) h.u = a.u + (int64_t)b0 * a.N;
+      if (a.u_free) h.u_free = a.u_free + (int64_t)b0 * a.n;
+      if (a.react) h.react = a.react + (int64_t)b0 * a.s;
       if (a.ext) h.ext = a.ext + (int64_t)b0 * a.N;
       if (a.axial) h.axial = a.axial + (int64_t)b0 * a.M;
       if (a.weight) h.weight = a.weight + b0;
