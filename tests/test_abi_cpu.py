@@ -185,3 +185,48 @@ def test_fused_path_is_chosen_by_shared_memory_not_by_size_alone():
     assert _lib.small_path_fits(3, 32, 119)            # the cube-7 trusses of the generator
     # 2-D: 80 joints, 400 members
     assert not _lib.small_path_fits(2, 80, 400) or _lib.Plan(2, conn[conn.max(axis=1) < 80][:400], np.r_[np.ones(2, np.uint8), np.zeros(78, np.uint8)]).info.path == 0
+
+
+def test_gencube_limits_and_argument_errors():
+    """tb_gencube_limits is host arithmetic (strides of the generator's fixed-stride scratch); bad parameters are refused
+    before any device work (generate.py:152-336 on the device, csrc/tb_gencube.cu)."""
+    import ctypes as C
+    L = _lib.lib()
+    prm = _lib.TbGencubeParams()
+    for i, g in enumerate((5, 5, 5)):
+        prm.grid[i] = g
+    prm.ncube_lo, prm.ncube_hi = 7, 7
+    prm.method, prm.link_type, prm.n_type, prm.max_attempts = 2, 3, 1, 8
+    prm.length_lo, prm.length_hi = 50.0, 150.0
+    mj, mm, mc = C.c_int32(), C.c_int32(), C.c_int32()
+    assert L.tb_gencube_limits(C.byref(prm), C.byref(mj), C.byref(mm), C.byref(mc)) == 0
+    assert (mj.value, mm.value, mc.value) == (56, 168, 7)          # 8 corners and 24 links per cube at most
+    prm.ncube_hi = 1000                                           # more cubes than cells: capped by the grid
+    assert L.tb_gencube_limits(C.byref(prm), C.byref(mj), C.byref(mm), C.byref(mc)) == 0
+    assert mc.value == 125 and mj.value == 216
+    prm.grid[0] = 50                                              # grid beyond TB_GEN_MAX_CELLS
+    assert L.tb_gencube_limits(C.byref(prm), None, None, None) == _lib.TB_ERR_TOO_LARGE
+    prm.grid[0] = 5
+    prm.ncube_lo = 0
+    assert L.tb_gencube_limits(C.byref(prm), None, None, None) == -3
+    prm.ncube_lo, prm.ncube_hi, prm.method = 7, 7, 9               # unknown GenerateMethod
+    assert L.tb_gencube(C.byref(prm), 4, *([None] * 13)) == -3
+    prm.method = 2
+    assert L.tb_gencube(C.byref(prm), 4, *([None] * 13)) == -1     # NULL outputs
+    assert L.tb_gencube(C.byref(prm), 0, *([None] * 13)) == 0      # empty batch
+    if not _has_cuda():
+        buf = (C.c_double * 8)()
+        p = C.cast(buf, C.c_void_p)
+        assert L.tb_gencube(C.byref(prm), 1, p, p, p, p, p, p, p, p, p, None, None, None, None) == _lib.TB_ERR_NO_DEVICE
+
+
+def test_compact_output_fields_are_part_of_the_abi():
+    """tb_batch_out carries the compact pair as its last two fields; the ragged entry points refuse them (no common n / s)."""
+    import ctypes as C
+    assert [f[0] for f in _lib.TbBatchOut._fields_] == ["u", "ext", "axial", "weight", "info", "u_free", "react"]
+    assert C.sizeof(_lib.TbBatchOut) == 7 * C.sizeof(C.c_void_p)
+    jo, mo = np.array([0, 3], np.int64), np.array([0, 2], np.int64)
+    ri = _lib.TbRaggedIn(3, 1, jo.ctypes.data, mo.ctypes.data, 0, 0, 0, 0, 0, 3, 2)
+    bo = _lib.TbBatchOut(None, None, None, None, None, 1234, None)
+    assert _lib.lib().tb_solve_ragged_host(C.byref(ri), C.byref(bo)) == -3
+    assert _lib.lib().tb_solve_ragged(C.byref(ri), C.byref(bo), None) == -3
