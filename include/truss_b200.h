@@ -361,6 +361,11 @@ int tb_fp64_peak(int32_t which, int32_t iters, double* tflops, float* ms);
  * step): largest relative error against 1/sqrt(d) over n values spread log-uniformly over [1e-290, 1e300]. */
 int tb_rsqrt_probe(int32_t n, double* max_rel_err);
 
+/* Exactness probe of the shared-divisor division the member geometry uses (one correctly rounded reciprocal of the length,
+ * then Markstein's multiply / FMA / FMA per numerator instead of four full divisions): counts the operand pairs out of n
+ * (random and adversarial significands and exponents, keyed by seed) whose quotient differs from IEEE division. */
+int tb_div_probe(int64_t n, uint64_t seed, uint64_t* mismatches);
+
 /* Optional per-kernel CUDA-event timing on the launching stream (bench.py's roofline line).
  * tb_profile_read adds the milliseconds / launch counts recorded since the last read into
  * ms[8] / count[8]; slots: 0 member geometry, 1 assembly, 2 blocked Cholesky+solve, 3 recovery,

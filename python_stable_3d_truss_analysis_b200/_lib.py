@@ -156,7 +156,7 @@ class TbRaggedIn(C.Structure):
 
 EXPORTS = ["tb_plan_create", "tb_plan_destroy", "tb_plan_query", "tb_plan_set_path", "tb_plan_get_maps",
            "tb_plan_get_scatter", "tb_solve", "tb_solve_host", "tb_solve_host_async", "tb_host_wait", "tb_solve_loadcases", "tb_solve_loadcases_host", "tb_fitness", "tb_fitness_host", "tb_solve_ragged",
-           "tb_solve_ragged_host", "tb_ga_init", "tb_ga_step", "tb_augment_ragged", "tb_json_scan", "tb_json_fill", "tb_gencube_limits", "tb_gencube", "tb_gencube_pack", "tb_pinned_alloc", "tb_pinned_free", "tb_small_path_limits", "tb_fp64_peak", "tb_rsqrt_probe", "tb_profile_enable", "tb_profile_read",
+           "tb_solve_ragged_host", "tb_ga_init", "tb_ga_step", "tb_augment_ragged", "tb_json_scan", "tb_json_fill", "tb_gencube_limits", "tb_gencube", "tb_gencube_pack", "tb_pinned_alloc", "tb_pinned_free", "tb_small_path_limits", "tb_fp64_peak", "tb_rsqrt_probe", "tb_div_probe", "tb_profile_enable", "tb_profile_read",
            "tb_launch_count", "tb_strerror", "tb_version", "tb_small_path_fits", "tb_debug_assemble_host", "tb_plan_ts_info", "tb_plan_ts_array", "tb_ts_phase_read"]
 
 _lib = None
@@ -195,6 +195,7 @@ def lib():
     L.tb_small_path_limits.argtypes = [C.POINTER(i32), C.POINTER(i32)]
     L.tb_fp64_peak.argtypes = [i32, i32, C.POINTER(dbl), C.POINTER(C.c_float)]
     L.tb_rsqrt_probe.argtypes = [i32, C.POINTER(dbl)]
+    L.tb_div_probe.argtypes = [i64, C.c_uint64, C.POINTER(C.c_uint64)]
     L.tb_augment_ragged.argtypes = [C.POINTER(TbRaggedIn), i32, vp, vp, vp, C.POINTER(TbAugmentParams), vp, vp, vp, vp, vp, vp]
     L.tb_gencube_limits.argtypes = [C.POINTER(TbGencubeParams), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
     L.tb_gencube.argtypes = [C.POINTER(TbGencubeParams), i32] + [vp] * 13

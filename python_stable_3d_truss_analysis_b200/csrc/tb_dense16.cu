@@ -202,9 +202,10 @@ __global__ void __launch_bounds__(128) k_dense16(const SmallArgs a, const int nb
           if (!(len > 0.0)) {
             bad |= 2;
           } else {
-            k = __ddiv_rn(__dmul_rn(e, ar), len);
+            const TbDivisor dv(len);                  // (one reciprocal for the four quotients of the member)
+            k = dv.div(__dmul_rn(e, ar));
 #pragma unroll
-            for (int i = 0; i < DIM; ++i) c[i] = __ddiv_rn(dx[i], len);
+            for (int i = 0; i < DIM; ++i) c[i] = dv.div(dx[i]);
           }
         }
         sMk[m] = k;

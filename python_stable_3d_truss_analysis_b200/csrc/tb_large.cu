@@ -88,9 +88,10 @@ __global__ void k_geom(const LargeArgs a) {
     } else if (!(len > 0.0)) {
       atomicMin(&a.status[b], TB_INFO_ZERO_LENGTH);
     } else {
-      k = __ddiv_rn(__dmul_rn(e, ar), len);
+      const TbDivisor dv(len);                  // (one reciprocal for the four quotients of the member)
+      k = dv.div(__dmul_rn(e, ar));
 #pragma unroll
-      for (int i = 0; i < DIM; ++i) c[i] = __ddiv_rn(dx[i], len);
+      for (int i = 0; i < DIM; ++i) c[i] = dv.div(dx[i]);
     }
     a.mk[idx] = k;
 #pragma unroll
@@ -204,9 +205,10 @@ __global__ void __launch_bounds__(256) k_prep(const LargeArgs a) {
         } else if (!(len > 0.0)) {
           flag = min(flag, TB_INFO_ZERO_LENGTH);
         } else {
-          k = __ddiv_rn(__dmul_rn(e[u], ar[u]), len);
+          const TbDivisor dv(len);                  // (one reciprocal for the four quotients of the member)
+          k = dv.div(__dmul_rn(e[u], ar[u]));
 #pragma unroll
-          for (int i = 0; i < DIM; ++i) c[i] = __ddiv_rn(dx[i], len);
+          for (int i = 0; i < DIM; ++i) c[i] = dv.div(dx[i]);
         }
         double* o = sMkc + m * NV;
         int t = 0;
@@ -942,10 +944,11 @@ __global__ void __launch_bounds__(256) k_recover(const LargeArgs a) {
 #pragma unroll
         for (int i = 1; i < DIM; ++i) l2 = __dadd_rn(l2, __dmul_rn(dx[i], dx[i]));
         const double len = __dsqrt_rn(l2);
-        km = __ddiv_rn(__dmul_rn(e, ar), len);
+        const TbDivisor dv(len);                  // (one reciprocal for the four quotients of the member)
+        km = dv.div(__dmul_rn(e, ar));
 #pragma unroll
         for (int i = 0; i < DIM; ++i) {
-          cm[i] = __ddiv_rn(dx[i], len);
+          cm[i] = dv.div(dx[i]);
           sRec[a.M + m * DIM + i] = cm[i];
         }
         wm = __dmul_rn(__dmul_rn(ar, len), rho);

@@ -1,5 +1,8 @@
 // FP64 pipe microbenchmarks.  MEASURED_PEAKS.json carries HBM and bf16 numbers only, so the
 // FP64 roofline denominators (vector DFMA, tensor DMMA) are measured on the box by these.
+#include <stdio.h>
+#include <stdlib.h>
+
 #include "tb_common.cuh"
 #include "tb_blocks.cuh"
 
@@ -73,6 +76,61 @@ __global__ void k_rsqrt_probe(int n, double* worst) {
 }
 
 }  // namespace
+
+namespace {
+// TbDivisor against __ddiv_rn: numerators and divisors spread over magnitudes and significand patterns (random bits,
+// all-ones / near-all-ones / power-of-two significands, tiny and huge exponents, zero numerators)
+__global__ void k_div_probe(long long n, unsigned long long seed, unsigned long long* mismatches) {
+  unsigned long long bad = 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    unsigned long long x = (unsigned long long)i * 0x9E3779B97F4A7C15ull + seed;
+    auto next = [&]() { x ^= x >> 12; x ^= x << 25; x ^= x >> 27; return x * 0x2545F4914F6CDD1Dull; };
+    const unsigned long long r0 = next(), r1 = next(), r2 = next();
+    unsigned long long mb = r0 & 0xfffffffffffffull, ma = r1 & 0xfffffffffffffull;
+    const int pat = (int)(r2 & 15);
+    if (pat == 0) mb = 0xfffffffffffffull;                       // significand all ones
+    if (pat == 1) mb = 0xffffffffffffeull;
+    if (pat == 2) mb = 0;                                        // power of two
+    if (pat == 3) mb = 1;
+    if (pat == 4) ma = 0xfffffffffffffull;
+    if (pat == 5) ma = mb;                                       // quotient a power of two
+    int eb = 1023 + (int)((r2 >> 8) % 41) - 20, ea = 1023 + (int)((r2 >> 16) % 61) - 30;
+    if (pat == 6) eb = 1 + (int)((r2 >> 24) % 40);               // tiny divisor
+    if (pat == 7) eb = 2046 - (int)((r2 >> 24) % 40);            // huge divisor
+    if (pat == 8) ea = 1 + (int)((r2 >> 24) % 40);
+    if (pat == 9) ea = 2046 - (int)((r2 >> 24) % 40);
+    double b = __longlong_as_double((long long)(((unsigned long long)eb << 52) | mb));
+    double a = __longlong_as_double((long long)(((unsigned long long)ea << 52) | ma));
+    if (pat == 10) a = 0.0;
+    if (r2 & (1ull << 40)) a = -a;
+    const TbDivisor d(b);
+    const double got = d.div(a), want = __ddiv_rn(a, b);
+    if (__double_as_longlong(got) != __double_as_longlong(want)) {
+      ++bad;
+      atomicAdd(mismatches + 1 + pat, 1ull);                     // (per operand pattern, for diagnosis)
+    }
+  }
+  if (bad) atomicAdd(mismatches, bad);
+}
+}  // namespace
+
+extern "C" int tb_div_probe(int64_t n, uint64_t seed, uint64_t* mismatches) {
+  if (!mismatches) return TB_ERR_NULL;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return TB_ERR_NO_DEVICE;
+  unsigned long long* d = nullptr;
+  TB_CUDA(cudaMalloc(&d, 17 * sizeof(unsigned long long)));
+  TB_CUDA(cudaMemset(d, 0, 17 * sizeof(unsigned long long)));
+  k_div_probe<<<148 * 8, 256>>>((long long)n, (unsigned long long)seed, d);
+  tb_count_launch(1);
+  unsigned long long h[17] = {};
+  cudaError_t e = cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  *mismatches = (uint64_t)h[0];
+  if (getenv("TB_DIV_PROBE_DEBUG"))
+    for (int i = 0; i < 16; ++i) fprintf(stderr, "[tb_div_probe] pattern %2d: %llu mismatches\n", i, h[1 + i]);
+  return (int)e;
+}
 
 extern "C" int tb_rsqrt_probe(int32_t n, double* max_rel_err) {
   if (!max_rel_err) return TB_ERR_NULL;

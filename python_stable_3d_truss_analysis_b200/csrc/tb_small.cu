@@ -170,9 +170,10 @@ __global__ void __launch_bounds__(SMALL_MAX_THREADS) k_small(const SmallArgs a) 
         if (!(len > 0.0)) {
           atomicMin(&sMeta[1], TB_INFO_ZERO_LENGTH);
         } else {
-          k = __ddiv_rn(__dmul_rn(e, ar), len);
+          const TbDivisor dv(len);                  // (one reciprocal for the four quotients of the member)
+          k = dv.div(__dmul_rn(e, ar));
 #pragma unroll
-          for (int i = 0; i < DIM; ++i) c[i] = __ddiv_rn(dx[i], len);
+          for (int i = 0; i < DIM; ++i) c[i] = dv.div(dx[i]);
         }
       }
       sMk[m] = k;
